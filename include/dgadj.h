@@ -1,0 +1,174 @@
+/* dgadj.h -- C-ABI of libdgadj.so: B200-native (sm_100a) batched 1-D nodal-DG forward march,
+ * reverse-time discrete adjoint march and per-element adjoint-weighted error indicator.
+ *
+ * The reference (wglao/Adjoint-ODE-Adaptivity) has NO native / FFI layer: its hot path is
+ * MATLAB + NumPy source.  Each entry point below therefore cites the reference *source
+ * routine* it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side (python/galerkin.py, python/Main_finite_difference.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary.
+ *   - every function returns DGADJ_OK (0) or a negative dgadj_status; nothing throws.
+ *     dgadj_last_error(h) gives a human-readable message for the last failure on h.
+ *   - `*_dev` pointers are CUDA device pointers on the handle's device, caller-owned and
+ *     borrowed for the call; work is enqueued on `stream` (a cudaStream_t cast to void*,
+ *     NULL = the legacy default stream) and is asynchronous -- the caller synchronises.
+ *   - `*_host` entry points take host pointers, stage through pinned memory, copy H2D,
+ *     run the same kernels, copy D2H and synchronise before returning.
+ *   - all matrices are fp64, row-major; fields are [B][Np][K] (node-major inside a
+ *     trajectory: element index fastest), the batched form of galerkin.py's (Np, K) arrays
+ *     (python/galerkin.py:216).
+ *   - a handle is bound to one device and is not thread-safe (one handle per GPU / rank).
+ *   - there is NO CPU fallback: dgadj_create fails with DGADJ_ERR_NO_DEVICE unless the
+ *     device has compute capability 10.x.
+ */
+#ifndef DGADJ_H
+#define DGADJ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGADJ_VERSION 100 /* 0.1.0 */
+
+typedef struct dgadj_handle dgadj_handle;
+
+typedef enum {
+  DGADJ_OK = 0,
+  DGADJ_ERR_INVALID = -1,     /* bad argument / shape */
+  DGADJ_ERR_NO_DEVICE = -2,   /* no sm_100 device (no CPU fallback exists) */
+  DGADJ_ERR_CUDA = -3,        /* a CUDA runtime call failed; see dgadj_last_error */
+  DGADJ_ERR_UNSUPPORTED = -4, /* valid request outside the compiled envelope (N, K, ...) */
+  DGADJ_ERR_STATE = -5,       /* operators / weights not set before a march */
+  DGADJ_ERR_NOMEM = -6
+} dgadj_status;
+
+enum { DGADJ_BC_INFLOW = 0,    /* utils/AdvecRHS1D.m:14-16 (inflow Dirichlet + free outflow) */
+       DGADJ_BC_PERIODIC = 1 };/* BASELINE config 1/2 text; not in the reference */
+enum { DGADJ_INFLOW_ZERO = 0,
+       DGADJ_INFLOW_SIN_AT = 1,   /* uin = -sin(a t)    utils/AdvecRHS1D.m:14 */
+       DGADJ_INFLOW_SIN_AAT = 2,  /* uin = -sin(a a t)  utils/One_code.mlx (quirk C-2) */
+       DGADJ_INFLOW_TABLE = 3 };  /* uin[n*nstages+s] supplied by the caller */
+enum { DGADJ_FUNC_LINEAR = 0,  /* J = sum jw o u(T)  (J = int psi u dx; getK 'J=int(u)') */
+       DGADJ_FUNC_INT_U2 = 1 };/* J = int u(T)^2 dx  (getK 'J=int(u^2)', Main_finite_difference.py:225) */
+enum { DGADJ_SCHEME_LSERK4 = 0,  /* utils/Globals1D.m:20-34 */
+       DGADJ_SCHEME_EULER = 1 }; /* matlab/fwd_euler_march.m / forwardSolve semantics */
+
+typedef struct {
+  int32_t device;     /* CUDA device ordinal */
+  int32_t N;          /* primal polynomial order, Np = N+1, 1 <= N <= 8 */
+  int32_t K;          /* elements per mesh, 1 <= K <= 1024 */
+  int32_t bc;         /* DGADJ_BC_* */
+  int32_t inflow;     /* DGADJ_INFLOW_* (bc = inflow only) */
+  int32_t functional; /* DGADJ_FUNC_* */
+  int32_t scheme;     /* DGADJ_SCHEME_* */
+  int32_t reserved;
+  double alpha;       /* flux parameter of AdvecRHS1D.m:9-11: 1 = central (reference), 0 = upwind */
+} dgadj_config;
+
+int dgadj_version(void);
+
+/* Replaces: the `Globals1D` state shared by every reference routine (utils/Globals1D.m:3-17). */
+int dgadj_create(const dgadj_config* cfg, dgadj_handle** out);
+void dgadj_destroy(dgadj_handle* h);
+const char* dgadj_last_error(const dgadj_handle* h);
+
+/* Operators of the primal space, as produced by StartUp1D (utils/StartUp1D.m:9-33) /
+ * BaseGalerkin1D.startUp1D (python/galerkin.py:199-237).  Host pointers, copied.
+ *   Dr[Np*Np], LIFT[Np*2], Mref[Np*Np] = inv(V V'), rx[Np*K], Fscale[2*K].              */
+int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double* Dr, const double* LIFT,
+                        const double* Mref, const double* rx, const double* Fscale);
+
+/* Operators of the enriched space (order N+1; matlab/MAIN.m:34 solves the adjoint at Ns+1)
+ * plus the nodal prolongation P[NpF*Np] = V_{N+1}(:,1:Np) inv(V_N).                      */
+int dgadj_set_enriched(dgadj_handle* h, int NpF, const double* DrF, const double* LIFTF,
+                       const double* MrefF, const double* rxF, const double* FscaleF,
+                       const double* P);
+
+/* Weights of a linear terminal functional J = sum_{i,k} jw[i,k] u[i,k] in both spaces
+ * (jw_c[Np*K], jw_f[NpF*K]); used when cfg.functional == DGADJ_FUNC_LINEAR.              */
+int dgadj_set_functional_weights(dgadj_handle* h, const double* jw_c, const double* jw_f);
+
+/* Caller-supplied inflow values uin[S*nstages] (cfg.inflow == DGADJ_INFLOW_TABLE).       */
+int dgadj_set_inflow_table(dgadj_handle* h, int n, const double* uin);
+
+/* Per-trajectory advection speed / time step: if a_dev (dt_dev) is NULL the scalar is used. */
+typedef struct {
+  int64_t B;            /* trajectories in this call */
+  int32_t S;            /* time steps */
+  int32_t reserved;
+  double t0;            /* start time (reference: time = 0) */
+  double a;             /* advection speed (AdvecRHS1D.m:1 argument `a`) */
+  double dt;            /* time step (One_code.mlx CFL rule, computed by the host) */
+  const double* a_dev;  /* [B] or NULL */
+  const double* dt_dev; /* [B] or NULL */
+} dgadj_march_args;
+
+/* Forward march.  Replaces: the `for tstep ... for INTRK=1:5` LSERK4 loop of
+ * utils/One_code.mlx with utils/AdvecRHS1D.m:8-19 inlined (and, with DGADJ_SCHEME_EULER,
+ * the explicit-Euler march matlab/fwd_euler_march.m / Main_finite_difference.py:34-51).
+ *   u0_dev[B][Np][K] -> uT_dev[B][Np][K]; hist_dev[B][S+1][Np][K] (or NULL) receives every
+ *   step's state (the reference hands the primal to the adjoint in memory, adj_march.m:4);
+ *   ckpt_dev (or NULL) receives the opaque forward checkpoints the adjoint consumes
+ *   (dgadj_ckpt_bytes(h, B, S) bytes).                                                   */
+int dgadj_forward(dgadj_handle* h, const dgadj_march_args* args, const double* u0_dev,
+                  double* uT_dev, double* hist_dev, void* ckpt_dev, void* stream);
+int64_t dgadj_ckpt_bytes(dgadj_handle* h, int64_t B, int32_t S);
+
+/* Reverse-time adjoint march + per-element indicator.  Replaces: matlab/adj_march.m:67-118
+ * (adjoint one order higher, err(k) = v_k' * residual) and errEst
+ * (python/Main_finite_difference.py:79-94), for the DG-in-space march.
+ *   uT_dev[B][Np][K] (terminal primal, for J and the terminal condition), ckpt_dev from
+ *   dgadj_forward -> J_dev[B], lam0_dev[B][NpF][K] (dJ/du0 in the enriched space, or NULL),
+ *   eta_dev[B][K] (signed; consumers take abs, matlab/MAIN.m:51).                        */
+int dgadj_adjoint(dgadj_handle* h, const dgadj_march_args* args, const double* uT_dev,
+                  const void* ckpt_dev, double* J_dev, double* lam0_dev, double* eta_dev,
+                  void* stream);
+
+/* Fused forward + adjoint + indicator: one persistent CTA marches a group of trajectories
+ * forward, then immediately backward, through a per-CTA checkpoint ring owned by the
+ * handle (so live checkpoints are #CTAs x S x state, never B x S).  Any output may be NULL. */
+int dgadj_fwd_adj(dgadj_handle* h, const dgadj_march_args* args, const double* u0_dev,
+                  double* uT_dev, double* J_dev, double* lam0_dev, double* eta_dev,
+                  void* stream);
+
+/* Same as dgadj_fwd_adj with HOST buffers (pinned staging, H2D, kernels, D2H, sync).
+ * a_host / dt_host: [B] or NULL.                                                         */
+int dgadj_fwd_adj_host(dgadj_handle* h, const dgadj_march_args* args, const double* a_host,
+                       const double* dt_host, const double* u0_host, double* uT_host,
+                       double* J_host, double* lam0_host, double* eta_host);
+int dgadj_forward_host(dgadj_handle* h, const dgadj_march_args* args, const double* a_host,
+                       const double* dt_host, const double* u0_host, double* uT_host,
+                       double* hist_host);
+
+/* Refine flag / ranking.  Replaces: ref_i = find(abs(err)==max(abs(err))) (matlab/MAIN.m:137),
+ * np.argmax(err_steps) (Main_finite_difference.py:337) and sort(...,'descend') (MAIN.m:99).
+ *   eta_dev[B][K] -> order_dev[B][K] int32 (elements by descending |eta|, ties by lowest
+ *   index; or NULL), flags_dev[B][K] uint8 (1 on the topk elements; or NULL).            */
+int dgadj_rank(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev, int32_t topk,
+               int32_t* order_dev, uint8_t* flags_dev, void* stream);
+
+/* Batch reduction feeding the cross-GPU all-reduce (python/Main_variable_params.py:340,
+ * jnp.mean(err_refine, axis=0)): sums_dev[K+4] = { sum_b |eta[b][k]| (k<K), sum|eta|,
+ * sum eta^2, max|eta|, sum_b J[b] } in a fixed, B-independent summation order.          */
+int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev,
+                            const double* J_dev, double* sums_dev, void* stream);
+
+/* Register-only DFMA microbenchmark: sustained fp64 FMA-pipe peak of the handle's device
+ * in TFLOP/s (the roofline denominator SURVEY section 8(d) asks to be measured).        */
+int dgadj_measure_dfma_peak(dgadj_handle* h, double seconds, double* tflops_out,
+                            double* sm_clock_mhz_out);
+
+/* Device properties used by the host to size batches. */
+int dgadj_device_info(dgadj_handle* h, int32_t* sm_count, int64_t* total_mem, int32_t* cc_major,
+                      int32_t* cc_minor);
+
+/* Number of kernel launches issued through this handle since creation (bench accounting). */
+int64_t dgadj_launch_count(const dgadj_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGADJ_H */
