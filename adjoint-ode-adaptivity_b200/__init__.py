@@ -1,0 +1,15 @@
+"""dgadj -- B200-native batched 1-D nodal-DG forward / adjoint march with adjoint-weighted error
+indicators: a from-scratch drop-in for the hot path of wglao/Adjoint-ODE-Adaptivity.
+
+The directory is named `adjoint-ode-adaptivity_b200` (not an importable identifier); load it
+with `dgadj_loader.load_package()` from the repo root, which registers it as the module
+`adjoint_ode_adaptivity_b200`.
+"""
+from . import _lib
+from ._lib import DgadjError
+from .galerkin import BaseGalerkin1D
+from .solver import AdvecDG1D
+from .sharding import shard_range, allreduce_indicators, batch_mean_refine
+
+__all__ = ["AdvecDG1D", "BaseGalerkin1D", "DgadjError", "shard_range", "allreduce_indicators",
+           "batch_mean_refine", "_lib"]

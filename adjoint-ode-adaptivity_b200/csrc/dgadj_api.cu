@@ -1,0 +1,1042 @@
+// dgadj_api.cu -- the C-ABI of libdgadj.so (include/dgadj.h): handle, operator upload,
+// launch planning, the chunked host-buffer pipeline, ranking / reduction / peak kernels.
+// The march kernels themselves live in dgadj_kernels.cuh (one object per order).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/dgadj.h"
+#include "dgadj_kernels.cuh"
+
+namespace dgadj {
+#define DGADJ_DECL_NP(n) \
+  cudaError_t march_launch_np##n(int, int, int, int, cudaStream_t, const KArgs*);
+DGADJ_DECL_NP(2) DGADJ_DECL_NP(3) DGADJ_DECL_NP(4) DGADJ_DECL_NP(5)
+DGADJ_DECL_NP(6) DGADJ_DECL_NP(7) DGADJ_DECL_NP(8) DGADJ_DECL_NP(9)
+static march_launch_fn launch_table[MAXNP] = {nullptr,          nullptr,          march_launch_np2,
+                                              march_launch_np3, march_launch_np4, march_launch_np5,
+                                              march_launch_np6, march_launch_np7, march_launch_np8,
+                                              march_launch_np9};
+
+// utils/Globals1D.m:20-34 -- low-storage RK (Carpenter-Kennedy) coefficients
+static const double kRk4a[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                                -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+static const double kRk4b[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                                1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                                2277821191437.0 / 14882151754819.0};
+static const double kRk4c[5] = {0.0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
+                                2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0};
+
+// ---------------------------------------------------------------------------------------
+// even/odd operator blocks (host).  z = T u with rows e_i = u_i + u_{N-i} (i < Np/2),
+// e_mid = u_mid (Np odd), o_i = u_i - u_{N-i};  T^-1: u_i = (e_i+o_i)/2, u_{N-i} = (e_i-o_i)/2.
+// ---------------------------------------------------------------------------------------
+static void eo_T(int Np, std::vector<double>& T, std::vector<double>& Ti) {
+  const int h = Np / 2, HE = (Np + 1) / 2;
+  T.assign((size_t)Np * Np, 0.0);
+  Ti.assign((size_t)Np * Np, 0.0);
+  for (int i = 0; i < h; ++i) {
+    T[(size_t)i * Np + i] = 1.0;
+    T[(size_t)i * Np + (Np - 1 - i)] = 1.0;
+    T[(size_t)(HE + i) * Np + i] = 1.0;
+    T[(size_t)(HE + i) * Np + (Np - 1 - i)] = -1.0;
+    Ti[(size_t)i * Np + i] = 0.5;
+    Ti[(size_t)i * Np + (HE + i)] = 0.5;
+    Ti[(size_t)(Np - 1 - i) * Np + i] = 0.5;
+    Ti[(size_t)(Np - 1 - i) * Np + (HE + i)] = -0.5;
+  }
+  if (Np & 1) {
+    T[(size_t)h * Np + h] = 1.0;
+    Ti[(size_t)h * Np + h] = 1.0;
+  }
+}
+// C[m x n] = A[m x k] B[k x n]
+static std::vector<double> matmul(const std::vector<double>& A, const std::vector<double>& B, int m, int k,
+                                  int n) {
+  std::vector<double> C((size_t)m * n, 0.0);
+  for (int i = 0; i < m; ++i)
+    for (int l = 0; l < k; ++l) {
+      const double a = A[(size_t)i * k + l];
+      if (a == 0.0) continue;
+      for (int j = 0; j < n; ++j) C[(size_t)i * n + j] += a * B[(size_t)l * n + j];
+    }
+  return C;
+}
+
+static int eo_operators(int Np, const double* Dr, const double* LIFT, double* DE, double* DO, double* LS,
+                        double* LA, double* violation) {
+  if (Np < 2 || Np > MAXNP || !Dr || !LIFT) return DGADJ_ERR_INVALID;
+  const int HE = (Np + 1) / 2, HO = Np / 2;
+  std::vector<double> T, Ti;
+  eo_T(Np, T, Ti);
+  std::vector<double> D(Dr, Dr + (size_t)Np * Np), L(LIFT, LIFT + (size_t)Np * 2);
+  std::vector<double> Dt = matmul(matmul(T, D, Np, Np, Np), Ti, Np, Np, Np);
+  const std::vector<double> G = {0.5, 0.5, 0.5, -0.5};  // (ge, go) -> (g0, g1)
+  std::vector<double> Lt = matmul(matmul(T, L, Np, Np, 2), G, Np, 2, 2);
+  for (int i = 0; i < HM * HM; ++i) DE[i] = DO[i] = 0.0;
+  for (int i = 0; i < HM; ++i) LS[i] = LA[i] = 0.0;
+  double scale = 0.0, viol = 0.0;
+  for (int i = 0; i < Np * Np; ++i) scale = fmax(scale, fabs(Dt[i]));
+  for (int i = 0; i < Np * 2; ++i) scale = fmax(scale, fabs(Lt[i]));
+  for (int i = 0; i < HE; ++i) {
+    for (int j = 0; j < HO; ++j) DE[i * HM + j] = Dt[(size_t)i * Np + HE + j];
+    for (int j = 0; j < HE; ++j) viol = fmax(viol, fabs(Dt[(size_t)i * Np + j]));
+    LS[i] = Lt[(size_t)i * 2 + 0];
+    viol = fmax(viol, fabs(Lt[(size_t)i * 2 + 1]));
+  }
+  for (int i = 0; i < HO; ++i) {
+    for (int j = 0; j < HE; ++j) DO[i * HM + j] = Dt[(size_t)(HE + i) * Np + j];
+    for (int j = 0; j < HO; ++j) viol = fmax(viol, fabs(Dt[(size_t)(HE + i) * Np + HE + j]));
+    LA[i] = Lt[(size_t)(HE + i) * 2 + 1];
+    viol = fmax(viol, fabs(Lt[(size_t)(HE + i) * 2 + 0]));
+  }
+  if (violation) *violation = scale > 0.0 ? viol / scale : 0.0;
+  return DGADJ_OK;
+}
+
+static int eo_prolongation(int Np, const double* P, double* PE, double* PO, double* violation) {
+  if (Np < 2 || Np + 1 > MAXNP || !P) return DGADJ_ERR_INVALID;
+  const int NpF = Np + 1;
+  const int HEc = (Np + 1) / 2, HOc = Np / 2, HEf = (NpF + 1) / 2, HOf = NpF / 2;
+  std::vector<double> Tc, Tci, Tf, Tfi;
+  eo_T(Np, Tc, Tci);
+  eo_T(NpF, Tf, Tfi);
+  std::vector<double> Pm(P, P + (size_t)NpF * Np);
+  std::vector<double> Pt = matmul(matmul(Tf, Pm, NpF, NpF, Np), Tci, NpF, Np, Np);
+  for (int i = 0; i < HM * HM; ++i) PE[i] = PO[i] = 0.0;
+  double scale = 0.0, viol = 0.0;
+  for (int i = 0; i < NpF * Np; ++i) scale = fmax(scale, fabs(Pt[i]));
+  for (int i = 0; i < HEf; ++i) {
+    for (int j = 0; j < HEc; ++j) PE[i * HM + j] = Pt[(size_t)i * Np + j];
+    for (int j = 0; j < HOc; ++j) viol = fmax(viol, fabs(Pt[(size_t)i * Np + HEc + j]));
+  }
+  for (int i = 0; i < HOf; ++i) {
+    for (int j = 0; j < HOc; ++j) PO[i * HM + j] = Pt[(size_t)(HEf + i) * Np + HEc + j];
+    for (int j = 0; j < HEc; ++j) viol = fmax(viol, fabs(Pt[(size_t)(HEf + i) * Np + j]));
+  }
+  if (violation) *violation = scale > 0.0 ? viol / scale : 0.0;
+  return DGADJ_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// rank / refine flag:  one CTA per trajectory, stable descending rank of |eta| by counting
+// (rank_k = #{j : |eta_j| > |eta_k|  or (== and j < k)}), exact and deterministic.  |eta| is
+// compared through its bit pattern (monotone for non-negative doubles; NaN ranks first).
+// ---------------------------------------------------------------------------------------
+__global__ void rank_kernel(long long B, int K, const double* __restrict__ eta, int topk,
+                            int32_t* __restrict__ order, uint8_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* ae = reinterpret_cast<unsigned long long*>(smem_raw);
+  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+      ae[k] = (unsigned long long)__double_as_longlong(fabs(eta[(size_t)b * K + k]));
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const unsigned long long v = ae[k];
+      int r = 0;
+      for (int j = 0; j < K; ++j) {
+        const unsigned long long w = ae[j];
+        r += (w > v) || (w == v && j < k);
+      }
+      if (order) order[(size_t)b * K + r] = k;
+      if (flags) flags[(size_t)b * K + k] = (r < topk) ? 1 : 0;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// batch reduction of the indicators in a fixed order.  Stage 1: block (x = 32 columns,
+// y = 8 row phases) sums rows b = y, y+8, ... in order, then the 8 phases in order.
+// Stage 2 (one block): ordered sums over k and over 256 lanes of J.
+// ---------------------------------------------------------------------------------------
+__global__ void reduce_cols_kernel(long long B, int K, const double* __restrict__ eta,
+                                   double* __restrict__ colsum, double* __restrict__ colsq,
+                                   double* __restrict__ colmax) {
+  __shared__ double s1[8][33], s2[8][33], s3[8][33];
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  double a1 = 0, a2 = 0, a3 = 0;
+  if (k < K) {
+    for (long long b = threadIdx.y; b < B; b += 8) {
+      const double v = fabs(eta[(size_t)b * K + k]);
+      a1 += v;
+      a2 = fma(v, v, a2);
+      a3 = fmax(a3, v);
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a1;
+  s2[threadIdx.y][threadIdx.x] = a2;
+  s3[threadIdx.y][threadIdx.x] = a3;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < K) {
+    for (int y = 1; y < 8; ++y) {
+      a1 += s1[y][threadIdx.x];
+      a2 += s2[y][threadIdx.x];
+      a3 = fmax(a3, s3[y][threadIdx.x]);
+    }
+    colsum[k] = a1;
+    colsq[k] = a2;
+    colmax[k] = a3;
+  }
+}
+__global__ void reduce_final_kernel(long long B, int K, const double* __restrict__ colsq,
+                                    const double* __restrict__ colmax, const double* __restrict__ J,
+                                    double* __restrict__ sums) {
+  __shared__ double sj[256];
+  double aj = 0;
+  if (J) {
+    for (long long b = threadIdx.x; b < B; b += 256) aj += J[b];
+  }
+  sj[threadIdx.x] = aj;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0, t2 = 0, t3 = 0, tj = 0;
+    for (int k = 0; k < K; ++k) {
+      t1 += sums[k];
+      t2 += colsq[k];
+      t3 = fmax(t3, colmax[k]);
+    }
+    for (int i = 0; i < 256; ++i) tj += sj[i];
+    sums[K + 0] = t1;
+    sums[K + 1] = t2;
+    sums[K + 2] = t3;
+    sums[K + 3] = tj;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// register-only DFMA peak microbenchmark (roofline denominator): 8 independent chains per
+// thread, 1024 threads per SM, 128 DFMA per loop trip.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) dfma_peak_kernel(double* out, int iters, double x, double y) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      a0 = fma(a0, x, y);
+      a1 = fma(a1, x, y);
+      a2 = fma(a2, x, y);
+      a3 = fma(a3, x, y);
+      a4 = fma(a4, x, y);
+      a5 = fma(a5, x, y);
+      a6 = fma(a6, x, y);
+      a7 = fma(a7, x, y);
+    }
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+
+
+// ---------------------------------------------------------------------------------------
+// single RHS evaluation in the plain nodal form of utils/AdvecRHS1D.m:8-19 (API parity and an
+// independent check of the even/odd march kernels; not a hot path).  One thread per element.
+// ---------------------------------------------------------------------------------------
+__global__ void rhs_kernel(long long B, int K, int Np, int bc, int inflow, double alpha, double t, double a_s,
+                           const double* __restrict__ a_arr, const double* __restrict__ Dr,
+                           const double* __restrict__ LIFT, const double* __restrict__ rxk,
+                           const double* __restrict__ fs0, const double* __restrict__ fs1,
+                           const double* __restrict__ uin_table, const double* __restrict__ u,
+                           double* __restrict__ rhs) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * K) return;
+  const long long b = gid / K;
+  const int k = (int)(gid - b * K);
+  const double a = a_arr ? a_arr[b] : a_s;
+  const double* ub = u + (size_t)b * Np * K;
+  double ul[MAXNP];
+  for (int i = 0; i < Np; ++i) ul[i] = ub[(size_t)i * K + k];
+  const double c0 = (a * -1.0 - (1.0 - alpha) * fabs(a * -1.0)) / 2.0;  // AdvecRHS1D.m:11
+  const double c1 = (a * 1.0 - (1.0 - alpha) * fabs(a * 1.0)) / 2.0;
+  double du0, du1;
+  if (bc == BC_PERIODIC) {
+    du0 = (ul[0] - ub[(size_t)(Np - 1) * K + (k == 0 ? K - 1 : k - 1)]) * c0;
+    du1 = (ul[Np - 1] - ub[(k == K - 1 ? 0 : k + 1)]) * c1;
+  } else {
+    du0 = (k == 0) ? 0.0 : (ul[0] - ub[(size_t)(Np - 1) * K + k - 1]) * c0;
+    du1 = (k == K - 1) ? 0.0 : (ul[Np - 1] - ub[k + 1]) * c1;
+    if (k == 0) {
+      double uin = 0.0;
+      if (inflow == INFLOW_SIN_AT) uin = -sin(a * t);
+      else if (inflow == INFLOW_SIN_AAT) uin = -sin(a * a * t);
+      else if (inflow == INFLOW_TABLE) uin = uin_table ? uin_table[0] : 0.0;
+      du0 = (ul[0] - uin) * c0;  // :14-15
+    }
+  }
+  const double g0 = fs0[k] * du0, g1 = fs1[k] * du1;
+  const double marx = -a * rxk[k];
+  double* rb = rhs + (size_t)b * Np * K;
+  for (int i = 0; i < Np; ++i) {
+    double acc = 0.0;
+    for (int j = 0; j < Np; ++j) acc += Dr[i * Np + j] * ul[j];
+    rb[(size_t)i * K + k] = marx * acc + (LIFT[i * 2] * g0 + LIFT[i * 2 + 1] * g1);  // :19
+  }
+}
+
+}  // namespace dgadj
+
+using namespace dgadj;
+
+// ---------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------
+struct LaunchPlan {
+  int ept, KT, tpc, block, ngroups, grid;
+  size_t smem;
+  size_t tile;  // doubles per checkpoint tile
+};
+
+struct dgadj_handle {
+  dgadj_config cfg;
+  int Np, NpF, K, nstages;
+  bool ops_set, enr_set, jw_set;
+  ConstOps cops;
+  double* d_mesh[2][3];  // [level]{rx, fs0, fs1} each [K]
+  double* d_nodal[2][2];  // [level]{Dr[Np*Np], LIFT[Np*2]} nodal copies (dgadj_rhs)
+  double* d_jwc;
+  double* d_jwf;
+  double* d_uin;
+  int uin_n;
+  double* ring;
+  size_t ring_bytes;
+  double* red_scratch;
+  size_t red_bytes;
+  int sm_count, cc_major, cc_minor;
+  size_t total_mem;
+  int tune_ept, tune_block, tune_grid;
+  // host pipeline
+  cudaStream_t s_in, s_k, s_out;
+  cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
+  double* dbuf[2];
+  size_t dbuf_bytes;
+  double* pin[2];
+  size_t pin_bytes;
+  bool pipe_init;
+  char err[512];
+  int64_t launches;
+};
+
+static int fail(dgadj_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+#define CUDA_TRY(h, call)                                                                      \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail((h), e_ == cudaErrorMemoryAllocation ? DGADJ_ERR_NOMEM : DGADJ_ERR_CUDA,      \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" int dgadj_version(void) { return DGADJ_VERSION; }
+
+extern "C" int dgadj_host_eo_operators(int Np, const double* Dr, const double* LIFT, double* DE, double* DO,
+                                       double* LS, double* LA, double* violation) {
+  if (!DE || !DO || !LS || !LA) return DGADJ_ERR_INVALID;
+  return eo_operators(Np, Dr, LIFT, DE, DO, LS, LA, violation);
+}
+extern "C" int dgadj_host_eo_prolongation(int Np, const double* P, double* PE, double* PO, double* violation) {
+  if (!PE || !PO) return DGADJ_ERR_INVALID;
+  return eo_prolongation(Np, P, PE, PO, violation);
+}
+
+extern "C" int dgadj_create(const dgadj_config* cfg, dgadj_handle** out) {
+  if (!cfg || !out) return DGADJ_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->N < 1 || cfg->N + 1 >= MAXNP) return DGADJ_ERR_UNSUPPORTED;  // Np <= 9 (enriched 10)
+  if (cfg->K < 1 || cfg->K > MAXBD) return DGADJ_ERR_UNSUPPORTED;
+  if (cfg->bc != DGADJ_BC_INFLOW && cfg->bc != DGADJ_BC_PERIODIC) return DGADJ_ERR_INVALID;
+  if (cfg->inflow < DGADJ_INFLOW_ZERO || cfg->inflow > DGADJ_INFLOW_TABLE) return DGADJ_ERR_INVALID;
+  if (cfg->functional != DGADJ_FUNC_LINEAR && cfg->functional != DGADJ_FUNC_INT_U2) return DGADJ_ERR_INVALID;
+  if (cfg->scheme != DGADJ_SCHEME_LSERK4 && cfg->scheme != DGADJ_SCHEME_EULER) return DGADJ_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    cudaGetLastError();
+    return DGADJ_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return DGADJ_ERR_NO_DEVICE;
+  if (prop.major != 10) return DGADJ_ERR_NO_DEVICE;  // sm_100a cubins only; no fallback path exists
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return DGADJ_ERR_CUDA;
+  dgadj_handle* h = new (std::nothrow) dgadj_handle();
+  if (!h) return DGADJ_ERR_NOMEM;
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->Np = cfg->N + 1;
+  h->NpF = cfg->N + 2;
+  h->K = cfg->K;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  h->total_mem = prop.totalGlobalMem;
+  if (cfg->scheme == DGADJ_SCHEME_LSERK4) {
+    h->nstages = 5;
+    for (int s = 0; s < 5; ++s) {
+      h->cops.rka[s] = kRk4a[s];
+      h->cops.rkb[s] = kRk4b[s];
+      h->cops.rkc[s] = kRk4c[s];
+    }
+  } else {  // forward Euler as a 1-stage low-storage scheme: a = 0, b = 1, c = 0
+    h->nstages = 1;
+    h->cops.rka[0] = 0.0;
+    h->cops.rkb[0] = 1.0;
+    h->cops.rkc[0] = 0.0;
+  }
+  *out = h;
+  return DGADJ_OK;
+}
+
+extern "C" void dgadj_destroy(dgadj_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (int lv = 0; lv < 2; ++lv)
+    for (int i = 0; i < 3; ++i) cudaFree(h->d_mesh[lv][i]);
+  for (int lv = 0; lv < 2; ++lv)
+    for (int i = 0; i < 2; ++i) cudaFree(h->d_nodal[lv][i]);
+  cudaFree(h->d_jwc);
+  cudaFree(h->d_jwf);
+  cudaFree(h->d_uin);
+  cudaFree(h->ring);
+  cudaFree(h->red_scratch);
+  if (h->pipe_init) {
+    cudaStreamDestroy(h->s_in);
+    cudaStreamDestroy(h->s_k);
+    cudaStreamDestroy(h->s_out);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(h->ev_in[i]);
+      cudaEventDestroy(h->ev_k[i]);
+      cudaEventDestroy(h->ev_out[i]);
+    }
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->dbuf[i]);
+    cudaFreeHost(h->pin[i]);
+  }
+  delete h;
+}
+
+extern "C" const char* dgadj_last_error(const dgadj_handle* h) { return h ? h->err : "null handle"; }
+
+static int upload(dgadj_handle* h, double** dst, const double* src, size_t n) {
+  if (*dst) {
+    cudaFree(*dst);
+    *dst = nullptr;
+  }
+  CUDA_TRY(h, cudaMalloc((void**)dst, n * sizeof(double)));
+  CUDA_TRY(h, cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
+  return DGADJ_OK;
+}
+
+static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const double* LIFT, const double* Mref,
+                     const double* rx, const double* Fscale) {
+  const int K = h->K;
+  StageOps so;
+  double viol = 0.0;
+  int rc = eo_operators(Np, Dr, LIFT, so.DE, so.DO, so.LS, so.LA, &viol);
+  if (rc != DGADJ_OK) return fail(h, rc, "bad operator arguments");
+  if (!(viol <= 1e-10))
+    return fail(h, DGADJ_ERR_UNSUPPORTED,
+                "Dr/LIFT are not centro-(anti)symmetric (relative violation %.3e): only mirror-symmetric "
+                "node sets (LGL, StartUp1D) are supported",
+                viol);
+  for (int s = 0; s < MAXSTAGES; ++s) h->cops.st[lv][s] = so;
+  for (int i = 0; i < Np * Np; ++i) h->cops.Mref[lv][i] = Mref ? Mref[i] : 0.0;
+  std::vector<double> rxk(K), f0(K), f1(K);
+  for (int k = 0; k < K; ++k) {
+    rxk[k] = rx[k];  // rx(1,k): the affine map makes rx constant inside an element
+    f0[k] = Fscale[k];
+    f1[k] = Fscale[K + k];
+    if (!(rxk[k] != 0.0) || !isfinite(rxk[k])) return fail(h, DGADJ_ERR_INVALID, "rx[%d] is zero or not finite", k);
+  }
+  rc = upload(h, &h->d_nodal[lv][0], Dr, (size_t)Np * Np);
+  if (rc) return rc;
+  rc = upload(h, &h->d_nodal[lv][1], LIFT, (size_t)Np * 2);
+  if (rc) return rc;
+  rc = upload(h, &h->d_mesh[lv][0], rxk.data(), K);
+  if (rc) return rc;
+  rc = upload(h, &h->d_mesh[lv][1], f0.data(), K);
+  if (rc) return rc;
+  return upload(h, &h->d_mesh[lv][2], f1.data(), K);
+}
+
+extern "C" int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double* Dr, const double* LIFT,
+                                   const double* Mref, const double* rx, const double* Fscale) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (Np != h->Np || K != h->K) return fail(h, DGADJ_ERR_INVALID, "Np/K (%d,%d) differ from the handle's (%d,%d)", Np, K, h->Np, h->K);
+  if (!Dr || !LIFT || !rx || !Fscale) return fail(h, DGADJ_ERR_INVALID, "null operator pointer");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int rc = set_level(h, 0, Np, Dr, LIFT, Mref, rx, Fscale);
+  if (rc) return rc;
+  h->ops_set = true;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_set_enriched(dgadj_handle* h, int NpF, const double* DrF, const double* LIFTF,
+                                  const double* MrefF, const double* rxF, const double* FscaleF,
+                                  const double* P) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (NpF != h->NpF) return fail(h, DGADJ_ERR_INVALID, "NpF %d differs from the handle's %d", NpF, h->NpF);
+  if (!DrF || !LIFTF || !rxF || !FscaleF || !P) return fail(h, DGADJ_ERR_INVALID, "null operator pointer");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int rc = set_level(h, 1, NpF, DrF, LIFTF, MrefF, rxF, FscaleF);
+  if (rc) return rc;
+  ProlongOps po;
+  double viol = 0.0;
+  rc = eo_prolongation(h->Np, P, po.PE, po.PO, &viol);
+  if (rc) return fail(h, rc, "bad prolongation");
+  if (!(viol <= 1e-10))
+    return fail(h, DGADJ_ERR_UNSUPPORTED, "prolongation is not centro-symmetric (relative violation %.3e)", viol);
+  h->cops.pr[0] = po;
+  h->cops.pr[1] = po;
+  for (int i = 0; i < NpF * h->Np; ++i) h->cops.P[i] = P[i];
+  h->enr_set = true;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_set_functional_weights(dgadj_handle* h, const double* jw_c, const double* jw_f) {
+  if (!h || !jw_c || !jw_f) return DGADJ_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int rc = upload(h, &h->d_jwc, jw_c, (size_t)h->Np * h->K);
+  if (rc) return rc;
+  rc = upload(h, &h->d_jwf, jw_f, (size_t)h->NpF * h->K);
+  if (rc) return rc;
+  h->jw_set = true;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_set_inflow_table(dgadj_handle* h, int n, const double* uin) {
+  if (!h || n <= 0 || !uin) return DGADJ_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int rc = upload(h, &h->d_uin, uin, (size_t)n);
+  if (rc) return rc;
+  h->uin_n = n;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_set_tuning(dgadj_handle* h, int32_t ept, int32_t block, int32_t grid) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (ept < 0 || ept > 2 || block < 0 || block > MAXBD || grid < 0) return fail(h, DGADJ_ERR_INVALID, "bad tuning");
+  h->tune_ept = ept;
+  h->tune_block = block;
+  h->tune_grid = grid;
+  return DGADJ_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch planning.  The shape depends only on (K, B, tuning) so that a forward call and the
+// adjoint call that consumes its checkpoints agree on the tile layout.
+// ---------------------------------------------------------------------------------------
+static int make_plan(dgadj_handle* h, int64_t B, int variant, LaunchPlan* pl) {
+  const int K = h->K;
+  int ept = h->tune_ept ? h->tune_ept : ((K % 2 == 0) ? 2 : 1);
+  if (ept == 2 && (K % 2)) return fail(h, DGADJ_ERR_INVALID, "elems_per_thread=2 needs an even K");
+  const int KT = K / ept;
+  const int bdmax = MAXBD / ept;
+  if (KT > bdmax) return fail(h, DGADJ_ERR_UNSUPPORTED, "K=%d does not fit one CTA", K);
+  int target = h->tune_block ? h->tune_block : bdmax / 2;
+  target = std::max(std::min(target, bdmax), KT);
+  int64_t tpc = std::max<int64_t>(1, std::min<int64_t>(target / KT, B));
+  int block = (int)((tpc * KT + 31) / 32 * 32);
+  if (block > bdmax) {  // rounding up overflowed the register-file budget
+    tpc = std::max<int64_t>(1, bdmax / KT);
+    block = (int)((tpc * KT + 31) / 32 * 32);
+    if (block > bdmax) block = bdmax;
+  }
+  pl->ept = ept;
+  pl->KT = KT;
+  pl->tpc = (int)tpc;
+  pl->block = block;
+  const int64_t ngroups = (B + tpc - 1) / tpc;
+  if (ngroups > 0x7fffffff) return fail(h, DGADJ_ERR_UNSUPPORTED, "batch too large");
+  pl->ngroups = (int)ngroups;
+  pl->smem = march_smem_bytes(h->Np, ept, block, variant);
+  if (pl->smem > 227 * 1024) return fail(h, DGADJ_ERR_UNSUPPORTED, "shared memory %zu B over budget", pl->smem);
+  int per_sm = std::max(1, std::min<int>(bdmax / block, (int)((227 * 1024) / pl->smem)));
+  int grid = h->tune_grid ? h->tune_grid : h->sm_count * per_sm;
+  pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ngroups));
+  pl->tile = (size_t)h->NpF * ept * block;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_plan(dgadj_handle* h, int64_t B, int32_t fused, int32_t* ept, int32_t* block,
+                          int32_t* tpc, int32_t* grid, int64_t* smem_bytes) {
+  if (!h || B <= 0) return DGADJ_ERR_INVALID;
+  LaunchPlan pl;
+  int rc = make_plan(h, B, fused ? VAR_FUSED : VAR_FWD, &pl);
+  if (rc) return rc;
+  if (ept) *ept = pl.ept;
+  if (block) *block = pl.block;
+  if (tpc) *tpc = pl.tpc;
+  if (grid) *grid = pl.grid;
+  if (smem_bytes) *smem_bytes = (int64_t)pl.smem;
+  return DGADJ_OK;
+}
+
+extern "C" int64_t dgadj_ckpt_bytes(dgadj_handle* h, int64_t B, int32_t S) {
+  if (!h || B <= 0 || S < 0) return DGADJ_ERR_INVALID;
+  LaunchPlan pl;
+  int rc = make_plan(h, B, VAR_FWD_RESID, &pl);
+  if (rc) return rc;
+  return (int64_t)((size_t)pl.ngroups * (size_t)S * pl.tile * sizeof(double));
+}
+
+static int check_args(dgadj_handle* h, const dgadj_march_args* a, bool need_enriched) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (!a) return fail(h, DGADJ_ERR_INVALID, "null march args");
+  if (a->B <= 0 || a->S < 0) return fail(h, DGADJ_ERR_INVALID, "B must be > 0 and S >= 0 (got %lld, %d)", (long long)a->B, a->S);
+  if (!h->ops_set) return fail(h, DGADJ_ERR_STATE, "dgadj_set_operators has not been called");
+  if (need_enriched) {
+    if (!h->enr_set) return fail(h, DGADJ_ERR_STATE, "dgadj_set_enriched has not been called");
+    if (h->cfg.functional == DGADJ_FUNC_LINEAR && !h->jw_set)
+      return fail(h, DGADJ_ERR_STATE, "dgadj_set_functional_weights has not been called");
+  }
+  if (h->cfg.bc == DGADJ_BC_INFLOW && h->cfg.inflow == DGADJ_INFLOW_TABLE) {
+    if (!h->d_uin || (int64_t)h->uin_n < (int64_t)a->S * h->nstages)
+      return fail(h, DGADJ_ERR_STATE, "inflow table missing or shorter than S*nstages");
+  }
+  return DGADJ_OK;
+}
+
+static void fill_params(dgadj_handle* h, const dgadj_march_args* a, const LaunchPlan& pl, KArgs* ka) {
+  memset(&ka->p, 0, sizeof(ka->p));
+  ka->c = h->cops;
+  MarchParams& p = ka->p;
+  p.B = a->B;
+  p.K = h->K;
+  p.S = a->S;
+  p.tpc = pl.tpc;
+  p.ngroups = pl.ngroups;
+  p.nstages = h->nstages;
+  p.bc = h->cfg.bc;
+  p.inflow = h->cfg.inflow;
+  p.func = h->cfg.functional;
+  p.alpha = h->cfg.alpha;
+  p.a = a->a;
+  p.dt = a->dt;
+  p.t0 = a->t0;
+  p.a_arr = a->a_dev;
+  p.dt_arr = a->dt_dev;
+  for (int lv = 0; lv < 2; ++lv) {
+    p.rxk[lv] = h->d_mesh[lv][0];
+    p.fs0[lv] = h->d_mesh[lv][1];
+    p.fs1[lv] = h->d_mesh[lv][2];
+  }
+  p.jw_c = h->d_jwc;
+  p.jw_f = h->d_jwf;
+  p.uin_table = h->d_uin;
+}
+
+static int launch(dgadj_handle* h, int variant, const LaunchPlan& pl, cudaStream_t st, const KArgs* ka) {
+  march_launch_fn fn = launch_table[h->Np];
+  if (!fn) return fail(h, DGADJ_ERR_UNSUPPORTED, "no kernel for Np=%d", h->Np);
+  cudaError_t e = fn(variant, pl.ept, pl.grid, pl.block, st, ka);
+  if (e != cudaSuccess) return fail(h, DGADJ_ERR_CUDA, "march kernel launch failed: %s", cudaGetErrorString(e));
+  h->launches++;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_forward(dgadj_handle* h, const dgadj_march_args* args, const double* u0_dev,
+                             double* uT_dev, double* hist_dev, void* ckpt_dev, void* stream) {
+  int rc = check_args(h, args, ckpt_dev != nullptr);
+  if (rc) return rc;
+  if (!u0_dev) return fail(h, DGADJ_ERR_INVALID, "u0_dev is null");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int variant = ckpt_dev ? VAR_FWD_RESID : VAR_FWD;
+  LaunchPlan pl;
+  rc = make_plan(h, args->B, variant, &pl);
+  if (rc) return rc;
+  KArgs ka;
+  fill_params(h, args, pl, &ka);
+  ka.p.u0 = u0_dev;
+  ka.p.uT = uT_dev;
+  ka.p.hist = hist_dev;
+  ka.p.ckpt = (double*)ckpt_dev;
+  ka.p.ckpt_by_block = 0;
+  return launch(h, variant, pl, (cudaStream_t)stream, &ka);
+}
+
+extern "C" int dgadj_adjoint(dgadj_handle* h, const dgadj_march_args* args, const double* uT_dev,
+                             const void* ckpt_dev, double* J_dev, double* lam0_dev, double* eta_dev,
+                             void* stream) {
+  int rc = check_args(h, args, true);
+  if (rc) return rc;
+  if (!uT_dev || (!ckpt_dev && args->S > 0)) return fail(h, DGADJ_ERR_INVALID, "uT_dev / ckpt_dev is null");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  LaunchPlan pl;
+  rc = make_plan(h, args->B, VAR_ADJ, &pl);
+  if (rc) return rc;
+  KArgs ka;
+  fill_params(h, args, pl, &ka);
+  ka.p.uT_in = uT_dev;
+  ka.p.ckpt = (double*)const_cast<void*>(ckpt_dev);
+  ka.p.ckpt_by_block = 0;
+  ka.p.J = J_dev;
+  ka.p.lam0 = lam0_dev;
+  ka.p.eta = eta_dev;
+  return launch(h, VAR_ADJ, pl, (cudaStream_t)stream, &ka);
+}
+
+static int ensure_ring(dgadj_handle* h, const LaunchPlan& pl, int S, cudaStream_t st) {
+  const size_t need = (size_t)pl.grid * (size_t)std::max(S, 1) * pl.tile * sizeof(double);
+  if (need <= h->ring_bytes) return DGADJ_OK;
+  if (h->ring) {
+    CUDA_TRY(h, cudaStreamSynchronize(st));  // a previous launch may still use the old ring
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->ring);
+    h->ring = nullptr;
+    h->ring_bytes = 0;
+  }
+  CUDA_TRY(h, cudaMalloc((void**)&h->ring, need));
+  h->ring_bytes = need;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_fwd_adj(dgadj_handle* h, const dgadj_march_args* args, const double* u0_dev,
+                             double* uT_dev, double* J_dev, double* lam0_dev, double* eta_dev,
+                             void* stream) {
+  int rc = check_args(h, args, true);
+  if (rc) return rc;
+  if (!u0_dev) return fail(h, DGADJ_ERR_INVALID, "u0_dev is null");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  LaunchPlan pl;
+  rc = make_plan(h, args->B, VAR_FUSED, &pl);
+  if (rc) return rc;
+  rc = ensure_ring(h, pl, args->S, (cudaStream_t)stream);
+  if (rc) return rc;
+  KArgs ka;
+  fill_params(h, args, pl, &ka);
+  ka.p.u0 = u0_dev;
+  ka.p.uT = uT_dev;
+  ka.p.ckpt = h->ring;
+  ka.p.ckpt_by_block = 1;
+  ka.p.J = J_dev;
+  ka.p.lam0 = lam0_dev;
+  ka.p.eta = eta_dev;
+  return launch(h, VAR_FUSED, pl, (cudaStream_t)stream, &ka);
+}
+
+// ---------------------------------------------------------------------------------------
+// host-buffer pipeline: the batch is cut into chunks; chunk c+1's H2D copy and chunk c-1's
+// D2H copy overlap chunk c's kernel (three streams, two device buffer sets).  Pinned host
+// buffers are copied from / to directly; pageable ones go through pinned staging.
+// ---------------------------------------------------------------------------------------
+static int ensure_pipe(dgadj_handle* h, size_t dev_bytes, size_t pin_bytes) {
+  if (!h->pipe_init) {
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_k, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+    h->pipe_init = true;
+  }
+  if (dev_bytes > h->dbuf_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(h->dbuf[i]);
+      h->dbuf[i] = nullptr;
+    }
+    h->dbuf_bytes = 0;
+    for (int i = 0; i < 2; ++i) CUDA_TRY(h, cudaMalloc((void**)&h->dbuf[i], dev_bytes));
+    h->dbuf_bytes = dev_bytes;
+  }
+  if (pin_bytes > h->pin_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) {
+      cudaFreeHost(h->pin[i]);
+      h->pin[i] = nullptr;
+    }
+    h->pin_bytes = 0;
+    for (int i = 0; i < 2; ++i) CUDA_TRY(h, cudaMallocHost((void**)&h->pin[i], pin_bytes));
+    h->pin_bytes = pin_bytes;
+  }
+  return DGADJ_OK;
+}
+
+static bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+struct HostIO {  // per-trajectory doubles of every stream that crosses the bus
+  size_t n_u0, n_a, n_dt;                    // inputs
+  size_t n_uT, n_J, n_lam, n_eta, n_hist;    // outputs
+  size_t in_total() const { return n_u0 + n_a + n_dt; }
+  size_t out_total() const { return n_uT + n_J + n_lam + n_eta + n_hist; }
+};
+
+static int host_pipeline(dgadj_handle* h, const dgadj_march_args* args, bool fused, const double* a_host,
+                         const double* dt_host, const double* u0_host, double* uT_host, double* J_host,
+                         double* lam0_host, double* eta_host, double* hist_host) {
+  int rc = check_args(h, args, fused);
+  if (rc) return rc;
+  if (!u0_host) return fail(h, DGADJ_ERR_INVALID, "u0_host is null");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int Np = h->Np, NpF = h->NpF, K = h->K, S = args->S;
+  const int64_t B = args->B;
+  HostIO io;
+  io.n_u0 = (size_t)Np * K;
+  io.n_a = a_host ? 1 : 0;
+  io.n_dt = dt_host ? 1 : 0;
+  io.n_uT = uT_host ? (size_t)Np * K : 0;
+  io.n_J = J_host ? 1 : 0;
+  io.n_lam = lam0_host ? (size_t)NpF * K : 0;
+  io.n_eta = eta_host ? (size_t)K : 0;
+  io.n_hist = hist_host ? (size_t)(S + 1) * Np * K : 0;
+  // chunk: a whole number of persistent waves (4 per CTA), bounded by a 1 GiB device buffer set
+  LaunchPlan pl0;
+  rc = make_plan(h, B, fused ? VAR_FUSED : VAR_FWD, &pl0);
+  if (rc) return rc;
+  const size_t per_traj = (io.in_total() + io.out_total()) * sizeof(double);
+  int64_t chunk = (int64_t)pl0.grid * pl0.tpc * 4;
+  const int64_t cap = std::max<int64_t>(pl0.tpc, (int64_t)((1ull << 30) / per_traj) / pl0.tpc * pl0.tpc);
+  chunk = std::max<int64_t>(pl0.tpc, std::min<int64_t>(std::min(chunk, cap), B));
+  const bool pinned = is_pinned(u0_host) && is_pinned(a_host) && is_pinned(dt_host) && is_pinned(uT_host) &&
+                      is_pinned(J_host) && is_pinned(lam0_host) && is_pinned(eta_host) && is_pinned(hist_host);
+  const size_t dev_bytes = (size_t)chunk * per_traj;
+  rc = ensure_pipe(h, dev_bytes, pinned ? 0 : dev_bytes);
+  if (rc) return rc;
+
+  int64_t done = 0;
+  int c = 0;
+  struct Pending { int64_t b0, nb; bool live; } pend[2] = {{0, 0, false}, {0, 0, false}};
+  auto drain = [&](int slot) -> int {  // pageable outputs: staging -> user memory
+    if (!pend[slot].live) return DGADJ_OK;
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_out[slot]));
+    if (!pinned) {
+      const int64_t b0 = pend[slot].b0, nb = pend[slot].nb;
+      const double* s = h->pin[slot] + (size_t)chunk * io.in_total();
+      if (uT_host) memcpy(uT_host + (size_t)b0 * io.n_uT, s, (size_t)nb * io.n_uT * sizeof(double));
+      s += (size_t)chunk * io.n_uT;
+      if (J_host) memcpy(J_host + (size_t)b0, s, (size_t)nb * sizeof(double));
+      s += (size_t)chunk * io.n_J;
+      if (lam0_host) memcpy(lam0_host + (size_t)b0 * io.n_lam, s, (size_t)nb * io.n_lam * sizeof(double));
+      s += (size_t)chunk * io.n_lam;
+      if (eta_host) memcpy(eta_host + (size_t)b0 * io.n_eta, s, (size_t)nb * io.n_eta * sizeof(double));
+      s += (size_t)chunk * io.n_eta;
+      if (hist_host) memcpy(hist_host + (size_t)b0 * io.n_hist, s, (size_t)nb * io.n_hist * sizeof(double));
+    }
+    pend[slot].live = false;
+    return DGADJ_OK;
+  };
+
+  while (done < B) {
+    const int slot = c & 1;
+    const int64_t nb = std::min<int64_t>(chunk, B - done);
+    rc = drain(slot);  // this buffer set's previous chunk has left the device
+    if (rc) return rc;
+    // device layout of a buffer set: [u0 | a | dt | uT | J | lam0 | eta | hist], each sized for `chunk`
+    double* d_u0 = h->dbuf[slot];
+    double* d_a = d_u0 + (size_t)chunk * io.n_u0;
+    double* d_dt = d_a + (size_t)chunk * io.n_a;
+    double* d_uT = d_dt + (size_t)chunk * io.n_dt;
+    double* d_J = d_uT + (size_t)chunk * io.n_uT;
+    double* d_lam = d_J + (size_t)chunk * io.n_J;
+    double* d_eta = d_lam + (size_t)chunk * io.n_lam;
+    double* d_hist = d_eta + (size_t)chunk * io.n_eta;
+    // ---- H2D
+    const double* src_u0 = u0_host + (size_t)done * io.n_u0;
+    const double* src_a = a_host ? a_host + done : nullptr;
+    const double* src_dt = dt_host ? dt_host + done : nullptr;
+    if (!pinned) {
+      double* s = h->pin[slot];
+      memcpy(s, src_u0, (size_t)nb * io.n_u0 * sizeof(double));
+      src_u0 = s;
+      s += (size_t)chunk * io.n_u0;
+      if (a_host) {
+        memcpy(s, src_a, (size_t)nb * sizeof(double));
+        src_a = s;
+        s += (size_t)chunk;
+      }
+      if (dt_host) {
+        memcpy(s, src_dt, (size_t)nb * sizeof(double));
+        src_dt = s;
+      }
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(d_u0, src_u0, (size_t)nb * io.n_u0 * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    if (a_host) CUDA_TRY(h, cudaMemcpyAsync(d_a, src_a, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    if (dt_host) CUDA_TRY(h, cudaMemcpyAsync(d_dt, src_dt, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(h, cudaEventRecord(h->ev_in[slot], h->s_in));
+    // ---- kernel
+    CUDA_TRY(h, cudaStreamWaitEvent(h->s_k, h->ev_in[slot], 0));
+    dgadj_march_args ca = *args;
+    ca.B = nb;
+    ca.a_dev = a_host ? d_a : nullptr;
+    ca.dt_dev = dt_host ? d_dt : nullptr;
+    if (fused)
+      rc = dgadj_fwd_adj(h, &ca, d_u0, uT_host ? d_uT : nullptr, J_host ? d_J : nullptr,
+                         lam0_host ? d_lam : nullptr, eta_host ? d_eta : nullptr, (void*)h->s_k);
+    else
+      rc = dgadj_forward(h, &ca, d_u0, uT_host ? d_uT : nullptr, hist_host ? d_hist : nullptr, nullptr, (void*)h->s_k);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_k[slot], h->s_k));
+    // ---- D2H
+    CUDA_TRY(h, cudaStreamWaitEvent(h->s_out, h->ev_k[slot], 0));
+    double* stage_out = pinned ? nullptr : h->pin[slot] + (size_t)chunk * io.in_total();
+    auto d2h = [&](double* user, double* dev, size_t n_per) -> int {
+      if (!n_per) return DGADJ_OK;
+      double* dst = pinned ? user + (size_t)done * n_per : stage_out;
+      CUDA_TRY(h, cudaMemcpyAsync(dst, dev, (size_t)nb * n_per * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+      if (!pinned) stage_out += (size_t)chunk * n_per;
+      return DGADJ_OK;
+    };
+    if ((rc = d2h(uT_host, d_uT, io.n_uT))) return rc;
+    if ((rc = d2h(J_host, d_J, io.n_J))) return rc;
+    if ((rc = d2h(lam0_host, d_lam, io.n_lam))) return rc;
+    if ((rc = d2h(eta_host, d_eta, io.n_eta))) return rc;
+    if ((rc = d2h(hist_host, d_hist, io.n_hist))) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_out[slot], h->s_out));
+    // the next H2D into this buffer set must wait for this chunk's D2H (drain() does, on the host)
+    pend[slot] = {done, nb, true};
+    done += nb;
+    ++c;
+  }
+  if ((rc = drain(0))) return rc;
+  if ((rc = drain(1))) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->s_out));
+  CUDA_TRY(h, cudaStreamSynchronize(h->s_k));
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_fwd_adj_host(dgadj_handle* h, const dgadj_march_args* args, const double* a_host,
+                                  const double* dt_host, const double* u0_host, double* uT_host,
+                                  double* J_host, double* lam0_host, double* eta_host) {
+  return host_pipeline(h, args, true, a_host, dt_host, u0_host, uT_host, J_host, lam0_host, eta_host, nullptr);
+}
+extern "C" int dgadj_forward_host(dgadj_handle* h, const dgadj_march_args* args, const double* a_host,
+                                  const double* dt_host, const double* u0_host, double* uT_host,
+                                  double* hist_host) {
+  return host_pipeline(h, args, false, a_host, dt_host, u0_host, uT_host, nullptr, nullptr, nullptr, hist_host);
+}
+
+// ---------------------------------------------------------------------------------------
+// rank / reduce / peak / info
+// ---------------------------------------------------------------------------------------
+
+extern "C" int dgadj_rhs(dgadj_handle* h, int64_t B, int32_t level, const double* u_dev, double t, double a,
+                         const double* a_dev, double* rhs_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || !u_dev || !rhs_dev || level < 0 || level > 1) return fail(h, DGADJ_ERR_INVALID, "bad rhs arguments");
+  if (!h->ops_set || (level == 1 && !h->enr_set)) return fail(h, DGADJ_ERR_STATE, "operators of level %d not set", level);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int Np = level ? h->NpF : h->Np;
+  const long long n = (long long)B * h->K;
+  rhs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      B, h->K, Np, h->cfg.bc, h->cfg.inflow, h->cfg.alpha, t, a, a_dev, h->d_nodal[level][0],
+      h->d_nodal[level][1], h->d_mesh[level][0], h->d_mesh[level][1], h->d_mesh[level][2], h->d_uin, u_dev,
+      rhs_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_rank(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev, int32_t topk,
+                          int32_t* order_dev, uint8_t* flags_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || K <= 0 || !eta_dev || topk < 0) return fail(h, DGADJ_ERR_INVALID, "bad rank arguments");
+  if ((size_t)K * 8 > 200 * 1024) return fail(h, DGADJ_ERR_UNSUPPORTED, "K too large for the ranking kernel");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int block = std::min(1024, (K + 31) / 32 * 32);
+  const int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count * 8);
+  const size_t smem = (size_t)K * sizeof(double);
+  if (smem > 48 * 1024)
+    CUDA_TRY(h, cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rank_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(B, K, eta_dev, topk, order_dev, flags_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev,
+                                       const double* J_dev, double* sums_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || K <= 0 || !eta_dev || !sums_dev) return fail(h, DGADJ_ERR_INVALID, "bad reduce arguments");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t need = (size_t)2 * K * sizeof(double);
+  if (need > h->red_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->red_scratch);
+    h->red_scratch = nullptr;
+    h->red_bytes = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->red_scratch, need));
+    h->red_bytes = need;
+  }
+  double* colsq = h->red_scratch;
+  double* colmax = h->red_scratch + K;
+  reduce_cols_kernel<<<(K + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(B, K, eta_dev, sums_dev, colsq, colmax);
+  CUDA_TRY(h, cudaGetLastError());
+  reduce_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(B, K, colsq, colmax, J_dev, sums_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 2;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_measure_dfma_peak(dgadj_handle* h, double seconds, double* tflops_out,
+                                       double* sm_clock_mhz_out) {
+  if (!h || !tflops_out) return DGADJ_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  double* d_out = nullptr;
+  CUDA_TRY(h, cudaMalloc((void**)&d_out, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(h, cudaEventCreate(&e0));
+  CUDA_TRY(h, cudaEventCreate(&e1));
+  const int grid = h->sm_count, block = 1024;
+  int iters = 2000;
+  double best = 0.0;
+  double spent = 0.0;
+  const double budget = seconds > 0 ? seconds : 0.5;
+  for (int rep = 0; rep < 64 && spent < budget; ++rep) {
+    CUDA_TRY(h, cudaEventRecord(e0, 0));
+    dfma_peak_kernel<<<grid, block>>>(d_out, iters, 0.999999, 1e-9);
+    CUDA_TRY(h, cudaEventRecord(e1, 0));
+    CUDA_TRY(h, cudaEventSynchronize(e1));
+    h->launches++;
+    float ms = 0;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 128.0 * (double)iters * (double)grid * (double)block;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0) best = std::max(best, tf);  // first launch warms up
+    spent += ms * 1e-3;
+    if (ms < 20.0f) iters *= 2;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops_out = best;
+  if (sm_clock_mhz_out) {
+    // clock implied by the measurement if the pipe retires 64 DFMA / SM / clk
+    *sm_clock_mhz_out = best * 1e12 / (2.0 * 64.0 * h->sm_count) / 1e6;
+  }
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_device_info(dgadj_handle* h, int32_t* sm_count, int64_t* total_mem, int32_t* cc_major,
+                                 int32_t* cc_minor) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (sm_count) *sm_count = h->sm_count;
+  if (total_mem) *total_mem = (int64_t)h->total_mem;
+  if (cc_major) *cc_major = h->cc_major;
+  if (cc_minor) *cc_minor = h->cc_minor;
+  return DGADJ_OK;
+}
+
+extern "C" int64_t dgadj_launch_count(const dgadj_handle* h) { return h ? h->launches : 0; }

@@ -1,0 +1,49 @@
+// dgadj_march_np.cu -- one translation unit per primal order: compiled 8 times with
+// -DDGADJ_NP=2..9 (N = 1..8) so the per-order kernels build in parallel.  Exports
+// dgadj::march_launch_np<NP>(variant, grid, block, stream, args).
+#define DGADJ_DEVICE_CODE 1
+#include "dgadj_kernels.cuh"
+
+#ifndef DGADJ_NP
+#error "compile with -DDGADJ_NP=<Np>"
+#endif
+
+namespace dgadj {
+
+template <int NP, int EPT, bool F, bool R, bool A>
+static cudaError_t launch_one(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
+  static bool attr_set = false;  // per variant instantiation (function-local static per template)
+  if (block > MAXBD / EPT) return cudaErrorInvalidConfiguration;
+  const size_t smem = march_smem_bytes(NP, EPT, block, variant);
+  auto kern = march_kernel<NP, EPT, F, R, A>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, block, smem, stream>>>(*ka);
+  return cudaGetLastError();
+}
+
+#define DGADJ_CAT2(a, b) a##b
+#define DGADJ_CAT(a, b) DGADJ_CAT2(a, b)
+
+template <int EPT>
+static cudaError_t launch_ept(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
+  switch (variant) {
+    case VAR_FWD: return launch_one<DGADJ_NP, EPT, true, false, false>(variant, grid, block, stream, ka);
+    case VAR_FWD_RESID: return launch_one<DGADJ_NP, EPT, true, true, false>(variant, grid, block, stream, ka);
+    case VAR_ADJ: return launch_one<DGADJ_NP, EPT, false, false, true>(variant, grid, block, stream, ka);
+    case VAR_FUSED: return launch_one<DGADJ_NP, EPT, true, true, true>(variant, grid, block, stream, ka);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t DGADJ_CAT(march_launch_np, DGADJ_NP)(int variant, int ept, int grid, int block,
+                                                 cudaStream_t stream, const KArgs* ka) {
+  if (ept == 1) return launch_ept<1>(variant, grid, block, stream, ka);
+  if (ept == 2) return launch_ept<2>(variant, grid, block, stream, ka);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace dgadj

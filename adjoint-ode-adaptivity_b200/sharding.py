@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing: the batch of trajectories shards over ranks with no data-path
+collective; the only exchange is the all-reduce of the per-rank indicator
+partials that feeds the batch-mean refinement rule of the reference
+(python/Main_variable_params.py:340-341: jnp.mean(err, axis=0) -> argmax)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(B: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of a global batch of B trajectories owned by `rank`."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_indicators(sums, group=None, ordered=True):
+    """Combine per-rank partials sums[K+4] = [sum_b|eta[b,k]| (K), sum|eta|, sum eta^2,
+    max|eta|, sum J] across ranks.  ordered=True all-gathers the partials and adds them in
+    rank order on every rank, so 1/2/4/8-GPU runs of the same global batch rank elements
+    identically (SURVEY hard part 6); ordered=False is a plain all-reduce (sum + max)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return sums
+    world = dist.get_world_size(group)
+    K = sums.numel() - 4
+    if ordered:
+        parts = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(parts, sums, group=group)
+        out = parts[0].clone()
+        for p in parts[1:]:
+            out[:K + 2] += p[:K + 2]
+            out[K + 2] = torch.maximum(out[K + 2], p[K + 2])
+            out[K + 3] += p[K + 3]
+        return out
+    out = sums.clone()
+    mx = out[K + 2:K + 3].clone()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    out[K + 2] = mx[0]
+    return out
+
+
+def batch_mean_refine(sums, B_global: int):
+    """Shared-mesh refinement decision from the reduced partials: mean indicator per element
+    and the element to refine (argmax, lowest index on ties -- np.argmax semantics,
+    python/Main_finite_difference.py:337; python/Main_variable_params.py:340-341)."""
+    s = sums.detach().cpu().numpy() if hasattr(sums, "detach") else np.asarray(sums)
+    K = s.size - 4
+    mean_ind = s[:K] / float(B_global)
+    return mean_ind, int(np.argmax(mean_ind))

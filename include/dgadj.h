@@ -13,8 +13,9 @@
  *   - `*_dev` pointers are CUDA device pointers on the handle's device, caller-owned and
  *     borrowed for the call; work is enqueued on `stream` (a cudaStream_t cast to void*,
  *     NULL = the legacy default stream) and is asynchronous -- the caller synchronises.
- *   - `*_host` entry points take host pointers, stage through pinned memory, copy H2D,
- *     run the same kernels, copy D2H and synchronise before returning.
+ *   - `*_host` entry points take host pointers (pinned or pageable), copy H2D in chunks,
+ *     run the same kernels overlapped with the copies, copy D2H and synchronise before
+ *     returning.
  *   - all matrices are fp64, row-major; fields are [B][Np][K] (node-major inside a
  *     trajectory: element index fastest), the batched form of galerkin.py's (Np, K) arrays
  *     (python/galerkin.py:216).
@@ -77,7 +78,9 @@ const char* dgadj_last_error(const dgadj_handle* h);
 
 /* Operators of the primal space, as produced by StartUp1D (utils/StartUp1D.m:9-33) /
  * BaseGalerkin1D.startUp1D (python/galerkin.py:199-237).  Host pointers, copied.
- *   Dr[Np*Np], LIFT[Np*2], Mref[Np*Np] = inv(V V'), rx[Np*K], Fscale[2*K].              */
+ *   Dr[Np*Np], LIFT[Np*2], Mref[Np*Np] = inv(V V'), rx[Np*K], Fscale[2*K].
+ * Dr must be centro-antisymmetric and LIFT centro-symmetric (true for every LGL operator
+ * set StartUp1D produces); anything else is rejected with DGADJ_ERR_UNSUPPORTED.          */
 int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double* Dr, const double* LIFT,
                         const double* Mref, const double* rx, const double* Fscale);
 
@@ -93,6 +96,11 @@ int dgadj_set_functional_weights(dgadj_handle* h, const double* jw_c, const doub
 
 /* Caller-supplied inflow values uin[S*nstages] (cfg.inflow == DGADJ_INFLOW_TABLE).       */
 int dgadj_set_inflow_table(dgadj_handle* h, int n, const double* uin);
+
+/* Launch-shape overrides for tuning sweeps (0 = automatic): elements per thread (1 or 2),
+ * target threads per CTA, CTAs in the persistent grid.                                   */
+int dgadj_set_tuning(dgadj_handle* h, int32_t elems_per_thread, int32_t block_threads,
+                     int32_t grid_ctas);
 
 /* Per-trajectory advection speed / time step: if a_dev (dt_dev) is NULL the scalar is used. */
 typedef struct {
@@ -134,7 +142,7 @@ int dgadj_fwd_adj(dgadj_handle* h, const dgadj_march_args* args, const double* u
                   double* uT_dev, double* J_dev, double* lam0_dev, double* eta_dev,
                   void* stream);
 
-/* Same as dgadj_fwd_adj with HOST buffers (pinned staging, H2D, kernels, D2H, sync).
+/* Same as dgadj_fwd_adj with HOST buffers (chunked H2D, kernels, D2H, sync).
  * a_host / dt_host: [B] or NULL.                                                         */
 int dgadj_fwd_adj_host(dgadj_handle* h, const dgadj_march_args* args, const double* a_host,
                        const double* dt_host, const double* u0_host, double* uT_host,
@@ -142,6 +150,12 @@ int dgadj_fwd_adj_host(dgadj_handle* h, const dgadj_march_args* args, const doub
 int dgadj_forward_host(dgadj_handle* h, const dgadj_march_args* args, const double* a_host,
                        const double* dt_host, const double* u0_host, double* uT_host,
                        double* hist_host);
+
+/* One evaluation of the semi-discrete right-hand side, rhsu = AdvecRHS1D(u, time, a)
+ * (utils/AdvecRHS1D.m:1-20), in the primal (level 0) or enriched (level 1) space:
+ *   u_dev[B][Np_level][K] -> rhs_dev[B][Np_level][K]; a_dev[B] or NULL (then `a`).       */
+int dgadj_rhs(dgadj_handle* h, int64_t B, int32_t level, const double* u_dev, double t, double a,
+              const double* a_dev, double* rhs_dev, void* stream);
 
 /* Refine flag / ranking.  Replaces: ref_i = find(abs(err)==max(abs(err))) (matlab/MAIN.m:137),
  * np.argmax(err_steps) (Main_finite_difference.py:337) and sort(...,'descend') (MAIN.m:99).
@@ -152,7 +166,7 @@ int dgadj_rank(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev, int
 
 /* Batch reduction feeding the cross-GPU all-reduce (python/Main_variable_params.py:340,
  * jnp.mean(err_refine, axis=0)): sums_dev[K+4] = { sum_b |eta[b][k]| (k<K), sum|eta|,
- * sum eta^2, max|eta|, sum_b J[b] } in a fixed, B-independent summation order.          */
+ * sum eta^2, max|eta|, sum_b J[b] } in a fixed, grid-independent summation order.        */
 int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev,
                             const double* J_dev, double* sums_dev, void* stream);
 
@@ -167,6 +181,19 @@ int dgadj_device_info(dgadj_handle* h, int32_t* sm_count, int64_t* total_mem, in
 
 /* Number of kernel launches issued through this handle since creation (bench accounting). */
 int64_t dgadj_launch_count(const dgadj_handle* h);
+
+/* Launch shape the handle would use for a batch of B trajectories (diagnostics / bench):
+ * elements per thread, threads per CTA, trajectories per CTA, CTAs, dynamic smem bytes.   */
+int dgadj_plan(dgadj_handle* h, int64_t B, int32_t fused, int32_t* ept, int32_t* block,
+               int32_t* tpc, int32_t* grid, int64_t* smem_bytes);
+
+/* Host-only utilities (no device needed; used by the CPU test-suite): the even/odd operator
+ * blocks the kernels run on, built from nodal Dr[Np*Np] / LIFT[Np*2] (and P[(Np+1)*Np]).
+ * Outputs are [5*5] / [5] arrays (row stride 5); *violation = largest entry of the blocks
+ * that must vanish by symmetry, relative to the largest operator entry.                  */
+int dgadj_host_eo_operators(int Np, const double* Dr, const double* LIFT, double* DE, double* DO,
+                            double* LS, double* LA, double* violation);
+int dgadj_host_eo_prolongation(int Np, const double* P, double* PE, double* PO, double* violation);
 
 #ifdef __cplusplus
 }

@@ -254,13 +254,17 @@ def fwd_adj_indicator(u0, gc, gf, a, dt, nsteps, alpha=1.0, bc=BC_INFLOW, inflow
     `lam` is the raw discrete adjoint dJ/du (mass included), so App. E.5's
     z^T M_k rho with z = M^-1 lam is the same number.  For a linear problem and linear J,
     sum_k eta[k] = J_f(P u^S) - J_f(u_f^S) exactly (tests check this effectivity).
-    Returns dict(uT, J, lam0, eta) -- eta signed; consumers take |eta| (MAIN.m:51)."""
+    Returns dict(uT, J, lam0, eta, eta_scale) -- eta signed; consumers take |eta| (MAIN.m:51).
+    eta is a sum of products lam*(P u^{n+1} - Phi_f(P u^n)) whose two parts cancel to
+    O(h^{N+1}); any two fp64 evaluations agree to eps * eta_scale (the sum of the absolute
+    values of the parts), not to eps * |eta| -- parity tests use eta_scale as the yardstick."""
     P = ops.prolongation(gc.N, gf.N)
     uT, hist = advec_march(u0, gc, a, dt, nsteps, alpha, bc, inflow, scheme, history=True, t0=t0)
     Jc = functional(uT, gc, func, psi)
     lam = functional_grad(P @ uT, gf, func, psi)
     lam_k = np.zeros_like(lam)
     eta = np.zeros(lam.shape[:-2] + (gc.K,))
+    eta_scale = np.zeros_like(eta)   # sum of |terms| before cancellation (fp64 agreement scale)
     times = [t0 + 0.0 * np.asarray(dt, dtype=float)]
     for n in range(nsteps):
         times.append(times[-1] + dt)           # same accumulation as the forward march
@@ -269,8 +273,9 @@ def fwd_adj_indicator(u0, gc, gf, a, dt, nsteps, alpha=1.0, bc=BC_INFLOW, inflow
         uf, _ = step(P @ hist[n], np.zeros_like(lam), t, dt, a, gf, alpha, bc, inflow, scheme)
         rho = P @ hist[n + 1] - uf
         eta += np.sum(lam * rho, axis=-2)
+        eta_scale += np.sum(np.abs(lam) * (np.abs(P @ hist[n + 1]) + np.abs(uf)), axis=-2)
         lam, lam_k = adjoint_step(lam, lam_k, dt, a, gf, alpha, bc, scheme)
-    return dict(uT=uT, J=Jc, lam0=lam, eta=eta, hist=hist)
+    return dict(uT=uT, J=Jc, lam0=lam, eta=eta, hist=hist, eta_scale=eta_scale)
 
 
 def rank_refine(eta, topk=1):

@@ -1,0 +1,193 @@
+"""CPU tests of the product's host side: the galerkin.py mirror against the oracle, the C
+library's host code (even/odd operator blocks) through an emulation of the kernel's algebra,
+the C-ABI surface, and the multi-GPU plumbing on gloo with world_size 2."""
+import ctypes as C
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import eo_emulator as em
+from oracle import advec
+from oracle import operators as ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- galerkin.py mirror
+@pytest.mark.parametrize("N", range(1, 10))
+def test_basegalerkin_matches_oracle(pkg, N):
+    g = pkg.BaseGalerkin1D(n=N, k=7, domain=(0.5, 3.0), n_gq=2 * N)
+    o = ops.fem_setup(N, 7, (0.5, 3.0), 2 * N)
+    pairs = [(g.r_lgl, o.r_lgl), (g.v, o.V), (g.inv_v, o.invV), (g.d_r, o.Dr), (g.lift, o.LIFT), (g.x, o.x),
+             (g.r_x, o.rx), (g.j_mat, o.J), (g.f_x, o.Fx), (g.n_x, o.nx), (g.f_scale, o.Fscale), (g.v_x, o.VX),
+             (g.r, o.r), (g.w, o.w), (g.phi, o.Phi), (g.mass, ops.mass_matrix(o.V))]
+    for a, b in pairs:
+        assert a.shape == b.shape
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-10)
+    assert np.array_equal(g.e_to_e, o.EToE) and np.array_equal(g.e_to_f, o.EToF)
+    assert np.array_equal(g.e_to_v, o.EToV)
+    np.testing.assert_allclose(g.prolongation_to(pkg.BaseGalerkin1D(n=N + 1, k=7, domain=(0.5, 3.0))),
+                               ops.prolongation(N, N + 1), atol=1e-11)
+
+
+def test_basegalerkin_interface(pkg):
+    """Attribute names / shapes / defaults of python/galerkin.py:18-24,199-263."""
+    g = pkg.BaseGalerkin1D()
+    assert (g.n, g.k, g.n_gq, g.n_fp, g.n_faces, g.node_tol) == (1, 2, 2, 1, 2, 1e-10)
+    assert list(g.domain) == [0.0, 1.0]
+    for name in ("n_p r v inv_v d_r lift x r_x j_mat f_mask f_x n_x f_scale e_to_e e_to_f v_map_m v_map_p "
+                 "v_map_b map_b map_i map_o v_map_i v_map_o v_x e_to_v w n_r phi").split():
+        assert hasattr(g, name), name
+    for name in ("jacobiGQ jacobiGL jacobiP vandermonde1D gradJacobiP gradVandermonde1D dMatrix1D lift1D "
+                 "geometricFactors1D normals1D connect1D buildMaps1D startUp1D").split():
+        assert callable(getattr(g, name)), name
+    g = pkg.BaseGalerkin1D(n=3, k=5)
+    assert g.x.shape == (4, 5) and g.r_x.shape == (4, 5) and g.f_scale.shape == (2, 5) and g.phi.shape == (3, 4)
+    # maps: 0-based into the row-major (Np, K) flattening; interior faces meet the neighbour's node
+    xf = g.x.ravel()
+    assert np.allclose(xf[g.v_map_m[1, :-1]], xf[g.v_map_p[1, :-1]])
+    assert g.v_map_p[1, 0] == g.v_map_m[0, 1]
+    assert (g.map_i, g.map_o, g.v_map_i, g.v_map_o) == (0, 9, 0, 19)
+    assert g.map_b.tolist() == [0, 9]
+
+
+def test_nonuniform_mesh(pkg):
+    vx = np.array([0.0, 0.25, 0.5, 1.0, 2.0])
+    g = pkg.BaseGalerkin1D(n=2, v_x=vx)
+    o = ops.startup_mesh(2, vx)
+    np.testing.assert_allclose(g.r_x, o.rx, rtol=1e-13)
+    np.testing.assert_allclose(g.f_scale, o.Fscale, rtol=1e-13)
+    assert g.k == 4
+
+
+# ---------------------------------------------------------------- C host code + kernel algebra
+CASES = [(4, 10, "periodic", 0.0), (4, 10, "inflow", 1.0), (3, 7, "inflow", 0.3), (8, 16, "periodic", 0.0),
+         (1, 5, "periodic", 1.0), (2, 20, "inflow", 1.0), (7, 6, "inflow", 0.0), (5, 8, "periodic", 0.5)]
+
+
+@pytest.mark.parametrize("N,K,bc,alpha", CASES)
+def test_even_odd_algebra_matches_oracle(pkg, lib, N, K, bc, alpha):
+    gc = pkg.BaseGalerkin1D(n=N, k=K, domain=(0, 2 * math.pi))
+    gf = pkg.BaseGalerkin1D(n=N + 1, k=K, domain=(0, 2 * math.pi))
+    oc = ops.startup_uniform(N, 0, 2 * math.pi, K)
+    of = ops.startup_uniform(N + 1, 0, 2 * math.pi, K)
+    a = 2 * math.pi
+    dt, S = advec.cfl_dt(oc, 0.15)
+    rng = np.random.default_rng(N * 100 + K)
+    u0 = np.sin(oc.x) + 0.1 * rng.standard_normal(oc.x.shape)
+    per = bc == "periodic"
+    ref = advec.fwd_adj_indicator(u0, oc, of, a, dt, S, alpha=alpha, bc=bc, inflow=advec.INFLOW_SIN_AT)
+    rk = (ops.rk4a, ops.rk4b, ops.rk4c)
+    out = em.fused(lib, gc, gf, gc.prolongation_to(gf), u0, a, dt, S, alpha, per, rk, gc.quad_weights(),
+                   gf.quad_weights(), inflow_fn=None if per else (lambda t: -np.sin(a * t)))
+    assert out["viol"] < 1e-13
+    np.testing.assert_allclose(out["uT"], ref["uT"], rtol=0, atol=1e-12 * np.max(np.abs(ref["uT"])))
+    np.testing.assert_allclose(out["lam0"], ref["lam0"], rtol=0, atol=1e-12 * np.max(np.abs(ref["lam0"])))
+    assert abs(out["J"] - ref["J"]) <= 1e-12 * max(1.0, abs(ref["J"]))
+    assert np.all(np.abs(out["eta"] - ref["eta"]) <= 1e-12 * ref["eta_scale"])
+
+
+def test_eo_rejects_asymmetric_operator(lib):
+    Np = 4
+    Dr = np.arange(16, dtype=float).reshape(4, 4)
+    LIFT = np.ones((4, 2))
+    DE, DO, LS, LA = np.zeros(25), np.zeros(25), np.zeros(5), np.zeros(5)
+    v = C.c_double()
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    assert lib.dgadj_host_eo_operators(Np, p(Dr), p(LIFT), p(DE), p(DO), p(LS), p(LA), C.byref(v)) == 0
+    assert v.value > 1e-3        # dgadj_set_operators refuses such a set (violation > 1e-10)
+    assert lib.dgadj_host_eo_operators(1, p(Dr), p(LIFT), p(DE), p(DO), p(LS), p(LA), C.byref(v)) == -1
+
+
+# ---------------------------------------------------------------- C-ABI surface
+def test_abi_exports_every_declared_symbol(pkg, lib):
+    with open(os.path.join(ROOT, "include", "dgadj.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = set(re.findall(r"\b(dgadj_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 24
+    assert declared == set(pkg._lib.PROTOTYPES), declared ^ set(pkg._lib.PROTOTYPES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.dgadj_version() == 100
+    assert C.sizeof(pkg._lib.Config) == 40 and C.sizeof(pkg._lib.MarchArgs) == 56
+
+
+def test_create_argument_checks_and_no_cpu_fallback(pkg, lib):
+    h = C.c_void_p(0)
+    cfg = pkg._lib.Config(device=0, N=4, K=10, bc=0, inflow=1, functional=0, scheme=0, reserved=0, alpha=1.0)
+    assert lib.dgadj_create(None, C.byref(h)) == pkg._lib.ERR_INVALID
+    bad = pkg._lib.Config(device=0, N=9, K=10, bc=0, inflow=1, functional=0, scheme=0, reserved=0, alpha=1.0)
+    assert lib.dgadj_create(C.byref(bad), C.byref(h)) == pkg._lib.ERR_UNSUPPORTED
+    bad = pkg._lib.Config(device=0, N=4, K=4096, bc=0, inflow=1, functional=0, scheme=0, reserved=0, alpha=1.0)
+    assert lib.dgadj_create(C.byref(bad), C.byref(h)) == pkg._lib.ERR_UNSUPPORTED
+    bad = pkg._lib.Config(device=0, N=4, K=10, bc=7, inflow=1, functional=0, scheme=0, reserved=0, alpha=1.0)
+    assert lib.dgadj_create(C.byref(bad), C.byref(h)) == pkg._lib.ERR_INVALID
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.dgadj_create(C.byref(cfg), C.byref(h)) == pkg._lib.ERR_NO_DEVICE
+        with pytest.raises(pkg.DgadjError):
+            pkg.AdvecDG1D(4, 10)
+
+
+# ---------------------------------------------------------------- sharding + gloo world_size 2
+def test_shard_range(pkg):
+    for B, W in [(10, 3), (65536, 8), (5, 8), (1, 1)]:
+        parts = [pkg.shard_range(B, r, W) for r in range(W)]
+        assert parts[0][0] == 0 and parts[-1][1] == B
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(W - 1))
+        assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+
+
+def test_batch_mean_refine(pkg):
+    sums = np.array([3.0, 9.0, 9.0, 1.0, 22.0, 0.0, 9.0, 0.0])
+    mean, idx = pkg.batch_mean_refine(sums, 3)
+    assert idx == 1 and mean.tolist() == [1.0, 3.0, 3.0, 1.0 / 3.0]
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+import dgadj_loader
+pkg = dgadj_loader.load_package()
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+K, B = 6, 11
+rng = np.random.default_rng(0)
+eta = rng.standard_normal((B, K)); J = rng.standard_normal(B)
+lo, hi = pkg.shard_range(B, rank, world)
+e, j = eta[lo:hi], J[lo:hi]
+part = torch.tensor(np.concatenate([np.abs(e).sum(0), [np.abs(e).sum(), (e**2).sum(), np.abs(e).max(), j.sum()]]))
+tot = pkg.allreduce_indicators(part, ordered=True)
+tot2 = pkg.allreduce_indicators(part, ordered=False)
+full = np.concatenate([np.abs(eta).sum(0), [np.abs(eta).sum(), (eta**2).sum(), np.abs(eta).max(), J.sum()]])
+assert np.allclose(tot.numpy(), full, rtol=1e-13), (tot, full)
+assert np.allclose(tot2.numpy(), full, rtol=1e-13)
+gathered = [torch.empty_like(tot) for _ in range(world)]
+dist.all_gather(gathered, tot)
+assert all(torch.equal(gathered[0], g) for g in gathered)      # bit-identical on every rank
+mean, idx = pkg.batch_mean_refine(tot, B)
+assert idx == int(np.argmax(np.abs(eta).sum(0)))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_two_rank_indicator_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
