@@ -518,6 +518,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
   for (int g = blockIdx.x; g < p.ngroups; g += gridDim.x) {
     const long long b = (long long)g * p.tpc + t_local;
     const bool active = in_tile && (b < p.B);
+    const long long bs = active ? b : 0;  // in-bounds index for per-trajectory parameter reads
     {
       // per-element stage coefficients -> shared memory (face coefficients
       // c_f = (a*nx - (1-alpha)|a*nx|)/2, nx = -1,+1; AdvecRHS1D.m:11; du(mapO) = 0, :16)
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
     }
     const size_t slot = p.ckpt_by_block ? (size_t)blockIdx.x : (size_t)g;
     double* ck = p.ckpt ? p.ckpt + slot * (size_t)p.S * tile : nullptr;
-    const size_t gofs = (size_t)(active ? b : 0) * NP * K + k0;  // this thread's column in [B][NP][K]
+    const size_t gofs = (size_t)bs * NP * K + k0;  // this thread's column in [B][NP][K]
 
     double u[EPT][NP];  // nodal terminal state (adjoint terminal condition / J)
     // ------------------------------------------------------------------ forward phase
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
             rf[e].zero();
             z[e].store(park + (size_t)e * BD, cstride);
           }
-          fwd_step<NPF, 1, EPT>(ka, cx, sm_tr, sm_coef + (size_t)3 * EPT * BD, f, rf, b, time, n);
+          fwd_step<NPF, 1, EPT>(ka, cx, sm_tr, sm_coef + (size_t)3 * EPT * BD, f, rf, bs, time, n);
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
             z[e].load(park + (size_t)e * BD, cstride);
@@ -600,9 +601,9 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
           EOVec<NP> r[EPT];
 #pragma unroll
           for (int e = 0; e < EPT; ++e) r[e].zero();
-          fwd_step<NP, 0, EPT>(ka, cx, sm_tr, sm_coef, z, r, b, time, n);
+          fwd_step<NP, 0, EPT>(ka, cx, sm_tr, sm_coef, z, r, bs, time, n);
         }
-        time += p.dt_arr ? p.dt_arr[active ? b : 0] : p.dt;  // `time = time+dt` accumulation of the mlx
+        time += p.dt_arr ? p.dt_arr[bs] : p.dt;  // `time = time+dt` accumulation of the mlx
         if (RESID) {
           // rho^n = P u^{n+1} - sigma  -> checkpoint tile [n][row][e][tid]  (coalesced);
           // P u^{n+1} stays in the park as the start of the next fine step.

@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the dgadj hot path (BASELINE.json metric):
+DG element-stage updates/s (forward + adjoint) of the fused LSERK4 forward march, reverse
+discrete-adjoint march and per-element error indicator, BASELINE config 2:
+linear advection N=8, K=1024, 65,536 random ICs per GPU (weak scaling), fp64.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # our arm (CUDA, C-ABI)
+    python bench.py --impl reference [--gpus N] [--steps K] [...]   # CPU arm: the oracle port
+    torchrun ... bench.py --gpus N ...                              # one rank per GPU (N > 1)
+
+A "step" is one pass of the hot path over the whole batch: fused fwd+adj+indicator kernel,
+per-trajectory refine flags, the fixed-order indicator reduction and (N > 1) its NCCL
+all-reduce.  `value` times that with the ICs resident in HBM; `e2e` times the same pass
+through the host-buffer C-ABI entry point (dgadj_fwd_adj_host) from pinned host memory,
+H2D of the ICs and D2H of the indicators inside the timed region.  One JSON line on stdout.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DG element-stage updates/s (fwd+adjoint)"
+UNIT = "updates/s"
+TWO_PI = 2.0 * math.pi
+
+
+def flops_per_update(Np):
+    """forward stage 2Np^2+12Np+6, adjoint stage 2Np^2+12Np+8 (FMA = 2);
+    mean per element-stage update.  Indicator / prolongation / ranking work is NOT counted."""
+    return 0.5 * ((2 * Np * Np + 12 * Np + 6) + (2 * Np * Np + 12 * Np + 8))
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    # workload overrides (defaults = BASELINE config 2); used by tuning sweeps / quick checks
+    p.add_argument("--N", type=int, default=8)
+    p.add_argument("--K", type=int, default=1024)
+    p.add_argument("--B", type=int, default=65536, help="trajectories per GPU")
+    p.add_argument("--S", type=int, default=200, help="LSERK4 steps per trajectory")
+    p.add_argument("--ept", type=int, default=0)
+    p.add_argument("--block", type=int, default=0)
+    p.add_argument("--grid", type=int, default=0)
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--cpu-B", type=int, default=48, help="CPU sample: trajectories per worker")
+    p.add_argument("--cpu-S", type=int, default=8)
+    return p.parse_args()
+
+
+def synth_ics_np(x, B, seed):
+    """u0[b] = sum_{m=1..4} A_{b,m} sin(m x + phi_{b,m}), A ~ N(0,1)/m, phi ~ U[0, 2pi)  (SURVEY 8d)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    u0 = np.zeros((B,) + x.shape)
+    for m in range(1, 5):
+        A = rng.standard_normal((B, 1, 1)) / m
+        ph = rng.uniform(0, TWO_PI, (B, 1, 1))
+        u0 += A * np.sin(m * x[None] + ph)
+    return u0
+
+
+def synth_ics_torch(torch, x, B, seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    xt = torch.tensor(x, device=device)[None]
+    u0 = torch.zeros((B,) + tuple(x.shape), dtype=torch.float64, device=device)
+    for m in range(1, 5):
+        A = torch.randn((B, 1, 1), dtype=torch.float64, device=device, generator=g) / m
+        ph = torch.rand((B, 1, 1), dtype=torch.float64, device=device, generator=g) * TWO_PI
+        u0 += A * torch.sin(m * xt + ph)
+    return u0
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the NumPy oracle (a port: the reference has no PDE adjoint / indicator code and its
+# forward march is a MATLAB live script; see oracle/__init__.py) on the box's host cores
+# ------------------------------------------------------------------------------------------
+def cpu_workers():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+def _oracle_worker(args):
+    N, K, B, S, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    return run_oracle_sample(N, K, B, S, seed)
+
+
+def run_oracle_sample(N, K, B, S, seed=1234):
+    """One bounded sample of the workload on one CPU core; returns (updates, seconds)."""
+    import numpy as np
+    from oracle import advec
+    from oracle import operators as ops
+    gc = ops.startup_uniform(N, 0.0, TWO_PI, K)
+    gf = ops.startup_uniform(N + 1, 0.0, TWO_PI, K)
+    dt, _ = advec.cfl_dt(gc, 1.0)
+    u0 = synth_ics_np(gc.x, B, seed)
+    t0 = time.perf_counter()
+    out = advec.fwd_adj_indicator(u0, gc, gf, TWO_PI, dt, S, alpha=0.0, bc=advec.BC_PERIODIC)
+    advec.rank_refine(out["eta"], 5)
+    sec = time.perf_counter() - t0
+    return 2 * 5 * S * K * B, sec
+
+
+class OraclePool:
+    """The NumPy oracle on all host cores: one single-threaded worker process per core, each
+    marching its own slice of the sample batch (the batch is embarrassingly parallel)."""
+
+    def __init__(self, workers):
+        import multiprocessing as mp
+        self.workers = workers
+        self.pool = mp.get_context("spawn").Pool(workers)
+        self.pool.map(_oracle_worker, [(2, 8, 2, 1, 0)] * workers)   # import numpy / warm the workers
+
+    def run(self, N, K, B_per_worker, S):
+        t0 = time.perf_counter()
+        res = self.pool.map(_oracle_worker, [(N, K, B_per_worker, S, 1234 + i) for i in range(self.workers)])
+        sec = time.perf_counter() - t0
+        return sum(r[0] for r in res), sec
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    workers = cpu_workers()
+    pool = OraclePool(workers)
+    for _ in range(a.warmup):
+        pool.run(a.N, a.K, max(2, a.cpu_B // 8), 2)
+    ups, secs = 0, 0.0
+    for _ in range(a.steps):
+        u, s = pool.run(a.N, a.K, a.cpu_B, a.cpu_S)
+        ups += u
+        secs += s
+    pool.close()
+    val = ups / secs
+    sample = (f"per step: {workers} workers x B={a.cpu_B} trajectories x S={a.cpu_S} LSERK4 steps of the config "
+              "(fwd + fine residual + adjoint + indicator + ranking, NumPy fp64 oracle port)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(a):
+    return {"workload": f"linear advection N={a.N}, K={a.K}, batch {a.B} random ICs per GPU, LSERK4 S={a.S} steps, "
+                        "fwd + adjoint (order N+1) + per-element indicator + refine flags, periodic, upwind",
+            "N": a.N, "K": a.K, "batch_per_gpu": a.B, "S": a.S, "bc": "periodic", "alpha": 0.0, "a": TWO_PI,
+            "dt_rule": "One_code.mlx CFL", "parallelism": f"batch-sharded x{a.gpus}",
+            "l2_policy": "inputs larger than L2 (ICs 4.8 GB + checkpoint ring 2.4 GB per GPU)"}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+        except Exception:
+            return out
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def ours(a):
+    import numpy as np
+    import torch
+    import dgadj_loader
+    pkg = dgadj_loader.load_package()        # ImportError if libdgadj.so is missing: no fallback
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device; there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, K, B, S = a.N, a.K, a.B, a.S
+    s = pkg.AdvecDG1D(N, K, domain=(0.0, TWO_PI), alpha=0.0, bc="periodic", device=local)
+    if a.ept or a.block or a.grid:
+        s.set_tuning(a.ept, a.block, a.grid)
+    dt, _ = s.cfl_dt(1.0)
+    u0 = synth_ics_torch(torch, s.g.x, B, 1234 + rank, dev)
+    out = dict(J=torch.empty(B, dtype=torch.float64, device=dev),
+               eta=torch.empty((B, K), dtype=torch.float64, device=dev))
+    B_global = B * world
+
+    def step_device():
+        r = s.fwd_adj(u0, TWO_PI, dt, S, want_uT=False, out=out)
+        _, flags = s.rank(r["eta"], topk=5, want_order=False)
+        sums = s.reduce_indicators(r["eta"], r["J"])
+        sums = pkg.allreduce_indicators(sums, ordered=True)
+        return sums, flags
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        sums, flags = step_device()
+    barrier()
+    # the dominant kernel alone (CUDA events on the launching stream), for the roofline
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    s.fwd_adj(u0, TWO_PI, dt, S, want_uT=False, out=out)
+    ev[1].record()
+    torch.cuda.synchronize()
+    kern_ms = ev[0].elapsed_time(ev[1])
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = []
+    e0.record()
+    for _ in range(a.steps):
+        sums, flags = step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = s.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    ms_per_step = ms / a.steps
+    updates_per_step = 2 * 5 * S * K * B_global
+    value = updates_per_step / (ms_per_step * 1e-3)
+    mean_ind, refine_idx = pkg.batch_mean_refine(sums, B_global)
+
+    # ---- end to end through the host-buffer C-ABI (pinned host memory, copies timed)
+    e2e = None
+    if not a.no_e2e:
+        h_u0 = torch.empty(u0.shape, dtype=torch.float64, pin_memory=True)
+        h_u0.copy_(u0)
+        h_eta = torch.empty((B, K), dtype=torch.float64, pin_memory=True)
+        h_J = torch.empty(B, dtype=torch.float64, pin_memory=True)
+        hout = dict(J=h_J.numpy(), eta=h_eta.numpy())
+        del u0
+        torch.cuda.empty_cache()
+
+        def step_host():
+            r = s.fwd_adj(h_u0.numpy(), TWO_PI, dt, S, want_uT=False, out=hout)   # returns synchronised
+            ae = np.abs(r["eta"])
+            return float(ae.max())
+
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            loss = step_host()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([sec], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t[0])
+        e2e = {"value": updates_per_step / (sec / a.steps), "unit": UNIT,
+               "h2d_bytes_per_step": int(B * s.Np * K * 8), "d2h_bytes_per_step": int(B * K * 8 + B * 8),
+               "ms_per_step": 1e3 * sec / a.steps, "api": "dgadj_fwd_adj_host (pinned host buffers)",
+               "check_max_abs_eta": loss}
+        # host path and device path run the same kernels on the same inputs
+        assert torch.equal(h_eta.to(dev), out["eta"]), "host-path indicators differ from device-path"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (fused march): fp64 FMA pipe, HBM secondary
+    peak_tf, peak_mhz = s.measure_dfma_peak(1.0)
+    fl = flops_per_update(s.Np) * 2 * 5 * S * K * B
+    ach_tf = fl / (kern_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ck_bytes = B * (2 * S * s.NpF * K * 8 + s.Np * K * 8 + K * 8 + 8)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = f"N{N}_K{K}_S{S}_B{B}"
+        traffic = tj.get(key)
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp64_fma", "kernel": "dgadj::march_kernel<NP=%d,EPT,fwd,resid,adj> (fused)" % s.Np,
+        "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
+        "peak_source": "measured live: register-only DFMA microbenchmark (dgadj_measure_dfma_peak); "
+                       "MEASURED_PEAKS.json has no fp64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
+        "algorithmic_flops_per_update": flops_per_update(s.Np), "kernel_ms": kern_ms,
+        "kernel_share_of_step": kern_ms / ms_per_step if world == 1 else None,
+        "hbm": {"achieved": ck_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ck_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"},
+        "traffic": traffic,
+    }
+    cpu = None
+    if not a.no_cpu and world == 1:
+        workers = cpu_workers()
+        pool = OraclePool(workers)
+        ups, sec = pool.run(N, K, a.cpu_B, a.cpu_S)
+        pool.close()
+        cpu = {"value": ups / sec, "unit": UNIT, "cores": workers, "kind": "port",
+               "sample": f"{workers} workers x B={a.cpu_B} trajectories x S={a.cpu_S} steps of the same workload, "
+                         f"NumPy oracle, {sec:.1f} s wall", "host_cpus": os.cpu_count()}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(a), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "plan": s.plan(B), "refine_element_batch_mean": refine_idx,
+        "frac_of_fp64_peak_whole_step": flops_per_update(s.Np) * updates_per_step / world / (ms_per_step * 1e-3) / 1e12 / peak_tf if peak_tf else None,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return reference_arm(a)
+    return ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

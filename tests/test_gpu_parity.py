@@ -1,0 +1,310 @@
+"""GPU parity tests: the CUDA path through the C-ABI (libdgadj.so via the ctypes host) against
+the NumPy oracle on identical inputs.  Tolerances (fp64, BASELINE.json north_star): 1e-12
+relative to the field's max norm for solutions / adjoints / J; 1e-12 * eta_scale for the
+indicators (eta cancels to O(h^(N+1)); eta_scale is the magnitude before cancellation, see
+oracle/advec.py); refine flags / rankings bit-exact on identical indicator input."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import advec
+from oracle import operators as ops
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+def make_ics(g, B, seed):
+    """Synthetic ICs of SURVEY section 8(d): sum_m A_m sin(m x + phi_m), A ~ N(0,1)/m."""
+    rng = np.random.default_rng(seed)
+    u0 = np.zeros((B,) + g.x.shape)
+    for m in range(1, 5):
+        A = rng.standard_normal((B, 1, 1)) / m
+        ph = rng.uniform(0, 2 * math.pi, (B, 1, 1))
+        u0 += A * np.sin(m * g.x[None] + ph)
+    return u0
+
+
+def oracle_pair(N, K, dom):
+    return ops.startup_uniform(N, dom[0], dom[1], K), ops.startup_uniform(N + 1, dom[0], dom[1], K)
+
+
+# ------------------------------------------------------------------ forward march
+def test_cfg1_forward_reference_path(pkg, torch):
+    """BASELINE config 1 as the reference runs it: N=4, K=10, [0,2pi], u0 = sin x, a = 2pi,
+    T = 2 (309 LSERK4 steps), AdvecRHS1D.m boundary data, alpha = 1."""
+    dom = (0.0, 2 * math.pi)
+    s = pkg.AdvecDG1D(4, 10, domain=dom, alpha=1.0, bc="inflow", inflow="sin_at")
+    g = ops.startup_uniform(4, dom[0], dom[1], 10)
+    dt, S = s.cfl_dt(2.0)
+    assert (S, dt) == (309, advec.cfl_dt(g, 2.0)[0])
+    u0 = np.sin(g.x)
+    ref, hist_ref = advec.advec_march(u0, g, 2 * math.pi, dt, S, 1.0, advec.BC_INFLOW, advec.INFLOW_SIN_AT, history=True)
+    uT, hist = s.forward(torch.tensor(u0, device="cuda"), 2 * math.pi, dt, S, history=True)
+    assert rel(uT.cpu().numpy()[0], ref) < TOL
+    assert rel(hist.cpu().numpy()[0], hist_ref) < TOL
+    assert np.linalg.norm(uT.cpu().numpy()) == pytest.approx(5.000011273277161, rel=1e-10)
+    uT_h = s.forward(u0, 2 * math.pi, dt, S)          # host-buffer entry point, same kernels
+    assert np.array_equal(uT_h, uT.cpu().numpy())
+
+
+def test_mlx_golden_forward(pkg, torch):
+    """utils/One_code.mlx: N=2, K=20, [0,1], 1341 steps, uin = -sin(a a t): the state the live
+    script printed (resu, 4 digits) and the oracle at 1e-12."""
+    s = pkg.AdvecDG1D(2, 20, domain=(0.0, 1.0), alpha=1.0, bc="inflow", inflow="sin_aat")
+    g = ops.startup_uniform(2, 0.0, 1.0, 20)
+    u0 = np.sin(2 * math.pi * g.x)
+    dt, S = s.cfl_dt(2.0)
+    assert S == 1341
+    out = advec.advec_march_mlx(u0, g, 2 * math.pi, 2.0, 1.0, advec.INFLOW_SIN_AAT)
+    uT, hist = s.forward(torch.tensor(u0, device="cuda"), 2 * math.pi, dt, S, history=True)
+    uT = uT.cpu().numpy()[0]
+    assert rel(uT, out["u"]) < 5e-12          # 1341 steps: rounding grows ~sqrt(steps)
+    assert uT[0, 0] == pytest.approx(4.050010240888256e-01, rel=1e-9)
+    # resu after the last stage = (u^S - u^{S-1} contribution): check against the golden print
+    with open(os.path.join(GOLD, "mlx_one_code.json")) as f:
+        items = {(it["name"], it["line"]): it for it in json.load(f)["items"]}
+    rhs_gold = np.array(items[("rhsu", 153)]["value"])
+    # rhsu printed by the mlx is AdvecRHS1D at the last stage input; evaluate ours there
+    h = hist.cpu().numpy()[0]
+    st = h[S - 1].copy()
+    res = np.zeros_like(st)
+    t = (S - 1) * dt
+    for k in range(4):
+        rhs = advec.AdvecRHS1D(st, t + ops.rk4c[k] * dt, 2 * math.pi, g, 1.0, advec.BC_INFLOW, advec.INFLOW_SIN_AAT)
+        res = ops.rk4a[k] * res + dt * rhs
+        st = st + ops.rk4b[k] * res
+    rhs_gpu = s.rhs(torch.tensor(st, device="cuda"), out["time"] - dt + ops.rk4c[4] * dt, 2 * math.pi).cpu().numpy()[0]
+    np.testing.assert_allclose(rhs_gpu, rhs_gold, rtol=0, atol=6e-4)      # 4 printed decimals of ~40
+    assert rel(rhs_gpu, out["rhsu"]) < 1e-9
+
+
+@pytest.mark.parametrize("N", range(1, 9))
+def test_forward_all_orders_batched_ragged(pkg, torch, N):
+    """Every compiled order, batch not a multiple of the CTA tile, per-trajectory a and dt."""
+    K, B, dom = 12, 37, (0.0, 2 * math.pi)
+    s = pkg.AdvecDG1D(N, K, domain=dom, alpha=0.0, bc="periodic")
+    g = ops.startup_uniform(N, dom[0], dom[1], K)
+    u0 = make_ics(g, B, 100 + N)
+    rng = np.random.default_rng(N)
+    a = rng.uniform(0.5, 2.0, B) * 2 * math.pi * np.where(rng.uniform(size=B) < 0.2, -1.0, 1.0)
+    dt0, S = s.cfl_dt(0.05)
+    dt = dt0 * rng.uniform(0.5, 1.0, B)
+    ref, _ = advec.advec_march(u0, g, a, dt, S, 0.0, advec.BC_PERIODIC)
+    uT = s.forward(torch.tensor(u0, device="cuda"), torch.tensor(a, device="cuda"), torch.tensor(dt, device="cuda"), S)
+    assert rel(uT.cpu().numpy(), ref) < TOL
+
+
+def test_forward_euler_scheme(pkg, torch):
+    """DGADJ_SCHEME_EULER = fwd_euler_march semantics (one stage, a=0, b=1)."""
+    dom = (0.0, 1.0)
+    s = pkg.AdvecDG1D(3, 9, domain=dom, alpha=0.0, bc="inflow", inflow="zero", scheme="euler")
+    g = ops.startup_uniform(3, 0, 1, 9)
+    u0 = make_ics(g, 5, 5)
+    ref, _ = advec.advec_march(u0, g, 1.3, 1e-4, 50, 0.0, advec.BC_INFLOW, advec.INFLOW_ZERO, scheme=advec.SCHEME_EULER)
+    uT = s.forward(torch.tensor(u0, device="cuda"), 1.3, 1e-4, 50)
+    assert rel(uT.cpu().numpy(), ref) < TOL
+
+
+def test_rhs_kernel_matches_AdvecRHS1D(pkg, torch):
+    for bc, inflow, alpha in [("inflow", "sin_at", 1.0), ("periodic", "zero", 0.0), ("inflow", "sin_aat", 0.4)]:
+        s = pkg.AdvecDG1D(5, 11, domain=(0.0, 2.0), alpha=alpha, bc=bc, inflow=inflow)
+        gc, gf = oracle_pair(5, 11, (0.0, 2.0))
+        for level, g in ((0, gc), (1, gf)):
+            u = make_ics(g, 4, 9)
+            a = np.array([1.0, -2.0, 0.5, 3.0])
+            ref = advec.AdvecRHS1D(u, 0.37, a, g, alpha, bc, {"sin_at": advec.INFLOW_SIN_AT, "sin_aat": advec.INFLOW_SIN_AAT, "zero": advec.INFLOW_ZERO}[inflow])
+            out = s.rhs(torch.tensor(u, device="cuda"), 0.37, torch.tensor(a, device="cuda"), level=level)
+            assert rel(out.cpu().numpy(), ref) < 1e-13
+
+
+# ------------------------------------------------------------------ fused forward + adjoint + indicator
+def check_fused(out, ref, B):
+    uT, J, eta, lam0 = (out[k].cpu().numpy() if hasattr(out[k], "cpu") else out[k] for k in ("uT", "J", "eta", "lam0"))
+    assert rel(uT, ref["uT"]) < TOL
+    assert rel(lam0, ref["lam0"]) < TOL
+    assert np.max(np.abs(J - ref["J"])) <= TOL * max(1.0, np.max(np.abs(ref["J"])))
+    ratio = np.max(np.abs(eta - ref["eta"]) / ref["eta_scale"])
+    assert ratio <= TOL, ratio
+    return eta
+
+
+@pytest.mark.parametrize("N,K,bc,alpha,inflow", [
+    (4, 10, "inflow", 1.0, "sin_at"),      # config 1, reference BC / flux
+    (4, 10, "periodic", 0.0, "zero"),      # config 1 as BASELINE words it
+    (8, 16, "periodic", 0.0, "zero"),      # config 2 order
+    (1, 6, "periodic", 1.0, "zero"),
+    (3, 7, "inflow", 0.3, "sin_aat"),      # odd K -> one element per thread
+    (7, 24, "inflow", 0.0, "zero"),
+    (2, 64, "periodic", 0.0, "zero"),
+])
+def test_fused_fwd_adj_indicator(pkg, torch, N, K, bc, alpha, inflow):
+    dom = (0.0, 2 * math.pi)
+    B = 19
+    s = pkg.AdvecDG1D(N, K, domain=dom, alpha=alpha, bc=bc, inflow=inflow)
+    gc, gf = oracle_pair(N, K, dom)
+    u0 = make_ics(gc, B, 7 * N + K)
+    a = 2 * math.pi
+    dt, S = s.cfl_dt(0.12)
+    oin = {"sin_at": advec.INFLOW_SIN_AT, "sin_aat": advec.INFLOW_SIN_AAT, "zero": advec.INFLOW_ZERO}[inflow]
+    ref = advec.fwd_adj_indicator(u0, gc, gf, a, dt, S, alpha, bc, oin)
+    out = s.fwd_adj(torch.tensor(u0, device="cuda"), a, dt, S, want_lam0=True)
+    eta = check_fused(out, ref, B)
+    # two-call path (forward with checkpoints, then adjoint) gives the same bits
+    uT2, ck = s.forward_checkpointed(torch.tensor(u0, device="cuda"), a, dt, S)
+    out2 = s.adjoint(uT2, ck, a, dt, S)
+    assert torch.equal(uT2, out["uT"]) and torch.equal(out2["eta"], out["eta"])
+    assert torch.equal(out2["lam0"], out["lam0"]) and torch.equal(out2["J"], out["J"])
+    # host-buffer entry point (pageable numpy): same bits again
+    outh = s.fwd_adj(u0, a, dt, S, want_lam0=True)
+    assert np.array_equal(outh["eta"], eta) and np.array_equal(outh["uT"], out["uT"].cpu().numpy())
+    # both launch shapes agree to rounding
+    if K % 2 == 0:
+        s.set_tuning(elems_per_thread=1)
+        out1 = s.fwd_adj(torch.tensor(u0, device="cuda"), a, dt, S, want_lam0=True)
+        check_fused(out1, ref, B)
+        s.set_tuning()
+
+
+def test_fused_functional_int_u2_and_weighted(pkg, torch):
+    dom = (0.0, 2.0)
+    gc, gf = oracle_pair(4, 10, dom)
+    u0 = make_ics(gc, 6, 11)
+    a, dt, S = 1.7, 2e-3, 40
+    s = pkg.AdvecDG1D(4, 10, domain=dom, alpha=0.0, bc="periodic", functional="int_u2")
+    ref = advec.fwd_adj_indicator(u0, gc, gf, a, dt, S, 0.0, advec.BC_PERIODIC, func=advec.FUNC_INT_U2)
+    check_fused(s.fwd_adj(torch.tensor(u0, device="cuda"), a, dt, S, want_lam0=True), ref, 6)
+    psi = lambda x: np.exp(-(x - 1.0) ** 2)
+    s = pkg.AdvecDG1D(4, 10, domain=dom, alpha=0.0, bc="periodic", psi=psi)
+    ref = advec.fwd_adj_indicator(u0, gc, gf, a, dt, S, 0.0, advec.BC_PERIODIC, psi=psi)
+    check_fused(s.fwd_adj(torch.tensor(u0, device="cuda"), a, dt, S, want_lam0=True), ref, 6)
+
+
+def test_fused_nonuniform_mesh_per_trajectory_speed(pkg, torch):
+    """Refined (non-uniform h) mesh, the shape the adaptive loop produces (matlab/MAIN.m:138-141)."""
+    vx = np.array([0.0, 0.125, 0.25, 0.5, 0.75, 1.0, 1.5, 2.0])
+    gc, gf = ops.startup_mesh(3, vx), ops.startup_mesh(4, vx)
+    B = 9
+    u0 = make_ics(gc, B, 3)
+    rng = np.random.default_rng(1)
+    a = rng.uniform(0.5, 2.0, B)
+    dt = 1e-3 / a
+    s = pkg.AdvecDG1D(3, v_x=vx, alpha=0.0, bc="inflow", inflow="sin_at")
+    ref = advec.fwd_adj_indicator(u0, gc, gf, a, dt, 60, 0.0, advec.BC_INFLOW, advec.INFLOW_SIN_AT)
+    out = s.fwd_adj(torch.tensor(u0, device="cuda"), torch.tensor(a, device="cuda"), torch.tensor(dt, device="cuda"), 60, want_lam0=True)
+    check_fused(out, ref, B)
+    outh = s.fwd_adj(u0, a, dt, 60, want_lam0=True)        # host path with per-trajectory arrays
+    assert np.array_equal(outh["eta"], out["eta"].cpu().numpy())
+
+
+def test_edge_cases(pkg, torch):
+    s = pkg.AdvecDG1D(2, 1, domain=(0.0, 1.0), alpha=0.0, bc="periodic")       # one element
+    g, gf = oracle_pair(2, 1, (0.0, 1.0))
+    u0 = make_ics(g, 3, 1)
+    ref = advec.fwd_adj_indicator(u0, g, gf, 1.0, 1e-3, 10, 0.0, advec.BC_PERIODIC)
+    check_fused(s.fwd_adj(torch.tensor(u0, device="cuda"), 1.0, 1e-3, 10, want_lam0=True), ref, 3)
+    out = s.fwd_adj(torch.tensor(u0, device="cuda"), 1.0, 1e-3, 0, want_lam0=True)   # S = 0: no steps
+    assert torch.equal(out["uT"], torch.tensor(u0, device="cuda")) and float(out["eta"].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        s.forward(torch.zeros((2, 5, 1), dtype=torch.float64, device="cuda"), 1.0, 1e-3, 1)
+    with pytest.raises(TypeError):
+        s.forward(torch.zeros((2, 3, 1), dtype=torch.float32, device="cuda"), 1.0, 1e-3, 1)
+    with pytest.raises(pkg.DgadjError):
+        pkg.AdvecDG1D(2, 4, bc="inflow", inflow="table").forward(torch.zeros((1, 3, 4), dtype=torch.float64, device="cuda"), 1.0, 1e-3, 2)
+    with pytest.raises(pkg.DgadjError):
+        s._check(s.lib.dgadj_fwd_adj(s._h, None, None, None, None, None, None, None))
+
+
+# ------------------------------------------------------------------ config-2 size: properties
+def test_cfg2_size_properties(pkg, torch):
+    """N=8, K=1024 (BASELINE config 2 mesh) at a batch the oracle cannot reach: parity on the
+    first trajectories, plus size-independent identities for all of them:
+      linearity of the march;  J_f(u_f^S) = <lam0, P u0>  (discrete adjoint identity);
+      sum_k eta_k = J_f(P u_c^S) - J_f(u_f^S)  (effectivity of the indicator)."""
+    N, K, B, dom = 8, 1024, 296, (0.0, 2 * math.pi)
+    s = pkg.AdvecDG1D(N, K, domain=dom, alpha=0.0, bc="periodic")
+    sf = pkg.AdvecDG1D(N + 1, K, domain=dom, alpha=0.0, bc="periodic")
+    gc, gf = oracle_pair(N, K, dom)
+    a = 2 * math.pi
+    dt, _ = s.cfl_dt(1.0)
+    assert dt == pytest.approx(1.8354859238600407e-05, rel=1e-12)
+    S = 12
+    u0 = make_ics(gc, B, 1234)
+    d_u0 = torch.tensor(u0, device="cuda")
+    out = s.fwd_adj(d_u0, a, dt, S, want_lam0=True)
+    ref = advec.fwd_adj_indicator(u0[:3], gc, gf, a, dt, S, 0.0, advec.BC_PERIODIC)
+    sub = {k: v[:3] for k, v in out.items()}
+    check_fused(sub, ref, 3)
+    # linearity
+    w = torch.tensor(np.random.default_rng(5).standard_normal(B), device="cuda")
+    comb = s.forward((w[:, None, None] * d_u0).sum(0, keepdim=True), a, dt, S)
+    lin = (w[:, None, None] * out["uT"]).sum(0, keepdim=True)
+    assert float((comb - lin).abs().max() / lin.abs().max()) < 1e-12
+    # adjoint identity and effectivity against a fine-space forward march of P u0
+    P = torch.tensor(s.P, device="cuda")
+    jw_f = torch.tensor(s.jw_f, device="cuda")
+    Pu0 = torch.einsum("ij,bjk->bik", P, d_u0).contiguous()
+    ufT = sf.forward(Pu0, a, dt, S)
+    Jf_f = (jw_f * ufT).sum((1, 2))
+    Jf_c = (jw_f * torch.einsum("ij,bjk->bik", P, out["uT"])).sum((1, 2))
+    dual = (out["lam0"] * Pu0).sum((1, 2))
+    scale = float((jw_f.abs() * ufT.abs()).sum((1, 2)).max())
+    assert float((dual - Jf_f).abs().max()) < 1e-11 * scale
+    assert float((out["eta"].sum(1) - (Jf_c - Jf_f)).abs().max()) < 1e-11 * scale
+
+
+# ------------------------------------------------------------------ ranking / reduction
+def test_rank_and_reduce(pkg, torch):
+    s = pkg.AdvecDG1D(2, 8)
+    rng = np.random.default_rng(0)
+    for B, K in [(1, 1), (5, 7), (33, 64), (4, 1024), (3, 1500)]:
+        eta = rng.standard_normal((B, K))
+        eta[:, K // 2] = eta[:, 0]                  # exact ties (|.| equal, opposite sign too)
+        eta[0, -1] = -eta[0, 0]
+        if K > 3:
+            eta[-1, :] = 0.0                        # all tied
+        for topk in (1, 5, K):
+            order_ref, flags_ref = advec.rank_refine(eta, min(topk, K))
+            order, flags = s.rank(torch.tensor(eta, device="cuda"), topk)
+            assert np.array_equal(order.cpu().numpy(), order_ref)
+            assert np.array_equal(flags.cpu().numpy(), flags_ref)
+        J = rng.standard_normal(B)
+        sums = s.reduce_indicators(torch.tensor(eta, device="cuda"), torch.tensor(J, device="cuda")).cpu().numpy()
+        ae = np.abs(eta)
+        full = np.concatenate([ae.sum(0), [ae.sum(), (eta ** 2).sum(), ae.max(), J.sum()]])
+        np.testing.assert_allclose(sums, full, rtol=1e-13, atol=1e-13)
+        sums2 = s.reduce_indicators(torch.tensor(eta, device="cuda"), torch.tensor(J, device="cuda")).cpu().numpy()
+        assert np.array_equal(sums, sums2)          # deterministic order
+
+
+def test_rank_agrees_with_oracle_indicators_away_from_ties(pkg, torch):
+    dom = (0.0, 2 * math.pi)
+    s = pkg.AdvecDG1D(4, 32, domain=dom, alpha=0.0, bc="periodic")
+    gc, gf = oracle_pair(4, 32, dom)
+    u0 = make_ics(gc, 8, 2)
+    dt, S = s.cfl_dt(0.1)
+    ref = advec.fwd_adj_indicator(u0, gc, gf, 2 * math.pi, dt, S, 0.0, advec.BC_PERIODIC)
+    out = s.fwd_adj(torch.tensor(u0, device="cuda"), 2 * math.pi, dt, S)
+    order, flags = s.rank(out["eta"], topk=5)
+    order_ref, flags_ref = advec.rank_refine(ref["eta"], 5)
+    ae = np.sort(np.abs(ref["eta"]), axis=1)
+    gaps_ok = np.min(np.diff(ae, axis=1), axis=1) > 10 * TOL * np.max(ref["eta_scale"], axis=1)
+    assert gaps_ok.any()
+    assert np.array_equal(order.cpu().numpy()[gaps_ok], order_ref[gaps_ok])
+    assert np.array_equal(flags.cpu().numpy()[gaps_ok], flags_ref[gaps_ok])
+    assert np.array_equal(order.cpu().numpy()[:, 0], np.argmax(np.abs(out["eta"].cpu().numpy()), axis=1))
