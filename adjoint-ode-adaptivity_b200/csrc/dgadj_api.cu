@@ -18,11 +18,11 @@ namespace dgadj {
 #define DGADJ_DECL_NP(n) \
   cudaError_t march_launch_np##n(int, int, int, int, cudaStream_t, const KArgs*);
 DGADJ_DECL_NP(2) DGADJ_DECL_NP(3) DGADJ_DECL_NP(4) DGADJ_DECL_NP(5)
-DGADJ_DECL_NP(6) DGADJ_DECL_NP(7) DGADJ_DECL_NP(8) DGADJ_DECL_NP(9)
-static march_launch_fn launch_table[MAXNP] = {nullptr,          nullptr,          march_launch_np2,
-                                              march_launch_np3, march_launch_np4, march_launch_np5,
-                                              march_launch_np6, march_launch_np7, march_launch_np8,
-                                              march_launch_np9};
+DGADJ_DECL_NP(6) DGADJ_DECL_NP(7) DGADJ_DECL_NP(8) DGADJ_DECL_NP(9) DGADJ_DECL_NP(10)
+// Np = 10 (N = 9) is forward-only: its enriched space would be Np = 11
+static march_launch_fn launch_table[MAXNP + 1] = {
+    nullptr,          nullptr,          march_launch_np2, march_launch_np3, march_launch_np4, march_launch_np5,
+    march_launch_np6, march_launch_np7, march_launch_np8, march_launch_np9, march_launch_np10};
 
 // utils/Globals1D.m:20-34 -- low-storage RK (Carpenter-Kennedy) coefficients
 static const double kRk4a[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
@@ -355,7 +355,7 @@ extern "C" int dgadj_host_eo_prolongation(int Np, const double* P, double* PE, d
 extern "C" int dgadj_create(const dgadj_config* cfg, dgadj_handle** out) {
   if (!cfg || !out) return DGADJ_ERR_INVALID;
   *out = nullptr;
-  if (cfg->N < 1 || cfg->N + 1 >= MAXNP) return DGADJ_ERR_UNSUPPORTED;  // Np <= 9 (enriched 10)
+  if (cfg->N < 1 || cfg->N + 1 > MAXNP) return DGADJ_ERR_UNSUPPORTED;  // Np <= 10; adjoint needs Np <= 9
   if (cfg->K < 1 || cfg->K > MAXBD) return DGADJ_ERR_UNSUPPORTED;
   if (cfg->bc != DGADJ_BC_INFLOW && cfg->bc != DGADJ_BC_PERIODIC) return DGADJ_ERR_INVALID;
   if (cfg->inflow < DGADJ_INFLOW_ZERO || cfg->inflow > DGADJ_INFLOW_TABLE) return DGADJ_ERR_INVALID;
@@ -488,6 +488,7 @@ extern "C" int dgadj_set_enriched(dgadj_handle* h, int NpF, const double* DrF, c
                                   const double* P) {
   if (!h) return DGADJ_ERR_INVALID;
   if (NpF != h->NpF) return fail(h, DGADJ_ERR_INVALID, "NpF %d differs from the handle's %d", NpF, h->NpF);
+  if (NpF > MAXNP) return fail(h, DGADJ_ERR_UNSUPPORTED, "the adjoint / indicator path supports N <= %d (N = %d is forward-only)", MAXNP - 2, h->cfg.N);
   if (!DrF || !LIFTF || !rxF || !FscaleF || !P) return fail(h, DGADJ_ERR_INVALID, "null operator pointer");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   int rc = set_level(h, 1, NpF, DrF, LIFTF, MrefF, rxF, FscaleF);

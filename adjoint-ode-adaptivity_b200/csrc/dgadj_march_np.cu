@@ -32,9 +32,11 @@ template <int EPT>
 static cudaError_t launch_ept(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
   switch (variant) {
     case VAR_FWD: return launch_one<DGADJ_NP, EPT, true, false, false>(variant, grid, block, stream, ka);
+#if DGADJ_NP + 1 <= 10  // the enriched space must fit MAXNP
     case VAR_FWD_RESID: return launch_one<DGADJ_NP, EPT, true, true, false>(variant, grid, block, stream, ka);
     case VAR_ADJ: return launch_one<DGADJ_NP, EPT, false, false, true>(variant, grid, block, stream, ka);
     case VAR_FUSED: return launch_one<DGADJ_NP, EPT, true, true, true>(variant, grid, block, stream, ka);
+#endif
     default: return cudaErrorInvalidValue;
   }
 }

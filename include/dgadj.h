@@ -59,7 +59,7 @@ enum { DGADJ_SCHEME_LSERK4 = 0,  /* utils/Globals1D.m:20-34 */
 
 typedef struct {
   int32_t device;     /* CUDA device ordinal */
-  int32_t N;          /* primal polynomial order, Np = N+1, 1 <= N <= 8 */
+  int32_t N;          /* primal polynomial order, Np = N+1, 1 <= N <= 8 (N = 9: forward march only) */
   int32_t K;          /* elements per mesh, 1 <= K <= 1024 */
   int32_t bc;         /* DGADJ_BC_* */
   int32_t inflow;     /* DGADJ_INFLOW_* (bc = inflow only) */

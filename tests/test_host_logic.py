@@ -121,7 +121,7 @@ def test_create_argument_checks_and_no_cpu_fallback(pkg, lib):
     h = C.c_void_p(0)
     cfg = pkg._lib.Config(device=0, N=4, K=10, bc=0, inflow=1, functional=0, scheme=0, reserved=0, alpha=1.0)
     assert lib.dgadj_create(None, C.byref(h)) == pkg._lib.ERR_INVALID
-    bad = pkg._lib.Config(device=0, N=9, K=10, bc=0, inflow=1, functional=0, scheme=0, reserved=0, alpha=1.0)
+    bad = pkg._lib.Config(device=0, N=10, K=10, bc=0, inflow=1, functional=0, scheme=0, reserved=0, alpha=1.0)
     assert lib.dgadj_create(C.byref(bad), C.byref(h)) == pkg._lib.ERR_UNSUPPORTED
     bad = pkg._lib.Config(device=0, N=4, K=4096, bc=0, inflow=1, functional=0, scheme=0, reserved=0, alpha=1.0)
     assert lib.dgadj_create(C.byref(bad), C.byref(h)) == pkg._lib.ERR_UNSUPPORTED
