@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgadj.so")
+LIB_PATH = os.environ.get("DGADJ_LIB") or os.path.join(_HERE, "libdgadj.so")   # DGADJ_LIB: A/B builds only
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 _STATUS = {OK: "OK", ERR_INVALID: "ERR_INVALID", ERR_NO_DEVICE: "ERR_NO_DEVICE", ERR_CUDA: "ERR_CUDA",

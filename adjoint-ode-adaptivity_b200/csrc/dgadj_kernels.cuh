@@ -6,7 +6,7 @@
 // Dr / LIFT / P / Mref / RK coefficients travel as a __grid_constant__ kernel parameter, i.e.
 // they sit in constant bank 0 and feed DFMA as constant-bank operands (all operator loops
 // are fully unrolled on the template order).  Neighbour traces cross threads through a
-// double-buffered shared-memory pair (one barrier per stage).
+// double-buffered shared-memory pair and a split arrive/wait mbarrier per stage.
 // HBM is touched for: the initial state, the final state, one coalesced checkpoint tile
 // per step (forward phase, STG) which the adjoint phase streams back with bulk-TMA
 // (cp.async.bulk + mbarrier, double buffered), and the outputs.
@@ -28,17 +28,20 @@ constexpr int HM = 5;  // max half dimension of the even/odd blocks ((MAXNP+1)/2
 
 // Operator blocks of one space in the even/odd basis (see EO<> in the device section):
 //   even-out = DE * odd-in  (+ LS * (g0+g1)),   odd-out = DO * even-in  (+ LA * (g0-g1))
-struct StageOps {
-  double DE[HM * HM];  // [i*HM + j], i < HE, j < HO
-  double DO[HM * HM];  // [i*HM + j], i < HO, j < HE
-  double LS[HM];
-  double LA[HM];
+// Stored as double2 pairs (row stride HP pairs) so that one 128-bit uniform constant load
+// (LDCU.128) feeds two DFMA per element: entry (i, j) is DE2[i*HP + j/2].{x,y}[j & 1].
+constexpr int HP = 3;  // pairs per row ((HM+1)/2)
+struct alignas(16) StageOps {
+  double2 DE2[HM * HP];  // i < HE, j < HO
+  double2 DO2[HM * HP];  // i < HO, j < HE
+  double2 LS2[HP];
+  double2 LA2[HP];
 };
 struct ProlongOps {
   double PE[HM * HM];  // even block of T_f P T_c^-1 : [i*HM + j], i < HE_f, j < HE_c
   double PO[HM * HM];  // odd block                  : [i*HM + j], i < HO_f, j < HO_c
 };
-struct ConstOps {
+struct alignas(16) ConstOps {
   StageOps st[2][MAXSTAGES];      // [level][stage]: identical copies per stage (see fwd_step)
   ProlongOps pr[2];               // identical copies (indexed by step parity)
   double Mref[2][MAXNP * MAXNP];  // nodal reference mass matrices inv(V V') (J = int u^2)
@@ -71,7 +74,7 @@ struct MarchParams {
 
 struct KArgs {
   MarchParams p;
-  ConstOps c;
+  alignas(16) ConstOps c;
 };
 
 enum { BC_INFLOW = 0, BC_PERIODIC = 1 };
@@ -98,6 +101,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -134,7 +140,31 @@ __device__ __forceinline__ void fence_mbar_init() {
 struct Ctx {
   int tid, BD, nbL, nbR, par;
   int flags;  // bit0 owns the first element, bit1 owns the last element, bit2 periodic
+  uint64_t* trbar;    // mbarrier of the trace exchange (one arrival per warp)
+  uint32_t trphase;   // its phase parity
 };
+
+#ifndef DGADJ_SPLIT_BARRIER
+#define DGADJ_SPLIT_BARRIER 1
+#endif
+// Trace exchange synchronisation.  Split form: a warp *arrives* as soon as its traces are in
+// shared memory and *waits* only when it needs its neighbours' -- the volume terms (80 % of a
+// stage) sit in between, so warps rarely block.  DGADJ_SPLIT_BARRIER=0 keeps a plain
+// __syncthreads() at the arrive point (for A/B measurements).
+__device__ __forceinline__ void trace_arrive(Ctx& cx) {
+#if DGADJ_SPLIT_BARRIER
+  __syncwarp();
+  if ((cx.tid & 31) == 0) mbar_arrive(cx.trbar);
+#else
+  __syncthreads();
+#endif
+}
+__device__ __forceinline__ void trace_wait(Ctx& cx) {
+#if DGADJ_SPLIT_BARRIER
+  mbar_wait(cx.trbar, cx.trphase);
+  cx.trphase ^= 1u;
+#endif
+}
 enum { CX_FIRST = 1, CX_LAST = 2, CX_PERIODIC = 4 };
 
 static __device__ __noinline__ double inflow_value(const MarchParams& p, long long b, double time, int n, int s,
@@ -215,9 +245,48 @@ struct EOVec {
 //     re = rka*re + DE zo + LS (g0+g1) ;  ro = rka*ro + DO ze + LA (g0-g1) ;  z += (rkb*m) r
 //     g0 = (u[0]-uL)*q0, g1 = (u[N]-uR)*q1,  q_f = dt*Fscale_f*c_f/m
 template <int NPX, int EPT>
-__device__ __forceinline__ void fwd_stage(const StageOps& so, EOVec<NPX> (&z)[EPT], EOVec<NPX> (&r)[EPT],
-                                          const double (&g0)[EPT], const double (&g1)[EPT], double rka,
-                                          const double (&bm)[EPT]) {
+__device__ __forceinline__ void fwd_stage_volume(const StageOps& so, const EOVec<NPX> (&z)[EPT],
+                                                 EOVec<NPX> (&r)[EPT], double rka) {
+  constexpr int HE = EO<NPX>::HE, HO = EO<NPX>::HO;
+#pragma unroll
+  for (int i = 0; i < HE; ++i) {
+    double acc[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) acc[e] = rka * r[e].e[i];
+#pragma unroll
+    for (int jp = 0; jp < (HO + 1) / 2; ++jp) {
+      const double2 c2 = so.DE2[i * HP + jp];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        acc[e] = fma(c2.x, z[e].o[2 * jp], acc[e]);
+        if (2 * jp + 1 < HO) acc[e] = fma(c2.y, z[e].o[2 * jp + 1 < HO ? 2 * jp + 1 : 0], acc[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) r[e].e[i] = acc[e];
+  }
+#pragma unroll
+  for (int i = 0; i < HO; ++i) {
+    double acc[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) acc[e] = rka * r[e].o[i];
+#pragma unroll
+    for (int jp = 0; jp < (HE + 1) / 2; ++jp) {
+      const double2 c2 = so.DO2[i * HP + jp];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        acc[e] = fma(c2.x, z[e].e[2 * jp], acc[e]);
+        if (2 * jp + 1 < HE) acc[e] = fma(c2.y, z[e].e[2 * jp + 1 < HE ? 2 * jp + 1 : 0], acc[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) r[e].o[i] = acc[e];
+  }
+}
+template <int NPX, int EPT>
+__device__ __forceinline__ void fwd_stage_surface(const StageOps& so, EOVec<NPX> (&z)[EPT], EOVec<NPX> (&r)[EPT],
+                                                  const double (&g0)[EPT], const double (&g1)[EPT],
+                                                  const double (&bm)[EPT]) {
   constexpr int HE = EO<NPX>::HE, HO = EO<NPX>::HO;
   double ge[EPT], go[EPT];
 #pragma unroll
@@ -226,41 +295,36 @@ __device__ __forceinline__ void fwd_stage(const StageOps& so, EOVec<NPX> (&z)[EP
     go[e] = g0[e] - g1[e];
   }
 #pragma unroll
-  for (int i = 0; i < HE; ++i) {
-    double acc[EPT];
+  for (int ip = 0; ip < (HE + 1) / 2; ++ip) {
+    const double2 c2 = so.LS2[ip];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) acc[e] = rka * r[e].e[i];
-#pragma unroll
-    for (int j = 0; j < HO; ++j) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) acc[e] = fma(so.DE[i * HM + j], z[e].o[j], acc[e]);
+    for (int e = 0; e < EPT; ++e) {
+      r[e].e[2 * ip] = fma(c2.x, ge[e], r[e].e[2 * ip]);
+      z[e].e[2 * ip] = fma(bm[e], r[e].e[2 * ip], z[e].e[2 * ip]);
+      if (2 * ip + 1 < HE) {
+        const int i1 = 2 * ip + 1 < HE ? 2 * ip + 1 : 0;
+        r[e].e[i1] = fma(c2.y, ge[e], r[e].e[i1]);
+        z[e].e[i1] = fma(bm[e], r[e].e[i1], z[e].e[i1]);
+      }
     }
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) r[e].e[i] = fma(so.LS[i], ge[e], acc[e]);
   }
 #pragma unroll
-  for (int i = 0; i < HO; ++i) {
-    double acc[EPT];
+  for (int ip = 0; ip < (HO + 1) / 2; ++ip) {
+    const double2 c2 = so.LA2[ip];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) acc[e] = rka * r[e].o[i];
-#pragma unroll
-    for (int j = 0; j < HE; ++j) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) acc[e] = fma(so.DO[i * HM + j], z[e].e[j], acc[e]);
+    for (int e = 0; e < EPT; ++e) {
+      r[e].o[2 * ip] = fma(c2.x, go[e], r[e].o[2 * ip]);
+      z[e].o[2 * ip] = fma(bm[e], r[e].o[2 * ip], z[e].o[2 * ip]);
+      if (2 * ip + 1 < HO) {
+        const int i1 = 2 * ip + 1 < HO ? 2 * ip + 1 : 0;
+        r[e].o[i1] = fma(c2.y, go[e], r[e].o[i1]);
+        z[e].o[i1] = fma(bm[e], r[e].o[i1], z[e].o[i1]);
+      }
     }
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) r[e].o[i] = fma(so.LA[i], go[e], acc[e]);
-  }
-#pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-#pragma unroll
-    for (int i = 0; i < HE; ++i) z[e].e[i] = fma(bm[e], r[e].e[i], z[e].e[i]);
-#pragma unroll
-    for (int i = 0; i < HO; ++i) z[e].o[i] = fma(bm[e], r[e].o[i], z[e].o[i]);
   }
 }
 
-// One full RK step (all stages) with the neighbour-trace exchange.  One barrier per stage.
+// One full RK step (all stages) with the neighbour-trace exchange.
 // coef = this thread's smem column of the level: {m, q0, q1} x EPT, each a row of BD.
 // The operator blocks are read from a per-stage copy (c.st[LV][s]) so that the constant
 // loads depend on the stage counter and stay inside the loop as uniform loads instead of
@@ -273,20 +337,23 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
   const int nst = ka.p.nstages;
 #pragma unroll 1
   for (int s = 0; s < nst; ++s) {
+    const StageOps& so = c.st[LV][s];
+    double* tA = tr + cx.par * cx.BD;  // left-edge values  u[0]    of the thread's first element
+    double* tB = tA + 2 * cx.BD;       // right-edge values u[Np-1] of the thread's last element
+    tA[cx.tid] = 0.5 * (z[0].e[0] + z[0].o[0]);
+    tB[cx.tid] = 0.5 * (z[EPT - 1].e[0] - z[EPT - 1].o[0]);
+    trace_arrive(cx);
+    fwd_stage_volume<NPX, EPT>(so, z, r, c.rka[s]);   // needs no neighbour data
+    trace_wait(cx);
+    double uL = tB[cx.nbL];
+    double uR = tA[cx.nbR];
+    cx.par ^= 1;
     double uF[EPT], uB[EPT];  // u[0], u[Np-1] of each element
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       uF[e] = 0.5 * (z[e].e[0] + z[e].o[0]);
       uB[e] = 0.5 * (z[e].e[0] - z[e].o[0]);
     }
-    double* tA = tr + cx.par * cx.BD;  // left-edge values  u[0]    of the thread's first element
-    double* tB = tA + 2 * cx.BD;       // right-edge values u[Np-1] of the thread's last element
-    tA[cx.tid] = uF[0];
-    tB[cx.tid] = uB[EPT - 1];
-    __syncthreads();
-    double uL = tB[cx.nbL];
-    double uR = tA[cx.nbR];
-    cx.par ^= 1;
     if (!(cx.flags & CX_PERIODIC)) {
       if (cx.flags & CX_FIRST) uL = inflow_value(ka.p, b, time, n, s, c.rkc[s]);
       if (cx.flags & CX_LAST) uR = uB[EPT - 1];
@@ -301,7 +368,7 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
       g1[e] = (uB[e] - right) * coef[(size_t)(2 * EPT + e) * cx.BD];
       bm[e] = rkb * coef[(size_t)e * cx.BD];
     }
-    fwd_stage<NPX, EPT>(c.st[LV][s], z, r, g0, g1, c.rka[s], bm);
+    fwd_stage_surface<NPX, EPT>(so, z, r, g0, g1, bm);
   }
 }
 
@@ -334,19 +401,24 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
     {
       double Ge[EPT], Go[EPT];
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        Ge[e] = so.LS[0] * w[e].e[0];
-        Go[e] = so.LA[0] * w[e].o[0];
+      for (int e = 0; e < EPT; ++e) Ge[e] = Go[e] = 0.0;
+#pragma unroll
+      for (int ip = 0; ip < (HE + 1) / 2; ++ip) {
+        const double2 c2 = so.LS2[ip];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          Ge[e] = fma(c2.x, w[e].e[2 * ip], Ge[e]);
+          if (2 * ip + 1 < HE) Ge[e] = fma(c2.y, w[e].e[2 * ip + 1 < HE ? 2 * ip + 1 : 0], Ge[e]);
+        }
       }
 #pragma unroll
-      for (int i = 1; i < HE; ++i) {
+      for (int ip = 0; ip < (HO + 1) / 2; ++ip) {
+        const double2 c2 = so.LA2[ip];
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) Ge[e] = fma(so.LS[i], w[e].e[i], Ge[e]);
-      }
-#pragma unroll
-      for (int i = 1; i < HO; ++i) {
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) Go[e] = fma(so.LA[i], w[e].o[i], Go[e]);
+        for (int e = 0; e < EPT; ++e) {
+          Go[e] = fma(c2.x, w[e].o[2 * ip], Go[e]);
+          if (2 * ip + 1 < HO) Go[e] = fma(c2.y, w[e].o[2 * ip + 1 < HO ? 2 * ip + 1 : 0], Go[e]);
+        }
       }
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
@@ -358,7 +430,48 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
     double* tB = tA + 2 * cx.BD;
     tA[cx.tid] = gam0[0];
     tB[cx.tid] = gam1[EPT - 1];
-    __syncthreads();
+    trace_arrive(cx);
+    // volume part (needs no neighbour data): mu_e += DO^T wo, mu_o += DE^T we (row i of the
+    // block times w[i], accumulated straight into mu), then w *= rka
+#pragma unroll
+    for (int i = 0; i < HO; ++i) {
+#pragma unroll
+      for (int jp = 0; jp < (HE + 1) / 2; ++jp) {
+        const double2 c2 = so.DO2[i * HP + jp];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          mu[e].e[2 * jp] = fma(c2.x, w[e].o[i], mu[e].e[2 * jp]);
+          if (2 * jp + 1 < HE) {
+            const int j1 = 2 * jp + 1 < HE ? 2 * jp + 1 : 0;
+            mu[e].e[j1] = fma(c2.y, w[e].o[i], mu[e].e[j1]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < HE; ++i) {
+#pragma unroll
+      for (int jp = 0; jp < (HO + 1) / 2; ++jp) {
+        const double2 c2 = so.DE2[i * HP + jp];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          mu[e].o[2 * jp] = fma(c2.x, w[e].e[i], mu[e].o[2 * jp]);
+          if (2 * jp + 1 < HO) {
+            const int j1 = 2 * jp + 1 < HO ? 2 * jp + 1 : 0;
+            mu[e].o[j1] = fma(c2.y, w[e].e[i], mu[e].o[j1]);
+          }
+        }
+      }
+    }
+    const double rka = c.rka[s];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+      for (int i = 0; i < HE; ++i) w[e].e[i] *= rka;
+#pragma unroll
+      for (int i = 0; i < HO; ++i) w[e].o[i] *= rka;
+    }
+    trace_wait(cx);
     double gam1L = tB[cx.nbL];  // right-face term of the left neighbour
     double gam0R = tA[cx.nbR];  // left-face term of the right neighbour
     cx.par ^= 1;
@@ -372,40 +485,6 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
       const double aN = gam1[e] - ((e == EPT - 1) ? gam0R : gam0[e + 1]);
       mu[e].e[0] = fma(0.5, a0 + aN, mu[e].e[0]);
       mu[e].o[0] = fma(0.5, a0 - aN, mu[e].o[0]);
-    }
-#pragma unroll
-    for (int j = 0; j < HE; ++j) {
-      double acc[EPT];
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) acc[e] = mu[e].e[j];
-#pragma unroll
-      for (int i = 0; i < HO; ++i) {
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) acc[e] = fma(so.DO[i * HM + j], w[e].o[i], acc[e]);
-      }
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) mu[e].e[j] = acc[e];
-    }
-#pragma unroll
-    for (int j = 0; j < HO; ++j) {
-      double acc[EPT];
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) acc[e] = mu[e].o[j];
-#pragma unroll
-      for (int i = 0; i < HE; ++i) {
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) acc[e] = fma(so.DE[i * HM + j], w[e].e[i], acc[e]);
-      }
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) mu[e].o[j] = acc[e];
-    }
-    const double rka = c.rka[s];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-#pragma unroll
-      for (int i = 0; i < HE; ++i) w[e].e[i] *= rka;
-#pragma unroll
-      for (int i = 0; i < HO; ++i) w[e].o[i] *= rka;
     }
   }
 }
@@ -467,13 +546,15 @@ __device__ __forceinline__ void prolong_eo(const ProlongOps& po, const EOVec<NP>
 //   big[NPF][EPT][BD]  forward: parked coarse state / sigma;  adjoint: TMA landing tile
 // Park / checkpoint row order of an even/odd state: e[0..HE), then o[0..HO).
 // ---------------------------------------------------------------------------------------
-template <int NP, int EPT, bool DO_FWD, bool RESID, bool DO_ADJ>
+// BDT > 0: blockDim.x is the compile-time constant BDT (all shared-memory strides fold into
+// immediate offsets); BDT = 0: any block size.
+template <int NP, int EPT, int BDT, bool DO_FWD, bool RESID, bool DO_ADJ>
 __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_constant__ KArgs ka) {
   constexpr int NPF = NP + 1;
   const MarchParams& p = ka.p;
   const ConstOps& c = ka.c;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int BD = blockDim.x;
+  const int BD = BDT > 0 ? BDT : (int)blockDim.x;
   const int tid = threadIdx.x;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sm_tr = reinterpret_cast<double*>(smem_raw + 16);
@@ -505,14 +586,15 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
   const uint32_t tile_bytes = (uint32_t)(tile * sizeof(double));
   uint32_t land_phase = 0u;  // completed phases of the landing buffer's mbarrier
 
-  if (DO_ADJ) {
-    if (tid == 0) {
-      mbar_init(&mbar[0], 1);
-      fence_mbar_init();
-    }
-    fence_proxy_async();
-    __syncthreads();
+  cx.trbar = &mbar[1];
+  cx.trphase = 0u;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);                  // TMA landing tile
+    mbar_init(&mbar[1], (uint32_t)(BD / 32));  // trace exchange: one arrival per warp
+    fence_mbar_init();
   }
+  fence_proxy_async();
+  __syncthreads();
 
 #pragma unroll 1
   for (int g = blockIdx.x; g < p.ngroups; g += gridDim.x) {

@@ -10,12 +10,12 @@
 
 namespace dgadj {
 
-template <int NP, int EPT, bool F, bool R, bool A>
-static cudaError_t launch_one(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
+template <int NP, int EPT, int BDT, bool F, bool R, bool A>
+static cudaError_t launch_bd(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
   static bool attr_set = false;  // per variant instantiation (function-local static per template)
   if (block > MAXBD / EPT) return cudaErrorInvalidConfiguration;
   const size_t smem = march_smem_bytes(NP, EPT, block, variant);
-  auto kern = march_kernel<NP, EPT, F, R, A>;
+  auto kern = march_kernel<NP, EPT, BDT, F, R, A>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
@@ -27,6 +27,16 @@ static cudaError_t launch_one(int variant, int grid, int block, cudaStream_t str
 
 #define DGADJ_CAT2(a, b) a##b
 #define DGADJ_CAT(a, b) DGADJ_CAT2(a, b)
+
+// the hot variants (forward, fused) also exist with the two common block sizes baked in
+template <int NP, int EPT, bool F, bool R, bool A>
+static cudaError_t launch_one(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
+  if (F && R == A) {
+    if (block == MAXBD / EPT) return launch_bd<NP, EPT, MAXBD / EPT, F, R, A>(variant, grid, block, stream, ka);
+    if (block == MAXBD / EPT / 2) return launch_bd<NP, EPT, MAXBD / EPT / 2, F, R, A>(variant, grid, block, stream, ka);
+  }
+  return launch_bd<NP, EPT, 0, F, R, A>(variant, grid, block, stream, ka);
+}
 
 template <int EPT>
 static cudaError_t launch_ept(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {

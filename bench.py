@@ -370,7 +370,7 @@ def ours(a):
     roofline = {
         "bound": "fp64_fma", "kernel": "dgadj::march_kernel<NP=%d,EPT,fwd,resid,adj> (fused)" % s.Np,
         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
-        "peak_source": "measured live: register-only DFMA microbenchmark (dgadj_measure_dfma_peak); "
+        "peak_source": "measured live: best of two register-resident DFMA microbenchmarks (register and constant-bank operand forms, dgadj_measure_dfma_peak); "
                        "MEASURED_PEAKS.json has no fp64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
         "algorithmic_flops_per_update": flops_per_update(s.Np), "kernel_ms": kern_ms,
         "kernel_share_of_step": kern_ms / ms_per_step if world == 1 else None,

@@ -1,0 +1,73 @@
+// tools/microbench.cu -- fp64 pipe ceilings for the instruction mixes of the march kernel.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench tools/microbench.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+struct CB { double c[5][64]; };   // five copies, indexed by a loop counter so loads stay in the loop
+
+// mode A: register operands only, NCH independent chains
+template <int NCH>
+__global__ void __launch_bounds__(1024, 1) k_reg(double* out, int iters, double x, double y) {
+  double a[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) a[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) a[i] = fma(a[i], x, y);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) s += a[i];
+  if (s == 123.456) out[0] = s;
+}
+// mode B: one uniform constant load per USE DFMAs (constants indexed by a runtime-varying copy id)
+template <int NCH, int USE>
+__global__ void __launch_bounds__(1024, 1) k_cst(const __grid_constant__ CB cb, double* out, int iters, double y) {
+  double a[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) a[i] = threadIdx.x + i;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    const double* c = cb.c[it % 5];
+#pragma unroll
+    for (int r = 0; r < 64; ++r) {
+#pragma unroll
+      for (int u = 0; u < USE; ++u) a[(r * USE + u) % NCH] = fma(a[(r * USE + u) % NCH], c[r], y);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) s += a[i];
+  if (s == 123.456) out[0] = s;
+}
+template <typename F>
+double run(F launch, double flops_per_iter_per_thread, int threads, int iters) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  launch(iters);
+  cudaDeviceSynchronize();
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0); launch(iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+  }
+  return flops_per_iter_per_thread * iters * (double)threads * 148 / (best * 1e-3) / 1e12;
+}
+int main() {
+  double* out; cudaMalloc(&out, 8);
+  CB cb; for (int i = 0; i < 5; ++i) for (int j = 0; j < 64; ++j) cb.c[i][j] = 0.999 + 1e-6 * j;
+  const int IT = 4000;
+  printf("reg  1024thr 8ch : %.2f TF\n", run([&](int it){ k_reg<8><<<148,1024>>>(out,it,0.999,1e-9); }, 2.0*16*8, 1024, IT));
+  printf("reg   512thr 8ch : %.2f TF\n", run([&](int it){ k_reg<8><<<148,512>>>(out,it,0.999,1e-9); }, 2.0*16*8, 512, IT));
+  printf("reg   512thr 4ch : %.2f TF\n", run([&](int it){ k_reg<4><<<148,512>>>(out,it,0.999,1e-9); }, 2.0*16*4, 512, IT));
+  printf("reg   512thr 2ch : %.2f TF\n", run([&](int it){ k_reg<2><<<148,512>>>(out,it,0.999,1e-9); }, 2.0*16*2, 512, IT));
+  printf("reg   256thr 8ch : %.2f TF\n", run([&](int it){ k_reg<8><<<148,256>>>(out,it,0.999,1e-9); }, 2.0*16*8, 256, IT));
+  printf("cst 1:1 512thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,1><<<148,512>>>(cb,out,it,1e-9); }, 2.0*64*1, 512, IT));
+  printf("cst 1:2 512thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,2><<<148,512>>>(cb,out,it,1e-9); }, 2.0*64*2, 512, IT));
+  printf("cst 1:4 512thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,4><<<148,512>>>(cb,out,it,1e-9); }, 2.0*64*4, 512, IT));
+  printf("cst 1:2 1024thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,2><<<148,1024>>>(cb,out,it,1e-9); }, 2.0*64*2, 1024, IT));
+  printf("cst 1:1 1024thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,1><<<148,1024>>>(cb,out,it,1e-9); }, 2.0*64*1, 1024, IT));
+  printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
