@@ -16,6 +16,8 @@ BC = {"inflow": 0, "periodic": 1}
 INFLOW = {"zero": 0, "sin_at": 1, "sin_aat": 2, "table": 3}
 FUNCTIONAL = {"int_u": 0, "linear": 0, "int_u2": 1}
 SCHEME = {"lserk4": 0, "euler": 1}
+FD_ODE = {"sin": 0, "linear": 1}
+FD_FUNCTIONAL = {"int_u": 0, "u_N": 1, "int_u2": 2}
 HM = 5  # row stride of the even/odd blocks (dgadj_kernels.cuh)
 
 
@@ -56,6 +58,7 @@ PROTOTYPES = {
     "dgadj_fwd_adj_host": (C.c_int, [_P, C.POINTER(MarchArgs), _P, _P, _P, _P, _P, _P, _P]),
     "dgadj_forward_host": (C.c_int, [_P, C.POINTER(MarchArgs), _P, _P, _P, _P, _P]),
     "dgadj_rhs": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_double, C.c_double, _P, _P, _P]),
+    "dgadj_fd_awr": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dgadj_rank": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "dgadj_reduce_indicators": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "dgadj_measure_dfma_peak": (C.c_int, [_P, C.c_double, _D, _D]),

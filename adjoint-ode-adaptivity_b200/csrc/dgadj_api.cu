@@ -11,8 +11,7 @@
 #include <new>
 #include <vector>
 
-#include "../../include/dgadj.h"
-#include "dgadj_kernels.cuh"
+#include "dgadj_internal.h"
 
 namespace dgadj {
 #define DGADJ_DECL_NP(n) \
@@ -306,64 +305,6 @@ __global__ void rhs_kernel(long long B, int K, int Np, int bc, int inflow, doubl
 
 }  // namespace dgadj
 
-using namespace dgadj;
-
-// ---------------------------------------------------------------------------------------
-// handle
-// ---------------------------------------------------------------------------------------
-struct LaunchPlan {
-  int ept, KT, tpc, block, ngroups, grid;
-  size_t smem;
-  size_t tile;  // doubles per checkpoint tile
-};
-
-struct dgadj_handle {
-  dgadj_config cfg;
-  int Np, NpF, K, nstages;
-  bool ops_set, enr_set, jw_set;
-  ConstOps cops;
-  double* d_mesh[2][3];  // [level]{rx, fs0, fs1} each [K]
-  double* d_nodal[2][2];  // [level]{Dr[Np*Np], LIFT[Np*2]} nodal copies (dgadj_rhs)
-  double* d_jwc;
-  double* d_jwf;
-  double* d_uin;
-  int uin_n;
-  double* ring;
-  size_t ring_bytes;
-  double* red_scratch;
-  size_t red_bytes;
-  int sm_count, cc_major, cc_minor;
-  size_t total_mem;
-  int tune_ept, tune_block, tune_grid;
-  // host pipeline
-  cudaStream_t s_in, s_k, s_out;
-  cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
-  double* dbuf[2];
-  size_t dbuf_bytes;
-  double* pin[2];
-  size_t pin_bytes;
-  bool pipe_init;
-  char err[512];
-  int64_t launches;
-};
-
-static int fail(dgadj_handle* h, int code, const char* fmt, ...) {
-  if (h) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(h->err, sizeof(h->err), fmt, ap);
-    va_end(ap);
-  }
-  return code;
-}
-#define CUDA_TRY(h, call)                                                                      \
-  do {                                                                                         \
-    cudaError_t e_ = (call);                                                                   \
-    if (e_ != cudaSuccess)                                                                     \
-      return fail((h), e_ == cudaErrorMemoryAllocation ? DGADJ_ERR_NOMEM : DGADJ_ERR_CUDA,      \
-                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-  } while (0)
-
 extern "C" int dgadj_version(void) { return DGADJ_VERSION; }
 
 extern "C" int dgadj_host_eo_operators(int Np, const double* Dr, const double* LIFT, double* DE, double* DO,
@@ -434,6 +375,7 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->d_uin);
   cudaFree(h->ring);
   cudaFree(h->red_scratch);
+  cudaFree(h->fd_scratch);
   if (h->pipe_init) {
     cudaStreamDestroy(h->s_in);
     cudaStreamDestroy(h->s_k);
@@ -1013,6 +955,7 @@ extern "C" int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, co
   if (need > h->red_bytes) {
     CUDA_TRY(h, cudaDeviceSynchronize());
     cudaFree(h->red_scratch);
+  cudaFree(h->fd_scratch);
     h->red_scratch = nullptr;
     h->red_bytes = 0;
     CUDA_TRY(h, cudaMalloc((void**)&h->red_scratch, need));

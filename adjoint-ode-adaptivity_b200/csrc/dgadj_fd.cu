@@ -1,0 +1,191 @@
+// dgadj_fd.cu -- the finite-difference path of python/Main_finite_difference.py, batched over
+// initial conditions on a shared time mesh (the batch pattern of Main_variable_params.py:330-344):
+//   forwardSolve (:34-51)  explicit Euler on the coarse mesh
+//   adjSolve     (:54-76)  discrete adjoint on the ref_factor-refined mesh.  The reference solves
+//                          (JF^T - I) v = -k densely; JF is sub-diagonal, so that system is the
+//                          backward recurrence v_N = 0, v_i = k_i + jf_i v_{i+1}
+//   errEst       (:79-94)  res[n] = u_f[n] - fwdUpdate(u_f, dt_f, n);  err = res * v
+//   driver       (:270-277, :337)  |err|, drop two entries, windows of ref_factor-1 at stride
+//                          ref_factor, argmax (lowest index on ties)
+// One thread marches one trajectory; the mesh-dependent interpolation tables (np.interp of
+// interpU, :24-31) are built once on the host and shared by the batch.  All arithmetic is
+// written unfused (__dmul_rn / __dadd_rn) to mirror NumPy's separate multiply and add.
+#include <math.h>
+
+#include <vector>
+
+#include "dgadj_internal.h"
+
+namespace dgadj {
+
+enum { FD_ODE_SIN = 0, FD_ODE_LINEAR = 1 };
+enum { FD_FUNC_INT_U = 0, FD_FUNC_U_N = 1, FD_FUNC_INT_U2 = 2 };
+constexpr int FD_MAX_REF = 16;
+
+struct FdTables {
+  const int* jc;       // [nf+1] coarse interval of fine node i (np.interp's binary search)
+  const double* dx;    // [nf+1] t_fine[i] - t_coarse[jc[i]]
+  const double* den;   // [n]    t_coarse[j+1] - t_coarse[j]
+  const double* dtf;   // [nf]   fine steps
+  const double* dtn;   // [n]    coarse steps
+  const unsigned char* exact;  // [nf+1] 1: fine node coincides with a coarse node (returns fp[j])
+};
+
+__device__ __forceinline__ double fd_interp(const double* __restrict__ uc, long long stride, const FdTables& t,
+                                            int i, int n) {
+  const int j = t.jc[i];
+  const double uj = uc[(size_t)j * stride];
+  if (t.exact[i] || j >= n) return uj;
+  // np.interp: slope = (fp[j+1]-fp[j])/(xp[j+1]-xp[j]);  res = slope*(x-xp[j]) + fp[j]
+  const double slope = __ddiv_rn(__dadd_rn(uc[(size_t)(j + 1) * stride], -uj), t.den[j]);
+  return __dadd_rn(__dmul_rn(slope, t.dx[i]), uj);
+}
+
+__global__ void fd_awr_kernel(long long B, int n, int rf, int ode, int func, FdTables t,
+                              const double* __restrict__ u0, double* __restrict__ uc /*[n+1][B] scratch*/,
+                              double* __restrict__ u_out, double* __restrict__ v_out,
+                              double* __restrict__ err_out, double* __restrict__ steps_out,
+                              int* __restrict__ idx_out) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int nf = n * rf;
+  // ---- forwardSolve: u[m] = fwdUpdate(u, dt, m)
+  double* ub = uc + b;  // column b of the [n+1][B] scratch (coalesced across the warp)
+  double u = u0[b];
+  ub[0] = u;
+  if (u_out) u_out[(size_t)b * (n + 1)] = u;
+  for (int m = 1; m <= n; ++m) {
+    const double dt = t.dtn[m - 1];
+    u = (ode == FD_ODE_LINEAR) ? __dmul_rn(__dadd_rn(1.0, dt), u) : __dadd_rn(u, __dmul_rn(sin(u), dt));
+    ub[(size_t)m * B] = u;
+    if (u_out) u_out[(size_t)b * (n + 1) + m] = u;
+  }
+  // ---- one backward sweep over the fine mesh: adjoint recurrence, residual, window sums
+  double v_next = 0.0;                                  // v[nf] = v0 = 0
+  double uf_next = fd_interp(ub, B, t, nf, n);          // u_fine[nf]
+  if (v_out) v_out[(size_t)b * (nf + 1) + nf] = 0.0;
+  double win[FD_MAX_REF];
+  double best = -1.0;
+  int best_idx = 0;
+  for (int i = nf - 1; i >= 0; --i) {
+    const double uf = fd_interp(ub, B, t, i, n);
+    const double dt = t.dtf[i];
+    double k, jf, upd;
+    if (ode == FD_ODE_LINEAR) {
+      jf = __dadd_rn(1.0, dt);                          // getJF :118-119
+      upd = __dmul_rn(__dadd_rn(1.0, dt), uf);          // fwdUpdate :112-113
+    } else {
+      jf = __dadd_rn(1.0, __dmul_rn(cos(uf), dt));      // getJF :138-139
+      upd = __dadd_rn(uf, __dmul_rn(sin(uf), dt));      // fwdUpdate :131-132
+    }
+    if (func == FD_FUNC_INT_U2) k = __dmul_rn(__dmul_rn(2.0, uf), dt);   // getK :225-227
+    else if (func == FD_FUNC_INT_U) k = dt;                              // :153-155
+    else k = (i == nf - 1) ? 1.0 : 0.0;                                  // :162-165
+    const double err = __dmul_rn(__dadd_rn(uf_next, -upd), v_next);      // err[i+1] = res[i+1]*v[i+1]
+    if (err_out) err_out[(size_t)b * (nf + 1) + i + 1] = err;
+    // window r covers fine entries 2 + r*rf + q, q = 0..rf-2  (:270-277)
+    const int pos = i + 1 - 2;
+    if (pos >= 0) {
+      const int r = pos / rf, q = pos - r * rf;
+      if (q < rf - 1) {
+        win[q] = fabs(err);
+        if (q == 0) {                                   // window complete: sum in ascending order
+          double s = win[0];
+          for (int qq = 1; qq < rf - 1; ++qq) s = __dadd_rn(s, win[qq]);
+          if (steps_out) steps_out[(size_t)b * n + r] = s;
+          if (s >= best) {                              // descending r: >= keeps the lowest index
+            best = s;
+            best_idx = r;
+          }
+        }
+      }
+    }
+    const double v = __dadd_rn(k, __dmul_rn(jf, v_next));
+    if (v_out) v_out[(size_t)b * (nf + 1) + i] = v;
+    v_next = v;
+    uf_next = uf;
+  }
+  if (err_out) err_out[(size_t)b * (nf + 1)] = __dmul_rn(0.0, v_next);   // res_u[0] = 0
+  if (idx_out) idx_out[b] = best_idx;
+}
+
+}  // namespace dgadj
+
+extern "C" int dgadj_fd_awr(dgadj_handle* h, int64_t B, int32_t n, int32_t ref_factor, int32_t ode,
+                            int32_t functional, const double* dt_host, const double* u0_dev, double* u_dev,
+                            double* v_dev, double* err_fine_dev, double* err_steps_dev, int32_t* ref_idx_dev,
+                            void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || n <= 0 || !dt_host || !u0_dev) return fail(h, DGADJ_ERR_INVALID, "bad fd_awr arguments");
+  if (ref_factor < 3 || ref_factor > FD_MAX_REF)
+    return fail(h, DGADJ_ERR_UNSUPPORTED, "ref_factor must be in [3, %d] (the reference requires > 2)", FD_MAX_REF);
+  if (ode != FD_ODE_SIN && ode != FD_ODE_LINEAR) return fail(h, DGADJ_ERR_INVALID, "unknown ode %d", ode);
+  if (functional < FD_FUNC_INT_U || functional > FD_FUNC_INT_U2) return fail(h, DGADJ_ERR_INVALID, "unknown functional %d", functional);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nf = n * ref_factor;
+  // ---- host tables: refineAll (:16-21), cumulative times, np.interp's interval search (:24-31)
+  std::vector<double> dtf(nf), tc(n + 1), tf(nf + 1), dx(nf + 1), den(n);
+  std::vector<int> jc(nf + 1);
+  std::vector<unsigned char> exact(nf + 1);
+  for (int j = 0; j < n; ++j)
+    for (int f = 0; f < ref_factor; ++f) dtf[j * ref_factor + f] = dt_host[j] / ref_factor;
+  tc[0] = 0.0;
+  for (int j = 0; j < n; ++j) tc[j + 1] = tc[j] + dt_host[j];   // np.cumsum: sequential
+  tf[0] = 0.0;
+  for (int i = 0; i < nf; ++i) tf[i + 1] = tf[i] + dtf[i];
+  for (int j = 0; j < n; ++j) den[j] = tc[j + 1] - tc[j];
+  for (int i = 0; i <= nf; ++i) {
+    const double x = tf[i];
+    int j;
+    if (x >= tc[n]) {
+      j = n;  // x beyond / at the last node: np.interp returns fp[-1] (right fill = fp[-1])
+    } else {
+      j = 0;  // largest j with tc[j] <= x
+      int lo = 0, hi = n;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        if (tc[mid] <= x) lo = mid; else hi = mid - 1;
+      }
+      j = lo;
+    }
+    jc[i] = j;
+    dx[i] = x - tc[j];
+    exact[i] = (j >= n || tc[j] == x) ? 1 : 0;
+  }
+  // ---- device scratch: tables + coarse states [n+1][B]
+  const size_t tbl_bytes = sizeof(int) * (nf + 1) + sizeof(double) * ((nf + 1) + n + nf + n) + (nf + 1) + 64;
+  const size_t need = ((tbl_bytes + 255) / 256) * 256 + sizeof(double) * (size_t)(n + 1) * (size_t)B;
+  if (need > h->fd_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->fd_scratch);
+    h->fd_scratch = nullptr;
+    h->fd_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->fd_scratch, need));
+    h->fd_bytes = need;
+  }
+  unsigned char* base = (unsigned char*)h->fd_scratch;
+  size_t off = 0;
+  auto put = [&](const void* src, size_t bytes, size_t align) -> void* {
+    off = (off + align - 1) / align * align;
+    void* d = base + off;
+    cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+    off += bytes;
+    return d;
+  };
+  FdTables t;
+  t.dx = (const double*)put(dx.data(), sizeof(double) * (nf + 1), 8);
+  t.den = (const double*)put(den.data(), sizeof(double) * n, 8);
+  t.dtf = (const double*)put(dtf.data(), sizeof(double) * nf, 8);
+  t.dtn = (const double*)put(dt_host, sizeof(double) * n, 8);
+  t.jc = (const int*)put(jc.data(), sizeof(int) * (nf + 1), 4);
+  t.exact = (const unsigned char*)put(exact.data(), nf + 1, 1);
+  CUDA_TRY(h, cudaStreamSynchronize(st));   // the host vectors go out of scope (pageable source)
+  double* uc = (double*)(base + ((tbl_bytes + 255) / 256) * 256);
+  const int block = 128;
+  fd_awr_kernel<<<(unsigned)((B + block - 1) / block), block, 0, st>>>(
+      B, n, ref_factor, ode, functional, t, u0_dev, uc, u_dev, v_dev, err_fine_dev, err_steps_dev, ref_idx_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}

@@ -1,0 +1,70 @@
+// dgadj_internal.h -- handle layout and error helpers shared by the translation units of
+// libdgadj.so.  Not part of the public ABI (include/dgadj.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/dgadj.h"
+#include "dgadj_kernels.cuh"
+
+using namespace dgadj;
+
+// ---------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------
+struct LaunchPlan {
+  int ept, KT, tpc, block, ngroups, grid;
+  size_t smem;
+  size_t tile;  // doubles per checkpoint tile
+};
+
+struct dgadj_handle {
+  dgadj_config cfg;
+  int Np, NpF, K, nstages;
+  bool ops_set, enr_set, jw_set;
+  ConstOps cops;
+  double* d_mesh[2][3];  // [level]{rx, fs0, fs1} each [K]
+  double* d_nodal[2][2];  // [level]{Dr[Np*Np], LIFT[Np*2]} nodal copies (dgadj_rhs)
+  double* d_jwc;
+  double* d_jwf;
+  double* d_uin;
+  int uin_n;
+  double* ring;
+  size_t ring_bytes;
+  double* red_scratch;
+  size_t red_bytes;
+  void* fd_scratch;     // dgadj_fd_awr: interpolation tables + coarse states
+  size_t fd_bytes;
+  int sm_count, cc_major, cc_minor;
+  size_t total_mem;
+  int tune_ept, tune_block, tune_grid;
+  // host pipeline
+  cudaStream_t s_in, s_k, s_out;
+  cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
+  double* dbuf[2];
+  size_t dbuf_bytes;
+  double* pin[2];
+  size_t pin_bytes;
+  bool pipe_init;
+  char err[512];
+  int64_t launches;
+};
+
+static inline int fail(dgadj_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+#define CUDA_TRY(h, call)                                                                      \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail((h), e_ == cudaErrorMemoryAllocation ? DGADJ_ERR_NOMEM : DGADJ_ERR_CUDA,      \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+

@@ -170,6 +170,22 @@ int dgadj_rank(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev, int
 int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev,
                             const double* J_dev, double* sums_dev, void* stream);
 
+/* Finite-difference path of python/Main_finite_difference.py, batched over initial conditions
+ * on a shared time mesh: forwardSolve (:34-51) -> adjSolve (:54-76, on the ref_factor-refined
+ * mesh) -> errEst (:79-94) -> per-step window sums and argmax (:270-277, :337).
+ *   ode: 0 = du/dt = sin(u) (:128-140), 1 = du/dt = u (:110-121);
+ *   functional: 0 = J = int u, 1 = J = u_N, 2 = J = int u^2 (getK, :153-227);
+ *   dt_host[n] coarse steps (host); u0_dev[B] -> u_dev[B][n+1], v_dev[B][n*rf+1],
+ *   err_fine_dev[B][n*rf+1] (signed), err_steps_dev[B][n], ref_idx_dev[B] int32 (0-based
+ *   np.argmax of err_steps; the reference refines element ref_idx, :337-341).  Any output
+ *   may be NULL.                                                                           */
+enum { DGADJ_FD_ODE_SIN = 0, DGADJ_FD_ODE_LINEAR = 1 };
+enum { DGADJ_FD_FUNC_INT_U = 0, DGADJ_FD_FUNC_U_N = 1, DGADJ_FD_FUNC_INT_U2 = 2 };
+int dgadj_fd_awr(dgadj_handle* h, int64_t B, int32_t n, int32_t ref_factor, int32_t ode,
+                 int32_t functional, const double* dt_host, const double* u0_dev, double* u_dev,
+                 double* v_dev, double* err_fine_dev, double* err_steps_dev, int32_t* ref_idx_dev,
+                 void* stream);
+
 /* Register-only DFMA microbenchmark: sustained fp64 FMA-pipe peak of the handle's device
  * in TFLOP/s (the roofline denominator SURVEY section 8(d) asks to be measured).        */
 int dgadj_measure_dfma_peak(dgadj_handle* h, double seconds, double* tflops_out,

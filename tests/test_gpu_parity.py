@@ -347,3 +347,51 @@ def test_rank_agrees_with_oracle_indicators_away_from_ties(pkg, torch):
     assert np.array_equal(order.cpu().numpy()[gaps_ok], order_ref[gaps_ok])
     assert np.array_equal(flags.cpu().numpy()[gaps_ok], flags_ref[gaps_ok])
     assert np.array_equal(order.cpu().numpy()[:, 0], np.argmax(np.abs(out["eta"].cpu().numpy()), axis=1))
+
+
+# ------------------------------------------------------------------ finite-difference path
+def _fd_cases():
+    with open(os.path.join(GOLD, "fd_reference.json")) as f:
+        return json.load(f)["cases"]
+
+
+def test_fd_path_against_reference_fixtures(pkg, torch):
+    """dgadj_fd_awr against outputs of the reference's own Main_finite_difference.py functions
+    (tests/golden/fd_reference.json, generated by importing the reference), every ODE /
+    functional / mesh / ref_factor combination of the fixture set."""
+    solvers = {}
+    for c in _fd_cases():
+        key = (c["ode"], c["functional"], c["ref_factor"])
+        if key not in solvers:
+            solvers[key] = pkg.FDAdjoint(ode=c["ode"], functional=c["functional"], ref_factor=c["ref_factor"])
+        out = solvers[key].solve(torch.tensor([c["u0"]], dtype=torch.float64, device="cuda"), np.diff(c["times"]))
+        np.testing.assert_allclose(out["u"].cpu().numpy()[0], c["u"], rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(out["v"].cpu().numpy()[0], c["v"], rtol=1e-11, atol=1e-13)     # dense solve vs recurrence
+        np.testing.assert_allclose(out["err_fine"].cpu().numpy()[0], c["err_fine"], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(out["err_steps"].cpu().numpy()[0], c["err_steps"], rtol=1e-10, atol=1e-14)
+        assert int(out["ref_idx"][0]) == c["ref_idx"]
+
+
+def test_fd_path_batched_against_oracle(pkg, torch):
+    """Batch of 4096 ICs u0 ~ U(-3, 3) (python/Main_variable_params.py:234) on a refined,
+    non-uniform mesh: every output against the NumPy oracle, argmax bit-exact."""
+    from oracle import fd as ofd
+    rng = np.random.default_rng(5)
+    times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.02, 1.98, 37))))
+    u0 = rng.uniform(-3, 3, 4096)
+    for ode, functional, rf in [("sin", "int_u2", 4), ("sin", "int_u", 3), ("linear", "u_N", 6)]:
+        ref = ofd.fd_awr(u0, np.diff(times), ref_factor=rf, functional=functional, ode=ode)
+        out = pkg.FDAdjoint(ode=ode, functional=functional, ref_factor=rf).solve(torch.tensor(u0, device="cuda"), np.diff(times))
+        for k in ("u", "v", "err_fine", "err_steps"):
+            a = out[k].cpu().numpy()
+            assert np.max(np.abs(a - ref[k])) <= 1e-12 * max(1.0, np.max(np.abs(ref[k]))), k
+        idx = out["ref_idx"].cpu().numpy()
+        assert np.array_equal(idx, np.argmax(out["err_steps"].cpu().numpy(), axis=1))     # exact on own input
+        es = np.sort(ref["err_steps"], axis=1)
+        clear = (es[:, -1] - es[:, -2]) > 1e-10 * es[:, -1]
+        assert np.array_equal(idx[clear], ref["ref_idx"][clear])
+    # only the refinement outputs requested -> nothing else is written
+    out = pkg.FDAdjoint().solve(torch.tensor(u0, device="cuda"), np.diff(times), want=("err_steps", "ref_idx"))
+    assert set(out) == {"err_steps", "ref_idx"}
+    new_times = pkg.refine_mesh(times, int(out["ref_idx"][0]))
+    assert new_times.size == times.size + 1 and np.all(np.diff(new_times) > 0)

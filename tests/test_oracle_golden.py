@@ -155,13 +155,14 @@ def _fd_cases():
         return json.load(f)["cases"]
 
 
-@pytest.mark.parametrize("idx", range(12))
+@pytest.mark.parametrize("idx", range(len(_fd_cases())))
 def test_fd_oracle_against_reference_fixtures(idx):
     """oracle/fd.py (recurrence form) against outputs of the reference's own
     python/Main_finite_difference.py functions (dense-solve form), fp64."""
     c = _fd_cases()[idx]
     times = np.array(c["times"])
-    out = fd.fd_awr(np.array([c["u0"]]), np.diff(times), ref_factor=c["ref_factor"])
+    out = fd.fd_awr(np.array([c["u0"]]), np.diff(times), ref_factor=c["ref_factor"], functional=c["functional"],
+                    ode=c["ode"])
     np.testing.assert_allclose(out["u"][0], c["u"], rtol=1e-13, atol=1e-14)
     np.testing.assert_allclose(out["v"][0], c["v"], rtol=1e-11, atol=1e-13)
     np.testing.assert_allclose(out["err_fine"][0], c["err_fine"], rtol=1e-10, atol=1e-14)
