@@ -59,6 +59,10 @@ PROTOTYPES = {
     "dgadj_forward_host": (C.c_int, [_P, C.POINTER(MarchArgs), _P, _P, _P, _P, _P]),
     "dgadj_rhs": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_double, C.c_double, _P, _P, _P]),
     "dgadj_fd_awr": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dgadj_tdg_march": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                  _P, _P, _P, _P, _P]),
+    "dgadj_tdg_adjoint": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                    _P, _P, _P, _P, _P]),
     "dgadj_rank": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "dgadj_reduce_indicators": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "dgadj_measure_dfma_peak": (C.c_int, [_P, C.c_double, _D, _D]),

@@ -376,6 +376,7 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->ring);
   cudaFree(h->red_scratch);
   cudaFree(h->fd_scratch);
+  cudaFree(h->tdg_scratch);
   if (h->pipe_init) {
     cudaStreamDestroy(h->s_in);
     cudaStreamDestroy(h->s_k);
@@ -956,6 +957,7 @@ extern "C" int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, co
     CUDA_TRY(h, cudaDeviceSynchronize());
     cudaFree(h->red_scratch);
   cudaFree(h->fd_scratch);
+  cudaFree(h->tdg_scratch);
     h->red_scratch = nullptr;
     h->red_bytes = 0;
     CUDA_TRY(h, cudaMalloc((void**)&h->red_scratch, need));

@@ -36,6 +36,8 @@ struct dgadj_handle {
   size_t red_bytes;
   void* fd_scratch;     // dgadj_fd_awr: interpolation tables + coarse states
   size_t fd_bytes;
+  double* tdg_scratch;  // dgadj_tdg_*: per-element constant blocks
+  size_t tdg_bytes;
   int sm_count, cc_major, cc_minor;
   size_t total_mem;
   int tune_ept, tune_block, tune_grid;

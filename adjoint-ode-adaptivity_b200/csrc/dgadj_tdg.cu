@@ -1,0 +1,282 @@
+// dgadj_tdg.cu -- DG-in-time ODE march and reverse-time DG adjoint with the per-element
+// adjoint-weighted indicator: matlab/dg_march.m:1-80 and matlab/adj_march.m:1-122, batched
+// over the initial value on a shared mesh (one thread per trajectory, elements in sequence,
+// the whole element system in registers).
+//
+// Everything that does not depend on the trajectory is computed once per mesh by the host
+// (fem_setup.m:1-41 operators, the polyfit/polyval interpolation of dg_march.m:47-49 /
+// adj_march.m:75-79 as matrices -- quirk C-5 -- including the mirrored quadrature interval
+// of adj_march.m:72,78 -- quirk C-3) and passed as per-element constant blocks:
+//   march   block: A[Np*Np] | Iq[nq*Np] | Phi[nq*Np] | w[nq] | hk
+//   adjoint block: A0[Na*Na] | f1[Na] | A2[Na*Na] | Ix[Na*Npp] | Iq[nq*Npp] | Phi[nq*Na] | w[nq] | hk
+// The device does what depends on the state: sin/cos at the quadrature points, the element
+// residual and Jacobian, Newton's iteration with the reference's stopping rule
+// (||dU||_2 <= tol, at most maxit+1 iterations: dg_march.m:36,44), the dense solves
+// (Gaussian elimination with partial pivoting, MATLAB's `\`), the indicator dot product.
+#include <math.h>
+
+#include "dgadj_internal.h"
+
+namespace dgadj {
+
+template <int N>
+__device__ __forceinline__ void solve_dense(double (&A)[N][N], double (&b)[N]) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    // partial pivoting: bring the largest |A[r][c]|, r >= c, to row c (branch-free row swaps)
+#pragma unroll
+    for (int r = c + 1; r < N; ++r) {
+      const bool sw = fabs(A[r][c]) > fabs(A[c][c]);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const double t = A[c][j];
+        A[c][j] = sw ? A[r][j] : t;
+        A[r][j] = sw ? t : A[r][j];
+      }
+      const double tb = b[c];
+      b[c] = sw ? b[r] : tb;
+      b[r] = sw ? tb : b[r];
+    }
+    const double inv = 1.0 / A[c][c];
+#pragma unroll
+    for (int r = c + 1; r < N; ++r) {
+      const double f = A[r][c] * inv;
+#pragma unroll
+      for (int j = c + 1; j < N; ++j) A[r][j] = fma(-f, A[c][j], A[r][j]);
+      b[r] = fma(-f, b[c], b[r]);
+    }
+  }
+#pragma unroll
+  for (int r = N - 1; r >= 0; --r) {
+    double s = b[r];
+#pragma unroll
+    for (int j = r + 1; j < N; ++j) s = fma(-A[r][j], b[j], s);
+    b[r] = s / A[r][r];
+  }
+}
+
+// forward march: y[b][k][:] = element solution, its[b][k] = Newton iterations
+template <int NP>
+__global__ void tdg_march_kernel(long long B, int Ks, int nq, int linear, double tol, int maxit,
+                                 const double* __restrict__ ec, const double* __restrict__ y0,
+                                 double* __restrict__ y, int* __restrict__ its) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int blk = NP * NP + 2 * nq * NP + nq + 1;
+  double uR = y0[b];
+  for (int k = 0; k < Ks; ++k) {
+    const double* A = ec + (size_t)k * blk;
+    const double* Iq = A + NP * NP;
+    const double* Phi = Iq + nq * NP;
+    const double* w = Phi + nq * NP;
+    const double hk2 = 0.5 * w[nq];
+    double U[NP];
+    int it = 0;
+    if (linear) {  // dg_march.m:11-25: one solve A U = F, F(1) = uR_prev
+      double M[NP][NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        U[i] = (i == 0) ? uR : 0.0;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) M[i][j] = A[i * NP + j];
+      }
+      solve_dense<NP>(M, U);
+      it = 1;
+    } else {  // dg_march.m:27-77
+#pragma unroll
+      for (int i = 0; i < NP; ++i) U[i] = uR;
+      double err = 1.0;
+      while (it <= maxit && err > tol) {
+        double Mt[NP], J[NP][NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          Mt[i] = 0.0;
+#pragma unroll
+          for (int j = 0; j < NP; ++j) J[i][j] = 0.0;
+        }
+        for (int q = 0; q < nq; ++q) {
+          double ur = 0.0, ph[NP];
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            ur = fma(Iq[q * NP + i], U[i], ur);
+            ph[i] = Phi[q * NP + i];
+          }
+          double sn, cs;
+          sincos(ur, &sn, &cs);
+          const double ws = w[q] * sn, wc = w[q] * cs;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            Mt[i] = fma(ph[i], ws, Mt[i]);
+            const double pw = ph[i] * wc;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) J[i][j] = fma(pw, ph[j], J[i][j]);
+          }
+        }
+        double R[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          double r = fma(hk2, Mt[i], (i == 0) ? uR : 0.0);   // M_tilde + F
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            r = fma(A[i * NP + j], U[j], r);                  // + A*U_old
+            J[i][j] = fma(hk2, J[i][j], A[i * NP + j]);       // dRdU = A + dMtdU
+          }
+          R[i] = r;
+        }
+        solve_dense<NP>(J, R);                                // delta_u = dRdU \ R
+        double e2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          U[i] -= R[i];
+          e2 = fma(R[i], R[i], e2);
+        }
+        err = sqrt(e2);
+        ++it;
+      }
+    }
+    uR = U[NP - 1];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) y[((size_t)b * Ks + k) * NP + i] = U[i];
+    if (its) its[(size_t)b * Ks + k] = it;
+  }
+}
+
+// reverse march: v[b][k][:], err[b][k]
+template <int NPP>
+__global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, double y0_hard,
+                                   const double* __restrict__ ec, const double* __restrict__ y,
+                                   double* __restrict__ v, double* __restrict__ err) {
+  constexpr int NA = NPP + 1;
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int blk = NA * NA + NA + NA * NA + NA * NPP + nq * NPP + nq * NA + nq + 1;
+  double vL = 0.0;
+  for (int k = Ks - 1; k >= 0; --k) {
+    const double* A0 = ec + (size_t)k * blk;
+    const double* f1 = A0 + NA * NA;
+    const double* A2 = f1 + NA;
+    const double* Ix = A2 + NA * NA;
+    const double* Iq = Ix + NA * NPP;
+    const double* Phi = Iq + nq * NPP;
+    const double* w = Phi + nq * NA;
+    const double hk2 = 0.5 * w[nq];
+    double Uk[NPP];
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) Uk[i] = y[((size_t)b * Ks + k) * NPP + i];
+    double Mt[NA], M[NA][NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      Mt[i] = 0.0;
+#pragma unroll
+      for (int j = 0; j < NA; ++j) M[i][j] = 0.0;
+    }
+    if (!linear) {
+      for (int q = 0; q < nq; ++q) {  // adj_march.m:78-82,104-105 (mirrored points: quirk C-3)
+        double ur = 0.0, ph[NA];
+#pragma unroll
+        for (int i = 0; i < NPP; ++i) ur = fma(Iq[q * NPP + i], Uk[i], ur);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) ph[i] = Phi[q * NA + i];
+        double sn, cs;
+        sincos(ur, &sn, &cs);
+        const double ws = w[q] * sn, wc = w[q] * cs;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          Mt[i] = fma(ph[i], ws, Mt[i]);
+          const double pw = ph[i] * wc;
+#pragma unroll
+          for (int j = 0; j < NA; ++j) M[i][j] = fma(pw, ph[j], M[i][j]);
+        }
+      }
+    }
+    double F[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      F[i] = f1[i] - ((i == NA - 1) ? vL : 0.0);          // F = M_k*1; F(end) -= vL_prev
+#pragma unroll
+      for (int j = 0; j < NA; ++j) M[i][j] = fma(-hk2, M[i][j], A0[i * NA + j]);   // A = A0 - M_v
+    }
+    solve_dense<NA>(M, F);                                  // v_k = A \ F
+    vL = F[0];
+    // indicator: err_k = v_k' * ( -A2*uh_k - M_tilde + F0 ),  F0(1) = y0 (k == 1) or y1{k-1}(end)
+    double uh[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NPP; ++j) s = fma(Ix[i * NPP + j], Uk[j], s);
+      uh[i] = s;
+    }
+    const double f0 = (k == 0) ? y0_hard : y[((size_t)b * Ks + (k - 1)) * NPP + NPP - 1];
+    double e = 0.0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double s = fma(-hk2, Mt[i], (i == 0) ? f0 : 0.0);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) s = fma(-A2[i * NA + j], uh[j], s);
+      e = fma(F[i], s, e);
+      if (v) v[((size_t)b * Ks + k) * NA + i] = F[i];
+    }
+    if (err) err[(size_t)b * Ks + k] = e;
+  }
+}
+
+static int tdg_consts(dgadj_handle* h, const double* host, size_t n, cudaStream_t st) {
+  const size_t need = n * sizeof(double);
+  if (need > h->tdg_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->tdg_scratch);
+    h->tdg_scratch = nullptr;
+    h->tdg_bytes = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->tdg_scratch, need));
+    h->tdg_bytes = need;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->tdg_scratch, host, need, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));  // pageable source may be released by the caller
+  return DGADJ_OK;
+}
+
+}  // namespace dgadj
+
+extern "C" int dgadj_tdg_march(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np, int32_t nq, int32_t linear,
+                               double tol, int32_t maxit, const double* elem_consts_host,
+                               const double* y0_dev, double* y_dev, int32_t* its_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || Ks <= 0 || nq < 0 || !elem_consts_host || !y0_dev || !y_dev) return fail(h, DGADJ_ERR_INVALID, "bad tdg_march arguments");
+  if (Np < 2 || Np > 6) return fail(h, DGADJ_ERR_UNSUPPORTED, "time-DG march supports 1 <= N <= 5 (Np = %d)", Np);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t blk = (size_t)Np * Np + 2 * (size_t)nq * Np + nq + 1;
+  int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
+  if (rc) return rc;
+  const int block = 128;
+  const unsigned grid = (unsigned)((B + block - 1) / block);
+#define DGADJ_TDG_M(n) case n: tdg_march_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, tol, maxit, h->tdg_scratch, y0_dev, y_dev, its_dev); break;
+  switch (Np) { DGADJ_TDG_M(2) DGADJ_TDG_M(3) DGADJ_TDG_M(4) DGADJ_TDG_M(5) DGADJ_TDG_M(6) }
+#undef DGADJ_TDG_M
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, int32_t nq,
+                                 int32_t linear, double y0_hard, const double* elem_consts_host,
+                                 const double* y_dev, double* v_dev, double* err_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || Ks <= 0 || nq < 0 || !elem_consts_host || !y_dev) return fail(h, DGADJ_ERR_INVALID, "bad tdg_adjoint arguments");
+  if (Np_primal < 2 || Np_primal > 6) return fail(h, DGADJ_ERR_UNSUPPORTED, "time-DG adjoint supports primal 1 <= N <= 5");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Na = Np_primal + 1;
+  const size_t blk = Na * Na + Na + Na * Na + Na * Np_primal + (size_t)nq * Np_primal + (size_t)nq * Na + nq + 1;
+  int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
+  if (rc) return rc;
+  const int block = 128;
+  const unsigned grid = (unsigned)((B + block - 1) / block);
+#define DGADJ_TDG_A(n) case n: tdg_adjoint_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, y0_hard, h->tdg_scratch, y_dev, v_dev, err_dev); break;
+  switch (Np_primal) { DGADJ_TDG_A(2) DGADJ_TDG_A(3) DGADJ_TDG_A(4) DGADJ_TDG_A(5) DGADJ_TDG_A(6) }
+#undef DGADJ_TDG_A
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}

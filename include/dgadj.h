@@ -186,6 +186,21 @@ int dgadj_fd_awr(dgadj_handle* h, int64_t B, int32_t n, int32_t ref_factor, int3
                  double* v_dev, double* err_fine_dev, double* err_steps_dev, int32_t* ref_idx_dev,
                  void* stream);
 
+/* DG-in-time ODE march (matlab/dg_march.m:1-80; u' = sin(u) with Newton, or the linear branch
+ * u' = u) and its reverse-time DG adjoint with the per-element indicator err(k)
+ * (matlab/adj_march.m:1-122), batched over the initial value on a shared mesh of Ks elements of
+ * one order.  The per-element constant blocks (everything fem_setup.m:1-41 and the
+ * polyfit/polyval interpolation produce; layout in csrc/dgadj_tdg.cu) are built by the host.
+ *   march:   y0_dev[B] -> y_dev[B][Ks][Np], its_dev[B][Ks] (Newton iterations; or NULL)
+ *   adjoint: y_dev (primal, Np_primal) -> v_dev[B][Ks][Np_primal+1] (or NULL), err_dev[B][Ks]
+ *            (signed; matlab/MAIN.m:51 takes abs); y0_hard = the `y0 = 1` of adj_march.m:9.  */
+int dgadj_tdg_march(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np, int32_t nq, int32_t linear,
+                    double tol, int32_t maxit, const double* elem_consts_host, const double* y0_dev,
+                    double* y_dev, int32_t* its_dev, void* stream);
+int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, int32_t nq,
+                      int32_t linear, double y0_hard, const double* elem_consts_host,
+                      const double* y_dev, double* v_dev, double* err_dev, void* stream);
+
 /* Register-only DFMA microbenchmark: sustained fp64 FMA-pipe peak of the handle's device
  * in TFLOP/s (the roofline denominator SURVEY section 8(d) asks to be measured).        */
 int dgadj_measure_dfma_peak(dgadj_handle* h, double seconds, double* tflops_out,

@@ -395,3 +395,49 @@ def test_fd_path_batched_against_oracle(pkg, torch):
     assert set(out) == {"err_steps", "ref_idx"}
     new_times = pkg.refine_mesh(times, int(out["ref_idx"][0]))
     assert new_times.size == times.size + 1 and np.all(np.diff(new_times) > 0)
+
+
+# ------------------------------------------------------------------ DG-in-time path
+@pytest.mark.parametrize("linear", [False, True])
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_tdg_march_and_adjoint(pkg, torch, n, linear):
+    """dgadj_tdg_march / dgadj_tdg_adjoint against the bug-for-bug oracle of dg_march.m /
+    adj_march.m on a refined mesh, batch of initial values; Newton iteration counts equal."""
+    from oracle import tdg as otdg
+    rng = np.random.default_rng(n)
+    times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.1, 1.9, 6))))
+    Ks = times.size - 1
+    Ns = n * np.ones(Ks, dtype=int)
+    y0 = np.concatenate(([1.0], rng.uniform(-3, 3, 255)))
+    s = pkg.TimeDG(linear=linear)
+    t1, y1, its = s.dg_march(Ns, Ks, times, torch.tensor(y0, device="cuda"))
+    t1r, y1r, itsr = otdg.dg_march(Ns, Ks, times, y0, linear=linear)
+    yr = np.stack(y1r, axis=1)
+    assert rel(y1.cpu().numpy(), yr) < 1e-11
+    assert np.array_equal(its.cpu().numpy(), np.stack(itsr, axis=1))
+    for a, b in zip(t1, t1r):
+        np.testing.assert_allclose(a, b, rtol=1e-14, atol=1e-15)
+    t2, v, err = s.adj_march(Ns + 1, Ks, times, y1, t1)
+    _, vr, errr = otdg.adj_march(Ns + 1, Ks, times, y1r, t1r, linear=linear)
+    assert rel(v.cpu().numpy(), np.stack(vr, axis=1)) < 1e-10
+    scale = np.max(np.abs(np.stack(vr, axis=1)), axis=(1, 2))[:, None] * np.max(np.abs(yr), axis=(1, 2))[:, None]
+    assert np.max(np.abs(err.cpu().numpy() - errr) / np.maximum(scale, 1.0)) < 1e-10
+    # the fine primal of MAIN.m:33 (order n + 2) runs too
+    _, y1f, _ = s.dg_march(Ns + 2, Ks, times, torch.tensor(y0, device="cuda"))
+    _, y1fr, _ = otdg.dg_march(Ns + 2, Ks, times, y0, linear=linear)
+    assert rel(y1f.cpu().numpy(), np.stack(y1fr, axis=1)) < 1e-10
+
+
+def test_tdg_reference_iteration0(pkg, torch):
+    """matlab/MAIN.m iteration 0 on the GPU: the numbers of init_nonlin.png."""
+    times, Ns = np.array([0.0, 1.0, 2.0]), np.array([1, 1])
+    s = pkg.TimeDG()
+    t1, y1, its = s.dg_march(Ns, 2, times, torch.tensor([1.0], dtype=torch.float64, device="cuda"))
+    assert its.cpu().numpy().tolist() == [[5, 4]]
+    np.testing.assert_allclose(y1.cpu().numpy().ravel(), [0.984104, 1.956225, 2.028961, 2.659823], atol=1e-6)
+    _, v, err = s.adj_march(Ns + 1, 2, times, y1, t1)
+    np.testing.assert_allclose(v.cpu().numpy().ravel(), [3.576932, 2.087720, 0.829270, 0.886616, 0.498711, -0.016913], atol=1e-6)
+    np.testing.assert_allclose(err.cpu().numpy().ravel(), [-0.843478, 0.092681], atol=1e-6)
+    from adjoint_ode_adaptivity_b200.tdg import refine
+    times2, Ns2, ref_i = refine(times, Ns, err.abs().mean(0).cpu().numpy(), 1)
+    assert ref_i == 0 and times2.tolist() == [0.0, 0.5, 1.0, 2.0]

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import advec, fd
+from oracle import advec, fd, tdg
 from oracle import operators as ops
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -168,3 +168,45 @@ def test_fd_oracle_against_reference_fixtures(idx):
     np.testing.assert_allclose(out["err_fine"][0], c["err_fine"], rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose(out["err_steps"][0], c["err_steps"], rtol=1e-10, atol=1e-14)
     assert int(out["ref_idx"][0]) == c["ref_idx"]
+
+
+# ---------------------------------------------------------------- DG-in-time path
+def test_tdg_matches_init_nonlin_png():
+    """matlab/MAIN.m iteration 0 (u' = sin u, y0 = 1, [0,2], Ks = 2, n = 1, adjoint order 2): the
+    values readable from the reference's figure init_nonlin.png -- bars ~0.84 / 0.09, adjoint
+    nodes ~3.57, 2.08, 0.83 | 0.89, 0.50, -0.02, primal ~0.98 -> 1.96 | 2.03 -> 2.66 -- and the
+    survey's 6-digit restatement values."""
+    times, Ns = np.array([0.0, 1.0, 2.0]), np.array([1, 1])
+    t1, y1, its = tdg.dg_march(Ns, 2, times, 1.0)
+    assert [int(i[0]) for i in its] == [5, 4]
+    np.testing.assert_allclose(np.concatenate([a[0] for a in y1]), [0.984104, 1.956225, 2.028961, 2.659823], atol=1e-6)
+    t2, v, err = tdg.adj_march(Ns + 1, 2, times, y1, t1)
+    np.testing.assert_allclose(np.concatenate([a[0] for a in v]),
+                               [3.576932, 2.087720, 0.829270, 0.886616, 0.498711, -0.016913], atol=1e-6)
+    np.testing.assert_allclose(err[0], [-0.843478, 0.092681], atol=1e-6)
+    assert np.allclose(np.abs(err[0]), [0.84, 0.09], atol=0.01)         # the png's bars
+    exact = 2 * np.arctan2(np.sin(0.5) * np.exp(2.0), np.cos(0.5))      # python/factory.py:130-131
+    assert abs(y1[1][0, -1] - exact) < 5e-3 and exact == pytest.approx(2.655911, abs=1e-6)
+
+
+def test_tdg_linear_branch_effectivity():
+    """Linear branches (u' = u): sum of indicators = J(u) - J(u_H) to 0.3 %."""
+    times, Ns = np.array([0.0, 0.5, 1.0]), np.array([1, 1])
+    t1, y1, _ = tdg.dg_march(Ns, 2, times, 1.0, linear=True)
+    np.testing.assert_allclose(np.concatenate([a[0] for a in y1]),
+                               [0.941176470588234, 1.647058823529412, 1.55017301038062, 2.712802768166089], rtol=1e-12)
+    _, v, err = tdg.adj_march(Ns + 1, 2, times, y1, t1, linear=True)
+    np.testing.assert_allclose(np.concatenate([a[0] for a in v]),
+                               [1.718294826216405, 1.115786179168438, 0.653395822131628,
+                                0.648725212464589, 0.28328611898017, 0.002832861189802], rtol=1e-11)
+    np.testing.assert_allclose(err[0], [0.0027474174512, 0.002744640599116], rtol=1e-9)
+    JuH = sum(0.5 * (t[-1] - t[0]) * (y[0, 0] + y[0, -1]) for t, y in zip(t1, y1))   # trapezoid-exact, N = 1
+    assert err.sum() == pytest.approx((np.e - 1.0) - JuH, rel=3e-3)
+    # exact linear primal: u0 e^t (python/factory.py:102-103)
+    t1f, y1f, _ = tdg.dg_march(Ns + 2, 2, times, 1.0, linear=True)
+    assert abs(y1f[1][0, -1] - np.e) < 1e-4
+
+
+def test_tdg_refine_rule():
+    times, Ns, ref_i = tdg.refine(np.array([0.0, 1.0, 2.0]), np.array([1, 1]), np.array([-0.84, 0.09]), 1)
+    assert ref_i == 0 and times.tolist() == [0.0, 0.5, 1.0, 2.0] and Ns.tolist() == [1, 1, 1]
