@@ -441,3 +441,47 @@ def test_tdg_reference_iteration0(pkg, torch):
     from adjoint_ode_adaptivity_b200.tdg import refine
     times2, Ns2, ref_i = refine(times, Ns, err.abs().mean(0).cpu().numpy(), 1)
     assert ref_i == 0 and times2.tolist() == [0.0, 0.5, 1.0, 2.0]
+
+
+# ------------------------------------------------------------------ adaptive loops (config 5)
+def test_adaptive_loop_fd_vs_reference_semantics(pkg, torch):
+    """30 argmax refinements of the FD path (snapshots at 5 / 10 / 30, cf. refine5.png ...):
+    batch of one reproduces python/Main_finite_difference.py's own loop; a batch of 512 ICs uses
+    the batch-mean rule of Main_variable_params.py:340-341.  Mesh sequences must be identical
+    to the oracle's."""
+    from oracle import fd as ofd
+    for B, seed in [(1, 0), (512, 3)]:
+        u0 = np.array([1.0]) if B == 1 else np.random.default_rng(seed).uniform(-3, 3, B)
+        hist = pkg.adapt_fd(torch.tensor(u0, device="cuda"), iters=30)
+        times = np.linspace(0.0, 2.0, 3)
+        for it in range(31):
+            ref = ofd.fd_awr(u0, np.diff(times))
+            mean_steps = ref["err_steps"].mean(axis=0)
+            assert np.array_equal(hist[it]["times"], times), it
+            np.testing.assert_allclose(hist[it]["err_steps"], mean_steps, rtol=1e-9, atol=1e-14)
+            idx = int(np.argmax(mean_steps))
+            assert hist[it]["ref_idx"] == idx
+            times = np.insert(times, idx + 1, 0.5 * (times[idx] + times[idx + 1]))
+        assert len(hist[5]["times"]) == 8 and len(hist[10]["times"]) == 13 and len(hist[30]["times"]) == 33
+        assert hist[30]["err_total"] < 0.2 * hist[0]["err_total"]
+    # SURVEY App. B.3: the first refinements of the reference run (u0 = 1): elements 0, 0, 3
+    hist = pkg.adapt_fd(torch.tensor([1.0], dtype=torch.float64, device="cuda"), iters=2)
+    assert [h["ref_idx"] for h in hist] == [0, 0, 3]
+    np.testing.assert_allclose(hist[0]["err_steps"], [0.436375956067089, 0.125822589823601], rtol=1e-12)
+
+
+def test_adaptive_loop_tdg(pkg, torch):
+    """matlab/MAIN.m loop on the GPU vs the oracle restatement: 12 refinements, batch of 64."""
+    from oracle import tdg as otdg
+    y0 = np.concatenate(([1.0], np.random.default_rng(1).uniform(0.2, 2.5, 63)))
+    hist = pkg.adapt_tdg(torch.tensor(y0, device="cuda"), iters=12)
+    times, Ns, Ks = np.linspace(0.0, 2.0, 3), np.ones(2, dtype=int), 2
+    for it in range(13):
+        t1, y1, _ = otdg.dg_march(Ns, Ks, times, y0)
+        _, _, err = otdg.adj_march(Ns + 1, Ks, times, y1, t1)
+        mean_err = np.abs(err).mean(axis=0)
+        assert np.array_equal(hist[it]["times"], times), it
+        np.testing.assert_allclose(hist[it]["err"], mean_err, rtol=1e-8, atol=1e-12)
+        times, Ns, ref_i = otdg.refine(times, Ns, mean_err, 1)
+        assert hist[it]["ref_idx"] == ref_i
+        Ks += 1
