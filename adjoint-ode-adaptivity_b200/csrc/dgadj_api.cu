@@ -956,8 +956,6 @@ extern "C" int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, co
   if (need > h->red_bytes) {
     CUDA_TRY(h, cudaDeviceSynchronize());
     cudaFree(h->red_scratch);
-  cudaFree(h->fd_scratch);
-  cudaFree(h->tdg_scratch);
     h->red_scratch = nullptr;
     h->red_bytes = 0;
     CUDA_TRY(h, cudaMalloc((void**)&h->red_scratch, need));
