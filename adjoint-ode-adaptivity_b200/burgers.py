@@ -1,0 +1,87 @@
+"""Inviscid Burgers DG march with the reference's slope limiter fused into every RK stage
+(BASELINE config 3).  Limiter: utils/SlopeLimitN.m / SlopeLimitLin.m / minmod.m; the Burgers
+right-hand side is build-specified (the reference has none).  The march
+writes the forward checkpoints a discrete adjoint needs (per-step states, per-stage limiter
+flags and wave speeds)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .galerkin import BaseGalerkin1D
+
+
+class BurgersDG1D:
+    def __init__(self, N, K=None, domain=(-1.0, 1.0), v_x=None, bc="periodic", device=0):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.g = g = BaseGalerkin1D(n=N, k=K, domain=domain, v_x=v_x)
+        self.N, self.Np, self.K, self.device, self.bc = N, N + 1, g.k, device, bc
+        if bc not in ("periodic", "free"):
+            raise ValueError("bc must be 'periodic' or 'free' (zero-jump ends)")
+        cfg = _lib.Config(device=device, N=N, K=self.K, bc=1 if bc == "periodic" else 0, inflow=0, functional=0,
+                          scheme=0, reserved=0, alpha=0.0)
+        self._h = C.c_void_p(0)
+        rc = self.lib.dgadj_create(C.byref(cfg), C.byref(self._h))
+        if rc != _lib.OK:
+            self._h = C.c_void_p(0)
+            raise _lib.DgadjError(rc, "dgadj_create failed (an sm_100 device is required; there is no CPU path)")
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self.ops = dict(Dr=c(g.d_r), LIFT=c(g.lift), Mref=c(g.mass), rx=c(g.r_x), Fscale=c(g.f_scale),
+                        V=c(g.v), invV=c(g.inv_v), x=c(g.x))
+        o = self.ops
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        self._check(self.lib.dgadj_set_operators(self._h, self.Np, self.K, p(o["Dr"]), p(o["LIFT"]), p(o["Mref"]),
+                                                 p(o["rx"]), p(o["Fscale"])))
+
+    def _check(self, rc):
+        if rc != _lib.OK:
+            raise _lib.DgadjError(rc, self.lib.dgadj_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.dgadj_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stable_dt(self, umax, cfl=0.25):
+        """dt = cfl * min node spacing / max wave speed."""
+        xmin = np.min(np.abs(self.g.x[0, :] - self.g.x[1, :]))
+        return cfl * xmin / umax
+
+    def forward(self, u0, dt, S, limit=True, history=False, checkpoints=False):
+        """u0: float64 CUDA tensor [B, Np, K]; dt scalar or CUDA tensor [B].
+        Returns dict(uT[, hist[B,S+1,Np,K]][, flags[B,S,K] uint8, maxvel[B,S,5]])."""
+        torch = self.torch
+        if not (isinstance(u0, torch.Tensor) and u0.is_cuda and u0.dtype == torch.float64):
+            raise TypeError("u0 must be a float64 CUDA tensor")
+        if u0.ndim == 2:
+            u0 = u0[None]
+        if u0.shape[1:] != (self.Np, self.K):
+            raise ValueError(f"expected (B, {self.Np}, {self.K}), got {tuple(u0.shape)}")
+        u0 = u0.contiguous()
+        B = u0.shape[0]
+        dt_s, dt_v = (float(dt), None) if np.isscalar(dt) else (0.0, dt.contiguous())
+        kw = dict(dtype=torch.float64, device=u0.device)
+        out = dict(uT=torch.empty_like(u0))
+        if history:
+            out["hist"] = torch.empty((B, S + 1, self.Np, self.K), **kw)
+        if checkpoints:
+            out["flags"] = torch.empty((B, S, self.K), dtype=torch.uint8, device=u0.device)
+            out["maxvel"] = torch.empty((B, S, 5), **kw)
+        ptr = lambda k: C.c_void_p(out[k].data_ptr()) if k in out else C.c_void_p(0)
+        o = self.ops
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        self._check(self.lib.dgadj_burgers_forward(
+            self._h, B, S, dt_s, C.c_void_p(dt_v.data_ptr()) if dt_v is not None else C.c_void_p(0), int(limit),
+            p(o["invV"]), p(o["V"]), p(o["x"]), C.c_void_p(u0.data_ptr()), ptr("uT"), ptr("hist"), ptr("flags"),
+            ptr("maxvel"), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out

@@ -377,6 +377,7 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->red_scratch);
   cudaFree(h->fd_scratch);
   cudaFree(h->tdg_scratch);
+  cudaFree(h->bg_scratch);
   if (h->pipe_init) {
     cudaStreamDestroy(h->s_in);
     cudaStreamDestroy(h->s_k);
@@ -459,6 +460,7 @@ extern "C" int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double*
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   int rc = set_level(h, 0, Np, Dr, LIFT, Mref, rx, Fscale);
   if (rc) return rc;
+  for (int i = 0; i < Np * Np; ++i) h->Dr_nodal[i] = Dr[i];
   h->ops_set = true;
   return DGADJ_OK;
 }

@@ -38,6 +38,9 @@ struct dgadj_handle {
   size_t fd_bytes;
   double* tdg_scratch;  // dgadj_tdg_*: per-element constant blocks
   size_t tdg_bytes;
+  double* bg_scratch;   // dgadj_burgers_forward: limiter geometry
+  size_t bg_bytes;
+  double Dr_nodal[MAXNP * MAXNP];  // host copy of the primal nodal Dr
   int sm_count, cc_major, cc_minor;
   size_t total_mem;
   int tune_ept, tune_block, tune_grid;

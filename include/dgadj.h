@@ -201,6 +201,19 @@ int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal,
                       int32_t linear, double y0_hard, const double* elem_consts_host,
                       const double* y_dev, double* v_dev, double* err_dev, void* stream);
 
+/* Inviscid Burgers forward march (LSERK4) with SlopeLimitN (utils/SlopeLimitN.m:9-32,
+ * SlopeLimitLin.m:10-18, minmod.m:6-12) applied to the initial state and after every stage,
+ * on the handle's primal operators (dgadj_set_operators) and boundary type (periodic, or
+ * zero-jump ends); writes the forward checkpoints an adjoint needs.  The reference has no
+ * Burgers right-hand side: it is build-specified (local Lax-Friedrichs).
+ *   V_host / invV_host [Np*Np], x_host [Np*K]: StartUp1D arrays the limiter uses;
+ *   u0_dev[B][Np][K] -> uT_dev; hist_dev[B][S+1][Np][K], flags_dev[B][S][K] (bit s = cell
+ *   limited after stage s), maxvel_dev[B][S][5] (max|u| per stage): each may be NULL.       */
+int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, double dt, const double* dt_dev,
+                          int32_t limit, const double* invV_host, const double* V_host,
+                          const double* x_host, const double* u0_dev, double* uT_dev,
+                          double* hist_dev, uint8_t* flags_dev, double* maxvel_dev, void* stream);
+
 /* Register-only DFMA microbenchmark: sustained fp64 FMA-pipe peak of the handle's device
  * in TFLOP/s (the roofline denominator SURVEY section 8(d) asks to be measured).        */
 int dgadj_measure_dfma_peak(dgadj_handle* h, double seconds, double* tflops_out,

@@ -485,3 +485,37 @@ def test_adaptive_loop_tdg(pkg, torch):
         times, Ns, ref_i = otdg.refine(times, Ns, mean_err, 1)
         assert hist[it]["ref_idx"] == ref_i
         Ks += 1
+
+
+# ------------------------------------------------------------------ Burgers + limiter (config 3)
+@pytest.mark.parametrize("N,K,bc", [(4, 256, "periodic"), (2, 63, "free"), (8, 40, "periodic"), (1, 16, "periodic")])
+def test_burgers_limited_march(pkg, torch, N, K, bc):
+    """dgadj_burgers_forward against oracle/burgers.py past shock formation: states at 1e-12,
+    limiter flags and wave speeds exactly (identical operator inputs)."""
+    from oracle import burgers as ob
+    s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc=bc)
+    g = oracle_view(s.g)
+    g.rx = s.g.r_x                                  # the Burgers kernel also takes rx(1,k)
+    g.rx = np.broadcast_to(s.g.r_x[0:1, :], s.g.r_x.shape).copy()
+    B = 24
+    rng = np.random.default_rng(N * 7 + K)
+    c, A, ph = rng.uniform(-0.5, 0.5, (B, 1, 1)), rng.uniform(0.5, 1.5, (B, 1, 1)), rng.uniform(0, 2 * np.pi, (B, 1, 1))
+    u0 = c + A * np.sin(np.pi * g.x[None] + ph)     # SURVEY section 8(d), config 3
+    dt = s.stable_dt(2.0)
+    S = int(np.ceil(0.5 / dt))                      # shocks form at t ~ 1/(pi A) ~ 0.2-0.6
+    S = min(S, 400)
+    ref, hist_r, flags_r, mv_r = ob.burgers_march(u0, g, dt, S, bc="periodic" if bc == "periodic" else "free", history=True)
+    out = s.forward(torch.tensor(u0, device="cuda"), dt, S, history=True, checkpoints=True)
+    flags = out["flags"].cpu().numpy()              # [B, S, K] bitmask over stages
+    bits = np.stack([(flags >> st) & 1 for st in range(5)], axis=0).astype(bool)     # [5, B, S, K]
+    fr = np.moveaxis(flags_r, (0, 1, 2), (2, 0, 1))                                   # [S,5,B,K] -> [5,B,S,K]
+    mism = np.mean(bits != fr)
+    assert fr.any()
+    assert mism == 0.0, mism
+    assert rel(out["maxvel"].cpu().numpy(), np.moveaxis(mv_r, (0, 1, 2), (1, 2, 0))) < 1e-12
+    assert rel(out["hist"].cpu().numpy(), np.moveaxis(hist_r, 0, 1)) < 1e-11
+    assert rel(out["uT"].cpu().numpy(), ref) < 1e-11
+    # unlimited march
+    ref2, _, _, _ = ob.burgers_march(u0, g, dt, 20, bc="periodic" if bc == "periodic" else "free", limit=False)
+    out2 = s.forward(torch.tensor(u0, device="cuda"), dt, 20, limit=False)
+    assert rel(out2["uT"].cpu().numpy(), ref2) < 1e-12
