@@ -253,7 +253,8 @@ def test_burgers_oracle_properties():
     v = limiter.cell_averages(hist, g)
     tv = np.abs(np.diff(np.concatenate([v, v[:, :1]], axis=1), axis=1)).sum(axis=1)
     assert np.max(np.diff(tv)) < 1e-10 and flags.any() and np.all(mv <= 1.2 + 1e-12)
-    # unlimited and limited agree while the solution is smooth (t << 1/pi)
+    # while the solution is smooth (t << 1/pi) the limiter only clips the extrema (a TVD minmod
+    # limiter does that) and the limited march stays close to the unlimited one
     uA, _, flA, _ = burgers.burgers_march(u0, g, dt, 5, limit=True)
     uB, _, _, _ = burgers.burgers_march(u0, g, dt, 5, limit=False)
-    assert not flA.any() and np.array_equal(uA, uB)
+    assert flA.mean() < 0.1 and np.max(np.abs(uA - uB)) < 1e-2
