@@ -407,6 +407,34 @@ static int upload(dgadj_handle* h, double** dst, const double* src, size_t n) {
   return DGADJ_OK;
 }
 
+static void scale_ops(const StageOps& src, double f, StageOps* dst) {
+  for (int i = 0; i < HM * HP; ++i) {
+    dst->DE2[i] = make_double2(src.DE2[i].x * f, src.DE2[i].y * f);
+    dst->DO2[i] = make_double2(src.DO2[i].x * f, src.DO2[i].y * f);
+  }
+  for (int i = 0; i < HP; ++i) {
+    dst->LS2[i] = make_double2(src.LS2[i].x * f, src.LS2[i].y * f);
+    dst->LA2[i] = make_double2(src.LA2[i].x * f, src.LA2[i].y * f);
+  }
+}
+
+// per-stage copies of the blocks with the stage scalings folded in (see ConstOps)
+static void rebuild_stage_ops(dgadj_handle* h) {
+  const int ns = h->nstages;
+  double sig[MAXSTAGES], sga[MAXSTAGES];
+  sig[0] = 1.0;
+  for (int s = 1; s < ns; ++s) sig[s] = h->cops.rka[s] * sig[s - 1];
+  sga[ns - 1] = 1.0;
+  for (int s = ns - 2; s >= 0; --s) sga[s] = h->cops.rka[s + 1] * sga[s + 1];
+  for (int s = 0; s < MAXSTAGES; ++s) {
+    const double f = s < ns ? 1.0 / sig[s] : 1.0, fa = s < ns ? sga[s] : 1.0;
+    for (int lv = 0; lv < 2; ++lv) scale_ops(h->base_ops[lv], f, &h->cops.st[lv][s]);
+    scale_ops(h->base_ops[1], fa, &h->cops.sta[s]);
+    h->cops.bsig[s] = s < ns ? h->cops.rkb[s] * sig[s] : 0.0;
+    h->cops.bsga[s] = s < ns ? h->cops.rkb[s] / sga[s] : 0.0;
+  }
+}
+
 static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const double* LIFT, const double* Mref,
                      const double* rx, const double* Fscale) {
   const int K = h->K;
@@ -432,7 +460,8 @@ static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const do
     ((i & 1) ? so.LS2[i / 2].y : so.LS2[i / 2].x) = LS[i];
     ((i & 1) ? so.LA2[i / 2].y : so.LA2[i / 2].x) = LA[i];
   }
-  for (int s = 0; s < MAXSTAGES; ++s) h->cops.st[lv][s] = so;
+  h->base_ops[lv] = so;
+  rebuild_stage_ops(h);
   for (int i = 0; i < Np * Np; ++i) h->cops.Mref[lv][i] = Mref ? Mref[i] : 0.0;
   std::vector<double> rxk(K), f0(K), f1(K);
   for (int k = 0; k < K; ++k) {

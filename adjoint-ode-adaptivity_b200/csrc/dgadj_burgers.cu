@@ -234,7 +234,7 @@ extern "C" int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, doub
   a.hist = hist_dev;
   a.flags = flags_dev;
   a.maxvel = maxvel_dev;
-  a.so = h->cops.st[0][0];
+  a.so = h->base_ops[0];
   for (int s = 0; s < 5; ++s) {
     a.rka[s] = h->cops.rka[s];
     a.rkb[s] = h->cops.rkb[s];

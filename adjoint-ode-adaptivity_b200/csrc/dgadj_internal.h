@@ -24,6 +24,7 @@ struct dgadj_handle {
   int Np, NpF, K, nstages;
   bool ops_set, enr_set, jw_set;
   ConstOps cops;
+  StageOps base_ops[2];  // unscaled even/odd blocks of both levels
   double* d_mesh[2][3];  // [level]{rx, fs0, fs1} each [K]
   double* d_nodal[2][2];  // [level]{Dr[Np*Np], LIFT[Np*2]} nodal copies (dgadj_rhs)
   double* d_jwc;

@@ -41,8 +41,16 @@ struct ProlongOps {
   double PE[HM * HM];  // even block of T_f P T_c^-1 : [i*HM + j], i < HE_f, j < HE_c
   double PO[HM * HM];  // odd block                  : [i*HM + j], i < HO_f, j < HO_c
 };
+// Stage scaling.  The low-storage recurrences  r_s = rka_s r_{s-1} + R_s  (forward) and
+// w_s = rka_{s+1} w_{s+1} + bm_s mu_s  (adjoint) are carried as r = sig_s r~, w = sga_s w~ with
+// sig_0 = 1, sig_s = rka_s sig_{s-1} and sga_last = 1, sga_s = rka_{s+1} sga_{s+1}: the rka
+// multiply disappears (r~_s = r~_{s-1} + R_s / sig_s) and the factors 1/sig_s, sga_s are folded
+// into the per-stage copies of the operator blocks, which exist anyway (see fwd_step).
 struct alignas(16) ConstOps {
-  StageOps st[2][MAXSTAGES];      // [level][stage]: identical copies per stage (see fwd_step)
+  StageOps st[2][MAXSTAGES];      // [level][stage]: forward blocks, scaled by 1/sig_s
+  StageOps sta[MAXSTAGES];        // enriched level, adjoint sweep: blocks scaled by sga_s
+  double bsig[MAXSTAGES];         // rkb_s * sig_s   (state update  z += bsig_s m r~)
+  double bsga[MAXSTAGES];         // rkb_s / sga_s   (adjoint update w~ += bsga_s m mu)
   ProlongOps pr[2];               // identical copies (indexed by step parity)
   double Mref[2][MAXNP * MAXNP];  // nodal reference mass matrices inv(V V') (J = int u^2)
   double P[MAXNP * MAXNP];        // nodal prolongation [NPF][NP], row stride NP
@@ -243,16 +251,17 @@ struct EOVec {
 // element and trajectory) and r = resu/m the reference update (utils/AdvecRHS1D.m:11,19 +
 // the mlx loop)   resu = rka*resu + dt*rhsu ;  u = u + rkb*resu   becomes
 //     re = rka*re + DE zo + LS (g0+g1) ;  ro = rka*ro + DO ze + LA (g0-g1) ;  z += (rkb*m) r
+// (the rka multiply is absorbed by the stage scaling described at ConstOps)
 //     g0 = (u[0]-uL)*q0, g1 = (u[N]-uR)*q1,  q_f = dt*Fscale_f*c_f/m
 template <int NPX, int EPT>
 __device__ __forceinline__ void fwd_stage_volume(const StageOps& so, const EOVec<NPX> (&z)[EPT],
-                                                 EOVec<NPX> (&r)[EPT], double rka) {
+                                                 EOVec<NPX> (&r)[EPT]) {
   constexpr int HE = EO<NPX>::HE, HO = EO<NPX>::HO;
 #pragma unroll
   for (int i = 0; i < HE; ++i) {
     double acc[EPT];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) acc[e] = rka * r[e].e[i];
+    for (int e = 0; e < EPT; ++e) acc[e] = r[e].e[i];
 #pragma unroll
     for (int jp = 0; jp < (HO + 1) / 2; ++jp) {
       const double2 c2 = so.DE2[i * HP + jp];
@@ -269,7 +278,7 @@ __device__ __forceinline__ void fwd_stage_volume(const StageOps& so, const EOVec
   for (int i = 0; i < HO; ++i) {
     double acc[EPT];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) acc[e] = rka * r[e].o[i];
+    for (int e = 0; e < EPT; ++e) acc[e] = r[e].o[i];
 #pragma unroll
     for (int jp = 0; jp < (HE + 1) / 2; ++jp) {
       const double2 c2 = so.DO2[i * HP + jp];
@@ -343,7 +352,7 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
     tA[cx.tid] = 0.5 * (z[0].e[0] + z[0].o[0]);
     tB[cx.tid] = 0.5 * (z[EPT - 1].e[0] - z[EPT - 1].o[0]);
     trace_arrive(cx);
-    fwd_stage_volume<NPX, EPT>(so, z, r, c.rka[s]);   // needs no neighbour data
+    fwd_stage_volume<NPX, EPT>(so, z, r);   // needs no neighbour data
     trace_wait(cx);
     double uL = tB[cx.nbL];
     double uR = tA[cx.nbR];
@@ -359,7 +368,7 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
       if (cx.flags & CX_LAST) uR = uB[EPT - 1];
     }
     double g0[EPT], g1[EPT], bm[EPT];
-    const double rkb = c.rkb[s];
+    const double rkb = c.bsig[s];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const double left = (e == 0) ? uL : uB[e - 1];
@@ -378,7 +387,7 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
 // Carried in the scaled even/odd form (mu = T^-T lu, w = m * T^-T lk):
 //   w += (rkb*m) mu ; G = {LS.we + LA.wo, LS.we - LA.wo} ; gam_f = q_f G_f ;
 //   mu_e += DO^T wo ; mu_o += DE^T we ; a0 = gam0 - gam1[left], aN = gam1 - gam0[right] ;
-//   mu_e[0] += (a0+aN)/2 ; mu_o[0] += (a0-aN)/2 ; w *= rka.
+//   mu_e[0] += (a0+aN)/2 ; mu_o[0] += (a0-aN)/2 ; w *= rka  (the last as a stage scaling, see ConstOps).
 template <int NPX, int LV, int EPT>
 __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __restrict__ tr,
                                          const double* __restrict__ coef, EOVec<NPX> (&mu)[EPT],
@@ -387,8 +396,8 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
   const ConstOps& c = ka.c;
 #pragma unroll 1
   for (int s = ka.p.nstages - 1; s >= 0; --s) {
-    const StageOps& so = c.st[LV][s];
-    const double rkb = c.rkb[s];
+    const StageOps& so = c.sta[s];
+    const double rkb = c.bsga[s];
     double gam0[EPT], gam1[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
@@ -432,7 +441,7 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
     tB[cx.tid] = gam1[EPT - 1];
     trace_arrive(cx);
     // volume part (needs no neighbour data): mu_e += DO^T wo, mu_o += DE^T we (row i of the
-    // block times w[i], accumulated straight into mu), then w *= rka
+    // block times w[i], accumulated straight into mu); the rka scaling of w lives in the blocks
 #pragma unroll
     for (int i = 0; i < HO; ++i) {
 #pragma unroll
@@ -462,14 +471,6 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
           }
         }
       }
-    }
-    const double rka = c.rka[s];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-#pragma unroll
-      for (int i = 0; i < HE; ++i) w[e].e[i] *= rka;
-#pragma unroll
-      for (int i = 0; i < HO; ++i) w[e].o[i] *= rka;
     }
     trace_wait(cx);
     double gam1L = tB[cx.nbL];  // right-face term of the left neighbour
@@ -821,6 +822,8 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
           mbar_expect_tx(&mbar[0], tile_bytes);
           tma_bulk_g2s(land, ck + (size_t)(n - 1) * tile, tile_bytes, &mbar[0]);
         }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) w[e].zero();  // w~ restarts every step (rka[0] = 0)
         adj_step<NPF, 1, EPT>(ka, cx, sm_tr, sm_coef + (size_t)3 * EPT * BD, mu, w);
       }
       if (active) {
