@@ -631,6 +631,7 @@ static void fill_params(dgadj_handle* h, const dgadj_march_args* a, const Launch
   p.tpc = pl.tpc;
   p.ngroups = pl.ngroups;
   p.nstages = h->nstages;
+  p.warp_local = (pl.KT <= 32 && 32 % pl.KT == 0) ? 1 : 0;
   p.bc = h->cfg.bc;
   p.inflow = h->cfg.inflow;
   p.func = h->cfg.functional;

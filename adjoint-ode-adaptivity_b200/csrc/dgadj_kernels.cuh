@@ -60,6 +60,7 @@ struct alignas(16) ConstOps {
 struct MarchParams {
   long long B;
   int K, S, tpc, ngroups, nstages, bc, inflow, func;
+  int warp_local;         // K/EPT divides 32: trajectories never straddle warps
   double alpha, a, dt, t0;
   const double* a_arr;
   const double* dt_arr;
@@ -145,6 +146,7 @@ __device__ __forceinline__ void fence_mbar_init() {
 // per-thread context.  A thread owns EPT adjacent elements of one trajectory.  Everything
 // that is not RK state lives in shared memory or in the constant bank.
 // ---------------------------------------------------------------------------------------
+enum { CX_FIRST = 1, CX_LAST = 2, CX_PERIODIC = 4 };
 struct Ctx {
   int tid, BD, nbL, nbR, par;
   int flags;  // bit0 owns the first element, bit1 owns the last element, bit2 periodic
@@ -159,21 +161,24 @@ struct Ctx {
 // shared memory and *waits* only when it needs its neighbours' -- the volume terms (80 % of a
 // stage) sit in between, so warps rarely block.  DGADJ_SPLIT_BARRIER=0 keeps a plain
 // __syncthreads() at the arrive point (for A/B measurements).
-__device__ __forceinline__ void trace_arrive(Ctx& cx) {
+// warp_local (a kernel parameter, hence uniform): every trajectory lives inside one warp, so
+// __syncwarp alone orders the exchange and the warps of a CTA never wait for one another.
+__device__ __forceinline__ void trace_arrive(Ctx& cx, int warp_local) {
 #if DGADJ_SPLIT_BARRIER
   __syncwarp();
-  if ((cx.tid & 31) == 0) mbar_arrive(cx.trbar);
+  if (!warp_local && (cx.tid & 31) == 0) mbar_arrive(cx.trbar);
 #else
   __syncthreads();
 #endif
 }
-__device__ __forceinline__ void trace_wait(Ctx& cx) {
+__device__ __forceinline__ void trace_wait(Ctx& cx, int warp_local) {
 #if DGADJ_SPLIT_BARRIER
-  mbar_wait(cx.trbar, cx.trphase);
-  cx.trphase ^= 1u;
+  if (!warp_local) {
+    mbar_wait(cx.trbar, cx.trphase);
+    cx.trphase ^= 1u;
+  }
 #endif
 }
-enum { CX_FIRST = 1, CX_LAST = 2, CX_PERIODIC = 4 };
 
 static __device__ __noinline__ double inflow_value(const MarchParams& p, long long b, double time, int n, int s,
                                             double rkc) {
@@ -351,9 +356,9 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
     double* tB = tA + 2 * cx.BD;       // right-edge values u[Np-1] of the thread's last element
     tA[cx.tid] = 0.5 * (z[0].e[0] + z[0].o[0]);
     tB[cx.tid] = 0.5 * (z[EPT - 1].e[0] - z[EPT - 1].o[0]);
-    trace_arrive(cx);
+    trace_arrive(cx, ka.p.warp_local);
     fwd_stage_volume<NPX, EPT>(so, z, r);   // needs no neighbour data
-    trace_wait(cx);
+    trace_wait(cx, ka.p.warp_local);
     double uL = tB[cx.nbL];
     double uR = tA[cx.nbR];
     cx.par ^= 1;
@@ -439,7 +444,7 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
     double* tB = tA + 2 * cx.BD;
     tA[cx.tid] = gam0[0];
     tB[cx.tid] = gam1[EPT - 1];
-    trace_arrive(cx);
+    trace_arrive(cx, ka.p.warp_local);
     // volume part (needs no neighbour data): mu_e += DO^T wo, mu_o += DE^T we (row i of the
     // block times w[i], accumulated straight into mu); the rka scaling of w lives in the blocks
 #pragma unroll
@@ -472,7 +477,7 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
         }
       }
     }
-    trace_wait(cx);
+    trace_wait(cx, ka.p.warp_local);
     double gam1L = tB[cx.nbL];  // right-face term of the left neighbour
     double gam0R = tA[cx.nbR];  // left-face term of the right neighbour
     cx.par ^= 1;
