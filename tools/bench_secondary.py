@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Secondary workloads of SURVEY section 8(d) (not the driver's headline; numbers go to profiles/):
+  sweep   config 4: parameter sweep, N=4, K=64, S=100, per-trajectory speed a and CFL dt
+  burgers config 3: Burgers + SlopeLimitN, N=4, K=256, B=16384, forward + checkpoints
+  tdg     config 5: DG-in-time march + adjoint (u' = sin u), B=4096 ICs, refined mesh
+  fd      config 5: finite-difference path, same ICs
+One JSON line per workload.  CUDA events on the launching stream, 3 warm-ups, best of 5."""
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import dgadj_loader
+
+pkg = dgadj_loader.load_package()
+dev = torch.device("cuda", 0)
+TWO_PI = 2 * math.pi
+
+
+def timeit(fn, warm=3, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def sweep(B=131072):
+    N, K, S = 4, 64, 100
+    s = pkg.AdvecDG1D(N, K, domain=(0.0, TWO_PI), alpha=0.0, bc="periodic")
+    n1 = int(round(math.sqrt(B)))
+    a = torch.linspace(0.5, 2.0, n1, dtype=torch.float64, device=dev) * TWO_PI
+    sig = torch.linspace(0.02, 0.2, B // n1, dtype=torch.float64, device=dev)
+    A, SG = torch.meshgrid(a, sig, indexing="ij")
+    A, SG = A.reshape(-1).contiguous(), SG.reshape(-1).contiguous()
+    B = A.numel()
+    x = torch.tensor(s.g.x, device=dev)[None]
+    u0 = torch.exp(-(x - math.pi) ** 2 / (2 * SG[:, None, None] ** 2)).contiguous()
+    dt0, _ = s.cfl_dt(1.0)
+    dt = (dt0 * TWO_PI / A).contiguous()                      # CFL rule with the trajectory's own speed
+    out = {}
+    ms = timeit(lambda: out.update(s.fwd_adj(u0, A, dt, S, want_uT=False)))
+    sums = s.reduce_indicators(out["eta"], out["J"])
+    ups = 2 * 5 * S * K * B
+    fl = 0.5 * ((2 * 25 + 60 + 6) + (2 * 25 + 60 + 8))
+    peak, _ = s.measure_dfma_peak(0.5)
+    return dict(workload="config 4: parameter sweep N=4 K=64 S=100, 1024 speeds x %d pulse widths per GPU" % (B // n1),
+                metric="DG element-stage updates/s (fwd+adjoint)", value=ups / (ms * 1e-3), ms=ms, B=B,
+                frac_fp64_peak=fl * ups / (ms * 1e-3) / 1e12 / peak, norms=dict(sum_abs_eta=float(sums[K]), max_abs_eta=float(sums[K + 2]), sum_J=float(sums[K + 3])),
+                plan=s.plan(B))
+
+
+def burgers(B=16384):
+    N, K = 4, 256
+    s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc="periodic")
+    g = torch.Generator(device=dev); g.manual_seed(1235)
+    c = torch.rand((B, 1, 1), dtype=torch.float64, device=dev, generator=g) - 0.5
+    A = torch.rand((B, 1, 1), dtype=torch.float64, device=dev, generator=g) + 0.5
+    ph = torch.rand((B, 1, 1), dtype=torch.float64, device=dev, generator=g) * TWO_PI
+    x = torch.tensor(s.g.x, device=dev)[None]
+    u0 = (c + A * torch.sin(math.pi * x + ph)).contiguous()
+    dt = s.stable_dt(2.0)
+    S = 200
+    ms = timeit(lambda: s.forward(u0, dt, S, checkpoints=True), warm=2, reps=3)
+    out = s.forward(u0, dt, S, checkpoints=True)
+    ups = 5 * S * K * B
+    return dict(workload="config 3: Burgers + SlopeLimitN every stage, N=4 K=256 B=%d S=%d, flags + wave-speed checkpoints" % (B, S),
+                metric="DG element-stage updates/s (forward, limited)", value=ups / (ms * 1e-3), ms=ms,
+                limited_fraction=float((out["flags"] != 0).double().mean()), T=S * dt)
+
+
+def tdg_fd(B=4096):
+    rng = np.random.default_rng(0)
+    y0 = torch.tensor(rng.uniform(-3, 3, B), device=dev)
+    times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.05, 1.95, 30))))
+    Ks = times.size - 1
+    Ns = np.ones(Ks, dtype=int)
+    s = pkg.TimeDG()
+    res = {}
+
+    def run():
+        t1, y1, its = s.dg_march(Ns, Ks, times, y0)
+        t2, v, err = s.adj_march(Ns + 1, Ks, times, y1, t1)
+        res.update(its=its)
+    ms = timeit(run)
+    its = res["its"].double()
+    nq = 31
+    r1 = dict(workload="config 5: time-DG march (Newton, u'=sin u) + adjoint + indicator, n=1, Ks=%d, B=%d" % (Ks, B),
+              metric="element-solves/s (forward Newton solve or adjoint solve+indicator)", value=2 * Ks * B / (ms * 1e-3), ms=ms,
+              mean_newton_its=float(its.mean()), sincos_per_s=float((its.sum() * nq + B * Ks * 5) / (ms * 1e-3)),
+              note="ms includes the host-side per-element constant setup (numpy) of both calls")
+    f = pkg.FDAdjoint()
+    ms = timeit(lambda: f.solve(y0, np.diff(times), want=("err_steps", "ref_idx")))
+    n = Ks
+    r2 = dict(workload="config 5: FD path forwardSolve+adjSolve+errEst+windows+argmax, n=%d steps, ref_factor 4, B=%d" % (n, B),
+              metric="fine-step updates/s (fwd step, adjoint step, residual step each count 1)", value=(n + 2 * 4 * n) * B / (ms * 1e-3), ms=ms)
+    Bbig = 1 << 20
+    y0b = torch.tensor(rng.uniform(-3, 3, Bbig), device=dev)
+    ms = timeit(lambda: f.solve(y0b, np.diff(times), want=("err_steps", "ref_idx")))
+    r3 = dict(r2, workload=r2["workload"].replace("B=%d" % B, "B=%d" % Bbig), value=(n + 2 * 4 * n) * Bbig / (ms * 1e-3), ms=ms)
+    return [r1, r2, r3]
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["sweep", "burgers", "tdg_fd"]
+    for w in which:
+        r = dict(sweep=sweep, burgers=burgers, tdg_fd=tdg_fd)[w]()
+        for line in (r if isinstance(r, list) else [r]):
+            print(json.dumps(line), flush=True)
