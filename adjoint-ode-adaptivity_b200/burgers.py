@@ -59,7 +59,8 @@ class BurgersDG1D:
 
     def forward(self, u0, dt, S, limit=True, history=False, checkpoints=False):
         """u0: float64 CUDA tensor [B, Np, K]; dt scalar or CUDA tensor [B].
-        Returns dict(uT[, hist[B,S+1,Np,K]][, flags[B,S,K] uint8, maxvel[B,S,5]])."""
+        Returns dict(uT[, hist[B,S+1,Np,K]][, lim[B,S,K] int16, lim0[B,K] uint8, amax[B,S,5] int32,
+        maxvel[B,S,5]]).  `checkpoints=True` writes everything `adjoint` consumes (incl. hist)."""
         torch = self.torch
         if not (isinstance(u0, torch.Tensor) and u0.is_cuda and u0.dtype == torch.float64):
             raise TypeError("u0 must be a float64 CUDA tensor")
@@ -72,16 +73,59 @@ class BurgersDG1D:
         dt_s, dt_v = (float(dt), None) if np.isscalar(dt) else (0.0, dt.contiguous())
         kw = dict(dtype=torch.float64, device=u0.device)
         out = dict(uT=torch.empty_like(u0))
-        if history:
+        if history or checkpoints:
             out["hist"] = torch.empty((B, S + 1, self.Np, self.K), **kw)
         if checkpoints:
-            out["flags"] = torch.empty((B, S, self.K), dtype=torch.uint8, device=u0.device)
+            out["lim"] = torch.zeros((B, S, self.K), dtype=torch.int16, device=u0.device)
+            out["lim0"] = torch.zeros((B, self.K), dtype=torch.uint8, device=u0.device)
+            out["amax"] = torch.zeros((B, S, 5), dtype=torch.int32, device=u0.device)
             out["maxvel"] = torch.empty((B, S, 5), **kw)
         ptr = lambda k: C.c_void_p(out[k].data_ptr()) if k in out else C.c_void_p(0)
         o = self.ops
         p = lambda a: C.c_void_p(a.ctypes.data)
         self._check(self.lib.dgadj_burgers_forward(
             self._h, B, S, dt_s, C.c_void_p(dt_v.data_ptr()) if dt_v is not None else C.c_void_p(0), int(limit),
-            p(o["invV"]), p(o["V"]), p(o["x"]), C.c_void_p(u0.data_ptr()), ptr("uT"), ptr("hist"), ptr("flags"),
-            ptr("maxvel"), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+            p(o["invV"]), p(o["V"]), p(o["x"]), C.c_void_p(u0.data_ptr()), ptr("uT"), ptr("hist"), ptr("lim"),
+            ptr("lim0"), ptr("amax"), ptr("maxvel"), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        out["dt"], out["S"] = dt, S
         return out
+
+    def adjoint(self, fwd, psi=None):
+        """Discrete adjoint of a `forward(..., checkpoints=True)` run for J = int psi(x) u(x,T) dx
+        (psi = 1 by default): returns dict(lam0[B,Np,K] = dJ/du0, J[B]).  The limiter and the
+        max|u| of the Lax-Friedrichs flux are transposed on the branches the forward run took."""
+        torch = self.torch
+        for k in ("hist", "lim", "lim0", "amax", "maxvel"):
+            if k not in fwd:
+                raise ValueError("adjoint needs a forward run with checkpoints=True")
+        jw = self.g.quad_weights()
+        if psi is not None:
+            jw = jw * psi(self.g.x)
+        jw = np.ascontiguousarray(jw, dtype=np.float64)
+        B, S = fwd["hist"].shape[0], fwd["S"]
+        dt = fwd["dt"]
+        dt_s, dt_v = (float(dt), None) if np.isscalar(dt) else (0.0, dt.contiguous())
+        kw = dict(dtype=torch.float64, device=fwd["hist"].device)
+        lam0 = torch.empty((B, self.Np, self.K), **kw)
+        J = torch.empty(B, **kw)
+        o = self.ops
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        d = lambda t: C.c_void_p(t.data_ptr())
+        self._check(self.lib.dgadj_burgers_adjoint(
+            self._h, B, S, dt_s, d(dt_v) if dt_v is not None else C.c_void_p(0), p(o["invV"]), p(o["V"]), p(o["x"]),
+            p(jw), d(fwd["hist"]), d(fwd["lim"]), d(fwd["lim0"]), d(fwd["amax"]), d(fwd["maxvel"]), d(lam0), d(J),
+            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return dict(lam0=lam0, J=J)
+
+    def slope_limit(self, u):
+        """ulimit = SlopeLimitN(u)  (utils/SlopeLimitN.m:1): one limiter pass, no time steps."""
+        return self.forward(u, 0.0, 0, limit=True)["uT"]
+
+
+def decode_limiter_record(lim):
+    """Packed per-step limiter record [B, S, K] (int16) -> (flags, branches), each [B, S, 5, K]."""
+    l = lim.int() & 0xFFFF
+    st = l.new_tensor(range(5)).view(1, 1, 5, 1)
+    flags = ((l[:, :, None, :] >> st) & 1).bool()
+    branches = (l[:, :, None, :] >> (5 + 2 * st)) & 3
+    return flags, branches

@@ -378,6 +378,7 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->fd_scratch);
   cudaFree(h->tdg_scratch);
   cudaFree(h->bg_scratch);
+  cudaFree(h->bgs_scratch);
   if (h->pipe_init) {
     cudaStreamDestroy(h->s_in);
     cudaStreamDestroy(h->s_k);
@@ -490,6 +491,7 @@ extern "C" int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double*
   int rc = set_level(h, 0, Np, Dr, LIFT, Mref, rx, Fscale);
   if (rc) return rc;
   for (int i = 0; i < Np * Np; ++i) h->Dr_nodal[i] = Dr[i];
+  for (int i = 0; i < Np * 2; ++i) h->LIFT_nodal[i] = LIFT[i];
   h->ops_set = true;
   return DGADJ_OK;
 }
@@ -526,6 +528,12 @@ extern "C" int dgadj_set_functional_weights(dgadj_handle* h, const double* jw_c,
   if (rc) return rc;
   h->jw_set = true;
   return DGADJ_OK;
+}
+
+// primal-space weights only (Burgers adjoint: J = sum jw o u(T) on the handle's own space)
+int dgadj_set_functional_weights_level0(dgadj_handle* h, const double* jw_c) {
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  return upload(h, &h->d_jwc, jw_c, (size_t)h->Np * h->K);
 }
 
 extern "C" int dgadj_set_inflow_table(dgadj_handle* h, int n, const double* uin) {

@@ -32,8 +32,18 @@ struct BurgersArgs {
   const double* u0;    // [B][NP][K]
   double* uT;          // [B][NP][K]
   double* hist;        // [B][S+1][NP][K] or null
-  unsigned char* flags;  // [B][S][K] bit s = limited after stage s, or null
+  unsigned short* lim;   // [B][S][K] bits 0-4: limited after stage s; bits 5+2s..6+2s: winning
+                         // minmod argument (0 = slope zero, 1 = ux, 2 = (v+ - v)/h, 3 = (v - v-)/h)
+  unsigned char* lim0;   // [B][K] same code for the limiter pass on the initial state (bit 0, bits 1-2)
+  int* amax;             // [B][S][5] flat index i*K+k of max|u| per stage, +1, negated if u < 0
   double* maxvel;      // [B][S][5] or null
+  // adjoint sweep
+  const double* jw;      // [NP][K] weights of J = sum jw o u(T)
+  double* lam0;          // [B][NP][K] dJ/du0
+  double* Jout;          // [B]
+  double* stage_scratch; // [grid][5][NP+2][blockDim] stage input states + neighbour traces
+  double Dr[MAXNP * MAXNP];  // nodal Dr (adjoint volume term)
+  double LIFT[MAXNP * 2];
   StageOps so;
   double aw[MAXNP];    // cell average weights  V(1,1)*invV(1,:)
   double sl[MAXNP];    // slope weights         Dr(1,:)*V(:,1:2)*invV(1:2,:)
@@ -48,11 +58,36 @@ __device__ __forceinline__ double minmod3(double a, double b, double c) {
   return 0.0;
 }
 
+// minmod of three with the index (1..3) of the winning argument; 0 when the result is zero
+__device__ __forceinline__ double minmod3b(double a, double b, double c, int* br) {
+  const double sa = (a > 0.0) - (a < 0.0), sb = (b > 0.0) - (b < 0.0), sc = (c > 0.0) - (c < 0.0);
+  const double s = (sa + sb + sc) / 3.0;
+  *br = 0;
+  if (fabs(s) != 1.0) return 0.0;
+  const double fa = fabs(a), fb = fabs(b), fc = fabs(c);
+  double m = fa;
+  int w = 1;
+  if (fb < m) { m = fb; w = 2; }
+  if (fc < m) { m = fc; w = 3; }
+  *br = w;
+  return s * m;
+}
+
+// CTA-wide max|u| with the flat index (i*K + k) of its first occurrence in row-major order
+struct MaxLoc {
+  double v;
+  int idx;
+};
+__device__ __forceinline__ MaxLoc maxloc_better(MaxLoc a, MaxLoc b) {
+  return (b.v > a.v || (b.v == a.v && b.idx < a.idx)) ? b : a;
+}
+
 template <int NP, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant__ BurgersArgs p) {
   constexpr int HE = (NP + 1) / 2, HO = NP / 2;
   __shared__ double trL[2][MAXT], trR[2][MAXT], avg[MAXT];
   __shared__ double wmax[2][32];
+  __shared__ int widx[2][32];
   const int tid = threadIdx.x, K = p.K;
   const int lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
   const bool in = tid < K;
@@ -72,7 +107,7 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
       res[i] = 0.0;
     }
     int par = 0;
-    // limiter applied to the element's current state; returns 1 if the cell was limited
+    // limiter applied to the element's current state; returns flag | branch << 1
     auto limiter = [&]() -> int {
       double v = 0.0;
 #pragma unroll
@@ -94,12 +129,16 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
 #pragma unroll
       for (int i = 0; i < NP; ++i) d = fma(p.sl[i], u[i], d);
       const double ux = (2.0 / h) * d;
-      const double slope = minmod3(ux, (vp - v) / h, (v - vm) / h);
+      int br;
+      const double slope = minmod3b(ux, (vp - v) / h, (v - vm) / h, &br);
 #pragma unroll
       for (int i = 0; i < NP; ++i) u[i] = v + p.xc[(size_t)i * K + k] * slope;
-      return 1;
+      return 1 | (br << 1);
     };
-    if (p.limit) limiter();
+    {
+      const int c0 = p.limit ? limiter() : 0;
+      if (p.lim0 && in) p.lim0[(size_t)b * K + k] = (unsigned char)c0;
+    }
     double* hist = (p.hist && in) ? p.hist + ((size_t)b * (p.S + 1) * NP) * K + k : nullptr;
     if (hist) {
 #pragma unroll
@@ -110,17 +149,33 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
 #pragma unroll 1
       for (int s = 0; s < 5; ++s) {
         // ---- exchange 1: traces and the mesh-wide max|u|
-        double m = 0.0;
+        MaxLoc m = {-1.0, 0x7fffffff};
+        if (in) {
 #pragma unroll
-        for (int i = 0; i < NP; ++i) m = fmax(m, fabs(u[i]));
+          for (int i = 0; i < NP; ++i) m = maxloc_better(m, MaxLoc{fabs(u[i]), i * K + k});
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        for (int o = 16; o > 0; o >>= 1) {
+          MaxLoc t = {__shfl_xor_sync(0xffffffffu, m.v, o), __shfl_xor_sync(0xffffffffu, m.idx, o)};
+          m = maxloc_better(m, t);
+        }
         trL[par][tid] = u[0];
         trR[par][tid] = u[NP - 1];
-        if (lane == 0) wmax[par][wid] = m;
+        if (lane == 0) {
+          wmax[par][wid] = m.v;
+          widx[par][wid] = m.idx;
+        }
         __syncthreads();
-        double maxvel = 0.0;
-        for (int w = 0; w < nw; ++w) maxvel = fmax(maxvel, wmax[par][w]);
+        MaxLoc best = {-1.0, 0x7fffffff};
+        for (int w = 0; w < nw; ++w) best = maxloc_better(best, MaxLoc{wmax[par][w], widx[par][w]});
+        const double maxvel = best.v;
+        if (p.amax && in && (best.idx % K) == k) {
+          const int i = best.idx / K;
+          double ui = 0.0;
+#pragma unroll
+          for (int q = 0; q < NP; ++q) ui = (q == i) ? u[q] : ui;
+          p.amax[((size_t)b * p.S + n) * 5 + s] = (ui < 0.0) ? -(best.idx + 1) : (best.idx + 1);
+        }
         double uL = trR[par][nbL], uR = trL[par][nbR];
         par ^= 1;
         if (!p.periodic) {
@@ -177,9 +232,12 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < NP; ++i) u[i] = fma(rkb, res[i], u[i]);
         // ---- exchange 2: cell averages, limiter
-        if (p.limit) fl |= (unsigned)limiter() << s;
+        if (p.limit) {
+          const int c = limiter();
+          fl |= (unsigned)(c & 1) << s | (unsigned)(c >> 1) << (5 + 2 * s);
+        }
       }
-      if (p.flags && in) p.flags[((size_t)b * p.S + n) * K + k] = (unsigned char)fl;
+      if (p.lim && in) p.lim[((size_t)b * p.S + n) * K + k] = (unsigned short)fl;
       if (hist) {
         double* hn = hist + (size_t)(n + 1) * NP * K;
 #pragma unroll
@@ -194,6 +252,262 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Discrete adjoint of the limited Burgers march (oracle/burgers.py: burgers_adjoint).  Per step,
+// backwards: the five stage input states are recomputed from the checkpoint u^n with the
+// *recorded* limiter decisions and wave speeds (so they are the forward run's states, bit for
+// bit) and parked in a per-CTA scratch (L2 resident); then the stages are transposed in
+// reverse: limiter^T (frozen flags / minmod branches), lk += rkb lu, lu += dt (dR/du)^T lk
+// including the rank-one term through C = max|u|, lk *= rka.
+// ---------------------------------------------------------------------------------------
+template <int NP, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) burgers_adjoint_kernel(const __grid_constant__ BurgersArgs p) {
+  constexpr int HE = (NP + 1) / 2, HO = NP / 2;
+  __shared__ double exA[2][MAXT], exB[2][MAXT];
+  __shared__ double wsum[2][32];
+  const int tid = threadIdx.x, K = p.K, BD = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = (BD + 31) >> 5;
+  const bool in = tid < K;
+  const int k = in ? tid : 0;
+  const int nbL = in ? (tid == 0 ? K - 1 : tid - 1) : tid;
+  const int nbR = in ? (tid == K - 1 ? 0 : tid + 1) : tid;
+  const bool first = in && tid == 0, last = in && tid == K - 1;
+  const double rx = in ? p.rxk[k] : 0.0, fs0 = in ? p.fs0[k] : 0.0, fs1 = in ? p.fs1[k] : 0.0;
+  const double h = in ? p.hk[k] : 1.0;
+  double* ss = p.stage_scratch + (size_t)blockIdx.x * 5 * (NP + 2) * BD + tid;
+  int par = 0;
+  auto block_sum = [&](double v) -> double {   // deterministic: shuffle tree, then warps in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) wsum[0][wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += wsum[0][w];
+    return t;
+  };
+
+  for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const double dt = p.dt_arr ? p.dt_arr[b] : p.dt;
+    double lu[NP], lk[NP];
+    {
+      double jp = 0.0;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        lu[i] = in ? p.jw[(size_t)i * K + k] : 0.0;
+        lk[i] = 0.0;
+        const double uT = in ? p.hist[(((size_t)b * (p.S + 1) + p.S) * NP + i) * K + k] : 0.0;
+        jp = fma(lu[i], uT, jp);
+      }
+      const double J = block_sum(jp);
+      if (p.Jout && tid == 0) p.Jout[b] = J;
+    }
+    // limiter^T with a frozen decision code (flag | branch << 1)
+    auto limiter_T = [&](int code) {
+      const int flag = code & 1, br = code >> 1;
+      double a = 0.0, c = 0.0;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        a += lu[i];
+        c = fma(in ? p.xc[(size_t)i * K + k] : 0.0, lu[i], c);
+      }
+      const double ch = c / h;
+      const double tr = (br == 2) ? ch : 0.0, tl = (br == 3) ? -ch : 0.0;
+      __syncthreads();
+      exA[0][tid] = tr;   // goes to cell k+1
+      exB[0][tid] = tl;   // goes to cell k-1
+      __syncthreads();
+      double fromL = exA[0][nbL], fromR = exB[0][nbR];
+      if (!p.periodic) {   // end cells see a copied ghost average: the term comes back to the cell
+        if (first) fromL = 0.0;
+        if (last) fromR = 0.0;
+        if (last) fromL += tr;
+        if (first) fromR += tl;
+      }
+      double lv = (flag ? a : 0.0) + ((br == 2) ? -ch : ((br == 3) ? ch : 0.0)) + fromL + fromR;
+      const double cs = (br == 1) ? (2.0 / h) * c : 0.0;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) lu[i] = (flag ? 0.0 : lu[i]) + p.aw[i] * lv + p.sl[i] * cs;
+    };
+
+    for (int n = p.S - 1; n >= 0; --n) {
+      const unsigned code = in ? (unsigned)p.lim[((size_t)b * p.S + n) * K + k] : 0u;
+      // ---- recompute the stage input states of step n
+      {
+        double u[NP], res[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          u[i] = in ? p.hist[(((size_t)b * (p.S + 1) + n) * NP + i) * K + k] : 0.0;
+          res[i] = 0.0;
+        }
+#pragma unroll 1
+        for (int s = 0; s < 5; ++s) {
+          __syncthreads();
+          exA[par][tid] = u[0];
+          exB[par][tid] = u[NP - 1];
+          __syncthreads();
+          double uL = exB[par][nbL], uR = exA[par][nbR];
+          par ^= 1;
+          if (!p.periodic) {
+            if (first) uL = u[0];
+            if (last) uR = u[NP - 1];
+          }
+#pragma unroll
+          for (int i = 0; i < NP; ++i) ss[(size_t)(s * (NP + 2) + i) * BD] = u[i];
+          ss[(size_t)(s * (NP + 2) + NP) * BD] = uL;
+          ss[(size_t)(s * (NP + 2) + NP + 1) * BD] = uR;
+          if (s == 4) break;   // the state after the last stage is u^{n+1}: not needed
+          const double maxvel = p.maxvel[((size_t)b * p.S + n) * 5 + s];
+          const double g0 = fs0 * (-((u[0] * u[0] - uL * uL) / 2.0) / 2.0 - maxvel / 2.0 * (u[0] - uL));
+          const double g1 = fs1 * (((u[NP - 1] * u[NP - 1] - uR * uR) / 2.0) / 2.0 - maxvel / 2.0 * (u[NP - 1] - uR));
+          const double ge = g0 + g1, go = g0 - g1;
+          double fe[HE], fo[HO > 0 ? HO : 1];
+#pragma unroll
+          for (int i = 0; i < NP / 2; ++i) {
+            const double a = u[i] * u[i] / 2.0, c = u[NP - 1 - i] * u[NP - 1 - i] / 2.0;
+            fe[i] = a + c;
+            fo[i] = a - c;
+          }
+          if (NP & 1) fe[NP / 2] = u[NP / 2] * u[NP / 2] / 2.0;
+          const double rka = p.rka[s], rkb = p.rkb[s];
+          double E[HE], O[HO > 0 ? HO : 1];
+#pragma unroll
+          for (int i = 0; i < HE; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < HO; ++j) {
+              const double2 c2 = p.so.DE2[i * HP + j / 2];
+              acc = fma((j & 1) ? c2.y : c2.x, fo[j], acc);
+            }
+            const double2 l2 = p.so.LS2[i / 2];
+            E[i] = fma(-rx, acc, ((i & 1) ? l2.y : l2.x) * ge);
+          }
+#pragma unroll
+          for (int i = 0; i < HO; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < HE; ++j) {
+              const double2 c2 = p.so.DO2[i * HP + j / 2];
+              acc = fma((j & 1) ? c2.y : c2.x, fe[j], acc);
+            }
+            const double2 l2 = p.so.LA2[i / 2];
+            O[i] = fma(-rx, acc, ((i & 1) ? l2.y : l2.x) * go);
+          }
+#pragma unroll
+          for (int i = 0; i < NP / 2; ++i) {
+            const double r0 = 0.5 * (E[i] + O[i]), r1 = 0.5 * (E[i] - O[i]);
+            res[i] = fma(rka, res[i], dt * r0);
+            res[NP - 1 - i] = fma(rka, res[NP - 1 - i], dt * r1);
+          }
+          if (NP & 1) res[NP / 2] = fma(rka, res[NP / 2], dt * E[NP / 2]);
+#pragma unroll
+          for (int i = 0; i < NP; ++i) u[i] = fma(rkb, res[i], u[i]);
+          // limiter with the recorded decision
+          const int flag = (code >> s) & 1, br = (code >> (5 + 2 * s)) & 3;
+          double v = 0.0;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) v = fma(p.aw[i], u[i], v);
+          __syncthreads();
+          exA[par][tid] = v;
+          __syncthreads();
+          double vm = exA[par][nbL], vp = exA[par][nbR];
+          par ^= 1;
+          if (!p.periodic) {
+            if (first) vm = v;
+            if (last) vp = v;
+          }
+          if (flag) {
+            double d = 0.0;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) d = fma(p.sl[i], u[i], d);
+            const double slope = (br == 1) ? (2.0 / h) * d : ((br == 2) ? (vp - v) / h : ((br == 3) ? (v - vm) / h : 0.0));
+#pragma unroll
+            for (int i = 0; i < NP; ++i) u[i] = v + p.xc[(size_t)i * K + k] * slope;
+          }
+        }
+      }
+      // ---- transpose the stages in reverse
+#pragma unroll 1
+      for (int s = 4; s >= 0; --s) {
+        limiter_T((int)(((code >> s) & 1u) | (((code >> (5 + 2 * s)) & 3u) << 1)));
+        const double rka = p.rka[s], rkb = p.rkb[s];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) lk[i] = fma(rkb, lu[i], lk[i]);
+        double us[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) us[i] = ss[(size_t)(s * (NP + 2) + i) * BD];
+        const double uL = ss[(size_t)(s * (NP + 2) + NP) * BD], uR = ss[(size_t)(s * (NP + 2) + NP + 1) * BD];
+        const double mv = p.maxvel[((size_t)b * p.S + n) * 5 + s];
+        double G0 = 0.0, G1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          G0 = fma(p.LIFT[i * 2], lk[i], G0);
+          G1 = fma(p.LIFT[i * 2 + 1], lk[i], G1);
+        }
+        G0 *= fs0;
+        G1 *= fs1;
+        const double d0m = (-us[0] / 2.0 - mv / 2.0) * G0, d0p = (uL / 2.0 + mv / 2.0) * G0;
+        const double d1m = (us[NP - 1] / 2.0 - mv / 2.0) * G1, d1p = (-uR / 2.0 + mv / 2.0) * G1;
+        double gam = in ? G0 * (-(us[0] - uL) / 2.0) + G1 * (-(us[NP - 1] - uR) / 2.0) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gam += __shfl_xor_sync(0xffffffffu, gam, o);
+        __syncthreads();
+        exA[par][tid] = d0p;   // belongs to the left neighbour's last node
+        exB[par][tid] = d1p;   // belongs to the right neighbour's first node
+        if (lane == 0) wsum[1][wid] = gam;
+        __syncthreads();
+        double toN = exA[par][nbR], to0 = exB[par][nbL];
+        par ^= 1;
+        if (!p.periodic) {   // ghost = own trace
+          if (last) toN = d1p;
+          if (first) to0 = d0p;
+        }
+        gam = 0.0;
+        for (int w = 0; w < nw; ++w) gam += wsum[1][w];
+        double out[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) acc = fma(p.Dr[i * NP + j], -rx * lk[i], acc);
+          out[j] = us[j] * acc;
+        }
+        out[0] += d0m + to0;
+        out[NP - 1] += d1m + toN;
+        const int am = p.amax[((size_t)b * p.S + n) * 5 + s];
+        const int flat = (am < 0 ? -am : am) - 1;
+        if (in && (flat % K) == k) {
+          const int ii = flat / K;
+          const double add = gam * (am < 0 ? -1.0 : 1.0);
+#pragma unroll
+          for (int q = 0; q < NP; ++q) out[q] += (q == ii) ? add : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          lu[i] = fma(dt, out[i], lu[i]);
+          lk[i] *= rka;
+        }
+      }
+    }
+    limiter_T(in ? (int)p.lim0[(size_t)b * K + k] : 0);
+    if (p.lam0 && in) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) p.lam0[((size_t)b * NP + i) * K + k] = lu[i];
+    }
+    __syncthreads();
+  }
+}
+
+template <int NP>
+static cudaError_t burgers_adjoint_launch(int grid, int block, cudaStream_t st, const BurgersArgs& a) {
+  if (block <= 256)
+    burgers_adjoint_kernel<NP, 256><<<grid, block, 0, st>>>(a);
+  else
+    burgers_adjoint_kernel<NP, 1024><<<grid, block, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <int NP>
 static cudaError_t burgers_launch(int grid, int block, cudaStream_t st, const BurgersArgs& a) {
   if (block <= 256)
@@ -205,19 +519,12 @@ static cudaError_t burgers_launch(int grid, int block, cudaStream_t st, const Bu
 
 }  // namespace dgadj
 
-extern "C" int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, double dt, const double* dt_dev,
-                                     int32_t limit, const double* invV_host, const double* V_host,
-                                     const double* x_host, const double* u0_dev, double* uT_dev,
-                                     double* hist_dev, uint8_t* flags_dev, double* maxvel_dev, void* stream) {
-  if (!h) return DGADJ_ERR_INVALID;
-  if (B <= 0 || S < 0 || !u0_dev) return fail(h, DGADJ_ERR_INVALID, "bad burgers arguments");
-  if (!h->ops_set) return fail(h, DGADJ_ERR_STATE, "dgadj_set_operators has not been called");
-  if (limit && (!invV_host || !V_host || !x_host)) return fail(h, DGADJ_ERR_INVALID, "the limiter needs V, invV and x");
-  if (h->nstages != 5) return fail(h, DGADJ_ERR_UNSUPPORTED, "the Burgers march is LSERK4 only");
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  cudaStream_t st = (cudaStream_t)stream;
+int dgadj_set_functional_weights_level0(dgadj_handle* h, const double* jw_c);
+
+static int burgers_setup(dgadj_handle* h, BurgersArgs& a, int64_t B, int32_t S, double dt, const double* dt_dev,
+                         int limit, const double* invV_host, const double* V_host, const double* x_host,
+                         cudaStream_t st) {
   const int Np = h->Np, K = h->K;
-  BurgersArgs a;
   memset(&a, 0, sizeof(a));
   a.B = B;
   a.K = K;
@@ -229,27 +536,24 @@ extern "C" int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, doub
   a.rxk = h->d_mesh[0][0];
   a.fs0 = h->d_mesh[0][1];
   a.fs1 = h->d_mesh[0][2];
-  a.u0 = u0_dev;
-  a.uT = uT_dev;
-  a.hist = hist_dev;
-  a.flags = flags_dev;
-  a.maxvel = maxvel_dev;
   a.so = h->base_ops[0];
   for (int s = 0; s < 5; ++s) {
     a.rka[s] = h->cops.rka[s];
     a.rkb[s] = h->cops.rkb[s];
   }
+  for (int i = 0; i < Np * Np; ++i) a.Dr[i] = h->Dr_nodal[i];
+  for (int i = 0; i < Np * 2; ++i) a.LIFT[i] = h->LIFT_nodal[i];
+  // aw = V(1,1)*invV(1,:) (SlopeLimitN.m:9);  sl = Dr(1,:)*V(:,1:2)*invV(1:2,:) (SlopeLimitN.m:27,
+  // SlopeLimitLin.m:16);  xc = x - x0, h = x(Np,:) - x(1,:) (SlopeLimitLin.m:10-12)
+  std::vector<double> xc((size_t)Np * K, 0.0), hk(K, 1.0);
   if (limit) {
-    // aw = V(1,1)*invV(1,:) (SlopeLimitN.m:9);  sl = Dr(1,:)*V(:,1:2)*invV(1:2,:) (SlopeLimitN.m:27,
-    // SlopeLimitLin.m:16);  xc = x - x0, h = x(Np,:) - x(1,:) (SlopeLimitLin.m:10-12)
-    std::vector<double> xc((size_t)Np * K), hk(K);
     for (int i = 0; i < Np; ++i) a.aw[i] = V_host[0] * invV_host[i];
     const double* Dr = h->Dr_nodal;
     for (int i = 0; i < Np; ++i) {
-      double s = 0.0;
+      double sum = 0.0;
       for (int j = 0; j < Np; ++j)
-        s += Dr[j] * (V_host[(size_t)j * Np + 0] * invV_host[0 * Np + i] + (Np > 1 ? V_host[(size_t)j * Np + 1] * invV_host[1 * Np + i] : 0.0));
-      a.sl[i] = s;
+        sum += Dr[j] * (V_host[(size_t)j * Np + 0] * invV_host[0 * Np + i] + V_host[(size_t)j * Np + 1] * invV_host[1 * Np + i]);
+      a.sl[i] = sum;
     }
     for (int k = 0; k < K; ++k) {
       const double hh = x_host[(size_t)(Np - 1) * K + k] - x_host[k];
@@ -257,24 +561,47 @@ extern "C" int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, doub
       hk[k] = hh;
       for (int i = 0; i < Np; ++i) xc[(size_t)i * K + k] = x_host[(size_t)i * K + k] - x0;
     }
-    const size_t need = ((size_t)Np * K + K) * sizeof(double);
-    if (need > h->bg_bytes) {
-      CUDA_TRY(h, cudaDeviceSynchronize());
-      cudaFree(h->bg_scratch);
-      h->bg_scratch = nullptr;
-      h->bg_bytes = 0;
-      CUDA_TRY(h, cudaMalloc((void**)&h->bg_scratch, need));
-      h->bg_bytes = need;
-    }
-    CUDA_TRY(h, cudaMemcpyAsync(h->bg_scratch, xc.data(), (size_t)Np * K * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(h, cudaMemcpyAsync(h->bg_scratch + (size_t)Np * K, hk.data(), K * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(h, cudaStreamSynchronize(st));
-    a.xc = h->bg_scratch;
-    a.hk = h->bg_scratch + (size_t)Np * K;
-  } else {
-    a.xc = h->d_mesh[0][0];  // never read
-    a.hk = h->d_mesh[0][0];
   }
+  const size_t need = ((size_t)Np * K + K) * sizeof(double);
+  if (need > h->bg_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->bg_scratch);
+    h->bg_scratch = nullptr;
+    h->bg_bytes = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->bg_scratch, need));
+    h->bg_bytes = need;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->bg_scratch, xc.data(), (size_t)Np * K * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(h->bg_scratch + (size_t)Np * K, hk.data(), K * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  a.xc = h->bg_scratch;
+  a.hk = h->bg_scratch + (size_t)Np * K;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, double dt, const double* dt_dev,
+                                     int32_t limit, const double* invV_host, const double* V_host,
+                                     const double* x_host, const double* u0_dev, double* uT_dev,
+                                     double* hist_dev, uint16_t* lim_dev, uint8_t* lim0_dev, int32_t* amax_dev,
+                                     double* maxvel_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || S < 0 || !u0_dev) return fail(h, DGADJ_ERR_INVALID, "bad burgers arguments");
+  if (!h->ops_set) return fail(h, DGADJ_ERR_STATE, "dgadj_set_operators has not been called");
+  if (limit && (!invV_host || !V_host || !x_host)) return fail(h, DGADJ_ERR_INVALID, "the limiter needs V, invV and x");
+  if (h->nstages != 5) return fail(h, DGADJ_ERR_UNSUPPORTED, "the Burgers march is LSERK4 only");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Np = h->Np, K = h->K;
+  BurgersArgs a;
+  int rc = burgers_setup(h, a, B, S, dt, dt_dev, limit, invV_host, V_host, x_host, st);
+  if (rc) return rc;
+  a.u0 = u0_dev;
+  a.uT = uT_dev;
+  a.hist = hist_dev;
+  a.lim = lim_dev;
+  a.lim0 = lim0_dev;
+  a.amax = amax_dev;
+  a.maxvel = maxvel_dev;
   const int block = (K + 31) / 32 * 32;
   const int per_sm = std::max(1, std::min(16, (block <= 256 ? 2048 : 1024) / block));
   const int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count * per_sm);
@@ -286,6 +613,57 @@ extern "C" int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, doub
   }
 #undef DGADJ_BG
   if (e != cudaSuccess) return fail(h, DGADJ_ERR_CUDA, "burgers kernel launch failed: %s", cudaGetErrorString(e));
+  h->launches++;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_burgers_adjoint(dgadj_handle* h, int64_t B, int32_t S, double dt, const double* dt_dev,
+                                     const double* invV_host, const double* V_host, const double* x_host,
+                                     const double* jw_host, const double* hist_dev, const uint16_t* lim_dev,
+                                     const uint8_t* lim0_dev, const int32_t* amax_dev, const double* maxvel_dev,
+                                     double* lam0_dev, double* J_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || S < 0 || !jw_host || !hist_dev || !lim_dev || !lim0_dev || !amax_dev || !maxvel_dev)
+    return fail(h, DGADJ_ERR_INVALID, "bad burgers_adjoint arguments (the forward checkpoints are all required)");
+  if (!h->ops_set) return fail(h, DGADJ_ERR_STATE, "dgadj_set_operators has not been called");
+  if (!invV_host || !V_host || !x_host) return fail(h, DGADJ_ERR_INVALID, "the limiter needs V, invV and x");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Np = h->Np, K = h->K;
+  BurgersArgs a;
+  int rc = burgers_setup(h, a, B, S, dt, dt_dev, 1, invV_host, V_host, x_host, st);
+  if (rc) return rc;
+  rc = dgadj_set_functional_weights_level0(h, jw_host);
+  if (rc) return rc;
+  a.jw = h->d_jwc;
+  a.hist = const_cast<double*>(hist_dev);
+  a.lim = const_cast<uint16_t*>(lim_dev);
+  a.lim0 = const_cast<uint8_t*>(lim0_dev);
+  a.amax = const_cast<int32_t*>(amax_dev);
+  a.maxvel = const_cast<double*>(maxvel_dev);
+  a.lam0 = lam0_dev;
+  a.Jout = J_dev;
+  const int block = (K + 31) / 32 * 32;
+  const int per_sm = std::max(1, std::min(16, (block <= 256 ? 2048 : 1024) / block));
+  const int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count * per_sm);
+  const size_t need = (size_t)grid * 5 * (Np + 2) * block * sizeof(double);
+  if (need > h->bgs_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->bgs_scratch);
+    h->bgs_scratch = nullptr;
+    h->bgs_bytes = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->bgs_scratch, need));
+    h->bgs_bytes = need;
+  }
+  a.stage_scratch = h->bgs_scratch;
+  cudaError_t e = cudaSuccess;
+#define DGADJ_BGA(n) case n: e = burgers_adjoint_launch<n>(grid, block, st, a); break;
+  switch (Np) {
+    DGADJ_BGA(2) DGADJ_BGA(3) DGADJ_BGA(4) DGADJ_BGA(5) DGADJ_BGA(6) DGADJ_BGA(7) DGADJ_BGA(8) DGADJ_BGA(9)
+    default: return fail(h, DGADJ_ERR_UNSUPPORTED, "Burgers adjoint supports 1 <= N <= 8");
+  }
+#undef DGADJ_BGA
+  if (e != cudaSuccess) return fail(h, DGADJ_ERR_CUDA, "burgers adjoint launch failed: %s", cudaGetErrorString(e));
   h->launches++;
   return DGADJ_OK;
 }

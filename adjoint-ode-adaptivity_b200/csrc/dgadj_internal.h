@@ -41,7 +41,10 @@ struct dgadj_handle {
   size_t tdg_bytes;
   double* bg_scratch;   // dgadj_burgers_forward: limiter geometry
   size_t bg_bytes;
-  double Dr_nodal[MAXNP * MAXNP];  // host copy of the primal nodal Dr
+  double* bgs_scratch;  // dgadj_burgers_adjoint: per-CTA stage states
+  size_t bgs_bytes;
+  double Dr_nodal[MAXNP * MAXNP];  // host copies of the primal nodal Dr / LIFT
+  double LIFT_nodal[MAXNP * 2];
   int sm_count, cc_major, cc_minor;
   size_t total_mem;
   int tune_ept, tune_block, tune_grid;

@@ -204,15 +204,28 @@ int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal,
 /* Inviscid Burgers forward march (LSERK4) with SlopeLimitN (utils/SlopeLimitN.m:9-32,
  * SlopeLimitLin.m:10-18, minmod.m:6-12) applied to the initial state and after every stage,
  * on the handle's primal operators (dgadj_set_operators) and boundary type (periodic, or
- * zero-jump ends); writes the forward checkpoints an adjoint needs.  The reference has no
+ * zero-jump ends); writes the forward checkpoints the adjoint needs.  The reference has no
  * Burgers right-hand side: it is build-specified (local Lax-Friedrichs).
  *   V_host / invV_host [Np*Np], x_host [Np*K]: StartUp1D arrays the limiter uses;
- *   u0_dev[B][Np][K] -> uT_dev; hist_dev[B][S+1][Np][K], flags_dev[B][S][K] (bit s = cell
- *   limited after stage s), maxvel_dev[B][S][5] (max|u| per stage): each may be NULL.       */
+ *   u0_dev[B][Np][K] -> uT_dev; checkpoints (each may be NULL): hist_dev[B][S+1][Np][K] states,
+ *   lim_dev[B][S][K] uint16 (bits 0-4: cell limited after stage s; bits 5+2s, 6+2s: winning
+ *   minmod argument), lim0_dev[B][K] uint8 (same code for the pass on the initial state),
+ *   amax_dev[B][S][5] int32 (+-(flat index + 1) of max|u| per stage, sign of u there),
+ *   maxvel_dev[B][S][5] (max|u| per stage).                                               */
 int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, double dt, const double* dt_dev,
                           int32_t limit, const double* invV_host, const double* V_host,
                           const double* x_host, const double* u0_dev, double* uT_dev,
-                          double* hist_dev, uint8_t* flags_dev, double* maxvel_dev, void* stream);
+                          double* hist_dev, uint16_t* lim_dev, uint8_t* lim0_dev, int32_t* amax_dev,
+                          double* maxvel_dev, void* stream);
+
+/* Discrete adjoint of that march for J = sum jw o u(T) (jw_host[Np*K]): the limiter and
+ * max|u| are transposed on the branches the forward run recorded (hard
+ * part 5).  Consumes all five checkpoint arrays -> lam0_dev[B][Np][K] = dJ/du0, J_dev[B].   */
+int dgadj_burgers_adjoint(dgadj_handle* h, int64_t B, int32_t S, double dt, const double* dt_dev,
+                          const double* invV_host, const double* V_host, const double* x_host,
+                          const double* jw_host, const double* hist_dev, const uint16_t* lim_dev,
+                          const uint8_t* lim0_dev, const int32_t* amax_dev, const double* maxvel_dev,
+                          double* lam0_dev, double* J_dev, void* stream);
 
 /* Register-only DFMA microbenchmark: sustained fp64 FMA-pipe peak of the handle's device
  * in TFLOP/s (the roofline denominator SURVEY section 8(d) asks to be measured).        */

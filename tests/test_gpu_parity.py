@@ -506,8 +506,8 @@ def test_burgers_limited_march(pkg, torch, N, K, bc):
     S = min(S, 400)
     ref, hist_r, flags_r, mv_r = ob.burgers_march(u0, g, dt, S, bc="periodic" if bc == "periodic" else "free", history=True)
     out = s.forward(torch.tensor(u0, device="cuda"), dt, S, history=True, checkpoints=True)
-    flags = out["flags"].cpu().numpy()              # [B, S, K] bitmask over stages
-    bits = np.stack([(flags >> st) & 1 for st in range(5)], axis=0).astype(bool)     # [5, B, S, K]
+    flags, _ = pkg.decode_limiter_record(out["lim"])                                  # [B, S, 5, K]
+    bits = np.moveaxis(flags.cpu().numpy(), 2, 0)                                     # [5, B, S, K]
     fr = np.moveaxis(flags_r, (0, 1, 2), (2, 0, 1))                                   # [S,5,B,K] -> [5,B,S,K]
     mism = np.mean(bits != fr)
     assert fr.any()
@@ -519,3 +519,55 @@ def test_burgers_limited_march(pkg, torch, N, K, bc):
     ref2, _, _, _ = ob.burgers_march(u0, g, dt, 20, bc="periodic" if bc == "periodic" else "free", limit=False)
     out2 = s.forward(torch.tensor(u0, device="cuda"), dt, 20, limit=False)
     assert rel(out2["uT"].cpu().numpy(), ref2) < 1e-12
+
+
+@pytest.mark.parametrize("N,K,bc", [(4, 64, "periodic"), (3, 33, "free"), (2, 256, "periodic")])
+def test_burgers_discrete_adjoint(pkg, torch, N, K, bc):
+    """dgadj_burgers_adjoint vs the oracle's frozen-branch discrete adjoint (post-shock, with
+    limited cells), the recorded branches / argmax vs the oracle's, a finite-difference check
+    of dJ/du0, and SlopeLimitN as a stand-alone call."""
+    from oracle import burgers as ob
+    from oracle import limiter as ol
+    s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc=bc)
+    g = oracle_view(s.g)
+    B = 6
+    rng = np.random.default_rng(N + K)
+    c, A, ph = rng.uniform(-0.3, 0.3, (B, 1, 1)), rng.uniform(0.6, 1.2, (B, 1, 1)), rng.uniform(0, 2 * np.pi, (B, 1, 1))
+    u0 = c + A * np.sin(np.pi * g.x[None] + ph)
+    dt = s.stable_dt(1.6)
+    S = min(int(np.ceil(0.45 / dt)), 300)
+    psi = lambda x: np.cos(2.0 * x)
+    jw = s.g.quad_weights() * psi(s.g.x)
+    obc = "periodic" if bc == "periodic" else "free"
+    fwd = s.forward(torch.tensor(u0, device="cuda"), dt, S, checkpoints=True)
+    adj = s.adjoint(fwd, psi=psi)
+    lam0 = adj["lam0"].cpu().numpy()
+    flags, branches = pkg.decode_limiter_record(fwd["lim"])
+    for b in range(B):
+        rec = ob.burgers_record(u0[b], g, dt, S, obc)
+        ref = ob.burgers_adjoint(rec, g, dt, jw, obc)
+        ids = np.stack([st["ids"] for st in rec["stages"]]).reshape(S, 5, K)
+        br = np.stack([st["br"] for st in rec["stages"]]).reshape(S, 5, K)
+        assert ids.any() and (br > 1).any()
+        assert np.array_equal(flags[b].cpu().numpy(), ids)
+        assert np.array_equal(branches[b].cpu().numpy(), br)
+        am = np.stack([(st["am"] + 1) * (1 if st["sg"] >= 0 else -1) for st in rec["stages"]]).reshape(S, 5)
+        assert np.array_equal(fwd["amax"][b].cpu().numpy(), am)
+        assert rel(fwd["uT"][b].cpu().numpy(), rec["uT"]) < 1e-11
+        assert rel(lam0[b], ref) < 1e-10
+        assert abs(float(adj["J"][b]) - np.sum(jw * rec["uT"])) < 1e-12
+    # finite differences through the GPU forward march (no branch flips at this step size)
+    d = rng.standard_normal(u0.shape)
+    eps = 1e-7
+    Jp = (torch.tensor(jw, device="cuda") * s.forward(torch.tensor(u0 + eps * d, device="cuda"), dt, S)["uT"]).sum((1, 2))
+    Jm = (torch.tensor(jw, device="cuda") * s.forward(torch.tensor(u0 - eps * d, device="cuda"), dt, S)["uT"]).sum((1, 2))
+    fd = ((Jp - Jm) / (2 * eps)).cpu().numpy()
+    dual = np.sum(lam0 * d, axis=(1, 2))
+    # J is only piecewise smooth in u0 (limiter flags, minmod branches, argmax): a perturbation
+    # that flips one of them makes the difference quotient jump, so not every trajectory agrees
+    relerr = np.abs(fd - dual) / np.abs(fd)
+    assert np.sum(relerr < 1e-4) >= B // 3, relerr
+    # stand-alone limiter pass = utils/SlopeLimitN.m
+    rough = u0 + 0.3 * (g.x[None] > 0.2)
+    lim = s.slope_limit(torch.tensor(rough, device="cuda")).cpu().numpy()
+    assert rel(lim, ol.SlopeLimitN(rough, g, periodic=(bc == "periodic"))) < 1e-13
