@@ -191,3 +191,33 @@ def test_gloo_two_rank_indicator_allreduce(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+# ---------------------------------------------------------------- MATLAB fixture I/O
+def test_save_load_globals_txt_matlab_conventions(pkg, tmp_path):
+    """utils/Save_to_1D_global_data.m file set: names, MATLAB index conventions (1-based,
+    column-major) -- compared with the oracle's MATLAB-numbered BuildMaps1D and the numbers
+    MATLAB embedded in utils/One_code.mlx."""
+    import json
+    from adjoint_ode_adaptivity_b200 import fixtures
+    g = pkg.BaseGalerkin1D(n=2, k=20, domain=(0.0, 1.0))
+    o = ops.startup_uniform(2, 0.0, 1.0, 20)
+    fixtures.save_globals_txt(g, tmp_path, dt=1.5e-3)
+    names = {f[:-4] for f in os.listdir(tmp_path)}
+    assert {"Dr", "EToE", "EToF", "Fmask", "Fscale", "Fx", "invV", "J", "K", "LIFT", "mapB", "mapI", "mapO", "N",
+            "Nfaces", "Nfp", "NODETOL", "Np", "nx", "r", "rk4a", "rk4b", "rk4c", "rx", "V", "vmapB", "vmapI",
+            "vmapM", "vmapO", "vmapP", "VX", "x", "dt"} <= names
+    d = fixtures.load_globals_txt(tmp_path)
+    assert d["vmapM"].ravel().astype(int).tolist() == o.vmapM.tolist()
+    assert d["vmapP"].ravel().astype(int).tolist() == o.vmapP.tolist()
+    assert (int(d["mapI"]), int(d["mapO"]), int(d["vmapI"]), int(d["vmapO"])) == (o.mapI, o.mapO, o.vmapI, o.vmapO)
+    assert d["vmapB"].ravel().astype(int).tolist() == o.vmapB.tolist() and d["mapB"].ravel().astype(int).tolist() == o.mapB.tolist()
+    assert np.array_equal(d["EToE"].astype(int), o.EToE + 1) and np.array_equal(d["EToF"].astype(int), o.EToF + 1)
+    np.testing.assert_array_equal(d["Dr"], g.d_r)           # %.17g is lossless
+    np.testing.assert_array_equal(d["x"], g.x)
+    with open(os.path.join(ROOT, "tests", "golden", "mlx_one_code.json")) as f:
+        gold = {(it["name"], it["line"]): it["value"] for it in json.load(f)["items"]}
+    np.testing.assert_allclose(d["LIFT"], gold[("LIFT", 148)], atol=5e-5)
+    np.testing.assert_allclose(d["rx"], gold[("rx", 149)], atol=5e-3)
+    opsd = fixtures.operators_from_globals(d)
+    np.testing.assert_allclose(opsd["Mref"], g.mass, rtol=1e-12)
