@@ -150,6 +150,50 @@ __global__ void rank_kernel(long long B, int K, const double* __restrict__ eta, 
   }
 }
 
+
+// top-k flags only (the refine flags of the bench / adaptive loop): one warp per trajectory,
+// topk rounds of "largest remaining |eta|, lowest index on ties" -- O(K topk) instead of the
+// O(K^2) counting rank above.
+__global__ void rank_topk_kernel(long long B, int K, const double* __restrict__ eta, int topk,
+                                 uint8_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  long long* key = reinterpret_cast<long long*>(smem_raw) + (size_t)wid * K;
+  for (long long b = (long long)blockIdx.x * nw + wid; b < B; b += (long long)gridDim.x * nw) {
+    for (int k = lane; k < K; k += 32) {
+      key[k] = __double_as_longlong(fabs(eta[(size_t)b * K + k]));
+      flags[(size_t)b * K + k] = 0;
+    }
+    __syncwarp();
+    for (int t = 0; t < topk && t < K; ++t) {
+      long long best = -2;
+      int bi = 0x7fffffff;
+      for (int k = lane; k < K; k += 32) {   // ascending k: strict > keeps the lowest index
+        const long long v = key[k];
+        if (v > best) {
+          best = v;
+          bi = k;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const long long ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) {
+          best = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        key[bi] = -1;   // removed (every |eta| bit pattern is >= 0)
+        flags[(size_t)b * K + bi] = 1;
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // batch reduction of the indicators in a fixed order.  Stage 1: block (x = 32 columns,
 // y = 8 row phases) sums rows b = y, y+8, ... in order, then the 8 phases in order.
@@ -976,6 +1020,17 @@ extern "C" int dgadj_rank(dgadj_handle* h, int64_t B, int32_t K, const double* e
   if (B <= 0 || K <= 0 || !eta_dev || topk < 0) return fail(h, DGADJ_ERR_INVALID, "bad rank arguments");
   if ((size_t)K * 8 > 200 * 1024) return fail(h, DGADJ_ERR_UNSUPPORTED, "K too large for the ranking kernel");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!order_dev && flags_dev && topk <= 16 && (size_t)K * 8 * 8 <= 96 * 1024) {
+    const int warps = 8;
+    const size_t sm = (size_t)K * sizeof(long long) * warps;
+    if (sm > 48 * 1024)
+      CUDA_TRY(h, cudaFuncSetAttribute(rank_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int g = (int)std::min<int64_t>((B + warps - 1) / warps, (int64_t)h->sm_count * 16);
+    rank_topk_kernel<<<g, warps * 32, sm, (cudaStream_t)stream>>>(B, K, eta_dev, topk, flags_dev);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return DGADJ_OK;
+  }
   const int block = std::min(1024, (K + 31) / 32 * 32);
   const int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count * 8);
   const size_t smem = (size_t)K * sizeof(double);

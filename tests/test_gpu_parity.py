@@ -322,6 +322,8 @@ def test_rank_and_reduce(pkg, torch):
             order, flags = s.rank(torch.tensor(eta, device="cuda"), topk)
             assert np.array_equal(order.cpu().numpy(), order_ref)
             assert np.array_equal(flags.cpu().numpy(), flags_ref)
+            _, flags2 = s.rank(torch.tensor(eta, device="cuda"), topk, want_order=False)   # top-k selection kernel
+            assert np.array_equal(flags2.cpu().numpy(), flags_ref)
         J = rng.standard_normal(B)
         sums = s.reduce_indicators(torch.tensor(eta, device="cuda"), torch.tensor(J, device="cuda")).cpu().numpy()
         ae = np.abs(eta)
