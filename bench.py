@@ -165,7 +165,7 @@ def reference_arm(a):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -397,13 +397,41 @@ def ours(a):
         "plan": s.plan(B), "refine_element_batch_mean": refine_idx,
         "frac_of_fp64_peak_whole_step": flops_per_update(s.Np) * updates_per_step / world / (ms_per_step * 1e-3) / 1e12 / peak_tf if peak_tf else None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+class StdoutGuard:
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version with printf)
+    write to fd 1 too, so fd 1 is pointed at stderr for the run and the JSON line goes to the
+    saved descriptor."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+
+GUARD = None
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if GUARD is not None:
+        GUARD.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global GUARD
+    GUARD = StdoutGuard()
     a = parse_args()
     if a.impl == "reference":
         return reference_arm(a)

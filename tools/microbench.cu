@@ -41,6 +41,34 @@ __global__ void __launch_bounds__(1024, 1) k_cst(const __grid_constant__ CB cb, 
   for (int i = 0; i < NCH; ++i) s += a[i];
   if (s == 123.456) out[0] = s;
 }
+// mode C: fp64 tensor-core MMA (mma.sync m8n8k4), NCH independent accumulator chains per warp,
+// optionally interleaved with DFMA chains (are they separate pipes on B200?)
+template <int NCH, int NFMA>
+__global__ void __launch_bounds__(1024, 1) k_dmma(double* out, int iters, double x, double y) {
+  double c0[NCH], c1[NCH], f[NFMA > 0 ? NFMA : 1];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) { c0[i] = threadIdx.x + i; c1[i] = i; }
+#pragma unroll
+  for (int i = 0; i < NFMA; ++i) f[i] = threadIdx.x + i;
+  const double a = x, b = 1.0 + 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+#pragma unroll
+      for (int i = 0; i < NFMA; ++i) f[i] = fma(f[i], x, y);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) s += c0[i] + c1[i];
+#pragma unroll
+  for (int i = 0; i < NFMA; ++i) s += f[i];
+  if (s == 123.456) out[0] = s;
+}
 template <typename F>
 double run(F launch, double flops_per_iter_per_thread, int threads, int iters) {
   cudaEvent_t e0, e1;
@@ -68,6 +96,11 @@ int main() {
   printf("cst 1:4 512thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,4><<<148,512>>>(cb,out,it,1e-9); }, 2.0*64*4, 512, IT));
   printf("cst 1:2 1024thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,2><<<148,1024>>>(cb,out,it,1e-9); }, 2.0*64*2, 1024, IT));
   printf("cst 1:1 1024thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,1><<<148,1024>>>(cb,out,it,1e-9); }, 2.0*64*1, 1024, IT));
+  // m8n8k4: 8*8*4*2 = 512 flop per warp instruction = 16 flop per thread
+  printf("dmma 512thr 4ch       : %.2f TF (mma only)\n", run([&](int it){ k_dmma<4,0><<<148,512>>>(out,it,0.999,1e-9); }, 16.0*8*4, 512, IT));
+  printf("dmma 1024thr 4ch      : %.2f TF (mma only)\n", run([&](int it){ k_dmma<4,0><<<148,1024>>>(out,it,0.999,1e-9); }, 16.0*8*4, 1024, IT));
+  printf("dmma+dfma 512thr 4+8  : %.2f TF (mma 16*4 + fma 2*8 per thread-iter)\n", run([&](int it){ k_dmma<4,8><<<148,512>>>(out,it,0.999,1e-9); }, (16.0*4+2.0*8)*8, 512, IT));
+  printf("dmma+dfma 1024thr 4+8 : %.2f TF\n", run([&](int it){ k_dmma<4,8><<<148,1024>>>(out,it,0.999,1e-9); }, (16.0*4+2.0*8)*8, 1024, IT));
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
