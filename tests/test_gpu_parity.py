@@ -573,3 +573,13 @@ def test_burgers_discrete_adjoint(pkg, torch, N, K, bc):
     rough = u0 + 0.3 * (g.x[None] > 0.2)
     lim = s.slope_limit(torch.tensor(rough, device="cuda")).cpu().numpy()
     assert rel(lim, ol.SlopeLimitN(rough, g, periodic=(bc == "periodic"))) < 1e-13
+
+
+def test_c_client_runs_on_gpu(tmp_path, torch):
+    """The plain-C client (tests/c_abi_smoke.c) marches on the GPU through dgadj_forward_host."""
+    import subprocess
+    from test_host_logic import build_c_client
+    exe = build_c_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "launches 1" in r.stdout

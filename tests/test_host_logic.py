@@ -221,3 +221,25 @@ def test_save_load_globals_txt_matlab_conventions(pkg, tmp_path):
     np.testing.assert_allclose(d["rx"], gold[("rx", 149)], atol=5e-3)
     opsd = fixtures.operators_from_globals(d)
     np.testing.assert_allclose(opsd["Mref"], g.mass, rtol=1e-12)
+
+
+# ---------------------------------------------------------------- a plain-C client of the ABI
+def build_c_client(tmp_path):
+    exe = str(tmp_path / "c_abi_smoke")
+    pkgdir = os.path.join(ROOT, "adjoint-ode-adaptivity_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", pkgdir, "-ldgadj", "-lm",
+                        "-Wl,-rpath," + pkgdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_client_compiles_and_refuses_cpu(tmp_path):
+    """include/dgadj.h is valid C99 and the library links from C; without a GPU the client gets
+    DGADJ_ERR_NO_DEVICE (exit code 3) -- there is no CPU fallback."""
+    import torch
+    exe = build_c_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if not torch.cuda.is_available():
+        assert r.returncode == 3, r.stdout + r.stderr
+        assert "create rc -2" in r.stdout
