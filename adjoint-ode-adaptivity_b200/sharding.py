@@ -42,6 +42,26 @@ def allreduce_indicators(sums, group=None, ordered=True):
     return out
 
 
+def gather_indicators(eta, group=None):
+    """All-gather the per-rank indicator slices eta[B_r, K] into the global [B, K] array on every
+    rank (rank order = batch order of `shard_range`); used when per-trajectory rankings are wanted
+    in one place.  Slices may have different lengths."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return eta
+    world = dist.get_world_size(group)
+    n = torch.tensor([eta.shape[0]], dtype=torch.int64, device=eta.device)
+    counts = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c[0]) for c in counts]
+    nmax = max(counts)
+    pad = eta if eta.shape[0] == nmax else torch.cat([eta, eta.new_zeros((nmax - eta.shape[0],) + eta.shape[1:])])
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad.contiguous(), group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
 def batch_mean_refine(sums, B_global: int):
     """Shared-mesh refinement decision from the reduced partials: mean indicator per element
     and the element to refine (argmax, lowest index on ties -- np.argmax semantics,

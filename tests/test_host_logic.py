@@ -173,6 +173,8 @@ dist.all_gather(gathered, tot)
 assert all(torch.equal(gathered[0], g) for g in gathered)      # bit-identical on every rank
 mean, idx = pkg.batch_mean_refine(tot, B)
 assert idx == int(np.argmax(np.abs(eta).sum(0)))
+full_eta = pkg.gather_indicators(torch.tensor(e))           # ragged slices (6 and 5 rows)
+assert torch.equal(full_eta, torch.tensor(eta))
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
