@@ -324,8 +324,7 @@ def ours(a):
 
         def step_host():
             r = s.fwd_adj(h_u0.numpy(), TWO_PI, dt, S, want_uT=False, out=hout)   # returns synchronised
-            ae = np.abs(r["eta"])
-            return float(ae.max())
+            return float(r["J"].sum())       # the step's scalar result, read on the host
 
         step_host()
         barrier()
@@ -341,7 +340,7 @@ def ours(a):
         e2e = {"value": updates_per_step / (sec / a.steps), "unit": UNIT,
                "h2d_bytes_per_step": int(B * s.Np * K * 8), "d2h_bytes_per_step": int(B * K * 8 + B * 8),
                "ms_per_step": 1e3 * sec / a.steps, "api": "dgadj_fwd_adj_host (pinned host buffers)",
-               "check_max_abs_eta": loss}
+               "check_sum_J": loss}
         # host path and device path run the same kernels on the same inputs
         assert torch.equal(h_eta.to(dev), out["eta"]), "host-path indicators differ from device-path"
 
