@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -872,7 +873,9 @@ static int host_pipeline(dgadj_handle* h, const dgadj_march_args* args, bool fus
   rc = make_plan(h, B, fused ? VAR_FUSED : VAR_FWD, &pl0);
   if (rc) return rc;
   const size_t per_traj = (io.in_total() + io.out_total()) * sizeof(double);
-  int64_t chunk = (int64_t)pl0.grid * pl0.tpc * 4;
+  int waves = 4;
+  if (const char* ev = getenv("DGADJ_HOST_WAVES")) waves = std::max(1, atoi(ev));  // tuning experiments only
+  int64_t chunk = (int64_t)pl0.grid * pl0.tpc * waves;
   const int64_t cap = std::max<int64_t>(pl0.tpc, (int64_t)((1ull << 30) / per_traj) / pl0.tpc * pl0.tpc);
   chunk = std::max<int64_t>(pl0.tpc, std::min<int64_t>(std::min(chunk, cap), B));
   const bool pinned = is_pinned(u0_host) && is_pinned(a_host) && is_pinned(dt_host) && is_pinned(uT_host) &&
