@@ -35,6 +35,7 @@ class TimeDG:
         self.torch = torch
         self.lib = _lib.load()
         self.linear, self.device, self.tol, self.maxit = bool(linear), device, float(tol), int(maxit)
+        self._cache = {}                        # per-element constants by (kind, order, element end points)
         cfg = _lib.Config(device=device, N=1, K=1, bc=1, inflow=0, functional=0, scheme=0, reserved=0, alpha=0.0)
         self._h = C.c_void_p(0)
         rc = self.lib.dgadj_create(C.byref(cfg), C.byref(self._h))
@@ -75,6 +76,11 @@ class TimeDG:
         blocks, nodes = [], []
         nq = 0
         for k in range(Ks):
+            key = ("m", N, float(times[k]), float(times[k + 1]))
+            if key in self._cache:
+                blk, x, nq = self._cache[key]
+                blocks.append(blk); nodes.append(x)
+                continue
             g = BaseGalerkin1D(n=N, k=1, domain=(times[k], times[k + 1]), n_gq=n_gq)
             x = g.x[:, 0]
             hk = x[-1] - x[0]                                     # :14 / :30
@@ -96,6 +102,7 @@ class TimeDG:
                 parts = [A.ravel(), Iq.ravel(), g.phi.ravel(), g.w, [hk]]
             blocks.append(np.concatenate([np.asarray(p, dtype=np.float64) for p in parts]))
             nodes.append(x)
+            self._cache[key] = (blocks[-1], x, nq)
         return np.ascontiguousarray(np.concatenate(blocks)), nodes, nq
 
     def adjoint_constants(self, Na, t1):
@@ -104,6 +111,11 @@ class TimeDG:
         nq = 0
         for tk in t1:
             tk = np.asarray(tk, dtype=np.float64)
+            key = ("a", Na, tk.tobytes())
+            if key in self._cache:
+                blk, x, nq = self._cache[key]
+                blocks.append(blk); nodes.append(x)
+                continue
             g = BaseGalerkin1D(n=Na, k=1, domain=(tk[0], tk[-1]), n_gq=1 if self.linear else 2 * Na)  # :17 / :71
             x = g.x[:, 0]
             hk = x[0] - x[-1]                                     # :18 / :72  negative (quirk C-3)
@@ -132,6 +144,7 @@ class TimeDG:
                 parts = [A0.ravel(), f1, A2.ravel(), Ix.ravel(), Iq.ravel(), g.phi.ravel(), g.w, [hk]]
             blocks.append(np.concatenate([np.asarray(p, dtype=np.float64) for p in parts]))
             nodes.append(x)
+            self._cache[key] = (blocks[-1], x, nq)
         return np.ascontiguousarray(np.concatenate(blocks)), nodes, nq
 
     # ------------------------------------------------------------------ reference-named entry points

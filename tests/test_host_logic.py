@@ -245,3 +245,12 @@ def test_c_client_compiles_and_refuses_cpu(tmp_path):
     if not torch.cuda.is_available():
         assert r.returncode == 3, r.stdout + r.stderr
         assert "create rc -2" in r.stdout
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No CPU fallback: with libdgadj.so absent the package import raises ImportError."""
+    code = ("import sys; sys.path.insert(0, %r); import dgadj_loader\n"
+            "try:\n    dgadj_loader.load_package()._lib.load()\nexcept ImportError as e:\n    print('IMPORTERROR', e); sys.exit(7)\n" % ROOT)
+    env = dict(os.environ, DGADJ_LIB=str(tmp_path / "nope" / "libdgadj.so"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 7 and "There is no CPU fallback" in r.stdout, r.stdout + r.stderr
