@@ -77,6 +77,7 @@ PROTOTYPES = {
                              C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "dgadj_host_eo_operators": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _D]),
     "dgadj_host_eo_prolongation": (C.c_int, [C.c_int, _P, _P, _P, _D]),
+    "dgadj_host_modal_operators": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _D]),
 }
 
 _lib = None

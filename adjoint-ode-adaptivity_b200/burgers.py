@@ -34,7 +34,7 @@ class BurgersDG1D:
                         V=c(g.v), invV=c(g.inv_v), x=c(g.x))
         o = self.ops
         p = lambda a: C.c_void_p(a.ctypes.data)
-        self._check(self.lib.dgadj_set_operators(self._h, self.Np, self.K, p(o["Dr"]), p(o["LIFT"]), p(o["Mref"]),
+        self._check(self.lib.dgadj_set_operators(self._h, self.Np, self.K, p(o["Dr"]), p(o["LIFT"]), p(o["V"]),
                                                  p(o["rx"]), p(o["Fscale"])))
 
     def _check(self, rc):

@@ -125,6 +125,70 @@ static int eo_prolongation(int Np, const double* P, double* PE, double* PO, doub
 }
 
 // ---------------------------------------------------------------------------------------
+// modal (orthonormal Legendre) operators (host):  D^ = V^-1 Dr V,  V^-1 LIFT = V^T E.
+// ---------------------------------------------------------------------------------------
+static bool invert_matrix(int n, const double* A, double* inv) {  // Gauss-Jordan, partial pivoting
+  std::vector<double> M((size_t)n * 2 * n, 0.0);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) M[(size_t)i * 2 * n + j] = A[(size_t)i * n + j];
+    M[(size_t)i * 2 * n + n + i] = 1.0;
+  }
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (fabs(M[(size_t)r * 2 * n + c]) > fabs(M[(size_t)piv * 2 * n + c])) piv = r;
+    if (M[(size_t)piv * 2 * n + c] == 0.0) return false;
+    if (piv != c)
+      for (int j = 0; j < 2 * n; ++j) std::swap(M[(size_t)c * 2 * n + j], M[(size_t)piv * 2 * n + j]);
+    const double d = 1.0 / M[(size_t)c * 2 * n + c];
+    for (int j = 0; j < 2 * n; ++j) M[(size_t)c * 2 * n + j] *= d;
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = M[(size_t)r * 2 * n + c];
+      if (f == 0.0) continue;
+      for (int j = 0; j < 2 * n; ++j) M[(size_t)r * 2 * n + j] -= f * M[(size_t)c * 2 * n + j];
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) inv[(size_t)i * n + j] = M[(size_t)i * 2 * n + n + j];
+  return true;
+}
+
+// Dnz: the non-zeros of D^ in the kernels' row-by-row order (nz_index); p[i] = P~_i(+1);
+// iV = V^-1.  *violation = largest entry that must vanish / identity that must hold, relative.
+static int modal_operators(int Np, const double* Dr, const double* LIFT, const double* V, double* Dnz, double* pv,
+                           double* iV, double* violation) {
+  if (Np < 2 || Np > MAXNP || !Dr || !LIFT || !V) return DGADJ_ERR_INVALID;
+  std::vector<double> Vm(V, V + (size_t)Np * Np), iVm((size_t)Np * Np);
+  if (!invert_matrix(Np, V, iVm.data())) return DGADJ_ERR_INVALID;
+  std::vector<double> D(Dr, Dr + (size_t)Np * Np), L(LIFT, LIFT + (size_t)Np * 2);
+  std::vector<double> Dh = matmul(matmul(iVm, D, Np, Np, Np), Vm, Np, Np, Np);
+  std::vector<double> Lh = matmul(iVm, L, Np, Np, 2);
+  double scale = 0.0, viol = 0.0, pscale = 0.0;
+  for (int i = 0; i < Np * Np; ++i) scale = fmax(scale, fabs(Dh[i]));
+  for (int i = 0; i < nz_count(Np) + 1 && i < MAXNZ; ++i) Dnz[i] = 0.0;
+  for (int i = 0; i < Np; ++i)
+    for (int j = 0; j < Np; ++j) {
+      const bool nz = (j > i) && ((j - i) & 1);
+      if (nz) Dnz[nz_index(Np, i, j)] = Dh[(size_t)i * Np + j];
+      else viol = fmax(viol, fabs(Dh[(size_t)i * Np + j]) / scale);
+    }
+  for (int i = 0; i < Np; ++i) {
+    pv[i] = V[(size_t)(Np - 1) * Np + i];
+    pscale = fmax(pscale, fabs(pv[i]));
+  }
+  for (int i = 0; i < Np; ++i) {
+    const double sgn = (i & 1) ? -1.0 : 1.0;
+    viol = fmax(viol, fabs(V[i] - sgn * pv[i]) / pscale);                  // P~_i(-1) = (-1)^i P~_i(+1)
+    viol = fmax(viol, fabs(Lh[(size_t)i * 2 + 1] - pv[i]) / pscale);        // V^-1 LIFT = V^T E
+    viol = fmax(viol, fabs(Lh[(size_t)i * 2 + 0] - sgn * pv[i]) / pscale);
+  }
+  for (int i = 0; i < Np * Np; ++i) iV[i] = iVm[i];
+  if (violation) *violation = viol;
+  return DGADJ_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // rank / refine flag:  one CTA per trajectory, stable descending rank of |eta| by counting
 // (rank_k = #{j : |eta_j| > |eta_k|  or (== and j < k)}), exact and deterministic.  |eta| is
 // compared through its bit pattern (monotone for non-negative doubles; NaN ranks first).
@@ -357,6 +421,11 @@ extern "C" int dgadj_host_eo_operators(int Np, const double* Dr, const double* L
   if (!DE || !DO || !LS || !LA) return DGADJ_ERR_INVALID;
   return eo_operators(Np, Dr, LIFT, DE, DO, LS, LA, violation);
 }
+extern "C" int dgadj_host_modal_operators(int Np, const double* Dr, const double* LIFT, const double* V,
+                                          double* Dnz, double* p, double* iV, double* violation) {
+  if (!Dnz || !p || !iV) return DGADJ_ERR_INVALID;
+  return modal_operators(Np, Dr, LIFT, V, Dnz, p, iV, violation);
+}
 extern "C" int dgadj_host_eo_prolongation(int Np, const double* P, double* PE, double* PO, double* violation) {
   if (!PE || !PO) return DGADJ_ERR_INVALID;
   return eo_prolongation(Np, P, PE, PO, violation);
@@ -416,7 +485,8 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   for (int lv = 0; lv < 2; ++lv)
     for (int i = 0; i < 2; ++i) cudaFree(h->d_nodal[lv][i]);
   cudaFree(h->d_jwc);
-  cudaFree(h->d_jwf);
+  cudaFree(h->d_jwm_c);
+  cudaFree(h->d_jwm_f);
   cudaFree(h->d_uin);
   cudaFree(h->ring);
   cudaFree(h->red_scratch);
@@ -453,18 +523,7 @@ static int upload(dgadj_handle* h, double** dst, const double* src, size_t n) {
   return DGADJ_OK;
 }
 
-static void scale_ops(const StageOps& src, double f, StageOps* dst) {
-  for (int i = 0; i < HM * HP; ++i) {
-    dst->DE2[i] = make_double2(src.DE2[i].x * f, src.DE2[i].y * f);
-    dst->DO2[i] = make_double2(src.DO2[i].x * f, src.DO2[i].y * f);
-  }
-  for (int i = 0; i < HP; ++i) {
-    dst->LS2[i] = make_double2(src.LS2[i].x * f, src.LS2[i].y * f);
-    dst->LA2[i] = make_double2(src.LA2[i].x * f, src.LA2[i].y * f);
-  }
-}
-
-// per-stage copies of the blocks with the stage scalings folded in (see ConstOps)
+// per-stage copies of D^ with the stage scalings folded in (see ConstOps)
 static void rebuild_stage_ops(dgadj_handle* h) {
   const int ns = h->nstages;
   double sig[MAXSTAGES], sga[MAXSTAGES];
@@ -474,16 +533,21 @@ static void rebuild_stage_ops(dgadj_handle* h) {
   for (int s = ns - 2; s >= 0; --s) sga[s] = h->cops.rka[s + 1] * sga[s + 1];
   for (int s = 0; s < MAXSTAGES; ++s) {
     const double f = s < ns ? 1.0 / sig[s] : 1.0, fa = s < ns ? sga[s] : 1.0;
-    for (int lv = 0; lv < 2; ++lv) scale_ops(h->base_ops[lv], f, &h->cops.st[lv][s]);
-    scale_ops(h->base_ops[1], fa, &h->cops.sta[s]);
+    for (int q = 0; q < MAXNZ; ++q) {
+      for (int lv = 0; lv < 2; ++lv) h->cops.st[lv][s].D[q] = h->Dnz[lv][q] * f;
+      h->cops.sta[s].D[q] = h->Dnz[1][q] * fa;
+    }
+    h->cops.isig[s] = f;
+    h->cops.sga[s] = fa;
     h->cops.bsig[s] = s < ns ? h->cops.rkb[s] * sig[s] : 0.0;
     h->cops.bsga[s] = s < ns ? h->cops.rkb[s] / sga[s] : 0.0;
   }
 }
 
-static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const double* LIFT, const double* Mref,
+static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const double* LIFT, const double* V,
                      const double* rx, const double* Fscale) {
   const int K = h->K;
+  // even/odd blocks of the nodal operators (Burgers kernels) -- also the symmetry check
   StageOps so;
   memset(&so, 0, sizeof(so));
   double DE[HM * HM], DO[HM * HM], LS[HM], LA[HM];
@@ -495,7 +559,6 @@ static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const do
                 "Dr/LIFT are not centro-(anti)symmetric (relative violation %.3e): only mirror-symmetric "
                 "node sets (LGL, StartUp1D) are supported",
                 viol);
-  // pack into the double2 layout of the kernels: entry (i, j) -> X2[i*HP + j/2].{x,y}
   for (int i = 0; i < HM; ++i) {
     for (int j = 0; j < HM; ++j) {
       double2& de = so.DE2[i * HP + j / 2];
@@ -507,8 +570,25 @@ static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const do
     ((i & 1) ? so.LA2[i / 2].y : so.LA2[i / 2].x) = LA[i];
   }
   h->base_ops[lv] = so;
+  // modal operators of the advection march
+  double iV[MAXNP * MAXNP];
+  memset(h->Dnz[lv], 0, sizeof(h->Dnz[lv]));
+  rc = modal_operators(Np, Dr, LIFT, V, h->Dnz[lv], h->cops.p[lv], iV, &viol);
+  if (rc != DGADJ_OK) return fail(h, rc, "bad operator arguments (singular V?)");
+  if (!(viol <= 1e-9))
+    return fail(h, DGADJ_ERR_UNSUPPORTED,
+                "V^-1 Dr V is not the parity-sparse upper-triangular Legendre derivative or V^-1 LIFT != V^T E "
+                "(relative violation %.3e): V must be the orthonormal Legendre Vandermonde of StartUp1D", viol);
+  for (int i = 0; i < Np * Np; ++i) h->Vhost[lv][i] = V[i];
+  if (lv == 0) {
+    for (int i = 0; i < Np * Np; ++i) {
+      h->cops.V[i] = V[i];
+      h->cops.iV[i] = iV[i];
+    }
+  } else {
+    for (int i = 0; i < Np * Np; ++i) h->cops.iVf[i] = iV[i];
+  }
   rebuild_stage_ops(h);
-  for (int i = 0; i < Np * Np; ++i) h->cops.Mref[lv][i] = Mref ? Mref[i] : 0.0;
   std::vector<double> rxk(K), f0(K), f1(K);
   for (int k = 0; k < K; ++k) {
     rxk[k] = rx[k];  // rx(1,k): the affine map makes rx constant inside an element
@@ -528,12 +608,12 @@ static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const do
 }
 
 extern "C" int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double* Dr, const double* LIFT,
-                                   const double* Mref, const double* rx, const double* Fscale) {
+                                   const double* V, const double* rx, const double* Fscale) {
   if (!h) return DGADJ_ERR_INVALID;
   if (Np != h->Np || K != h->K) return fail(h, DGADJ_ERR_INVALID, "Np/K (%d,%d) differ from the handle's (%d,%d)", Np, K, h->Np, h->K);
-  if (!Dr || !LIFT || !rx || !Fscale) return fail(h, DGADJ_ERR_INVALID, "null operator pointer");
+  if (!Dr || !LIFT || !V || !rx || !Fscale) return fail(h, DGADJ_ERR_INVALID, "null operator pointer");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  int rc = set_level(h, 0, Np, Dr, LIFT, Mref, rx, Fscale);
+  int rc = set_level(h, 0, Np, Dr, LIFT, V, rx, Fscale);
   if (rc) return rc;
   for (int i = 0; i < Np * Np; ++i) h->Dr_nodal[i] = Dr[i];
   for (int i = 0; i < Np * 2; ++i) h->LIFT_nodal[i] = LIFT[i];
@@ -542,34 +622,50 @@ extern "C" int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double*
 }
 
 extern "C" int dgadj_set_enriched(dgadj_handle* h, int NpF, const double* DrF, const double* LIFTF,
-                                  const double* MrefF, const double* rxF, const double* FscaleF,
+                                  const double* VF, const double* rxF, const double* FscaleF,
                                   const double* P) {
   if (!h) return DGADJ_ERR_INVALID;
   if (NpF != h->NpF) return fail(h, DGADJ_ERR_INVALID, "NpF %d differs from the handle's %d", NpF, h->NpF);
   if (NpF > MAXNP) return fail(h, DGADJ_ERR_UNSUPPORTED, "the adjoint / indicator path supports N <= %d (N = %d is forward-only)", MAXNP - 2, h->cfg.N);
-  if (!DrF || !LIFTF || !rxF || !FscaleF || !P) return fail(h, DGADJ_ERR_INVALID, "null operator pointer");
+  if (!DrF || !LIFTF || !VF || !rxF || !FscaleF || !P) return fail(h, DGADJ_ERR_INVALID, "null operator pointer");
+  if (!h->ops_set) return fail(h, DGADJ_ERR_STATE, "dgadj_set_operators must be called before dgadj_set_enriched");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  int rc = set_level(h, 1, NpF, DrF, LIFTF, MrefF, rxF, FscaleF);
+  int rc = set_level(h, 1, NpF, DrF, LIFTF, VF, rxF, FscaleF);
   if (rc) return rc;
-  ProlongOps po;
+  // the kernels inject the coarse modes into the enriched space: V_f^-1 P V_c must be (I; 0)
+  const int Np = h->Np;
+  std::vector<double> iVf(h->cops.iVf, h->cops.iVf + (size_t)NpF * NpF), Pm(P, P + (size_t)NpF * Np),
+      Vc(h->Vhost[0], h->Vhost[0] + (size_t)Np * Np);
+  std::vector<double> Ph = matmul(matmul(iVf, Pm, NpF, NpF, Np), Vc, NpF, Np, Np);
   double viol = 0.0;
-  rc = eo_prolongation(h->Np, P, po.PE, po.PO, &viol);
-  if (rc) return fail(h, rc, "bad prolongation");
-  if (!(viol <= 1e-10))
-    return fail(h, DGADJ_ERR_UNSUPPORTED, "prolongation is not centro-symmetric (relative violation %.3e)", viol);
-  h->cops.pr[0] = po;
-  h->cops.pr[1] = po;
-  for (int i = 0; i < NpF * h->Np; ++i) h->cops.P[i] = P[i];
+  for (int i = 0; i < NpF; ++i)
+    for (int j = 0; j < Np; ++j) viol = fmax(viol, fabs(Ph[(size_t)i * Np + j] - (i == j ? 1.0 : 0.0)));
+  if (!(viol <= 1e-9))
+    return fail(h, DGADJ_ERR_UNSUPPORTED,
+                "P is not the Legendre prolongation V_f(:,1:Np) inv(V_c) (deviation %.3e from the modal injection)", viol);
   h->enr_set = true;
   return DGADJ_OK;
+}
+
+// modal weights of a nodal weight field: (V^T jw)[i][k] = sum_j V[j][i] jw[j][k]
+static std::vector<double> modal_weights(const double* V, int Np, int K, const double* jw) {
+  std::vector<double> out((size_t)Np * K, 0.0);
+  for (int i = 0; i < Np; ++i)
+    for (int j = 0; j < Np; ++j) {
+      const double v = V[(size_t)j * Np + i];
+      for (int k = 0; k < K; ++k) out[(size_t)i * K + k] += v * jw[(size_t)j * K + k];
+    }
+  return out;
 }
 
 extern "C" int dgadj_set_functional_weights(dgadj_handle* h, const double* jw_c, const double* jw_f) {
   if (!h || !jw_c || !jw_f) return DGADJ_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  int rc = upload(h, &h->d_jwc, jw_c, (size_t)h->Np * h->K);
+  if (!h->ops_set || !h->enr_set) return fail(h, DGADJ_ERR_STATE, "set the operators of both spaces before the functional weights");
+  std::vector<double> mc = modal_weights(h->Vhost[0], h->Np, h->K, jw_c), mf = modal_weights(h->Vhost[1], h->NpF, h->K, jw_f);
+  int rc = upload(h, &h->d_jwm_c, mc.data(), mc.size());
   if (rc) return rc;
-  rc = upload(h, &h->d_jwf, jw_f, (size_t)h->NpF * h->K);
+  rc = upload(h, &h->d_jwm_f, mf.data(), mf.size());
   if (rc) return rc;
   h->jw_set = true;
   return DGADJ_OK;
@@ -699,8 +795,8 @@ static void fill_params(dgadj_handle* h, const dgadj_march_args* a, const Launch
     p.fs0[lv] = h->d_mesh[lv][1];
     p.fs1[lv] = h->d_mesh[lv][2];
   }
-  p.jw_c = h->d_jwc;
-  p.jw_f = h->d_jwf;
+  p.jw_c = h->d_jwm_c;
+  p.jw_f = h->d_jwm_f;
   p.uin_table = h->d_uin;
 }
 

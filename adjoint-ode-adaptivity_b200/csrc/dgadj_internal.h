@@ -24,11 +24,14 @@ struct dgadj_handle {
   int Np, NpF, K, nstages;
   bool ops_set, enr_set, jw_set;
   ConstOps cops;
-  StageOps base_ops[2];  // unscaled even/odd blocks of both levels
+  StageOps base_ops[2];  // even/odd blocks of the nodal operators (Burgers kernels)
+  double Dnz[2][MAXNZ];   // unscaled non-zeros of the modal derivative, both levels
+  double Vhost[2][MAXNP * MAXNP];  // host copies of the Vandermonde matrices
   double* d_mesh[2][3];  // [level]{rx, fs0, fs1} each [K]
   double* d_nodal[2][2];  // [level]{Dr[Np*Np], LIFT[Np*2]} nodal copies (dgadj_rhs)
-  double* d_jwc;
-  double* d_jwf;
+  double* d_jwc;          // nodal primal weights (Burgers adjoint)
+  double* d_jwm_c;        // modal weights V^T jw of the linear functional, primal / enriched
+  double* d_jwm_f;
   double* d_uin;
   int uin_n;
   double* ring;

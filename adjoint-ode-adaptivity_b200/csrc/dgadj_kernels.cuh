@@ -1,9 +1,9 @@
 // dgadj_kernels.cuh -- persistent sm_100a kernels for the batched 1-D nodal-DG march.
 //
-// Mapping: one thread owns one element of one trajectory for the whole march; its Np nodal
-// values, the RK residual and its metric terms live in registers.  A CTA owns `tpc`
+// Mapping: one thread owns EPT adjacent elements of one trajectory for the whole march; their
+// Np modal (Legendre) coefficients and the RK residual live in registers.  A CTA owns `tpc`
 // trajectories (tpc*K <= blockDim) and loops over trajectory groups (persistent grid).
-// Dr / LIFT / P / Mref / RK coefficients travel as a __grid_constant__ kernel parameter, i.e.
+// The modal operators and RK coefficients travel as a __grid_constant__ kernel parameter, i.e.
 // they sit in constant bank 0 and feed DFMA as constant-bank operands (all operator loops
 // are fully unrolled on the template order).  Neighbour traces cross threads through a
 // double-buffered shared-memory pair and a split arrive/wait mbarrier per stage.
@@ -26,10 +26,9 @@ constexpr int MAXBD = 1024;
 
 constexpr int HM = 5;  // max half dimension of the even/odd blocks ((MAXNP+1)/2)
 
-// Operator blocks of one space in the even/odd basis (see EO<> in the device section):
+// Even/odd blocks of a nodal operator set (used by the Burgers kernels, whose flux is nodal):
 //   even-out = DE * odd-in  (+ LS * (g0+g1)),   odd-out = DO * even-in  (+ LA * (g0-g1))
-// Stored as double2 pairs (row stride HP pairs) so that one 128-bit uniform constant load
-// (LDCU.128) feeds two DFMA per element: entry (i, j) is DE2[i*HP + j/2].{x,y}[j & 1].
+// stored as double2 pairs: entry (i, j) is DE2[i*HP + j/2].{x,y}[j & 1].
 constexpr int HP = 3;  // pairs per row ((HM+1)/2)
 struct alignas(16) StageOps {
   double2 DE2[HM * HP];  // i < HE, j < HO
@@ -37,23 +36,45 @@ struct alignas(16) StageOps {
   double2 LS2[HP];
   double2 LA2[HP];
 };
-struct ProlongOps {
-  double PE[HM * HM];  // even block of T_f P T_c^-1 : [i*HM + j], i < HE_f, j < HE_c
-  double PO[HM * HM];  // odd block                  : [i*HM + j], i < HO_f, j < HO_c
+
+// The advection march runs in the orthonormal Legendre (modal) basis  u^ = V^-1 u :
+//   * D^ = V^-1 Dr V is strictly upper triangular and couples only modes of opposite parity:
+//     floor(Np^2/4) non-zeros instead of Np^2 (Np = 10: 25 instead of 100);
+//   * V^-1 LIFT = V^T E: column f holds the basis values at the faces, p_i = P~_i(+1) and
+//     P~_i(-1) = (-1)^i p_i -- the same Np numbers give the traces u(-1), u(+1) and the lift;
+//   * the prolongation to order N+1 is the injection (u^, 0): no arithmetic;
+//   * V^T M V = I: J = int u^2 is J_k |u^|^2.
+// Non-zeros of D^ row by row: (i, j) with j = i+1, i+3, ... < Np.
+constexpr int MAXNZ = 26;  // 25 for Np = 10, padded to a multiple of 2
+__host__ __device__ constexpr int nz_row_offset(int NPX, int i) {
+  int o = 0;
+  for (int q = 0; q < i; ++q) o += (NPX - q) / 2;
+  return o;
+}
+__host__ __device__ constexpr int nz_index(int NPX, int i, int j) { return nz_row_offset(NPX, i) + (j - i - 1) / 2; }
+__host__ __device__ constexpr int nz_count(int NPX) { return nz_row_offset(NPX, NPX); }
+
+struct alignas(16) ModalStage {
+  double D[MAXNZ];
 };
 // Stage scaling.  The low-storage recurrences  r_s = rka_s r_{s-1} + R_s  (forward) and
 // w_s = rka_{s+1} w_{s+1} + bm_s mu_s  (adjoint) are carried as r = sig_s r~, w = sga_s w~ with
 // sig_0 = 1, sig_s = rka_s sig_{s-1} and sga_last = 1, sga_s = rka_{s+1} sga_{s+1}: the rka
-// multiply disappears (r~_s = r~_{s-1} + R_s / sig_s) and the factors 1/sig_s, sga_s are folded
-// into the per-stage copies of the operator blocks, which exist anyway (see fwd_step).
+// multiply disappears (r~_s = r~_{s-1} + R_s / sig_s); the factors 1/sig_s, sga_s are folded
+// into per-stage copies of D^ -- copies that exist anyway, because indexing the constants by
+// the stage counter is what keeps ptxas from hoisting (and then spilling) the loop-invariant
+// constant loads out of the stage loop.
 struct alignas(16) ConstOps {
-  StageOps st[2][MAXSTAGES];      // [level][stage]: forward blocks, scaled by 1/sig_s
-  StageOps sta[MAXSTAGES];        // enriched level, adjoint sweep: blocks scaled by sga_s
+  ModalStage st[2][MAXSTAGES];    // [level][stage]: D^ / sig_s            (forward sweeps)
+  ModalStage sta[MAXSTAGES];      // enriched level: D^ * sga_s            (adjoint sweep)
+  double p[2][MAXNP];             // [level] p_i = P~_i(+1)
+  double isig[MAXSTAGES];         // 1 / sig_s
+  double sga[MAXSTAGES];
   double bsig[MAXSTAGES];         // rkb_s * sig_s   (state update  z += bsig_s m r~)
   double bsga[MAXSTAGES];         // rkb_s / sga_s   (adjoint update w~ += bsga_s m mu)
-  ProlongOps pr[2];               // identical copies (indexed by step parity)
-  double Mref[2][MAXNP * MAXNP];  // nodal reference mass matrices inv(V V') (J = int u^2)
-  double P[MAXNP * MAXNP];        // nodal prolongation [NPF][NP], row stride NP
+  double V[MAXNP * MAXNP];        // primal Vandermonde, row stride Np   (u = V u^ : outputs)
+  double iV[MAXNP * MAXNP];       // its inverse                          (u^ = V^-1 u : inputs)
+  double iVf[MAXNP * MAXNP];      // inverse of the enriched Vandermonde  (lam0 = V_f^-T mu)
   double rka[MAXSTAGES], rkb[MAXSTAGES], rkc[MAXSTAGES];
 };
 
@@ -67,7 +88,7 @@ struct MarchParams {
   const double* rxk[2];   // [level][K]   rx(1,k)
   const double* fs0[2];   // [level][K]   Fscale(1,k)
   const double* fs1[2];   // [level][K]   Fscale(2,k)
-  const double* jw_c;     // [NP][K]
+  const double* jw_c;     // [NP][K]   modal weights V^T jw of the linear functional
   const double* jw_f;     // [NPF][K]
   const double* uin_table;
   const double* u0;
@@ -158,7 +179,7 @@ struct Ctx {
 #define DGADJ_SPLIT_BARRIER 1
 #endif
 // Trace exchange synchronisation.  Split form: a warp *arrives* as soon as its traces are in
-// shared memory and *waits* only when it needs its neighbours' -- the volume terms (80 % of a
+// shared memory and *waits* only when it needs its neighbours' -- the volume terms (most of a
 // stage) sit in between, so warps rarely block.  DGADJ_SPLIT_BARRIER=0 keeps a plain
 // __syncthreads() at the arrive point (for A/B measurements).
 // warp_local (a kernel parameter, hence uniform): every trajectory lives inside one warp, so
@@ -181,7 +202,7 @@ __device__ __forceinline__ void trace_wait(Ctx& cx, int warp_local) {
 }
 
 static __device__ __noinline__ double inflow_value(const MarchParams& p, long long b, double time, int n, int s,
-                                            double rkc) {
+                                                   double rkc) {
   const double a = p.a_arr ? p.a_arr[b] : p.a;
   const double dt = p.dt_arr ? p.dt_arr[b] : p.dt;
   const double t = time + rkc * dt;
@@ -193,288 +214,141 @@ static __device__ __noinline__ double inflow_value(const MarchParams& p, long lo
   }
 }
 
-// Symmetric / antisymmetric ("even/odd") nodal representation of one element.  LGL nodes are
-// mirror-symmetric, so Dr is centro-antisymmetric and LIFT / P are centro-symmetric; in
-//     ze[i] = u[i] + u[N-i] (i < Np/2),  ze[mid] = u[mid] (Np odd),   zo[i] = u[i] - u[N-i]
-// Dr maps odd -> even and even -> odd (two half-size blocks DE, DO), LIFT maps g0+g1 -> even
-// and g0-g1 -> odd, P maps even -> even and odd -> odd.  The whole march runs in this
-// basis: Np^2/2 instead of Np^2 DFMA per mat-vec.  The host builds the blocks from the
-// caller's nodal Dr / LIFT / P (dgadj_api.cu: dgadj_build_const_ops) and rejects operators
-// that do not have the symmetry.
+// modal coefficients of one element; rows <-> a strided column (park / landing / checkpoint tile)
 template <int NPX>
-struct EO {
-  static constexpr int HE = (NPX + 1) / 2;  // even (symmetric) dimension, holds the mid node
-  static constexpr int HO = NPX / 2;        // odd (antisymmetric) dimension
-};
-
-// One element's state in the even/odd basis (row order everywhere: e[0..HE), o[0..HO)).
-template <int NPX>
-struct EOVec {
-  double e[EO<NPX>::HE];
-  double o[EO<NPX>::HO];
+struct MVec {
+  double v[NPX];
   __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int i = 0; i < EO<NPX>::HE; ++i) e[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < EO<NPX>::HO; ++i) o[i] = 0.0;
+    for (int i = 0; i < NPX; ++i) v[i] = 0.0;
   }
-  // rows <-> a strided column (shared memory park / landing tile / checkpoint tile)
   __device__ __forceinline__ void load(const double* col, size_t stride) {
 #pragma unroll
-    for (int i = 0; i < EO<NPX>::HE; ++i) e[i] = col[(size_t)i * stride];
-#pragma unroll
-    for (int i = 0; i < EO<NPX>::HO; ++i) o[i] = col[(size_t)(EO<NPX>::HE + i) * stride];
+    for (int i = 0; i < NPX; ++i) v[i] = col[(size_t)i * stride];
   }
   __device__ __forceinline__ void store(double* col, size_t stride) const {
 #pragma unroll
-    for (int i = 0; i < EO<NPX>::HE; ++i) col[(size_t)i * stride] = e[i];
-#pragma unroll
-    for (int i = 0; i < EO<NPX>::HO; ++i) col[(size_t)(EO<NPX>::HE + i) * stride] = o[i];
-  }
-  // z = T u
-  __device__ __forceinline__ void from_nodal(const double (&u)[NPX]) {
-#pragma unroll
-    for (int i = 0; i < NPX / 2; ++i) {
-      e[i] = u[i] + u[NPX - 1 - i];
-      o[i] = u[i] - u[NPX - 1 - i];
-    }
-    if (NPX & 1) e[NPX / 2] = u[NPX / 2];
-  }
-  // u = T^-1 z  (half = 0.5)  or  lam = T^T mu (half = 1.0)
-  __device__ __forceinline__ void to_nodal(double (&u)[NPX], double half) const {
-#pragma unroll
-    for (int i = 0; i < NPX / 2; ++i) {
-      u[i] = half * (e[i] + o[i]);
-      u[NPX - 1 - i] = half * (e[i] - o[i]);
-    }
-    if (NPX & 1) u[NPX / 2] = e[NPX / 2];
+    for (int i = 0; i < NPX; ++i) col[(size_t)i * stride] = v[i];
   }
 };
 
-// One RK stage in the scaled-residual even/odd form, for the EPT elements of a thread (each
-// operator constant is fetched once and used EPT times).  With m = -a*rx*dt (constant per
-// element and trajectory) and r = resu/m the reference update (utils/AdvecRHS1D.m:11,19 +
-// the mlx loop)   resu = rka*resu + dt*rhsu ;  u = u + rkb*resu   becomes
-//     re = rka*re + DE zo + LS (g0+g1) ;  ro = rka*ro + DO ze + LA (g0-g1) ;  z += (rkb*m) r
-// (the rka multiply is absorbed by the stage scaling described at ConstOps)
-//     g0 = (u[0]-uL)*q0, g1 = (u[N]-uR)*q1,  q_f = dt*Fscale_f*c_f/m
-template <int NPX, int EPT>
-__device__ __forceinline__ void fwd_stage_volume(const StageOps& so, const EOVec<NPX> (&z)[EPT],
-                                                 EOVec<NPX> (&r)[EPT]) {
-  constexpr int HE = EO<NPX>::HE, HO = EO<NPX>::HO;
+// traces of a modal state: u(-1) = Se - So, u(+1) = Se + So, S{e,o} = sum over even / odd modes
+template <int NPX>
+__device__ __forceinline__ void traces(const double (&pv)[MAXNP], const MVec<NPX>& z, double& uF, double& uB) {
+  double Se = pv[0] * z.v[0], So = (NPX > 1) ? pv[1] * z.v[1] : 0.0;
 #pragma unroll
-  for (int i = 0; i < HE; ++i) {
-    double acc[EPT];
+  for (int i = 2; i < NPX; i += 2) Se = fma(pv[i], z.v[i], Se);
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) acc[e] = r[e].e[i];
-#pragma unroll
-    for (int jp = 0; jp < (HO + 1) / 2; ++jp) {
-      const double2 c2 = so.DE2[i * HP + jp];
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        acc[e] = fma(c2.x, z[e].o[2 * jp], acc[e]);
-        if (2 * jp + 1 < HO) acc[e] = fma(c2.y, z[e].o[2 * jp + 1 < HO ? 2 * jp + 1 : 0], acc[e]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) r[e].e[i] = acc[e];
-  }
-#pragma unroll
-  for (int i = 0; i < HO; ++i) {
-    double acc[EPT];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) acc[e] = r[e].o[i];
-#pragma unroll
-    for (int jp = 0; jp < (HE + 1) / 2; ++jp) {
-      const double2 c2 = so.DO2[i * HP + jp];
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        acc[e] = fma(c2.x, z[e].e[2 * jp], acc[e]);
-        if (2 * jp + 1 < HE) acc[e] = fma(c2.y, z[e].e[2 * jp + 1 < HE ? 2 * jp + 1 : 0], acc[e]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) r[e].o[i] = acc[e];
-  }
-}
-template <int NPX, int EPT>
-__device__ __forceinline__ void fwd_stage_surface(const StageOps& so, EOVec<NPX> (&z)[EPT], EOVec<NPX> (&r)[EPT],
-                                                  const double (&g0)[EPT], const double (&g1)[EPT],
-                                                  const double (&bm)[EPT]) {
-  constexpr int HE = EO<NPX>::HE, HO = EO<NPX>::HO;
-  double ge[EPT], go[EPT];
-#pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-    ge[e] = g0[e] + g1[e];
-    go[e] = g0[e] - g1[e];
-  }
-#pragma unroll
-  for (int ip = 0; ip < (HE + 1) / 2; ++ip) {
-    const double2 c2 = so.LS2[ip];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      r[e].e[2 * ip] = fma(c2.x, ge[e], r[e].e[2 * ip]);
-      z[e].e[2 * ip] = fma(bm[e], r[e].e[2 * ip], z[e].e[2 * ip]);
-      if (2 * ip + 1 < HE) {
-        const int i1 = 2 * ip + 1 < HE ? 2 * ip + 1 : 0;
-        r[e].e[i1] = fma(c2.y, ge[e], r[e].e[i1]);
-        z[e].e[i1] = fma(bm[e], r[e].e[i1], z[e].e[i1]);
-      }
-    }
-  }
-#pragma unroll
-  for (int ip = 0; ip < (HO + 1) / 2; ++ip) {
-    const double2 c2 = so.LA2[ip];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      r[e].o[2 * ip] = fma(c2.x, go[e], r[e].o[2 * ip]);
-      z[e].o[2 * ip] = fma(bm[e], r[e].o[2 * ip], z[e].o[2 * ip]);
-      if (2 * ip + 1 < HO) {
-        const int i1 = 2 * ip + 1 < HO ? 2 * ip + 1 : 0;
-        r[e].o[i1] = fma(c2.y, go[e], r[e].o[i1]);
-        z[e].o[i1] = fma(bm[e], r[e].o[i1], z[e].o[i1]);
-      }
-    }
-  }
+  for (int i = 3; i < NPX; i += 2) So = fma(pv[i], z.v[i], So);
+  uF = Se - So;
+  uB = Se + So;
 }
 
-// One full RK step (all stages) with the neighbour-trace exchange.
+// One RK step (all stages) in the scaled modal form.  Reference update (utils/AdvecRHS1D.m:11,19
+// + the LSERK4 loop of utils/One_code.mlx), with m = -a*rx*dt per element and r = resu/m:
+//     r^ = rka r^ + D^ u^ + p o {se | so} ;  u^ += (rkb m) r^
+//     g0 = (u(-1) - uL) q0,  g1 = (u(+1) - uR) q1,  q_f = dt Fscale_f c_f / m,
+//     se = g1 + g0 (even modes), so = g1 - g0 (odd modes)
+// (the rka multiply is absorbed by the stage scaling described at ConstOps).
 // coef = this thread's smem column of the level: {m, q0, q1} x EPT, each a row of BD.
-// The operator blocks are read from a per-stage copy (c.st[LV][s]) so that the constant
-// loads depend on the stage counter and stay inside the loop as uniform loads instead of
-// being hoisted out of it into (and spilled from) the register budget.
 template <int NPX, int LV, int EPT>
 __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __restrict__ tr,
-                                         const double* __restrict__ coef, EOVec<NPX> (&z)[EPT],
-                                         EOVec<NPX> (&r)[EPT], long long b, double time, int n) {
+                                         const double* __restrict__ coef, MVec<NPX> (&z)[EPT],
+                                         MVec<NPX> (&r)[EPT], long long b, double time, int n) {
   const ConstOps& c = ka.c;
   const int nst = ka.p.nstages;
 #pragma unroll 1   // (fully unrolling the stages was measured 7 % slower: 5x the code, more spills)
   for (int s = 0; s < nst; ++s) {
-    const StageOps& so = c.st[LV][s];
-    double* tA = tr + cx.par * cx.BD;  // left-edge values  u[0]    of the thread's first element
-    double* tB = tA + 2 * cx.BD;       // right-edge values u[Np-1] of the thread's last element
-    tA[cx.tid] = 0.5 * (z[0].e[0] + z[0].o[0]);
-    tB[cx.tid] = 0.5 * (z[EPT - 1].e[0] - z[EPT - 1].o[0]);
+    const ModalStage& so = c.st[LV][s];
+    double uF[EPT], uB[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) traces<NPX>(c.p[LV], z[e], uF[e], uB[e]);
+    double* tA = tr + cx.par * cx.BD;  // left-edge values  u(-1) of the thread's first element
+    double* tB = tA + 2 * cx.BD;       // right-edge values u(+1) of the thread's last element
+    tA[cx.tid] = uF[0];
+    tB[cx.tid] = uB[EPT - 1];
     trace_arrive(cx, ka.p.warp_local);
-    fwd_stage_volume<NPX, EPT>(so, z, r);   // needs no neighbour data
+    // volume terms (no neighbour data): r^_i += sum_{j = i+1, i+3, ...} D^_ij u^_j
+#pragma unroll
+    for (int i = 0; i < NPX - 1; ++i) {
+      double acc[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) acc[e] = r[e].v[i];
+#pragma unroll
+      for (int j = i + 1; j < NPX; j += 2) {
+        const double d = so.D[nz_index(NPX, i, j)];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) acc[e] = fma(d, z[e].v[j], acc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) r[e].v[i] = acc[e];
+    }
     trace_wait(cx, ka.p.warp_local);
     double uL = tB[cx.nbL];
     double uR = tA[cx.nbR];
     cx.par ^= 1;
-    double uF[EPT], uB[EPT];  // u[0], u[Np-1] of each element
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      uF[e] = 0.5 * (z[e].e[0] + z[e].o[0]);
-      uB[e] = 0.5 * (z[e].e[0] - z[e].o[0]);
-    }
     if (!(cx.flags & CX_PERIODIC)) {
       if (cx.flags & CX_FIRST) uL = inflow_value(ka.p, b, time, n, s, c.rkc[s]);
       if (cx.flags & CX_LAST) uR = uB[EPT - 1];
     }
-    double g0[EPT], g1[EPT], bm[EPT];
-    const double rkb = c.bsig[s];
+    const double isig = c.isig[s], rkb = c.bsig[s];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const double left = (e == 0) ? uL : uB[e - 1];
       const double right = (e == EPT - 1) ? uR : uF[e + 1];
-      g0[e] = (uF[e] - left) * coef[(size_t)(1 * EPT + e) * cx.BD];
-      g1[e] = (uB[e] - right) * coef[(size_t)(2 * EPT + e) * cx.BD];
-      bm[e] = rkb * coef[(size_t)e * cx.BD];
+      const double g0 = (uF[e] - left) * coef[(size_t)(1 * EPT + e) * cx.BD];
+      const double g1 = (uB[e] - right) * coef[(size_t)(2 * EPT + e) * cx.BD];
+      const double se = (g1 + g0) * isig, sd = (g1 - g0) * isig;
+      const double bm = rkb * coef[(size_t)e * cx.BD];
+#pragma unroll
+      for (int i = 0; i < NPX; ++i) {
+        r[e].v[i] = fma(c.p[LV][i], (i & 1) ? sd : se, r[e].v[i]);
+        z[e].v[i] = fma(bm, r[e].v[i], z[e].v[i]);
+      }
     }
-    fwd_stage_surface<NPX, EPT>(so, z, r, g0, g1, bm);
   }
 }
 
 // Reverse of one RK step: stages s = last..0  
 //   lk += rkb*lu ; lu += dt*L^T lk ; lk *= rka,   dt*L^T lk = m*Dr^T lk + scatter(g),
 //   g_f = dt*Fscale_f*c_f * (LIFT[:,f] . lk).
-// Carried in the scaled even/odd form (mu = T^-T lu, w = m * T^-T lk):
-//   w += (rkb*m) mu ; G = {LS.we + LA.wo, LS.we - LA.wo} ; gam_f = q_f G_f ;
-//   mu_e += DO^T wo ; mu_o += DE^T we ; a0 = gam0 - gam1[left], aN = gam1 - gam0[right] ;
-//   mu_e[0] += (a0+aN)/2 ; mu_o[0] += (a0-aN)/2 ; w *= rka  (the last as a stage scaling, see ConstOps).
+// Carried in the scaled modal form (mu = V^T lu, w = m V^T lk, w = sga_s w~):
+//   w~ += (bsga_s m) mu ; Gse = sum_even p_i w_i, Gso = sum_odd p_i w_i ;
+//   gam0 = q0 (Gse - Gso), gam1 = q1 (Gse + Gso) ; a0 = gam0 - gam1[left], aN = gam1 - gam0[right] ;
+//   mu_j += sum_{i < j, i+j odd} D^_ij w_i + p_j {aN + a0 | aN - a0}.
 template <int NPX, int LV, int EPT>
 __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __restrict__ tr,
-                                         const double* __restrict__ coef, EOVec<NPX> (&mu)[EPT],
-                                         EOVec<NPX> (&w)[EPT]) {
-  constexpr int HE = EO<NPX>::HE, HO = EO<NPX>::HO;
+                                         const double* __restrict__ coef, MVec<NPX> (&mu)[EPT],
+                                         MVec<NPX> (&w)[EPT]) {
   const ConstOps& c = ka.c;
 #pragma unroll 1
   for (int s = ka.p.nstages - 1; s >= 0; --s) {
-    const StageOps& so = c.sta[s];
-    const double rkb = c.bsga[s];
+    const ModalStage& so = c.sta[s];
+    const double rkb = c.bsga[s], sga = c.sga[s];
     double gam0[EPT], gam1[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const double bm = rkb * coef[(size_t)e * cx.BD];
 #pragma unroll
-      for (int i = 0; i < HE; ++i) w[e].e[i] = fma(bm, mu[e].e[i], w[e].e[i]);
-#pragma unroll
-      for (int i = 0; i < HO; ++i) w[e].o[i] = fma(bm, mu[e].o[i], w[e].o[i]);
-    }
-    {
-      double Ge[EPT], Go[EPT];
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) Ge[e] = Go[e] = 0.0;
-#pragma unroll
-      for (int ip = 0; ip < (HE + 1) / 2; ++ip) {
-        const double2 c2 = so.LS2[ip];
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          Ge[e] = fma(c2.x, w[e].e[2 * ip], Ge[e]);
-          if (2 * ip + 1 < HE) Ge[e] = fma(c2.y, w[e].e[2 * ip + 1 < HE ? 2 * ip + 1 : 0], Ge[e]);
-        }
-      }
-#pragma unroll
-      for (int ip = 0; ip < (HO + 1) / 2; ++ip) {
-        const double2 c2 = so.LA2[ip];
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          Go[e] = fma(c2.x, w[e].o[2 * ip], Go[e]);
-          if (2 * ip + 1 < HO) Go[e] = fma(c2.y, w[e].o[2 * ip + 1 < HO ? 2 * ip + 1 : 0], Go[e]);
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        gam0[e] = (Ge[e] + Go[e]) * coef[(size_t)(1 * EPT + e) * cx.BD];
-        gam1[e] = (Ge[e] - Go[e]) * coef[(size_t)(2 * EPT + e) * cx.BD];
-      }
+      for (int i = 0; i < NPX; ++i) w[e].v[i] = fma(bm, mu[e].v[i], w[e].v[i]);
+      double Gd, Gs;  // (Gse - Gso), (Gse + Gso)
+      traces<NPX>(c.p[LV], w[e], Gd, Gs);
+      gam0[e] = Gd * (sga * coef[(size_t)(1 * EPT + e) * cx.BD]);
+      gam1[e] = Gs * (sga * coef[(size_t)(2 * EPT + e) * cx.BD]);
     }
     double* tA = tr + cx.par * cx.BD;
     double* tB = tA + 2 * cx.BD;
     tA[cx.tid] = gam0[0];
     tB[cx.tid] = gam1[EPT - 1];
     trace_arrive(cx, ka.p.warp_local);
-    // volume part (needs no neighbour data): mu_e += DO^T wo, mu_o += DE^T we (row i of the
-    // block times w[i], accumulated straight into mu); the rka scaling of w lives in the blocks
+    // volume part (no neighbour data): mu_j += D^_ij w_i, row i of D^ times w_i
 #pragma unroll
-    for (int i = 0; i < HO; ++i) {
+    for (int i = 0; i < NPX - 1; ++i) {
 #pragma unroll
-      for (int jp = 0; jp < (HE + 1) / 2; ++jp) {
-        const double2 c2 = so.DO2[i * HP + jp];
+      for (int j = i + 1; j < NPX; j += 2) {
+        const double d = so.D[nz_index(NPX, i, j)];
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          mu[e].e[2 * jp] = fma(c2.x, w[e].o[i], mu[e].e[2 * jp]);
-          if (2 * jp + 1 < HE) {
-            const int j1 = 2 * jp + 1 < HE ? 2 * jp + 1 : 0;
-            mu[e].e[j1] = fma(c2.y, w[e].o[i], mu[e].e[j1]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < HE; ++i) {
-#pragma unroll
-      for (int jp = 0; jp < (HO + 1) / 2; ++jp) {
-        const double2 c2 = so.DE2[i * HP + jp];
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          mu[e].o[2 * jp] = fma(c2.x, w[e].e[i], mu[e].o[2 * jp]);
-          if (2 * jp + 1 < HO) {
-            const int j1 = 2 * jp + 1 < HO ? 2 * jp + 1 : 0;
-            mu[e].o[j1] = fma(c2.y, w[e].e[i], mu[e].o[j1]);
-          }
-        }
+        for (int e = 0; e < EPT; ++e) mu[e].v[j] = fma(d, w[e].v[i], mu[e].v[j]);
       }
     }
     trace_wait(cx, ka.p.warp_local);
@@ -489,8 +363,9 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
     for (int e = 0; e < EPT; ++e) {
       const double a0 = gam0[e] - ((e == 0) ? gam1L : gam1[e - 1]);
       const double aN = gam1[e] - ((e == EPT - 1) ? gam0R : gam0[e + 1]);
-      mu[e].e[0] = fma(0.5, a0 + aN, mu[e].e[0]);
-      mu[e].o[0] = fma(0.5, a0 - aN, mu[e].o[0]);
+      const double ae = aN + a0, ao = aN - a0;
+#pragma unroll
+      for (int i = 0; i < NPX; ++i) mu[e].v[i] = fma(c.p[LV][i], (i & 1) ? ao : ae, mu[e].v[i]);
     }
   }
 }
@@ -509,35 +384,15 @@ static __device__ __noinline__ double traj_sum(double* red, int tid, int KT, boo
   return s;
 }
 
-// zf = P~ z : even and odd blocks of the prolongation
-template <int NP, int EPT>
-__device__ __forceinline__ void prolong_eo(const ProlongOps& po, const EOVec<NP> (&z)[EPT],
-                                           EOVec<NP + 1> (&f)[EPT]) {
+// dense Np x Np change of basis at the ends of a march (once per trajectory, not a hot loop)
+template <int N1, bool TRANSPOSED>
+__device__ __forceinline__ void apply_matrix(const double* M, const double (&x)[N1], double (&y)[N1]) {
 #pragma unroll
-  for (int i = 0; i < EO<NP + 1>::HE; ++i) {
-    double acc[EPT];
+  for (int i = 0; i < N1; ++i) {
+    double acc = 0.0;
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) acc[e] = po.PE[i * HM] * z[e].e[0];
-#pragma unroll
-    for (int j = 1; j < EO<NP>::HE; ++j) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) acc[e] = fma(po.PE[i * HM + j], z[e].e[j], acc[e]);
-    }
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) f[e].e[i] = acc[e];
-  }
-#pragma unroll
-  for (int i = 0; i < EO<NP + 1>::HO; ++i) {
-    double acc[EPT];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) acc[e] = po.PO[i * HM] * z[e].o[0];
-#pragma unroll
-    for (int j = 1; j < EO<NP>::HO; ++j) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) acc[e] = fma(po.PO[i * HM + j], z[e].o[j], acc[e]);
-    }
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) f[e].o[i] = acc[e];
+    for (int j = 0; j < N1; ++j) acc = fma(TRANSPOSED ? M[j * N1 + i] : M[i * N1 + j], x[j], acc);
+    y[i] = acc;
   }
 }
 
@@ -550,10 +405,9 @@ __device__ __forceinline__ void prolong_eo(const ProlongOps& po, const EOVec<NP>
 //   tr[4][BD]          trace exchange, double buffered {left[2], right[2]} (also reduction pad)
 //   coef[2][3][EPT][BD] per-element {m, q0, q1} for the primal and the enriched level
 //   big[NPF][EPT][BD]  forward: parked coarse state / sigma;  adjoint: TMA landing tile
-// Park / checkpoint row order of an even/odd state: e[0..HE), then o[0..HO).
-// ---------------------------------------------------------------------------------------
 // BDT > 0: blockDim.x is the compile-time constant BDT (all shared-memory strides fold into
 // immediate offsets); BDT = 0: any block size.
+// ---------------------------------------------------------------------------------------
 template <int NP, int EPT, int BDT, bool DO_FWD, bool RESID, bool DO_ADJ>
 __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_constant__ KArgs ka) {
   constexpr int NPF = NP + 1;
@@ -638,41 +492,41 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
     double* ck = p.ckpt ? p.ckpt + slot * (size_t)p.S * tile : nullptr;
     const size_t gofs = (size_t)bs * NP * K + k0;  // this thread's column in [B][NP][K]
 
-    double u[EPT][NP];  // nodal terminal state (adjoint terminal condition / J)
+    MVec<NP> z[EPT];  // primal modal state (at the end of the forward phase: u^(T))
     // ------------------------------------------------------------------ forward phase
-    if (DO_FWD) {
-      EOVec<NP> z[EPT];
+    {
+      // nodal input (u0, or the terminal primal of an adjoint-only call) -> modal
+      const double* src = DO_FWD ? p.u0 : p.uT_in;
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
+        double u[NP];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) u[e][i] = active ? p.u0[gofs + (size_t)i * K + e] : 0.0;
-        z[e].from_nodal(u[e]);
+        for (int i = 0; i < NP; ++i) u[i] = active ? src[gofs + (size_t)i * K + e] : 0.0;
+        apply_matrix<NP, false>(c.iV, u, z[e].v);
       }
+    }
+    if (DO_FWD) {
       double* hist = (p.hist && active) ? p.hist + (size_t)b * (p.S + 1) * NP * K + k0 : nullptr;
       if (hist) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
 #pragma unroll
-          for (int i = 0; i < NP; ++i) hist[(size_t)i * K + e] = u[e][i];
+          for (int i = 0; i < NP; ++i) hist[(size_t)i * K + e] = p.u0[gofs + (size_t)i * K + e];
         }
       }
       double time = p.t0;
       double* park = sm_big + tid;  // element e, row i at park[(i*EPT + e)*BD]
-      if (RESID) {  // P u^0 waits in the park for the first fine step
-        EOVec<NPF> f[EPT];
-        prolong_eo<NP, EPT>(c.pr[1], z, f);
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) f[e].store(park + (size_t)e * BD, cstride);
-      }
 #pragma unroll 1
       for (int n = 0; n < p.S; ++n) {
         if (RESID) {
-          // fine one-step image of the injected coarse state: sigma = Phi_f(P u^n).
-          // park holds P u^n on entry; the coarse state takes its place during the fine step.
-          EOVec<NPF> f[EPT], rf[EPT];
+          // fine one-step image of the injected coarse state: sigma = Phi_f(P u^n); in the modal
+          // basis P u^n is (u^, 0).  The coarse state waits in the park meanwhile.
+          MVec<NPF> f[EPT], rf[EPT];
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
-            f[e].load(park + (size_t)e * BD, cstride);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) f[e].v[i] = z[e].v[i];
+            f[e].v[NP] = 0.0;
             rf[e].zero();
             z[e].store(park + (size_t)e * BD, cstride);
           }
@@ -686,27 +540,21 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
         {
           // scaled RK residual; rka[0] = 0 (checked by the host) so it need not survive the
           // step boundary -- exactly `rk4a(1)*resu` of the mlx
-          EOVec<NP> r[EPT];
+          MVec<NP> r[EPT];
 #pragma unroll
           for (int e = 0; e < EPT; ++e) r[e].zero();
           fwd_step<NP, 0, EPT>(ka, cx, sm_tr, sm_coef, z, r, bs, time, n);
         }
         time += p.dt_arr ? p.dt_arr[bs] : p.dt;  // `time = time+dt` accumulation of the mlx
         if (RESID) {
-          // rho^n = P u^{n+1} - sigma  -> checkpoint tile [n][row][e][tid]  (coalesced);
-          // P u^{n+1} stays in the park as the start of the next fine step.
+          // rho^n = P u^{n+1} - sigma  -> checkpoint tile [n][row][e][tid]  (coalesced)
           double* dst = ck + (size_t)n * tile + tid;
-          EOVec<NPF> f[EPT];
-          prolong_eo<NP, EPT>(c.pr[n & 1], z, f);
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
 #pragma unroll
-            for (int i = 0; i < NPF; ++i) {  // row i of the e/o order
+            for (int i = 0; i < NPF; ++i) {
               const size_t o = (size_t)(i * EPT + e) * BD;
-              const double v = (i < EO<NPF>::HE) ? f[e].e[i < EO<NPF>::HE ? i : 0]
-                                                 : f[e].o[i >= EO<NPF>::HE ? i - EO<NPF>::HE : 0];
-              dst[o] = v - park[o];
-              park[o] = v;
+              dst[o] = ((i < NP) ? z[e].v[i < NP ? i : 0] : 0.0) - park[o];
             }
           }
         }
@@ -714,26 +562,21 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
           double* hn = hist + (size_t)(n + 1) * NP * K;
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
-            z[e].to_nodal(u[e], 0.5);
+            double u[NP];
+            apply_matrix<NP, false>(c.V, z[e].v, u);
 #pragma unroll
-            for (int i = 0; i < NP; ++i) hn[(size_t)i * K + e] = u[e][i];
+            for (int i = 0; i < NP; ++i) hn[(size_t)i * K + e] = u[i];
           }
         }
       }
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) z[e].to_nodal(u[e], 0.5);
       if (p.uT && active) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
+          double u[NP];
+          apply_matrix<NP, false>(c.V, z[e].v, u);
 #pragma unroll
-          for (int i = 0; i < NP; ++i) p.uT[gofs + (size_t)i * K + e] = u[e][i];
+          for (int i = 0; i < NP; ++i) p.uT[gofs + (size_t)i * K + e] = u[i];
         }
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) u[e][i] = active ? p.uT_in[gofs + (size_t)i * K + e] : 0.0;
       }
     }
 
@@ -751,61 +594,37 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
         mbar_expect_tx(&mbar[0], tile_bytes);
         tma_bulk_g2s(land, ck + (size_t)(p.S - 1) * tile, tile_bytes, &mbar[0]);
       }
-      // terminal condition lam^S = dJ_f/du at P u^S, and J of the coarse solution
-      EOVec<NPF> mu[EPT];
+      // terminal condition mu^S = V_f^T dJ_f/du at P u^S, and J of the coarse solution
+      MVec<NPF> mu[EPT];
       double jpart = 0.0;
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
         const int k = k0 + e;
-        double lu[NPF];
         if (p.func == FUNC_LINEAR) {
 #pragma unroll
-          for (int i = 0; i < NPF; ++i) lu[i] = in_tile ? p.jw_f[(size_t)i * K + k] : 0.0;
+          for (int i = 0; i < NPF; ++i) mu[e].v[i] = in_tile ? p.jw_f[(size_t)i * K + k] : 0.0;
 #pragma unroll
-          for (int i = 0; i < NP; ++i) jpart = fma(in_tile ? p.jw_c[(size_t)i * K + k] : 0.0, u[e][i], jpart);
+          for (int i = 0; i < NP; ++i) jpart = fma(in_tile ? p.jw_c[(size_t)i * K + k] : 0.0, z[e].v[i], jpart);
         } else {
+          // J = int u^2 dx = sum_k J_k |u^_k|^2 in the orthonormal basis; dJ_f/du^ = 2 J_k (u^, 0)
           const double jacC = in_tile ? 1.0 / p.rxk[0][k] : 0.0, jacF = in_tile ? 1.0 / p.rxk[1][k] : 0.0;
+          double n2 = 0.0;
 #pragma unroll
           for (int i = 0; i < NP; ++i) {
-            double acc = c.Mref[0][i * NP] * u[e][0];
-#pragma unroll
-            for (int j = 1; j < NP; ++j) acc = fma(c.Mref[0][i * NP + j], u[e][j], acc);
-            jpart = fma(u[e][i], jacC * acc, jpart);
+            n2 = fma(z[e].v[i], z[e].v[i], n2);
+            mu[e].v[i] = 2.0 * jacF * z[e].v[i];
           }
-          double uf[NPF];
-#pragma unroll
-          for (int i = 0; i < NPF; ++i) {
-            double acc = c.P[i * NP] * u[e][0];
-#pragma unroll
-            for (int j = 1; j < NP; ++j) acc = fma(c.P[i * NP + j], u[e][j], acc);
-            uf[i] = acc;
-          }
-#pragma unroll
-          for (int i = 0; i < NPF; ++i) {
-            double acc = c.Mref[1][i * NPF] * uf[0];
-#pragma unroll
-            for (int j = 1; j < NPF; ++j) acc = fma(c.Mref[1][i * NPF + j], uf[j], acc);
-            lu[i] = 2.0 * jacF * acc;
-          }
-        }
-        // mu = T^-T lam : halves of the mirrored sums / differences
-        mu[e].from_nodal(lu);
-#pragma unroll
-        for (int i = 0; i < NPF / 2; ++i) {
-          mu[e].e[i] *= 0.5;
-          mu[e].o[i] *= 0.5;
+          mu[e].v[NP] = 0.0;
+          jpart = fma(jacC, n2, jpart);
         }
       }
       const double Jtot = traj_sum(sm_tr, tid, KT, (cx.flags & CX_FIRST) != 0, jpart);
       if (p.J && active && (cx.flags & CX_FIRST)) p.J[b] = Jtot;
 
-      EOVec<NPF> w[EPT];
+      MVec<NPF> w[EPT];
       double eta[EPT];
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        w[e].zero();
-        eta[e] = 0.0;
-      }
+      for (int e = 0; e < EPT; ++e) eta[e] = 0.0;
 #pragma unroll 1
       for (int n = p.S - 1; n >= 0; --n) {
         // eta[k] += lam^{n+1} . rho^n ; the tile is consumed at once, so one landing buffer
@@ -816,11 +635,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
 #pragma unroll
-          for (int i = 0; i < EO<NPF>::HE; ++i)
-            eta[e] = fma(mu[e].e[i], rho[(size_t)(i * EPT + e) * BD], eta[e]);
-#pragma unroll
-          for (int i = 0; i < EO<NPF>::HO; ++i)
-            eta[e] = fma(mu[e].o[i], rho[(size_t)((EO<NPF>::HE + i) * EPT + e) * BD], eta[e]);
+          for (int i = 0; i < NPF; ++i) eta[e] = fma(mu[e].v[i], rho[(size_t)(i * EPT + e) * BD], eta[e]);
         }
         __syncthreads();  // every thread has consumed the landing tile
         if (tid == 0 && n >= 1) {
@@ -837,7 +652,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_cons
           if (p.eta) p.eta[(size_t)b * K + k0 + e] = eta[e];
           if (p.lam0) {
             double lu[NPF];
-            mu[e].to_nodal(lu, 1.0);  // lam = T^T mu
+            apply_matrix<NPF, true>(c.iVf, mu[e].v, lu);  // lam = V_f^-T mu
             double* l0 = p.lam0 + (size_t)b * NPF * K + k0 + e;
 #pragma unroll
             for (int i = 0; i < NPF; ++i) l0[(size_t)i * K] = lu[i];

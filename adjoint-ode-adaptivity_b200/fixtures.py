@@ -70,6 +70,6 @@ def operators_from_globals(d):
     """Operator arrays in the layout dgadj_set_operators expects, from loaded MATLAB globals
     (Mref = inv(V V'))."""
     V = np.asarray(d["V"])
-    return dict(Dr=np.ascontiguousarray(d["Dr"]), LIFT=np.ascontiguousarray(d["LIFT"]),
+    return dict(Dr=np.ascontiguousarray(d["Dr"]), LIFT=np.ascontiguousarray(d["LIFT"]), V=np.ascontiguousarray(V),
                 Mref=np.ascontiguousarray(np.linalg.inv(V @ V.T)), rx=np.ascontiguousarray(d["rx"]),
                 Fscale=np.ascontiguousarray(d["Fscale"]), x=np.ascontiguousarray(d["x"]))

@@ -81,18 +81,18 @@ class AdvecDG1D:
         g, gf = self.g, self.gf
         c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         # keep the contiguous copies alive across the ctypes calls (and for inspection)
-        self.ops_c = dict(Dr=c(g.d_r), LIFT=c(g.lift), Mref=c(g.mass), rx=c(g.r_x), Fscale=c(g.f_scale))
-        self.ops_f = dict(Dr=c(gf.d_r), LIFT=c(gf.lift), Mref=c(gf.mass), rx=c(gf.r_x), Fscale=c(gf.f_scale))
+        self.ops_c = dict(Dr=c(g.d_r), LIFT=c(g.lift), V=c(g.v), rx=c(g.r_x), Fscale=c(g.f_scale))
+        self.ops_f = dict(Dr=c(gf.d_r), LIFT=c(gf.lift), V=c(gf.v), rx=c(gf.r_x), Fscale=c(gf.f_scale))
         self.P = c(g.prolongation_to(gf))
         o = self.ops_c
         self._check(self.lib.dgadj_set_operators(
-            self._h, self.Np, self.K, _np_ptr(o["Dr"]), _np_ptr(o["LIFT"]), _np_ptr(o["Mref"]),
+            self._h, self.Np, self.K, _np_ptr(o["Dr"]), _np_ptr(o["LIFT"]), _np_ptr(o["V"]),
             _np_ptr(o["rx"]), _np_ptr(o["Fscale"])))
         self.has_adjoint = self.NpF <= 10        # N = 9 is forward-only (enriched space would be Np = 11)
         if self.has_adjoint:
             o = self.ops_f
             self._check(self.lib.dgadj_set_enriched(
-                self._h, self.NpF, _np_ptr(o["Dr"]), _np_ptr(o["LIFT"]), _np_ptr(o["Mref"]),
+                self._h, self.NpF, _np_ptr(o["Dr"]), _np_ptr(o["LIFT"]), _np_ptr(o["V"]),
                 _np_ptr(o["rx"]), _np_ptr(o["Fscale"]), _np_ptr(self.P)))
             self.set_linear_functional(psi)
 

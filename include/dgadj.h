@@ -78,16 +78,18 @@ const char* dgadj_last_error(const dgadj_handle* h);
 
 /* Operators of the primal space, as produced by StartUp1D (utils/StartUp1D.m:9-33) /
  * BaseGalerkin1D.startUp1D (python/galerkin.py:199-237).  Host pointers, copied.
- *   Dr[Np*Np], LIFT[Np*2], Mref[Np*Np] = inv(V V'), rx[Np*K], Fscale[2*K].
- * Dr must be centro-antisymmetric and LIFT centro-symmetric (true for every LGL operator
- * set StartUp1D produces); anything else is rejected with DGADJ_ERR_UNSUPPORTED.          */
+ *   Dr[Np*Np], LIFT[Np*2], V[Np*Np] (Vandermonde1D.m: V(i,j) = P~_{j-1}(r_i), orthonormal
+ *   Legendre), rx[Np*K], Fscale[2*K].
+ * The march runs in the modal basis of V: V^-1 Dr V must be the (parity-sparse, strictly upper
+ * triangular) Legendre derivative and V^-1 LIFT = V^T E -- true for every operator set
+ * StartUp1D produces; anything else is rejected with DGADJ_ERR_UNSUPPORTED.               */
 int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double* Dr, const double* LIFT,
-                        const double* Mref, const double* rx, const double* Fscale);
+                        const double* V, const double* rx, const double* Fscale);
 
 /* Operators of the enriched space (order N+1; matlab/MAIN.m:34 solves the adjoint at Ns+1)
  * plus the nodal prolongation P[NpF*Np] = V_{N+1}(:,1:Np) inv(V_N).                      */
 int dgadj_set_enriched(dgadj_handle* h, int NpF, const double* DrF, const double* LIFTF,
-                       const double* MrefF, const double* rxF, const double* FscaleF,
+                       const double* VF, const double* rxF, const double* FscaleF,
                        const double* P);
 
 /* Weights of a linear terminal functional J = sum_{i,k} jw[i,k] u[i,k] in both spaces
@@ -246,11 +248,15 @@ int dgadj_plan(dgadj_handle* h, int64_t B, int32_t fused, int32_t* ept, int32_t*
 
 /* Host-only utilities (no device needed; used by the CPU test-suite): the even/odd operator
  * blocks the kernels run on, built from nodal Dr[Np*Np] / LIFT[Np*2] (and P[(Np+1)*Np]).
- * Outputs are [5*5] / [5] arrays (row stride 5); *violation = largest entry of the blocks
+ * (the Burgers kernels use them).  Outputs are [5*5] / [5] arrays (row stride 5); *violation = largest entry of the blocks
  * that must vanish by symmetry, relative to the largest operator entry.                  */
 int dgadj_host_eo_operators(int Np, const double* Dr, const double* LIFT, double* DE, double* DO,
                             double* LS, double* LA, double* violation);
 int dgadj_host_eo_prolongation(int Np, const double* P, double* PE, double* PO, double* violation);
+/* The modal operators the advection march runs on: Dnz[26] = non-zeros of V^-1 Dr V row by row
+ * ((i, j), j = i+1, i+3, ...), p[Np] = P~_i(+1), iV[Np*Np] = V^-1; *violation as above.   */
+int dgadj_host_modal_operators(int Np, const double* Dr, const double* LIFT, const double* V,
+                               double* Dnz, double* p, double* iV, double* violation);
 
 #ifdef __cplusplus
 }

@@ -20,10 +20,12 @@ int main(void) {
   if (rc == DGADJ_ERR_NO_DEVICE) { printf("no sm_100 device: no CPU fallback (expected without a GPU)\n"); return 3; }
   if (rc != DGADJ_OK) return 1;
   /* N = 1 operators on 4 elements of width 0.25 (StartUp1D by hand) */
-  const double Dr[4] = {-0.5, 0.5, -0.5, 0.5}, LIFT[4] = {2.0, -1.0, -1.0, 2.0}, Mref[4] = {2.0 / 3, 1.0 / 3, 1.0 / 3, 2.0 / 3};
+  const double Dr[4] = {-0.5, 0.5, -0.5, 0.5}, LIFT[4] = {2.0, -1.0, -1.0, 2.0};
+  const double s2 = sqrt(0.5), s32 = sqrt(1.5);
+  const double V[4] = {s2, -s32, s2, s32};   /* orthonormal Legendre P~_0, P~_1 at r = -1, +1 */
   double rx[8], Fs[8];
   for (int i = 0; i < 8; ++i) { rx[i] = 8.0; Fs[i] = 8.0; }
-  rc = dgadj_set_operators(h, 2, 4, Dr, LIFT, Mref, rx, Fs);
+  rc = dgadj_set_operators(h, 2, 4, Dr, LIFT, V, rx, Fs);
   if (rc) { printf("set_operators: %s\n", dgadj_last_error(h)); return 1; }
   double u0[8] = {0.1, 0.4, 0.4, 0.9, 0.9, 0.3, 0.3, 0.1}, uT[8];   /* [Np][K] */
   dgadj_march_args a;

@@ -11,7 +11,8 @@ import sys
 import numpy as np
 import pytest
 
-import eo_emulator as em
+import eo_emulator as eo
+import modal_emulator as em
 from oracle import advec
 from oracle import operators as ops
 
@@ -71,7 +72,9 @@ CASES = [(4, 10, "periodic", 0.0), (4, 10, "inflow", 1.0), (3, 7, "inflow", 0.3)
 
 
 @pytest.mark.parametrize("N,K,bc,alpha", CASES)
-def test_even_odd_algebra_matches_oracle(pkg, lib, N, K, bc, alpha):
+def test_modal_algebra_matches_oracle(pkg, lib, N, K, bc, alpha):
+    """The kernel's formulation (modal basis, parity-sparse derivative, stage scalings, injection
+    as prolongation) on the operators the C library's host code builds, against the oracle."""
     gc = pkg.BaseGalerkin1D(n=N, k=K, domain=(0, 2 * math.pi))
     gf = pkg.BaseGalerkin1D(n=N + 1, k=K, domain=(0, 2 * math.pi))
     oc = ops.startup_uniform(N, 0, 2 * math.pi, K)
@@ -83,13 +86,53 @@ def test_even_odd_algebra_matches_oracle(pkg, lib, N, K, bc, alpha):
     per = bc == "periodic"
     ref = advec.fwd_adj_indicator(u0, oc, of, a, dt, S, alpha=alpha, bc=bc, inflow=advec.INFLOW_SIN_AT)
     rk = (ops.rk4a, ops.rk4b, ops.rk4c)
-    out = em.fused(lib, gc, gf, gc.prolongation_to(gf), u0, a, dt, S, alpha, per, rk, gc.quad_weights(),
-                   gf.quad_weights(), inflow_fn=None if per else (lambda t: -np.sin(a * t)))
-    assert out["viol"] < 1e-13
+    out = em.fused(lib, gc, gf, u0, a, dt, S, alpha, per, rk, gc.quad_weights(), gf.quad_weights(),
+                   inflow_fn=None if per else (lambda t: -np.sin(a * t)))
+    assert out["viol"] < 1e-12
     np.testing.assert_allclose(out["uT"], ref["uT"], rtol=0, atol=1e-12 * np.max(np.abs(ref["uT"])))
     np.testing.assert_allclose(out["lam0"], ref["lam0"], rtol=0, atol=1e-12 * np.max(np.abs(ref["lam0"])))
     assert abs(out["J"] - ref["J"]) <= 1e-12 * max(1.0, abs(ref["J"]))
     assert np.all(np.abs(out["eta"] - ref["eta"]) <= 1e-12 * ref["eta_scale"])
+
+
+def test_modal_operator_structure(pkg, lib):
+    """V^-1 Dr V is strictly upper triangular and parity sparse (floor(Np^2/4) non-zeros), the
+    lift is V^T E, the prolongation is the injection; a wrong V is reported."""
+    for N in range(1, 10):
+        g = pkg.BaseGalerkin1D(n=N, k=3)
+        o = em.modal_ops(lib, g)
+        Np = N + 1
+        assert o["viol"] < 1e-12
+        assert np.count_nonzero(o["D"]) == (Np * Np) // 4
+        np.testing.assert_allclose(o["V"] @ o["D"] @ o["iV"], g.d_r, atol=1e-11)
+        np.testing.assert_allclose(o["p"], g.v[-1, :], rtol=0, atol=0)
+        gf = pkg.BaseGalerkin1D(n=N + 1, k=3)
+        Ph = np.linalg.inv(gf.v) @ g.prolongation_to(gf) @ g.v
+        np.testing.assert_allclose(Ph, np.eye(Np + 1, Np), atol=1e-12)
+    g = pkg.BaseGalerkin1D(n=4, k=3)
+    Dnz, p, iV = np.zeros(26), np.zeros(5), np.zeros((5, 5))
+    v = C.c_double()
+    ptr = lambda a: C.c_void_p(a.ctypes.data)
+    Vbad = np.ascontiguousarray(g.v[:, ::-1])             # permuted modes: not the Legendre ordering
+    Dr, LIFT = np.ascontiguousarray(g.d_r), np.ascontiguousarray(g.lift)
+    assert lib.dgadj_host_modal_operators(5, ptr(Dr), ptr(LIFT), ptr(Vbad), ptr(Dnz), ptr(p), ptr(iV), C.byref(v)) == 0
+    assert v.value > 1e-3                                 # dgadj_set_operators refuses it (> 1e-9)
+
+
+def test_even_odd_blocks_reproduce_the_nodal_derivative(pkg, lib):
+    """dgadj_host_eo_operators (used by the Burgers kernels): the half-size blocks applied to the
+    symmetric / antisymmetric parts give Dr u and LIFT g."""
+    for N in (1, 4, 7, 8):
+        g = pkg.BaseGalerkin1D(n=N, k=2)
+        b = eo.eo_blocks(lib, g)
+        assert b["viol"] < 1e-13
+        rng = np.random.default_rng(N)
+        u = rng.standard_normal((N + 1, 3))
+        e, o = eo.to_eo(u)
+        g2 = rng.standard_normal((2, 3))
+        E = b["DE"] @ o + b["LS"][:, None] * (g2[0] + g2[1])
+        O = b["DO"] @ e + b["LA"][:, None] * (g2[0] - g2[1])
+        np.testing.assert_allclose(eo.from_eo(E, O, 0.5), g.d_r @ u + g.lift @ g2, atol=1e-11)
 
 
 def test_eo_rejects_asymmetric_operator(lib):
