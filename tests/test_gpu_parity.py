@@ -181,7 +181,9 @@ def test_fused_fwd_adj_indicator(pkg, torch, N, K, bc, alpha, inflow):
     uT2, ck = s.forward_checkpointed(torch.tensor(u0, device="cuda"), a, dt, S)
     out2 = s.adjoint(uT2, ck, a, dt, S)
     assert torch.equal(uT2, out["uT"]) and torch.equal(out2["eta"], out["eta"])
-    assert torch.equal(out2["lam0"], out["lam0"]) and torch.equal(out2["J"], out["J"])
+    assert torch.equal(out2["lam0"], out["lam0"])
+    # J: the adjoint-only call re-derives the modal terminal state from the nodal uT (rounding)
+    assert float((out2["J"] - out["J"]).abs().max()) <= 1e-13 * max(1.0, float(out["J"].abs().max()))
     # host-buffer entry point (pageable numpy): same bits again
     outh = s.fwd_adj(u0, a, dt, S, want_lam0=True)
     assert np.array_equal(outh["eta"], eta) and np.array_equal(outh["uT"], out["uT"].cpu().numpy())
