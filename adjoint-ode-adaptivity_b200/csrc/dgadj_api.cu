@@ -688,7 +688,7 @@ extern "C" int dgadj_set_inflow_table(dgadj_handle* h, int n, const double* uin)
 
 extern "C" int dgadj_set_tuning(dgadj_handle* h, int32_t ept, int32_t block, int32_t grid) {
   if (!h) return DGADJ_ERR_INVALID;
-  if (ept < 0 || ept > 2 || block < 0 || block > MAXBD || grid < 0) return fail(h, DGADJ_ERR_INVALID, "bad tuning");
+  if (ept < 0 || ept == 3 || ept > 4 || block < 0 || block > MAXBD || grid < 0) return fail(h, DGADJ_ERR_INVALID, "bad tuning");
   h->tune_ept = ept;
   h->tune_block = block;
   h->tune_grid = grid;
@@ -701,8 +701,8 @@ extern "C" int dgadj_set_tuning(dgadj_handle* h, int32_t ept, int32_t block, int
 // ---------------------------------------------------------------------------------------
 static int make_plan(dgadj_handle* h, int64_t B, int variant, LaunchPlan* pl) {
   const int K = h->K;
-  int ept = h->tune_ept ? h->tune_ept : ((K % 2 == 0) ? 2 : 1);
-  if (ept == 2 && (K % 2)) return fail(h, DGADJ_ERR_INVALID, "elems_per_thread=2 needs an even K");
+  int ept = h->tune_ept ? h->tune_ept : ((K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1));
+  if (ept > 1 && (K % ept)) return fail(h, DGADJ_ERR_INVALID, "elems_per_thread=%d needs K divisible by it", ept);
   const int KT = K / ept;
   const int bdmax = MAXBD / ept;
   if (KT > bdmax) return fail(h, DGADJ_ERR_UNSUPPORTED, "K=%d does not fit one CTA", K);

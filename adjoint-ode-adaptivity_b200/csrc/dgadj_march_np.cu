@@ -55,6 +55,7 @@ cudaError_t DGADJ_CAT(march_launch_np, DGADJ_NP)(int variant, int ept, int grid,
                                                  cudaStream_t stream, const KArgs* ka) {
   if (ept == 1) return launch_ept<1>(variant, grid, block, stream, ka);
   if (ept == 2) return launch_ept<2>(variant, grid, block, stream, ka);
+  if (ept == 4) return launch_ept<4>(variant, grid, block, stream, ka);
   return cudaErrorInvalidValue;
 }
 

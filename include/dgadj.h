@@ -99,7 +99,7 @@ int dgadj_set_functional_weights(dgadj_handle* h, const double* jw_c, const doub
 /* Caller-supplied inflow values uin[S*nstages] (cfg.inflow == DGADJ_INFLOW_TABLE).       */
 int dgadj_set_inflow_table(dgadj_handle* h, int n, const double* uin);
 
-/* Launch-shape overrides for tuning sweeps (0 = automatic): elements per thread (1 or 2),
+/* Launch-shape overrides for tuning sweeps (0 = automatic): elements per thread (1, 2 or 4),
  * target threads per CTA, CTAs in the persistent grid.                                   */
 int dgadj_set_tuning(dgadj_handle* h, int32_t elems_per_thread, int32_t block_threads,
                      int32_t grid_ctas);
