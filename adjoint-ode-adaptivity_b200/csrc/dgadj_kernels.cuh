@@ -268,20 +268,17 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
     tA[cx.tid] = uF[0];
     tB[cx.tid] = uB[EPT - 1];
     trace_arrive(cx, ka.p.warp_local);
-    // volume terms (no neighbour data): r^_i += sum_{j = i+1, i+3, ...} D^_ij u^_j
+    // volume terms (no neighbour data): r^_i += sum_{j = i+1, i+3, ...} D^_ij u^_j, walked by
+    // diagonals (j - i = 1, 3, ...) so that consecutive DFMA hit different accumulators: no
+    // dependent chain is ever issued back to back (DFMA latency ~20 cycles, 2 warps/scheduler)
 #pragma unroll
-    for (int i = 0; i < NPX - 1; ++i) {
-      double acc[EPT];
+    for (int d = 1; d < NPX; d += 2) {
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) acc[e] = r[e].v[i];
+      for (int i = 0; i + d < NPX; ++i) {
+        const double cij = so.D[nz_index(NPX, i, i + d)];
 #pragma unroll
-      for (int j = i + 1; j < NPX; j += 2) {
-        const double d = so.D[nz_index(NPX, i, j)];
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) acc[e] = fma(d, z[e].v[j], acc[e]);
+        for (int e = 0; e < EPT; ++e) r[e].v[i] = fma(cij, z[e].v[i + d], r[e].v[i]);
       }
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) r[e].v[i] = acc[e];
     }
     trace_wait(cx, ka.p.warp_local);
     double uL = tB[cx.nbL];
@@ -341,14 +338,14 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
     tA[cx.tid] = gam0[0];
     tB[cx.tid] = gam1[EPT - 1];
     trace_arrive(cx, ka.p.warp_local);
-    // volume part (no neighbour data): mu_j += D^_ij w_i, row i of D^ times w_i
+    // volume part (no neighbour data): mu_j += D^_ij w_i, walked by diagonals (see fwd_step)
 #pragma unroll
-    for (int i = 0; i < NPX - 1; ++i) {
+    for (int d = 1; d < NPX; d += 2) {
 #pragma unroll
-      for (int j = i + 1; j < NPX; j += 2) {
-        const double d = so.D[nz_index(NPX, i, j)];
+      for (int i = 0; i + d < NPX; ++i) {
+        const double cij = so.D[nz_index(NPX, i, i + d)];
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) mu[e].v[j] = fma(d, w[e].v[i], mu[e].v[j]);
+        for (int e = 0; e < EPT; ++e) mu[e].v[i + d] = fma(cij, w[e].v[i], mu[e].v[i + d]);
       }
     }
     trace_wait(cx, ka.p.warp_local);
