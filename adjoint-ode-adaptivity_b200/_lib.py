@@ -76,7 +76,6 @@ PROTOTYPES = {
     "dgadj_plan": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                              C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "dgadj_host_eo_operators": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _D]),
-    "dgadj_host_eo_prolongation": (C.c_int, [C.c_int, _P, _P, _P, _D]),
     "dgadj_host_modal_operators": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _D]),
 }
 

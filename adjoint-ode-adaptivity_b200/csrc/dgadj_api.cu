@@ -100,30 +100,6 @@ static int eo_operators(int Np, const double* Dr, const double* LIFT, double* DE
   return DGADJ_OK;
 }
 
-static int eo_prolongation(int Np, const double* P, double* PE, double* PO, double* violation) {
-  if (Np < 2 || Np + 1 > MAXNP || !P) return DGADJ_ERR_INVALID;
-  const int NpF = Np + 1;
-  const int HEc = (Np + 1) / 2, HOc = Np / 2, HEf = (NpF + 1) / 2, HOf = NpF / 2;
-  std::vector<double> Tc, Tci, Tf, Tfi;
-  eo_T(Np, Tc, Tci);
-  eo_T(NpF, Tf, Tfi);
-  std::vector<double> Pm(P, P + (size_t)NpF * Np);
-  std::vector<double> Pt = matmul(matmul(Tf, Pm, NpF, NpF, Np), Tci, NpF, Np, Np);
-  for (int i = 0; i < HM * HM; ++i) PE[i] = PO[i] = 0.0;
-  double scale = 0.0, viol = 0.0;
-  for (int i = 0; i < NpF * Np; ++i) scale = fmax(scale, fabs(Pt[i]));
-  for (int i = 0; i < HEf; ++i) {
-    for (int j = 0; j < HEc; ++j) PE[i * HM + j] = Pt[(size_t)i * Np + j];
-    for (int j = 0; j < HOc; ++j) viol = fmax(viol, fabs(Pt[(size_t)i * Np + HEc + j]));
-  }
-  for (int i = 0; i < HOf; ++i) {
-    for (int j = 0; j < HOc; ++j) PO[i * HM + j] = Pt[(size_t)(HEf + i) * Np + HEc + j];
-    for (int j = 0; j < HEc; ++j) viol = fmax(viol, fabs(Pt[(size_t)(HEf + i) * Np + j]));
-  }
-  if (violation) *violation = scale > 0.0 ? viol / scale : 0.0;
-  return DGADJ_OK;
-}
-
 // ---------------------------------------------------------------------------------------
 // modal (orthonormal Legendre) operators (host):  D^ = V^-1 Dr V,  V^-1 LIFT = V^T E.
 // ---------------------------------------------------------------------------------------
@@ -425,10 +401,6 @@ extern "C" int dgadj_host_modal_operators(int Np, const double* Dr, const double
                                           double* Dnz, double* p, double* iV, double* violation) {
   if (!Dnz || !p || !iV) return DGADJ_ERR_INVALID;
   return modal_operators(Np, Dr, LIFT, V, Dnz, p, iV, violation);
-}
-extern "C" int dgadj_host_eo_prolongation(int Np, const double* P, double* PE, double* PO, double* violation) {
-  if (!PE || !PO) return DGADJ_ERR_INVALID;
-  return eo_prolongation(Np, P, PE, PO, violation);
 }
 
 extern "C" int dgadj_create(const dgadj_config* cfg, dgadj_handle** out) {

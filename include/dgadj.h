@@ -247,12 +247,11 @@ int dgadj_plan(dgadj_handle* h, int64_t B, int32_t fused, int32_t* ept, int32_t*
                int32_t* tpc, int32_t* grid, int64_t* smem_bytes);
 
 /* Host-only utilities (no device needed; used by the CPU test-suite): the even/odd operator
- * blocks the kernels run on, built from nodal Dr[Np*Np] / LIFT[Np*2] (and P[(Np+1)*Np]).
+ * blocks of a nodal operator set Dr[Np*Np] / LIFT[Np*2]
  * (the Burgers kernels use them).  Outputs are [5*5] / [5] arrays (row stride 5); *violation = largest entry of the blocks
  * that must vanish by symmetry, relative to the largest operator entry.                  */
 int dgadj_host_eo_operators(int Np, const double* Dr, const double* LIFT, double* DE, double* DO,
                             double* LS, double* LA, double* violation);
-int dgadj_host_eo_prolongation(int Np, const double* P, double* PE, double* PO, double* violation);
 /* The modal operators the advection march runs on: Dnz[26] = non-zeros of V^-1 Dr V row by row
  * ((i, j), j = i+1, i+3, ...), p[Np] = P~_i(+1), iV[Np*Np] = V^-1; *violation as above.   */
 int dgadj_host_modal_operators(int Np, const double* Dr, const double* LIFT, const double* V,
