@@ -246,10 +246,10 @@ int64_t dgadj_launch_count(const dgadj_handle* h);
 int dgadj_plan(dgadj_handle* h, int64_t B, int32_t fused, int32_t* ept, int32_t* block,
                int32_t* tpc, int32_t* grid, int64_t* smem_bytes);
 
-/* Host-only utilities (no device needed; used by the CPU test-suite): the even/odd operator
- * blocks of a nodal operator set Dr[Np*Np] / LIFT[Np*2]
- * (the Burgers kernels use them).  Outputs are [5*5] / [5] arrays (row stride 5); *violation = largest entry of the blocks
- * that must vanish by symmetry, relative to the largest operator entry.                  */
+/* Host-only utilities (no device needed; used by the CPU test-suite): the even/odd
+ * (symmetric / antisymmetric) blocks of a nodal operator set Dr[Np*Np] / LIFT[Np*2], which the
+ * Burgers kernels use for Dr f.  Outputs are [5*5] / [5] arrays (row stride 5); *violation =
+ * largest entry that must vanish by symmetry, relative to the largest operator entry.     */
 int dgadj_host_eo_operators(int Np, const double* Dr, const double* LIFT, double* DE, double* DO,
                             double* LS, double* LA, double* violation);
 /* The modal operators the advection march runs on: Dnz[26] = non-zeros of V^-1 Dr V row by row

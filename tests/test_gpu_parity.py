@@ -585,3 +585,40 @@ def test_c_client_runs_on_gpu(tmp_path, torch):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "launches 1" in r.stdout
+
+
+def test_fused_randomised_configurations(pkg, torch):
+    """Seeded sweep over orders, mesh sizes (incl. K not divisible by 2 / 4, one trajectory per
+    warp, several per CTA), boundary types, flux parameters, batch sizes that leave ragged groups,
+    per-trajectory speeds, and every launch-shape override -- each against the oracle."""
+    rng = np.random.default_rng(2024)
+    for trial in range(28):
+        N = int(rng.integers(1, 9))
+        K = int(rng.choice([1, 2, 3, 4, 6, 8, 12, 16, 20, 31, 32, 36, 48, 64, 100, 128]))
+        bc = str(rng.choice(["periodic", "inflow"]))
+        alpha = float(rng.choice([0.0, 1.0, 0.35]))
+        inflow = str(rng.choice(["sin_at", "sin_aat", "zero"]))
+        B = int(rng.integers(1, 40))
+        S = int(rng.integers(1, 12))
+        s = pkg.AdvecDG1D(N, K, domain=(-1.0, 1.5), alpha=alpha, bc=bc, inflow=inflow)
+        epts = [e for e in (1, 2, 4) if K % e == 0]
+        ept = int(rng.choice(epts + [0]))
+        block = int(rng.choice([0, 32, 64, 128, 256]))
+        grid = int(rng.choice([0, 1, 3, 7]))
+        try:
+            s.set_tuning(ept, block, grid)
+            gc, gf = oracle_pair(s)
+            u0 = make_ics(gc, B, trial)
+            a = rng.uniform(0.3, 2.0, B) * rng.choice([-1.0, 1.0], B) if rng.uniform() < 0.5 else float(rng.uniform(0.5, 2.0))
+            dt0 = 0.2 * np.min(np.abs(gc.x[0] - gc.x[1])) / 2.0
+            dt = dt0 * rng.uniform(0.5, 1.0, B) if rng.uniform() < 0.5 else float(dt0)
+            oin = {"sin_at": advec.INFLOW_SIN_AT, "sin_aat": advec.INFLOW_SIN_AAT, "zero": advec.INFLOW_ZERO}[inflow]
+            ref = advec.fwd_adj_indicator(u0, gc, gf, a, dt, S, alpha, bc, oin)
+            dev = lambda v: v if np.isscalar(v) else torch.tensor(v, device="cuda")
+            out = s.fwd_adj(torch.tensor(u0, device="cuda"), dev(a), dev(dt), S, want_lam0=True)
+            check_fused(out, ref, B)
+        except AssertionError as e:
+            raise AssertionError(f"trial {trial}: N={N} K={K} bc={bc} alpha={alpha} inflow={inflow} B={B} S={S} "
+                                 f"tuning=({ept},{block},{grid}) plan={s.plan(B)}: {e}")
+        finally:
+            s.close()
