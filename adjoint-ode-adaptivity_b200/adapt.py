@@ -18,6 +18,7 @@ from . import _lib
 from .fd import FDAdjoint, refine_mesh
 from .sharding import allreduce_indicators
 from .tdg import TimeDG, refine as tdg_refine
+from .solver import AdvecDG1D
 
 
 def _batch_reduce(obj, eta, B_global=None):
@@ -74,4 +75,38 @@ def adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=30, linear=False, device=0,
                          max_newton_its=int(its.max()), yT_mean=float(y1[:, -1, -1].mean())))
         times, Ns, Ks = times_new, Ns_new, Ks + 1
     s.close()
+    return hist
+
+
+def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic", inflow="zero", cfl=0.25, psi=None,
+                device=0, B_global=None):
+    """Adjoint-driven h-refinement of the DG-in-space advection march (BASELINE config 5 for the
+    PDE path: non-uniform h): per iteration the batch is marched forward and backward on the
+    current mesh, the per-element indicators are reduced over the batch in a fixed order, and the
+    `topk` elements with the largest batch-mean |eta| are split at their midpoints
+    (matlab/MAIN.m:137-141 applied to space; batch rule python/Main_variable_params.py:340-341).
+
+    u0_fn(x) -> float64 CUDA tensor [B, Np, K] of initial conditions at the nodes x[Np, K]
+    (re-evaluated on every mesh).  Returns the history (mesh, mean indicator, refined elements,
+    J mean) per iteration."""
+    import torch
+    v_x = np.asarray(v_x, dtype=np.float64)
+    hist = []
+    for it in range(iters + 1):
+        s = AdvecDG1D(N, v_x=v_x, alpha=alpha, bc=bc, inflow=inflow, psi=psi, device=device)
+        xmin = np.min(np.abs(s.g.x[0, :] - s.g.x[1, :]))
+        S = int(np.ceil(T / (cfl * xmin / abs(a))))
+        dt = T / S
+        u0 = u0_fn(s.g.x)
+        out = s.fwd_adj(u0, a, dt, S, want_uT=False)
+        sums = allreduce_indicators(s.reduce_indicators(out["eta"], out["J"]), ordered=True)
+        Bg = B_global if B_global is not None else u0.shape[0]
+        K = s.K
+        mean_eta = (sums[:K] / float(Bg)).cpu().numpy()
+        order = np.argsort(-mean_eta, kind="stable")[:topk]            # ties by lowest index
+        hist.append(dict(it=it, v_x=v_x.copy(), K=K, S=S, mean_eta=mean_eta, refined=np.sort(order),
+                         eta_total=float(mean_eta.sum()), J_mean=float(sums[K + 3]) / float(Bg)))
+        s.close()
+        mids = 0.5 * (v_x[order] + v_x[order + 1])
+        v_x = np.sort(np.concatenate([v_x, mids]))
     return hist

@@ -622,3 +622,33 @@ def test_fused_randomised_configurations(pkg, torch):
                                  f"tuning=({ept},{block},{grid}) plan={s.plan(B)}: {e}")
         finally:
             s.close()
+
+
+def test_adaptive_loop_advection_nonuniform_h(pkg, torch):
+    """h-refinement of the DG-in-space march driven by the batch-mean indicator: meshes become
+    non-uniform, the oracle run on the same meshes agrees, refinement goes where the pulses are
+    and the summed indicator drops."""
+    B, N = 12, 3
+    rng = np.random.default_rng(4)
+    centres = rng.uniform(0.8, 1.2, B)
+
+    def u0_np(x):
+        return np.exp(-((x[None] - centres[:, None, None]) / 0.12) ** 2)
+
+    u0_fn = lambda x: torch.tensor(u0_np(x), device="cuda")
+    v_x0 = np.linspace(0.0, 3.0, 13)
+    a, T = 1.0, 0.6
+    hist = pkg.adapt_advec(u0_fn, N, v_x0, a, T, iters=6, topk=2, bc="inflow", inflow="zero", alpha=0.0)
+    assert [h["K"] for h in hist] == [12, 14, 16, 18, 20, 22, 24]
+    for h in hist[:4]:                                    # oracle on the same (non-uniform) meshes
+        gc, gf = ops.startup_mesh(N, h["v_x"]), ops.startup_mesh(N + 1, h["v_x"])
+        for g in (gc, gf):
+            g.rx = np.broadcast_to(g.rx[0:1, :], g.rx.shape).copy()
+        ref = advec.fwd_adj_indicator(u0_np(gc.x), gc, gf, a, T / h["S"], h["S"], 0.0, advec.BC_INFLOW, advec.INFLOW_ZERO)
+        mean_ref = np.abs(ref["eta"]).mean(axis=0)
+        np.testing.assert_allclose(h["mean_eta"], mean_ref, rtol=1e-6, atol=1e-9 * mean_ref.max())
+        assert np.array_equal(h["refined"], np.sort(np.argsort(-mean_ref, kind="stable")[:2]))
+    widths = np.diff(hist[-1]["v_x"])
+    assert widths.min() < 0.5 * widths.max()              # non-uniform h
+    assert 0.5 < hist[-1]["v_x"][np.argmin(widths)] < 2.0   # refined where the pulses travel
+    assert hist[-1]["eta_total"] < 0.5 * hist[0]["eta_total"]
