@@ -652,3 +652,26 @@ def test_adaptive_loop_advection_nonuniform_h(pkg, torch):
     assert widths.min() < 0.5 * widths.max()              # non-uniform h
     assert 0.5 < hist[-1]["v_x"][np.argmin(widths)] < 2.0   # refined where the pulses travel
     assert hist[-1]["eta_total"] < 0.5 * hist[0]["eta_total"]
+
+
+def test_matlab_named_entry_points(pkg, torch):
+    """AdvecRHS1D / SlopeLimitN / dg_march / adj_march / fwd_euler_march under the reference's names."""
+    from oracle import fd as ofd
+    from oracle import limiter as ol
+    m = pkg.matlab_names
+    s = pkg.AdvecDG1D(3, 8, domain=(0.0, 1.0), alpha=1.0, bc="inflow", inflow="sin_at")
+    g = oracle_view(s.g)
+    u = make_ics(g, 2, 0)
+    rhs = m.AdvecRHS1D(s, torch.tensor(u, device="cuda"), 0.3, 2.0)
+    assert rel(rhs.cpu().numpy(), advec.AdvecRHS1D(u, 0.3, 2.0, g, 1.0, advec.BC_INFLOW, advec.INFLOW_SIN_AT)) < 1e-13
+    b = pkg.BurgersDG1D(3, 8, domain=(0.0, 1.0), bc="free")
+    rough = u + (g.x[None] > 0.5)
+    assert rel(m.SlopeLimitN(b, torch.tensor(rough, device="cuda")).cpu().numpy(), ol.SlopeLimitN(rough, oracle_view(b.g))) < 1e-13
+    times = np.array([0.0, 0.3, 0.5, 1.1, 2.0])
+    y0 = np.array([1.0, -0.5, 2.2])
+    t, y = m.fwd_euler_march(torch.tensor(y0, device="cuda"), times)
+    assert rel(y.cpu().numpy(), ofd.forwardSolve(y0, np.diff(times))) < 1e-14
+    tdg = pkg.TimeDG()
+    t1, y1 = m.dg_march(tdg, np.ones(4, dtype=int), 4, times, torch.tensor(y0, device="cuda"))
+    t2, v, err = m.adj_march(tdg, 2 * np.ones(4, dtype=int), 4, times, y1, t1)
+    assert y1.shape == (3, 4, 2) and v.shape == (3, 4, 3) and err.shape == (3, 4)
