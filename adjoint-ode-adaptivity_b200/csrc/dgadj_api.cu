@@ -563,7 +563,11 @@ static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const do
   rebuild_stage_ops(h);
   std::vector<double> rxk(K), f0(K), f1(K);
   for (int k = 0; k < K; ++k) {
-    rxk[k] = rx[k];  // rx(1,k): the affine map makes rx constant inside an element
+    // the affine map makes rx constant inside an element; the caller's Np values differ by the
+    // cancellation noise of J = Dr*x only: take their mean (zero-mean deviation from every node)
+    double sum = 0.0;
+    for (int i = 0; i < Np; ++i) sum += rx[(size_t)i * K + k];
+    rxk[k] = sum / Np;
     f0[k] = Fscale[k];
     f1[k] = Fscale[K + k];
     if (!(rxk[k] != 0.0) || !isfinite(rxk[k])) return fail(h, DGADJ_ERR_INVALID, "rx[%d] is zero or not finite", k);

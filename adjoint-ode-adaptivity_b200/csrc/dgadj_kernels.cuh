@@ -85,7 +85,7 @@ struct MarchParams {
   double alpha, a, dt, t0;
   const double* a_arr;
   const double* dt_arr;
-  const double* rxk[2];   // [level][K]   rx(1,k)
+  const double* rxk[2];   // [level][K]   per-element rx (mean of rx(:,k))
   const double* fs0[2];   // [level][K]   Fscale(1,k)
   const double* fs1[2];   // [level][K]   Fscale(2,k)
   const double* jw_c;     // [NP][K]   modal weights V^T jw of the linear functional

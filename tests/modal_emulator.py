@@ -35,7 +35,7 @@ class Level:
 
     def __init__(self, lib, g, a, dt, alpha, periodic):
         self.o = modal_ops(lib, g)
-        rx = g.r_x[0, :]
+        rx = g.r_x.sum(axis=0) / g.r_x.shape[0]        # the kernel's per-element rx: mean over the nodes
         sg = np.sign(a)
         e0 = 0.5 * (-1.0 - (1.0 - alpha) * sg)
         e1 = 0.5 * (1.0 - (1.0 - alpha) * sg)

@@ -44,10 +44,10 @@ def oracle_view(g):
     """Oracle operator namespace over the product's own arrays: parity means identical inputs.
     (The operator chain itself is checked against the oracle's in tests/test_host_logic.py; two
     fp64 realisations of StartUp1D differ by the cancellation noise of J = Dr*x, ~1e-13, which a
-    long march would turn into a spurious 1e-12-level gap.)  rx is taken element-constant, the
-    way the kernel consumes it -- see test_rx_cancellation_noise_of_the_reference."""
+    long march would turn into a spurious 1e-12-level gap.)  rx is taken element-constant (mean over the
+    element's nodes), the way the kernel consumes it -- see test_rx_cancellation_noise_of_the_reference."""
     from types import SimpleNamespace
-    rx = np.broadcast_to(g.r_x[0:1, :], g.r_x.shape).copy()
+    rx = np.broadcast_to(g.r_x.sum(axis=0, keepdims=True) / g.r_x.shape[0], g.r_x.shape).copy()
     return SimpleNamespace(N=g.n, Np=g.n_p, K=g.k, Dr=g.d_r, LIFT=g.lift, rx=rx, J=g.j_mat, Fscale=g.f_scale,
                            x=g.x, V=g.v, invV=g.inv_v, VX=g.v_x)
 
@@ -200,7 +200,7 @@ def test_rx_cancellation_noise_of_the_reference(pkg, torch):
     AdvecRHS1D.m:19).  In exact arithmetic rx is constant inside an element; computed as Dr*x it
     carries cancellation noise ~ eps |x| ||Dr|| / h that differs from node to node (1e-13
     relative at N=8 near x = 2 pi with K = 24).  The kernel takes one value per element
-    (node 0).  Against the oracle fed the same element-constant rx the adjoint agrees to
+    (the mean over its nodes).  Against the oracle fed the same element-constant rx the adjoint agrees to
     rounding; against the per-node reference semantics the gap is the noise times the step
     count, still far below the discretisation error but above 1e-12 on this mesh."""
     N, K, dom = 7, 24, (0.0, 2 * math.pi)
@@ -499,8 +499,6 @@ def test_burgers_limited_march(pkg, torch, N, K, bc):
     from oracle import burgers as ob
     s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc=bc)
     g = oracle_view(s.g)
-    g.rx = s.g.r_x                                  # the Burgers kernel also takes rx(1,k)
-    g.rx = np.broadcast_to(s.g.r_x[0:1, :], s.g.r_x.shape).copy()
     B = 24
     rng = np.random.default_rng(N * 7 + K)
     c, A, ph = rng.uniform(-0.5, 0.5, (B, 1, 1)), rng.uniform(0.5, 1.5, (B, 1, 1)), rng.uniform(0, 2 * np.pi, (B, 1, 1))
@@ -643,7 +641,7 @@ def test_adaptive_loop_advection_nonuniform_h(pkg, torch):
     for h in hist[:4]:                                    # oracle on the same (non-uniform) meshes
         gc, gf = ops.startup_mesh(N, h["v_x"]), ops.startup_mesh(N + 1, h["v_x"])
         for g in (gc, gf):
-            g.rx = np.broadcast_to(g.rx[0:1, :], g.rx.shape).copy()
+            g.rx = np.broadcast_to(g.rx.sum(axis=0, keepdims=True) / g.rx.shape[0], g.rx.shape).copy()
         ref = advec.fwd_adj_indicator(u0_np(gc.x), gc, gf, a, T / h["S"], h["S"], 0.0, advec.BC_INFLOW, advec.INFLOW_ZERO)
         mean_ref = np.abs(ref["eta"]).mean(axis=0)
         np.testing.assert_allclose(h["mean_eta"], mean_ref, rtol=1e-6, atol=1e-9 * mean_ref.max())
