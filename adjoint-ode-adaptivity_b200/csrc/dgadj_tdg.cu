@@ -7,8 +7,14 @@
 // (fem_setup.m:1-41 operators, the polyfit/polyval interpolation of dg_march.m:47-49 /
 // adj_march.m:75-79 as matrices -- quirk C-5 -- including the mirrored quadrature interval
 // of adj_march.m:72,78 -- quirk C-3) and passed as per-element constant blocks:
-//   march   block: A[Np*Np] | Iq[nq*Np] | Phi[nq*Np] | w[nq] | hk
-//   adjoint block: A0[Na*Na] | f1[Na] | A2[Na*Na] | Ix[Na*Npp] | Iq[nq*Npp] | Phi[nq*Na] | w[nq] | hk
+//   march   block: A[Np*Np] | Iq[nq*Np] | Phi[nq*Np] | w[nq] | hk | np_k
+//   adjoint block: A0[Na*Na] | f1[Na] | A2[Na*Na] | Ix[Na*Npp] | Iq[nq*Npp] | Phi[nq*Na] | w[nq] | hk | na_k | last_{k-1}
+// Mixed orders over the mesh (Ns(k), matlab/MAIN.m:21,141): Np / Na / nq are the
+// mesh maxima and every element's block is padded to them by the host -- identity rows in the
+// system matrices, zero rows/columns in the interpolation matrices, zero quadrature weights --
+// so the padded unknowns stay exactly 0 and the leading np_k x np_k system is eliminated with
+// the same pivots and the same arithmetic as an unpadded solve.  np_k / na_k = the element's
+// own node counts, last_{k-1} = index of the last primal node of the element before it.
 // The device does what depends on the state: sin/cos at the quadrature points, the element
 // residual and Jacobian, Newton's iteration with the reference's stopping rule
 // (||dU||_2 <= tol, at most maxit+1 iterations: dg_march.m:36,44), the dense solves
@@ -62,7 +68,7 @@ __global__ void tdg_march_kernel(long long B, int Ks, int nq, int linear, double
                                  double* __restrict__ y, int* __restrict__ its) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const int blk = NP * NP + 2 * nq * NP + nq + 1;
+  const int blk = NP * NP + 2 * nq * NP + nq + 2;
   double uR = y0[b];
   for (int k = 0; k < Ks; ++k) {
     const double* A = ec + (size_t)k * blk;
@@ -70,6 +76,7 @@ __global__ void tdg_march_kernel(long long B, int Ks, int nq, int linear, double
     const double* Phi = Iq + nq * NP;
     const double* w = Phi + nq * NP;
     const double hk2 = 0.5 * w[nq];
+    const int npk = (int)w[nq + 1];
     double U[NP];
     int it = 0;
     if (linear) {  // dg_march.m:11-25: one solve A U = F, F(1) = uR_prev
@@ -84,7 +91,7 @@ __global__ void tdg_march_kernel(long long B, int Ks, int nq, int linear, double
       it = 1;
     } else {  // dg_march.m:27-77
 #pragma unroll
-      for (int i = 0; i < NP; ++i) U[i] = uR;
+      for (int i = 0; i < NP; ++i) U[i] = (i < npk) ? uR : 0.0;
       double err = 1.0;
       while (it <= maxit && err > tol) {
         double Mt[NP], J[NP][NP];
@@ -134,9 +141,11 @@ __global__ void tdg_march_kernel(long long B, int Ks, int nq, int linear, double
         ++it;
       }
     }
-    uR = U[NP - 1];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) y[((size_t)b * Ks + k) * NP + i] = U[i];
+    for (int i = 0; i < NP; ++i) {
+      if (i == npk - 1) uR = U[i];
+      y[((size_t)b * Ks + k) * NP + i] = U[i];
+    }
     if (its) its[(size_t)b * Ks + k] = it;
   }
 }
@@ -149,7 +158,7 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
   constexpr int NA = NPP + 1;
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const int blk = NA * NA + NA + NA * NA + NA * NPP + nq * NPP + nq * NA + nq + 1;
+  const int blk = NA * NA + NA + NA * NA + NA * NPP + nq * NPP + nq * NA + nq + 3;
   double vL = 0.0;
   for (int k = Ks - 1; k >= 0; --k) {
     const double* A0 = ec + (size_t)k * blk;
@@ -160,6 +169,7 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
     const double* Phi = Iq + nq * NPP;
     const double* w = Phi + nq * NA;
     const double hk2 = 0.5 * w[nq];
+    const int nak = (int)w[nq + 1], lastprev = (int)w[nq + 2];
     double Uk[NPP];
 #pragma unroll
     for (int i = 0; i < NPP; ++i) Uk[i] = y[((size_t)b * Ks + k) * NPP + i];
@@ -192,7 +202,7 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
     double F[NA];
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
-      F[i] = f1[i] - ((i == NA - 1) ? vL : 0.0);          // F = M_k*1; F(end) -= vL_prev
+      F[i] = f1[i] - ((i == nak - 1) ? vL : 0.0);          // F = M_k*1; F(end) -= vL_prev
 #pragma unroll
       for (int j = 0; j < NA; ++j) M[i][j] = fma(-hk2, M[i][j], A0[i * NA + j]);   // A = A0 - M_v
     }
@@ -207,7 +217,7 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
       for (int j = 0; j < NPP; ++j) s = fma(Ix[i * NPP + j], Uk[j], s);
       uh[i] = s;
     }
-    const double f0 = (k == 0) ? y0_hard : y[((size_t)b * Ks + (k - 1)) * NPP + NPP - 1];
+    const double f0 = (k == 0) ? y0_hard : y[((size_t)b * Ks + (k - 1)) * NPP + lastprev];
     double e = 0.0;
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
@@ -218,6 +228,76 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
       if (v) v[((size_t)b * Ks + k) * NA + i] = F[i];
     }
     if (err) err[(size_t)b * Ks + k] = e;
+  }
+}
+
+// Radau-reconstructed adjoint, matlab/adj_rec.m:18-71 (linear branch; the reference's nonlinear
+// branch is unfinished and returns zeros, handled by the host): adjoint solved at the PRIMAL
+// order, interpolated to the element's Radau points, extended by the inflow value and
+// re-interpolated at the nodes of order N+1, where the indicator is evaluated.
+//   block: A0[NP*NP] | f1[NP] | R[NP*NP] | H[NA*NA] | A2[NA*NA] | Ix[NA*NP] | np_k | last_{k-1}
+// (NA = NP + 1; same padding rules as above).  v[b][k][:] = [v at the Radau points; v at t_{k+1}].
+template <int NP>
+__global__ void tdg_adjrec_kernel(long long B, int Ks, double y0_hard, const double* __restrict__ ec,
+                                  const double* __restrict__ y, double* __restrict__ v,
+                                  double* __restrict__ err) {
+  constexpr int NA = NP + 1;
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  constexpr int blk = NP * NP + NP + NP * NP + NA * NA + NA * NA + NA * NP + 2;
+  double vL = 0.0;
+  for (int k = Ks - 1; k >= 0; --k) {
+    const double* A0 = ec + (size_t)k * blk;
+    const double* f1 = A0 + NP * NP;
+    const double* R = f1 + NP;
+    const double* H = R + NP * NP;
+    const double* A2 = H + NA * NA;
+    const double* Ix = A2 + NA * NA;
+    const int npk = (int)Ix[NA * NP], lastprev = (int)Ix[NA * NP + 1];
+    double M[NP][NP], F[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      F[i] = f1[i] - ((i == npk - 1) ? vL : 0.0);           // adj_rec.m:31
+#pragma unroll
+      for (int j = 0; j < NP; ++j) M[i][j] = A0[i * NP + j];
+    }
+    solve_dense<NP>(M, F);                                   // :40  v_s = A \ F
+    double vrec[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double s = (i == npk) ? vL : 0.0;                      // :44  v_rec(end+1) = vL_prev
+      if (i < NP) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) s = fma(R[i * NP + j], F[j], s);
+      }
+      vrec[i] = s;
+    }
+    double Uk[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) Uk[i] = y[((size_t)b * Ks + k) * NP + i];
+    const double f0 = (k == 0) ? y0_hard : y[((size_t)b * Ks + (k - 1)) * NP + lastprev];
+    double uh[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) s = fma(Ix[i * NP + j], Uk[j], s);
+      uh[i] = s;
+    }
+    double e = 0.0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double vh = 0.0, r = (i == 0) ? f0 : 0.0;
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        vh = fma(H[i * NA + j], vrec[j], vh);                // :65
+        r = fma(-A2[i * NA + j], uh[j], r);                  // :66
+      }
+      e = fma(vh, r, e);
+      if (v) v[((size_t)b * Ks + k) * NA + i] = vrec[i];
+    }
+    if (err) err[(size_t)b * Ks + k] = e;
+    vL = vrec[0];                                            // :69
   }
 }
 
@@ -246,7 +326,7 @@ extern "C" int dgadj_tdg_march(dgadj_handle* h, int64_t B, int32_t Ks, int32_t N
   if (Np < 2 || Np > 6) return fail(h, DGADJ_ERR_UNSUPPORTED, "time-DG march supports 1 <= N <= 5 (Np = %d)", Np);
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t blk = (size_t)Np * Np + 2 * (size_t)nq * Np + nq + 1;
+  const size_t blk = (size_t)Np * Np + 2 * (size_t)nq * Np + nq + 2;
   int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
   if (rc) return rc;
   const int block = 128;
@@ -268,7 +348,7 @@ extern "C" int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t Na = Np_primal + 1;
-  const size_t blk = Na * Na + Na + Na * Na + Na * Np_primal + (size_t)nq * Np_primal + (size_t)nq * Na + nq + 1;
+  const size_t blk = Na * Na + Na + Na * Na + Na * Np_primal + (size_t)nq * Np_primal + (size_t)nq * Na + nq + 3;
   int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
   if (rc) return rc;
   const int block = 128;
@@ -276,6 +356,29 @@ extern "C" int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t
 #define DGADJ_TDG_A(n) case n: tdg_adjoint_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, y0_hard, h->tdg_scratch, y_dev, v_dev, err_dev); break;
   switch (Np_primal) { DGADJ_TDG_A(2) DGADJ_TDG_A(3) DGADJ_TDG_A(4) DGADJ_TDG_A(5) DGADJ_TDG_A(6) }
 #undef DGADJ_TDG_A
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_tdg_adjoint_rec(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, double y0_hard,
+                                     const double* elem_consts_host, const double* y_dev, double* v_dev,
+                                     double* err_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || Ks <= 0 || !elem_consts_host || !y_dev) return fail(h, DGADJ_ERR_INVALID, "bad tdg_adjoint_rec arguments");
+  // utils/Globals1D.m:37-42 tabulates Radau points up to m = 5  =>  N <= 4
+  if (Np_primal < 2 || Np_primal > 5) return fail(h, DGADJ_ERR_UNSUPPORTED, "adj_rec supports 1 <= N <= 4 (Radau tables of Globals1D.m)");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Np = Np_primal, Na = Np + 1;
+  const size_t blk = Np * Np + Np + Np * Np + Na * Na + Na * Na + Na * Np + 2;
+  int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
+  if (rc) return rc;
+  const int block = 128;
+  const unsigned grid = (unsigned)((B + block - 1) / block);
+#define DGADJ_TDG_R(n) case n: tdg_adjrec_kernel<n><<<grid, block, 0, st>>>(B, Ks, y0_hard, h->tdg_scratch, y_dev, v_dev, err_dev); break;
+  switch (Np_primal) { DGADJ_TDG_R(2) DGADJ_TDG_R(3) DGADJ_TDG_R(4) DGADJ_TDG_R(5) }
+#undef DGADJ_TDG_R
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return DGADJ_OK;

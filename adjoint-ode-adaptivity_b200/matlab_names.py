@@ -6,6 +6,7 @@ handles (argument order and meaning follow the .m files; batching adds a leading
     [t, y]      = dg_march(tdg, Ns, Ks, times, y0)                matlab/dg_march.m:1
     [t, v, err] = adj_march(tdg, Ns, Ks, times, y1, t1)           matlab/adj_march.m:1  (primal passed
                                                                   explicitly instead of the globals y1, t1)
+    [t, v, err] = adj_rec(tdg, Ns, Ks, times, y1, t1)             matlab/adj_rec.m:1
     [t, y]      = fwd_euler_march(y0, times, ode)                 matlab/fwd_euler_march.m:1 (a broken stub in
                                                                   the reference; semantics of forwardSolve,
                                                                   python/Main_finite_difference.py:34-51)
@@ -32,6 +33,10 @@ def dg_march(tdg, Ns, Ks, times, y0, x_true=None, u_true=None):
 
 def adj_march(tdg, Ns, Ks, times, y1, t1):
     return tdg.adj_march(Ns, Ks, times, y1, t1)
+
+
+def adj_rec(tdg, Ns, Ks, times, y1, t1):
+    return tdg.adj_rec(Ns, Ks, times, y1, t1)
 
 
 def fwd_euler_march(y0, times, ode="sin", device=0):

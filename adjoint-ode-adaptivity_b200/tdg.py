@@ -7,7 +7,8 @@ Host side (this file, once per mesh): the per-element constants -- fem_setup ope
 (matlab/fem_setup.m:1-41 through `BaseGalerkin1D`), the polyfit/polyval interpolation of
 dg_march.m:47-49 / adj_march.m:75-79 as matrices, including the reference's mirrored
 quadrature interval (adj_march.m:72,78).  Device side (csrc/dgadj_tdg.cu):
-everything that depends on the trajectory.  Orders must be uniform over the mesh.
+everything that depends on the trajectory.  Orders may differ between elements (Ns(k),
+matlab/MAIN.m:21,141): the per-element blocks are padded to the mesh maxima.
 """
 from __future__ import annotations
 
@@ -27,6 +28,17 @@ def _polyfit_matrix(x_from, deg, x_to):
     for j in range(n):
         M[:, j] = np.polyval(np.polyfit(x_from, eye[j], deg), x_to)
     return M
+
+
+# utils/Globals1D.m:37-42: left Radau points as the reference tabulates them (six-digit decimals
+# for m = 4, 5 -- kept as written)
+RADAU = {
+    1: np.array([-1.0]),
+    2: np.array([-1.0, 1.0 / 3.0]),
+    3: np.array([-1.0, (1.0 - np.sqrt(6.0)) / 5.0, (1.0 + np.sqrt(6.0)) / 5.0]),
+    4: np.array([-1.0, -0.575319, 0.181066, 0.822824]),
+    5: np.array([-1.0, -0.72048, -0.167181, 0.446314, 0.885792]),
+}
 
 
 class TimeDG:
@@ -62,60 +74,72 @@ class TimeDG:
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
     @staticmethod
-    def _uniform(Ns):
+    def _orders(Ns, Ks):
         Ns = np.asarray(Ns).astype(int).ravel()
-        if not np.all(Ns == Ns[0]):
-            raise _lib.DgadjError(_lib.ERR_UNSUPPORTED, "mixed orders over the mesh are not supported")
-        return int(Ns[0])
+        if Ns.size == 1:
+            Ns = np.repeat(Ns, Ks)
+        if Ns.size != Ks or Ns.min() < 1:
+            raise _lib.DgadjError(_lib.ERR_INVALID, "Ns must hold one order >= 1 per element")
+        return Ns
+
+    @staticmethod
+    def _pad(M, rows, cols, identity=False):
+        """Pad a per-element matrix to the mesh-wide (rows, cols): zeros, or identity rows for a
+        system matrix, so that the padded unknowns are exactly 0 (layout note in csrc/dgadj_tdg.cu)."""
+        M = np.atleast_2d(np.asarray(M, dtype=np.float64))
+        out = np.zeros((rows, cols))
+        out[:M.shape[0], :M.shape[1]] = M
+        if identity:
+            for i in range(M.shape[0], rows):
+                out[i, i] = 1.0
+        return out.ravel()
 
     # ------------------------------------------------------------------ constants
-    def march_constants(self, N, times):
-        """Per-element block A | Iq | Phi | w | hk of dg_march.m (layout: csrc/dgadj_tdg.cu)."""
-        Ks = len(times) - 1
-        n_gq = 1 if self.linear else 30 * N                       # dg_march.m:13 / :29
-        blocks, nodes = [], []
-        nq = 0
-        for k in range(Ks):
-            key = ("m", N, float(times[k]), float(times[k + 1]))
-            if key in self._cache:
-                blk, x, nq = self._cache[key]
-                blocks.append(blk); nodes.append(x)
-                continue
-            g = BaseGalerkin1D(n=N, k=1, domain=(times[k], times[k + 1]), n_gq=n_gq)
+    def _march_element(self, N, t0, t1):
+        key = ("m", N, float(t0), float(t1))
+        if key not in self._cache:
+            n_gq = 1 if self.linear else 30 * N                   # dg_march.m:13 / :29
+            g = BaseGalerkin1D(n=N, k=1, domain=(t0, t1), n_gq=n_gq)
             x = g.x[:, 0]
             hk = x[-1] - x[0]                                     # :14 / :30
             Minv = g.mass
             S = Minv @ g.d_r                                      # :16 / :53
             Np = g.n_p
             Bm = np.zeros((Np, Np))
+            el = dict(x=x, hk=hk, Np=Np, nq=0)
             if self.linear:
                 Bm[-1, -1] = 1.0                                  # :17
-                A = -S.T + Bm - hk / 2 * Minv                     # :15,:18
-                parts = [A.ravel(), [hk]]
-                nq = 0
+                el["A"] = -S.T + Bm - hk / 2 * Minv               # :15,:18
             else:
                 Bm[-1, -1] = -1.0                                 # :54
-                A = S.T + Bm                                      # :57
+                el["A"] = S.T + Bm                                # :57
                 x_interp = x[0] + (1 + g.r) * hk / 2              # :48
-                Iq = _polyfit_matrix(x, N, x_interp)              # :47-49
-                nq = g.n_r
-                parts = [A.ravel(), Iq.ravel(), g.phi.ravel(), g.w, [hk]]
-            blocks.append(np.concatenate([np.asarray(p, dtype=np.float64) for p in parts]))
-            nodes.append(x)
-            self._cache[key] = (blocks[-1], x, nq)
-        return np.ascontiguousarray(np.concatenate(blocks)), nodes, nq
+                el["Iq"] = _polyfit_matrix(x, N, x_interp)        # :47-49
+                el["Phi"], el["w"], el["nq"] = g.phi, g.w, g.n_r
+            self._cache[key] = el
+        return self._cache[key]
 
-    def adjoint_constants(self, Na, t1):
-        """Per-element block A0 | f1 | A2 | Ix | Iq | Phi | w | hk of adj_march.m."""
-        blocks, nodes = [], []
-        nq = 0
-        for tk in t1:
-            tk = np.asarray(tk, dtype=np.float64)
-            key = ("a", Na, tk.tobytes())
-            if key in self._cache:
-                blk, x, nq = self._cache[key]
-                blocks.append(blk); nodes.append(x)
-                continue
+    def march_constants(self, Ns, times):
+        """Per-element block A | Iq | Phi | w | hk | np_k of dg_march.m, padded to the largest
+        order / quadrature of the mesh (layout: csrc/dgadj_tdg.cu).  Returns (blocks, node
+        arrays, Np_max, nq_max)."""
+        Ks = len(times) - 1
+        Ns = self._orders(Ns, Ks)
+        els = [self._march_element(int(Ns[k]), times[k], times[k + 1]) for k in range(Ks)]
+        NP = max(e["Np"] for e in els)
+        nq = max(e["nq"] for e in els)
+        blocks = []
+        for e in els:
+            parts = [self._pad(e["A"], NP, NP, identity=True)]
+            if not self.linear:
+                parts += [self._pad(e["Iq"], nq, NP), self._pad(e["Phi"], nq, NP), self._pad(e["w"], 1, nq)]
+            parts += [[e["hk"], float(e["Np"])]]
+            blocks.append(np.concatenate([np.asarray(p, dtype=np.float64) for p in parts]))
+        return np.ascontiguousarray(np.concatenate(blocks)), [e["x"] for e in els], NP, nq
+
+    def _adjoint_element(self, Na, tk):
+        key = ("a", Na, tk.tobytes())
+        if key not in self._cache:
             g = BaseGalerkin1D(n=Na, k=1, domain=(tk[0], tk[-1]), n_gq=1 if self.linear else 2 * Na)  # :17 / :71
             x = g.x[:, 0]
             hk = x[0] - x[-1]                                     # :18 / :72  negative (quirk C-3)
@@ -123,63 +147,149 @@ class TimeDG:
             S = Minv @ g.d_r
             Np = g.n_p
             deg = len(tk) - 1                                     # :36 / :75
-            Ix = _polyfit_matrix(tk, deg, x)
             M = hk / 2 * Minv
-            f1 = M @ np.ones(Np)                                  # :28 / :96
+            el = dict(x=x, hk=hk, Na=Np, Npp=len(tk), nq=0, Ix=_polyfit_matrix(tk, deg, x),
+                      f1=M @ np.ones(Np))                         # :28 / :96
             if self.linear:
                 m = np.zeros((Np, Np)); m[0, 0] = -1.0            # :21
-                A0 = -S.T + m - M                                 # :22
+                el["A0"] = -S.T + m - M                           # :22
                 m2 = np.zeros((Np, Np)); m2[-1, -1] = 1.0         # :40
-                A2 = -S.T + m2 + M                                # :41
-                parts = [A0.ravel(), f1, A2.ravel(), Ix.ravel(), [hk]]
-                nq = 0
+                el["A2"] = -S.T + m2 + M                          # :41
             else:
                 Bm = np.zeros((Np, Np)); Bm[0, 0] = -1.0          # :85
-                A0 = -S.T + Bm                                    # :86 without M_v (state dependent)
+                el["A0"] = -S.T + Bm                              # :86 without M_v (state dependent)
                 B2 = np.zeros((Np, Np)); B2[-1, -1] = -1.0        # :107
-                A2 = -S.T - B2                                    # :115
+                el["A2"] = -S.T - B2                              # :115
                 r_interp = tk[0] + (1 + g.r) * hk / 2             # :78 (mirrored interval)
-                Iq = _polyfit_matrix(tk, deg, r_interp)
-                nq = g.n_r
-                parts = [A0.ravel(), f1, A2.ravel(), Ix.ravel(), Iq.ravel(), g.phi.ravel(), g.w, [hk]]
+                el["Iq"] = _polyfit_matrix(tk, deg, r_interp)
+                el["Phi"], el["w"], el["nq"] = g.phi, g.w, g.n_r
+            self._cache[key] = el
+        return self._cache[key]
+
+    def adjoint_constants(self, Nas, t1):
+        """Per-element block A0 | f1 | A2 | Ix | Iq | Phi | w | hk | na_k | last_{k-1} of
+        adj_march.m, padded to the mesh maxima.  Returns (blocks, node arrays, Npp_max, nq_max)."""
+        Ks = len(t1)
+        Nas = self._orders(Nas, Ks)
+        els = [self._adjoint_element(int(Nas[k]), np.asarray(t1[k], dtype=np.float64)) for k in range(Ks)]
+        for e in els:
+            if e["Na"] != e["Npp"] + 1:
+                raise _lib.DgadjError(_lib.ERR_UNSUPPORTED,
+                                      "adjoint order must be primal order + 1 on every element (matlab/MAIN.m:34)")
+        NPP = max(e["Npp"] for e in els)
+        NA = NPP + 1
+        nq = max(e["nq"] for e in els)
+        blocks = []
+        for k, e in enumerate(els):
+            parts = [self._pad(e["A0"], NA, NA, identity=True), self._pad(e["f1"], 1, NA), self._pad(e["A2"], NA, NA),
+                     self._pad(e["Ix"], NA, NPP)]
+            if not self.linear:
+                parts += [self._pad(e["Iq"], nq, NPP), self._pad(e["Phi"], nq, NA), self._pad(e["w"], 1, nq)]
+            parts += [[e["hk"], float(e["Na"]), float(els[k - 1]["Npp"] - 1 if k > 0 else 0)]]
             blocks.append(np.concatenate([np.asarray(p, dtype=np.float64) for p in parts]))
-            nodes.append(x)
-            self._cache[key] = (blocks[-1], x, nq)
-        return np.ascontiguousarray(np.concatenate(blocks)), nodes, nq
+        return np.ascontiguousarray(np.concatenate(blocks)), [e["x"] for e in els], NPP, nq
 
     # ------------------------------------------------------------------ reference-named entry points
     def dg_march(self, Ns, Ks, times, y0, x_true=None, u_true=None):
         """[t, y] = dg_march(Ns, Ks, times, y0, x_true, u_true)  (matlab/dg_march.m:1).
-        y0: float64 CUDA tensor [B].  Returns (t, y, its): t = list of Ks node arrays,
-        y[B, Ks, Np], its[B, Ks] Newton iteration counts (the reference prints them, :70)."""
+        y0: float64 CUDA tensor [B].  Ns: one order per element (or a scalar); orders may differ
+        between elements (Ns(k), matlab/MAIN.m:21,141).  Returns (t, y, its): t = list of Ks node
+        arrays, y[B, Ks, Np_max] (element k holds len(t[k]) values, zero beyond), its[B, Ks]
+        Newton iteration counts (the reference prints them, :70)."""
         torch = self.torch
-        N = self._uniform(Ns)
         y0 = y0.contiguous().view(-1)
         B = y0.numel()
-        consts, nodes, nq = self.march_constants(N, np.asarray(times, dtype=np.float64))
-        y = torch.empty((B, Ks, N + 1), dtype=torch.float64, device=y0.device)
+        consts, nodes, NP, nq = self.march_constants(Ns, np.asarray(times, dtype=np.float64))
+        y = torch.empty((B, Ks, NP), dtype=torch.float64, device=y0.device)
         its = torch.empty((B, Ks), dtype=torch.int32, device=y0.device)
-        self._check(self.lib.dgadj_tdg_march(self._h, B, Ks, N + 1, nq, int(self.linear), self.tol, self.maxit,
+        self._check(self.lib.dgadj_tdg_march(self._h, B, Ks, NP, nq, int(self.linear), self.tol, self.maxit,
                                              C.c_void_p(consts.ctypes.data), C.c_void_p(y0.data_ptr()),
                                              C.c_void_p(y.data_ptr()), C.c_void_p(its.data_ptr()), self._stream()))
         return nodes, y, its
 
     def adj_march(self, Ns, Ks, times, y1, t1, y0=1.0):
         """[t, v, err] = adj_march(Ns, Ks, times)  (matlab/adj_march.m:1); the primal the
-        reference reads from globals (`y1`, `t1`, :4) is passed explicitly.  Ns = adjoint orders
-        (matlab/MAIN.m:34 passes Ns+1).  Returns (t, v[B, Ks, Na+1], err[B, Ks]) -- err signed."""
+        reference reads from globals (`y1`, `t1`, :4) is passed explicitly as dg_march returned it.
+        Ns = adjoint orders, primal order + 1 on every element (matlab/MAIN.m:34 passes Ns+1).
+        Returns (t, v[B, Ks, Na_max], err[B, Ks]) -- err signed, v zero beyond len(t[k])."""
         torch = self.torch
-        Na = self._uniform(Ns)
-        Npp = y1.shape[2]
-        if Na + 1 != Npp + 1:
-            raise _lib.DgadjError(_lib.ERR_UNSUPPORTED, "adjoint order must be primal order + 1 (matlab/MAIN.m:34)")
         B = y1.shape[0]
-        consts, nodes, nq = self.adjoint_constants(Na, t1)
-        v = torch.empty((B, Ks, Na + 1), dtype=torch.float64, device=y1.device)
+        consts, nodes, NPP, nq = self.adjoint_constants(Ns, t1)
+        if y1.shape[2] != NPP:
+            raise _lib.DgadjError(_lib.ERR_INVALID, "y1 must be the [B, Ks, Np_max] array dg_march returned")
+        v = torch.empty((B, Ks, NPP + 1), dtype=torch.float64, device=y1.device)
         err = torch.empty((B, Ks), dtype=torch.float64, device=y1.device)
-        self._check(self.lib.dgadj_tdg_adjoint(self._h, B, Ks, Npp, nq, int(self.linear), float(y0),
+        self._check(self.lib.dgadj_tdg_adjoint(self._h, B, Ks, NPP, nq, int(self.linear), float(y0),
                                                C.c_void_p(consts.ctypes.data), C.c_void_p(y1.contiguous().data_ptr()),
                                                C.c_void_p(v.data_ptr()), C.c_void_p(err.data_ptr()), self._stream()))
+        return nodes, v, err
+
+
+    # ------------------------------------------------------------------ adj_rec.m
+    def adjrec_constants(self, Ns, t1):
+        """Per-element block A0 | f1 | R | H | A2 | Ix | np_k | last_{k-1} of the linear branch
+        of adj_rec.m (layout: csrc/dgadj_tdg.cu), padded to the largest order of the mesh."""
+        Ks = len(t1)
+        Ns = self._orders(Ns, Ks)
+        els = []
+        for k in range(Ks):
+            tk = np.asarray(t1[k], dtype=np.float64)
+            N = int(Ns[k])
+            if N + 1 != len(tk):
+                raise _lib.DgadjError(_lib.ERR_INVALID, "adj_rec takes the primal orders (matlab/MAIN.m:35)")
+            if N + 1 not in RADAU:
+                raise _lib.DgadjError(_lib.ERR_UNSUPPORTED, "utils/Globals1D.m:37-42 tabulates Radau points for N <= 4 only")
+            key = ("r", N, tk.tobytes())
+            if key not in self._cache:
+                g = BaseGalerkin1D(n=N, k=1, domain=(tk[0], tk[-1]), n_gq=1)       # adj_rec.m:20
+                x = g.x[:, 0]
+                hk = x[0] - x[-1]                                 # :21 (negative)
+                M = hk / 2 * g.mass                               # :22
+                S = g.mass @ g.d_r                                # :23
+                Np = g.n_p
+                m = np.zeros((Np, Np)); m[0, 0] = -1.0            # :24
+                rad_m = N + 1                                     # :36
+                rad_x = tk[0] + (1 + RADAU[rad_m]) * abs(hk) / 2  # :37-38
+                x_rec = np.concatenate([rad_x, [tk[-1]]])         # :46
+                ge = BaseGalerkin1D(n=rad_m, k=1, domain=(tk[0], tk[-1]), n_gq=1)  # :50 (hk kept)
+                xe = ge.x[:, 0]
+                me = np.zeros((ge.n_p, ge.n_p)); me[-1, -1] = 1.0                  # :53
+                self._cache[key] = dict(
+                    Np=Np, x_rec=x_rec, A0=-S.T + m - M, f1=M @ np.ones(Np),       # :25, :31
+                    R=_polyfit_matrix(x, Np - 1, rad_x),                           # :42-44
+                    H=_polyfit_matrix(x_rec, rad_m, xe),                           # :47-48, :65
+                    A2=-(ge.mass @ ge.d_r).T + me + hk / 2 * ge.mass,              # :51-54
+                    Ix=_polyfit_matrix(tk, len(tk) - 1, xe))                       # :62-64
+            els.append(self._cache[key])
+        NP = max(e["Np"] for e in els)
+        NA = NP + 1
+        blocks = []
+        for k, e in enumerate(els):
+            parts = [self._pad(e["A0"], NP, NP, identity=True), self._pad(e["f1"], 1, NP), self._pad(e["R"], NP, NP),
+                     self._pad(e["H"], NA, NA), self._pad(e["A2"], NA, NA), self._pad(e["Ix"], NA, NP),
+                     [float(e["Np"]), float(els[k - 1]["Np"] - 1 if k > 0 else 0)]]
+            blocks.append(np.concatenate([np.asarray(p, dtype=np.float64) for p in parts]))
+        return np.ascontiguousarray(np.concatenate(blocks)), [e["x_rec"] for e in els], NP
+
+    def adj_rec(self, Ns, Ks, times, y1, t1, y0=1.0):
+        """[t, v, err] = adj_rec(Ns, Ks, times)  (matlab/adj_rec.m:1; disabled in the reference,
+        matlab/MAIN.m:35): the adjoint solved at the primal order Ns and reconstructed to order
+        Ns+1 through the Radau points.  Linear problem (`TimeDG(linear=True)`): adj_rec.m:18-71 on
+        the device; returns (t, v[B, Ks, Np_max+1], err[B, Ks]) with t[k] = [Radau points; t_{k+1}].
+        Nonlinear (`linear = false`, the setting the file ships with, :11): the reference's branch
+        is unfinished -- it returns empty cells and err = 0 (:73-87) -- and so does this."""
+        torch = self.torch
+        B = y1.shape[0]
+        if not self.linear:
+            return [None] * Ks, [None] * Ks, torch.zeros((B, Ks), dtype=torch.float64, device=y1.device)
+        consts, nodes, NP = self.adjrec_constants(Ns, t1)
+        if y1.shape[2] != NP:
+            raise _lib.DgadjError(_lib.ERR_INVALID, "y1 must be the [B, Ks, Np_max] array dg_march returned")
+        v = torch.empty((B, Ks, NP + 1), dtype=torch.float64, device=y1.device)
+        err = torch.empty((B, Ks), dtype=torch.float64, device=y1.device)
+        self._check(self.lib.dgadj_tdg_adjoint_rec(self._h, B, Ks, NP, float(y0), C.c_void_p(consts.ctypes.data),
+                                                   C.c_void_p(y1.contiguous().data_ptr()), C.c_void_p(v.data_ptr()),
+                                                   C.c_void_p(err.data_ptr()), self._stream()))
         return nodes, v, err
 
 

@@ -190,18 +190,27 @@ int dgadj_fd_awr(dgadj_handle* h, int64_t B, int32_t n, int32_t ref_factor, int3
 
 /* DG-in-time ODE march (matlab/dg_march.m:1-80; u' = sin(u) with Newton, or the linear branch
  * u' = u) and its reverse-time DG adjoint with the per-element indicator err(k)
- * (matlab/adj_march.m:1-122), batched over the initial value on a shared mesh of Ks elements of
- * one order.  The per-element constant blocks (everything fem_setup.m:1-41 and the
- * polyfit/polyval interpolation produce; layout in csrc/dgadj_tdg.cu) are built by the host.
+ * (matlab/adj_march.m:1-122), batched over the initial value on a shared mesh of Ks elements.
+ * Orders may differ between elements (Ns(k), matlab/MAIN.m:21,141): Np / Np_primal / nq are
+ * the mesh maxima and each element's block carries its own node count.  The per-element
+ * constant blocks (everything fem_setup.m:1-41 and the polyfit/polyval interpolation produce;
+ * layout and padding rules in csrc/dgadj_tdg.cu) are built by the host.
  *   march:   y0_dev[B] -> y_dev[B][Ks][Np], its_dev[B][Ks] (Newton iterations; or NULL)
  *   adjoint: y_dev (primal, Np_primal) -> v_dev[B][Ks][Np_primal+1] (or NULL), err_dev[B][Ks]
- *            (signed; matlab/MAIN.m:51 takes abs); y0_hard = the `y0 = 1` of adj_march.m:9.  */
+ *            (signed; matlab/MAIN.m:51 takes abs); y0_hard = the `y0 = 1` of adj_march.m:9.
+ *   adjoint_rec: matlab/adj_rec.m:18-71 (linear branch) -- the adjoint solved at the primal
+ *            order and reconstructed to order N+1 through the Radau points of
+ *            utils/Globals1D.m:37-42 (N <= 4); v_dev[B][Ks][Np_primal+1] = values at
+ *            [Radau points; t_{k+1}], err_dev as above.  */
 int dgadj_tdg_march(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np, int32_t nq, int32_t linear,
                     double tol, int32_t maxit, const double* elem_consts_host, const double* y0_dev,
                     double* y_dev, int32_t* its_dev, void* stream);
 int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, int32_t nq,
                       int32_t linear, double y0_hard, const double* elem_consts_host,
                       const double* y_dev, double* v_dev, double* err_dev, void* stream);
+int dgadj_tdg_adjoint_rec(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, double y0_hard,
+                          const double* elem_consts_host, const double* y_dev, double* v_dev,
+                          double* err_dev, void* stream);
 
 /* Inviscid Burgers forward march (LSERK4) with SlopeLimitN (utils/SlopeLimitN.m:9-32,
  * SlopeLimitLin.m:10-18, minmod.m:6-12) applied to the initial state and after every stage,

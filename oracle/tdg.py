@@ -1,6 +1,6 @@
 """Oracle: DG-in-time ODE solver, reverse-time DG adjoint and per-element adjoint-weighted
 indicator -- bug-for-bug NumPy restatement of matlab/dg_march.m, matlab/adj_march.m (both
-branches) and the semantics of matlab/err_contribution.m (TEST INFRASTRUCTURE, see
+branches), matlab/adj_rec.m and the semantics of matlab/err_contribution.m (TEST INFRASTRUCTURE, see
 oracle/__init__.py).  Batched over the initial value y0 (shared mesh `times`, shared orders),
 the batch pattern of python/Main_variable_params.py:330-339.
 
@@ -152,6 +152,75 @@ def adj_march(Ns, Ks, times, y1, t1, linear=False, y0_hard=1.0):
             err[:, k] = np.einsum("bi,bi->b", vk, -(uh @ A2.T) - Mt + F0)   # :117
         vL = vk[:, 0].copy()                                    # :33 / :100
         t[k] = el["x"]; v[k] = vk
+    return t, v, err
+
+
+# utils/Globals1D.m:37-42 -- left Radau points as the reference tabulates them: exact for
+# m <= 3, SIX-DIGIT decimals for m = 4, 5 (kept as written: bug-for-bug)
+RADAU = {
+    1: np.array([-1.0]),
+    2: np.array([-1.0, 1.0 / 3.0]),
+    3: np.array([-1.0, (1.0 - np.sqrt(6.0)) / 5.0, (1.0 + np.sqrt(6.0)) / 5.0]),
+    4: np.array([-1.0, -0.575319, 0.181066, 0.822824]),
+    5: np.array([-1.0, -0.72048, -0.167181, 0.446314, 0.885792]),
+}
+
+
+def adjrec_element(N, tk_primal):
+    """Per-element constants of the linear branch of adj_rec.m (matlab/adj_rec.m:18-71)."""
+    tspan = (tk_primal[0], tk_primal[-1])
+    g = ops.fem_setup(N, 1, tspan, 1)                            # :20
+    x = g.x[:, 0]
+    hk = x[0] - x[-1]                                           # :21 (negative, as in adj_march)
+    Minv = ops.mass_matrix(g.V)
+    M = hk / 2 * Minv                                           # :22
+    S = Minv @ g.Dr                                             # :23
+    Np = g.Np
+    m = np.zeros((Np, Np)); m[0, 0] = -1.0                      # :24
+    rad_m = N + 1                                               # :36
+    rad_x = tspan[0] + (1 + RADAU[rad_m]) * abs(hk) / 2         # :37-38
+    x_rec = np.concatenate([rad_x, [tspan[1]]])                 # :46
+    ge = ops.fem_setup(rad_m, 1, tspan, 1)                      # :50  (hk is NOT recomputed)
+    xe = ge.x[:, 0]
+    Minv_e = ops.mass_matrix(ge.V)
+    Me = hk / 2 * Minv_e                                        # :51
+    Se = Minv_e @ ge.Dr                                         # :52
+    me = np.zeros((ge.Np, ge.Np)); me[-1, -1] = 1.0             # :53
+    return dict(Np=Np, x_rec=x_rec,
+                A=-S.T + m - M,                                 # :25
+                f1=M @ np.ones(Np),                             # :31
+                R=_polyfit_matrix(x, Np - 1, rad_x),            # :42-44  v_s -> Radau points
+                H=_polyfit_matrix(x_rec, rad_m, xe),            # :47-48,:65  v_rec -> enriched nodes
+                A2=-Se.T + me + Me,                             # :54
+                Ix=_polyfit_matrix(tk_primal, len(tk_primal) - 1, xe))   # :62-64
+
+
+def adj_rec(Ns, Ks, times, y1, t1, linear=False, y0_hard=1.0):
+    """matlab/adj_rec.m:1-88 -- adjoint at the PRIMAL order, reconstructed to order N+1 through
+    the Radau points plus the inflow value (disabled in the reference: MAIN.m:35).  Ns = primal
+    orders (MAIN.m:35 passes Ns).  linear=True: adj_rec.m:18-71.  linear=False is the branch the
+    file ships with (`linear = false`, :11): unfinished -- it assembles a mass matrix per element
+    and returns empty cells and err = 0 (:73-87); restated as exactly that.
+    Returns (t, v, err): t[k] = [Radau points; t_{k+1}], v[k] (B, N_k+2), err (B, Ks) signed."""
+    B = y1[0].shape[0]
+    t, v = [None] * Ks, [None] * Ks
+    err = np.zeros((B, Ks))
+    if not linear:
+        return t, v, err
+    vL = np.zeros(B)
+    for k in range(Ks - 1, -1, -1):
+        el = adjrec_element(int(Ns[k]), t1[k])
+        F = np.tile(el["f1"], (B, 1)); F[:, -1] -= vL           # :31
+        vs = np.linalg.solve(el["A"], F.T).T                    # :40
+        vrec = np.concatenate([vs @ el["R"].T, vL[:, None]], axis=1)     # :44
+        vh = vrec @ el["H"].T                                   # :65
+        uh = y1[k] @ el["Ix"].T                                 # :64
+        F0 = np.zeros_like(uh)
+        F0[:, 0] = y0_hard if k == 0 else y1[k - 1][:, -1]      # :55-59 (y0 = 1, :9)
+        err[:, k] = np.einsum("bi,bi->b", vh, -(uh @ el["A2"].T) + F0)   # :66
+        v[k] = vrec                                             # :68
+        vL = vrec[:, 0].copy()                                  # :69
+        t[k] = el["x_rec"]                                      # :70
     return t, v, err
 
 

@@ -432,6 +432,79 @@ def test_tdg_march_and_adjoint(pkg, torch, n, linear):
     assert rel(y1f.cpu().numpy(), np.stack(y1fr, axis=1)) < 1e-10
 
 
+@pytest.mark.parametrize("linear", [False, True])
+def test_tdg_mixed_orders(pkg, torch, linear):
+    """Per-element orders Ns(k) (matlab/MAIN.m:21,141): the padded-block march and
+    adjoint against the oracle, which runs each element at its own order."""
+    from oracle import tdg as otdg
+    rng = np.random.default_rng(11)
+    times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.1, 1.9, 5))))
+    Ks = times.size - 1
+    Ns = np.array([1, 3, 2, 4, 1, 2])
+    y0 = np.concatenate(([1.0], rng.uniform(-3, 3, 127)))
+    s = pkg.TimeDG(linear=linear)
+    t1, y1, its = s.dg_march(Ns, Ks, times, torch.tensor(y0, device="cuda"))
+    t1r, y1r, itsr = otdg.dg_march(Ns, Ks, times, y0, linear=linear)
+    y1h = y1.cpu().numpy()
+    assert y1h.shape == (128, Ks, 5)
+    assert np.array_equal(its.cpu().numpy(), np.stack(itsr, axis=1))
+    for k in range(Ks):
+        assert len(t1[k]) == Ns[k] + 1
+        assert rel(y1h[:, k, :Ns[k] + 1], y1r[k]) < 1e-11
+        assert np.all(y1h[:, k, Ns[k] + 1:] == 0.0)
+    t2, v, err = s.adj_march(Ns + 1, Ks, times, y1, t1)
+    _, vr, errr = otdg.adj_march(Ns + 1, Ks, times, y1r, t1r, linear=linear)
+    vh = v.cpu().numpy()
+    vmax = max(np.max(np.abs(a)) for a in vr)
+    for k in range(Ks):
+        assert len(t2[k]) == Ns[k] + 2
+        assert np.max(np.abs(vh[:, k, :Ns[k] + 2] - vr[k])) < 1e-10 * vmax
+        assert np.all(vh[:, k, Ns[k] + 2:] == 0.0)
+    scale = vmax * max(np.max(np.abs(a)) for a in y1r)
+    assert np.max(np.abs(err.cpu().numpy() - errr)) < 1e-10 * max(scale, 1.0)
+    # a uniform mesh through the same path gives the same bits as before padding existed
+    Nu = 2 * np.ones(Ks, dtype=int)
+    _, ya, _ = s.dg_march(Nu, Ks, times, torch.tensor(y0, device="cuda"))
+    _, yb, _ = s.dg_march(2, Ks, times, torch.tensor(y0, device="cuda"))
+    assert torch.equal(ya, yb)
+
+
+@pytest.mark.parametrize("orders", [[1], [2], [3], [4], [1, 3, 2, 4, 1, 2]])
+def test_tdg_adj_rec(pkg, torch, orders):
+    """dgadj_tdg_adjoint_rec against the restatement of matlab/adj_rec.m:18-71 (Radau-reconstructed
+    adjoint, linear problem), uniform and mixed orders; and the unfinished nonlinear branch
+    (adj_rec.m:73-87) returns what the reference's returns: nothing and zeros."""
+    from oracle import tdg as otdg
+    rng = np.random.default_rng(13)
+    times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.1, 1.9, 5))))
+    Ks = times.size - 1
+    Ns = np.array(orders) if len(orders) > 1 else orders[0] * np.ones(Ks, dtype=int)
+    y0 = np.concatenate(([1.0], rng.uniform(-3, 3, 63)))
+    s = pkg.TimeDG(linear=True)
+    t1, y1, _ = s.dg_march(Ns, Ks, times, torch.tensor(y0, device="cuda"))
+    t1r, y1r, _ = otdg.dg_march(Ns, Ks, times, y0, linear=True)
+    t3, v, err = s.adj_rec(Ns, Ks, times, y1, t1)
+    t3r, vr, errr = otdg.adj_rec(Ns, Ks, times, y1r, t1r, linear=True)
+    vh = v.cpu().numpy()
+    vmax = max(np.max(np.abs(a)) for a in vr)
+    for k in range(Ks):
+        np.testing.assert_allclose(t3[k], t3r[k], rtol=1e-14, atol=1e-15)
+        assert np.max(np.abs(vh[:, k, :Ns[k] + 2] - vr[k])) < 1e-10 * vmax
+        assert np.all(vh[:, k, Ns[k] + 2:] == 0.0)
+    scale = vmax * max(np.max(np.abs(a)) for a in y1r)
+    assert np.max(np.abs(err.cpu().numpy() - errr)) < 1e-10 * max(scale, 1.0)
+    # the reconstruction is worth an order: its total estimate is close to adj_march at N+1
+    _, _, err2 = s.adj_march(Ns + 1, Ks, times, y1, t1)
+    tot, tot2 = err.sum(1).cpu().numpy(), err2.sum(1).cpu().numpy()
+    assert np.max(np.abs(tot - tot2)) < 0.15 * np.max(np.abs(tot2)) + 1e-9
+    from adjoint_ode_adaptivity_b200 import matlab_names as m
+    t4, v4, err4 = m.adj_rec(s, Ns, Ks, times, y1, t1)
+    assert torch.equal(err4, err)
+    sn = pkg.TimeDG(linear=False)
+    tn, vn, errn = sn.adj_rec(Ns, Ks, times, y1, t1)
+    assert tn == [None] * Ks and vn == [None] * Ks and float(errn.abs().max()) == 0.0
+
+
 def test_tdg_reference_iteration0(pkg, torch):
     """matlab/MAIN.m iteration 0 on the GPU: the numbers of init_nonlin.png."""
     times, Ns = np.array([0.0, 1.0, 2.0]), np.array([1, 1])

@@ -299,3 +299,91 @@ def test_missing_library_fails_loudly(tmp_path):
     env = dict(os.environ, DGADJ_LIB=str(tmp_path / "nope" / "libdgadj.so"))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 7 and "There is no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+def _tdg_host(pkg, linear):
+    """A TimeDG with only its host-side constant builders (no device handle)."""
+    from adjoint_ode_adaptivity_b200.tdg import TimeDG
+    s = object.__new__(TimeDG)
+    s.linear, s._cache, s._h = linear, {}, None
+    return s
+
+
+@pytest.mark.parametrize("linear", [False, True])
+def test_tdg_padded_blocks_reproduce_mixed_orders(pkg, linear):
+    """Mixed per-element orders (matlab/MAIN.m:21,141) are run by the device on blocks padded to
+    the mesh maxima (layout: csrc/dgadj_tdg.cu).  NumPy emulation of that padded arithmetic --
+    same blocks, same element recurrences -- against the oracle running each element at its
+    own order: the padding must be inert."""
+    from oracle import tdg as otdg
+    rng = np.random.default_rng(5)
+    times = np.array([0.0, 0.3, 0.8, 1.1, 2.0])
+    Ks, Ns = 4, np.array([2, 1, 3, 1])
+    y0 = rng.uniform(-3, 3, 6)
+    s = _tdg_host(pkg, linear)
+    consts, nodes, NP, nq = s.march_constants(Ns, times)
+    blk = NP * NP + 2 * nq * NP + nq + 2
+    assert consts.size == blk * Ks and NP == 4
+    t1r, y1r, itsr = otdg.dg_march(Ns, Ks, times, y0, linear=linear)
+    y = np.zeros((y0.size, Ks, NP))
+    for b in range(y0.size):
+        uR = y0[b]
+        for k in range(Ks):
+            c = consts[k * blk:(k + 1) * blk]
+            A = c[:NP * NP].reshape(NP, NP)
+            Iq = c[NP * NP:NP * NP + nq * NP].reshape(nq, NP)
+            Phi = c[NP * NP + nq * NP:NP * NP + 2 * nq * NP].reshape(nq, NP)
+            w = c[NP * NP + 2 * nq * NP:NP * NP + 2 * nq * NP + nq]
+            hk, npk = c[-2], int(c[-1])
+            assert npk == Ns[k] + 1
+            F = np.zeros(NP); F[0] = uR
+            if linear:
+                U = np.linalg.solve(A, F)
+            else:
+                U = np.where(np.arange(NP) < npk, uR, 0.0)
+                it, err = 0, 1.0
+                while it <= 500 and err > 1e-7:
+                    ur = Iq @ U
+                    R = A @ U + hk / 2 * Phi.T @ (w * np.sin(ur)) + F
+                    J = A + hk / 2 * Phi.T @ ((w * np.cos(ur))[:, None] * Phi)
+                    dU = np.linalg.solve(J, R)
+                    U = U - dU
+                    err = np.linalg.norm(dU)
+                    it += 1
+                assert it == itsr[k][b]
+            assert np.all(U[npk:] == 0.0)
+            uR = U[npk - 1]
+            y[b, k] = U
+            np.testing.assert_allclose(U[:npk], y1r[k][b], rtol=1e-11, atol=1e-13)
+    # adjoint blocks
+    consts, nodes2, NPP, nq = s.adjoint_constants(Ns + 1, nodes)
+    NA = NPP + 1
+    blk = 2 * NA * NA + NA + NA * NPP + nq * NPP + nq * NA + nq + 3
+    assert consts.size == blk * Ks and NPP == NP
+    _, vr, errr = otdg.adj_march(Ns + 1, Ks, times, y1r, t1r, linear=linear)
+    for b in range(y0.size):
+        vL = 0.0
+        for k in range(Ks - 1, -1, -1):
+            c = consts[k * blk:(k + 1) * blk]
+            o = 0
+            A0 = c[o:o + NA * NA].reshape(NA, NA); o += NA * NA
+            f1 = c[o:o + NA]; o += NA
+            A2 = c[o:o + NA * NA].reshape(NA, NA); o += NA * NA
+            Ix = c[o:o + NA * NPP].reshape(NA, NPP); o += NA * NPP
+            Iq = c[o:o + nq * NPP].reshape(nq, NPP); o += nq * NPP
+            Phi = c[o:o + nq * NA].reshape(nq, NA); o += nq * NA
+            w = c[o:o + nq]; o += nq
+            hk, nak, lastprev = c[o], int(c[o + 1]), int(c[o + 2])
+            assert nak == Ns[k] + 2 and (k == 0 or lastprev == Ns[k - 1])
+            Uk = y[b, k]
+            ur = Iq @ Uk
+            Mv = hk / 2 * Phi.T @ ((w * np.cos(ur))[:, None] * Phi) if nq else 0.0
+            Mt = hk / 2 * Phi.T @ (w * np.sin(ur)) if nq else 0.0
+            F = f1.copy(); F[nak - 1] -= vL
+            vk = np.linalg.solve(A0 - Mv, F)
+            vL = vk[0]
+            F0 = np.zeros(NA); F0[0] = 1.0 if k == 0 else y[b, k - 1, lastprev]
+            e = vk @ (-(A2 @ (Ix @ Uk)) - Mt + F0)
+            assert np.all(vk[nak:] == 0.0)
+            np.testing.assert_allclose(vk[:nak], vr[k][b], rtol=1e-9, atol=1e-11)
+            np.testing.assert_allclose(e, errr[b, k], rtol=1e-9, atol=1e-11)
