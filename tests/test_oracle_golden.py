@@ -207,6 +207,37 @@ def test_tdg_linear_branch_effectivity():
     assert abs(y1f[1][0, -1] - np.e) < 1e-4
 
 
+def test_tdg_adj_rec_restatement():
+    """matlab/adj_rec.m (disabled in the reference, MAIN.m:35; no reference output exists for it:
+    parity unpinned).  What can be checked: the reconstructed adjoint converges to the exact
+    adjoint of u' = u, J = int u dt on [0, 2]  (v = e^{2-t} - 1), the element sum of the
+    indicator is an error estimate for J, mixed orders run, and the shipped nonlinear branch
+    returns nothing (adj_rec.m:73-87)."""
+    times = np.array([0.0, 0.5, 1.0, 2.0])
+    dev = []
+    for N in (1, 2, 3, 4):
+        Ns = N * np.ones(3, dtype=int)
+        t1, y1, _ = tdg.dg_march(Ns, 3, times, 1.0, linear=True)
+        t, v, err = tdg.adj_rec(Ns, 3, times, y1, t1, linear=True)
+        for k in range(3):
+            assert t[k].size == N + 2 and t[k][0] == times[k] and t[k][-1] == times[k + 1]
+            assert v[k].shape == (1, N + 2)
+        dev.append(max(np.max(np.abs(v[k][0] - (np.exp(2.0 - t[k]) - 1.0))) for k in range(3)))
+        # J(u) - J(u_H) for u' = u, u(0) = 1: exact J = e^2 - 1
+        JuH = 0.0
+        for tt, yy in zip(t1, y1):
+            P = np.polyint(np.polyfit(tt, yy[0], N))
+            JuH += np.polyval(P, tt[-1]) - np.polyval(P, tt[0])
+        assert err.sum() == pytest.approx((np.exp(2.0) - 1.0) - JuH, rel=0.2, abs=1e-9)
+    assert dev[0] > dev[1] > dev[2] > dev[3] and dev[3] < 1e-5
+    Ns = np.array([1, 3, 2])
+    t1, y1, _ = tdg.dg_march(Ns, 3, times, np.array([1.0, -0.4]), linear=True)
+    t, v, err = tdg.adj_rec(Ns, 3, times, y1, t1, linear=True)
+    assert [a.shape for a in v] == [(2, 3), (2, 5), (2, 4)] and np.all(np.isfinite(err))
+    t, v, err = tdg.adj_rec(Ns, 3, times, y1, t1)            # linear = false, as shipped (:11)
+    assert t == [None] * 3 and v == [None] * 3 and not err.any()
+
+
 def test_tdg_refine_rule():
     times, Ns, ref_i = tdg.refine(np.array([0.0, 1.0, 2.0]), np.array([1, 1]), np.array([-0.84, 0.09]), 1)
     assert ref_i == 0 and times.tolist() == [0.0, 0.5, 1.0, 2.0] and Ns.tolist() == [1, 1, 1]
