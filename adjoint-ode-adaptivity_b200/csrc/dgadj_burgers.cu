@@ -17,6 +17,15 @@
 
 #include "dgadj_internal.h"
 
+// resident CTAs per SM the 256-thread kernels are compiled for (measured on config 3, N = 4:
+// forward 4.90 / 4.77 / 5.22 / 5.46e10 updates/s at 1 / 2 / 3 / 4, adjoint 2.17 / 3.21 / 2.75 / 2.69e10)
+#ifndef BG_MINB_FWD
+#define BG_MINB_FWD(NP) ((NP) <= 5 ? 4 : ((NP) <= 7 ? 2 : 1))
+#endif
+#ifndef BG_MINB_ADJ
+#define BG_MINB_ADJ(NP) ((NP) <= 5 ? 2 : 1)
+#endif
+
 namespace dgadj {
 
 struct BurgersArgs {
@@ -50,44 +59,47 @@ struct BurgersArgs {
   double rka[5], rkb[5];
 };
 
+// utils/minmod.m:7-11: s = sum(sign(v))/3; |s| == 1 -> s * min|v|, else 0.  |s| == 1 exactly when
+// the three arguments are all > 0 or all < 0, and then s * min|v| is min(v) resp. max(v) with
+// the same bits (a product with +-1 is exact): no division, no sign arithmetic.
 __device__ __forceinline__ double minmod3(double a, double b, double c) {
-  // utils/minmod.m:7-11: s = sum(sign(v))/3; |s| == 1 -> s * min|v|, else 0
-  const double sa = (a > 0.0) - (a < 0.0), sb = (b > 0.0) - (b < 0.0), sc = (c > 0.0) - (c < 0.0);
-  const double s = (sa + sb + sc) / 3.0;
-  if (fabs(s) == 1.0) return s * fmin(fabs(a), fmin(fabs(b), fabs(c)));
-  return 0.0;
+  const bool pos = (a > 0.0) & (b > 0.0) & (c > 0.0), neg = (a < 0.0) & (b < 0.0) & (c < 0.0);
+  const double lo = fmin(a, fmin(b, c)), hi = fmax(a, fmax(b, c));
+  return pos ? lo : (neg ? hi : 0.0);
 }
 
-// minmod of three with the index (1..3) of the winning argument; 0 when the result is zero
+// minmod of three with the index (1..3) of the winning argument (first smallest |v|, as
+// MATLAB's min picks it); 0 when the result is zero
 __device__ __forceinline__ double minmod3b(double a, double b, double c, int* br) {
-  const double sa = (a > 0.0) - (a < 0.0), sb = (b > 0.0) - (b < 0.0), sc = (c > 0.0) - (c < 0.0);
-  const double s = (sa + sb + sc) / 3.0;
+  const bool pos = (a > 0.0) & (b > 0.0) & (c > 0.0), neg = (a < 0.0) & (b < 0.0) & (c < 0.0);
   *br = 0;
-  if (fabs(s) != 1.0) return 0.0;
+  if (!(pos | neg)) return 0.0;
   const double fa = fabs(a), fb = fabs(b), fc = fabs(c);
   double m = fa;
   int w = 1;
   if (fb < m) { m = fb; w = 2; }
   if (fc < m) { m = fc; w = 3; }
   *br = w;
-  return s * m;
+  return pos ? m : -m;
 }
 
-// CTA-wide max|u| with the flat index (i*K + k) of its first occurrence in row-major order
-struct MaxLoc {
-  double v;
-  int idx;
-};
-__device__ __forceinline__ MaxLoc maxloc_better(MaxLoc a, MaxLoc b) {
-  return (b.v > a.v || (b.v == a.v && b.idx < a.idx)) ? b : a;
+// warp-wide max of values that are >= 0 or exactly -1.0 (the filler of idle lanes): for those the
+// bit pattern is ordered like the value (high word as a signed int, then the low word), so two
+// integer warp reductions (redux.sync) replace a five-step shuffle tree of double compares
+__device__ __forceinline__ double warp_max_nonneg(double m) {
+  const int hi = __double2hiint(m);
+  const int mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned lo = (hi == mh) ? (unsigned)__double2loint(m) : 0u;
+  const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+  return __hiloint2double(mh, (int)ml);
 }
 
 template <int NP, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant__ BurgersArgs p) {
+__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burgers_kernel(const __grid_constant__ BurgersArgs p) {
   constexpr int HE = (NP + 1) / 2, HO = NP / 2;
   __shared__ double trL[2][MAXT], trR[2][MAXT], avg[MAXT];
   __shared__ double wmax[2][32];
-  __shared__ int widx[2][32];
+  __shared__ int cand[2];
   const int tid = threadIdx.x, K = p.K;
   const int lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
   const bool in = tid < K;
@@ -97,6 +109,10 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
   const bool first = in && tid == 0, last = in && tid == K - 1;
   const double rx = in ? p.rxk[k] : 0.0, fs0 = in ? p.fs0[k] : 0.0, fs1 = in ? p.fs1[k] : 0.0;
   const double h = in ? p.hk[k] : 1.0;
+  const double twoh = 2.0 / h;
+  if (tid < 2) cand[tid] = 0x7fffffff;
+  int* pend = nullptr;   // where the argmax still being voted on goes (uniform over the CTA)
+  __syncthreads();
 
   for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
     const double dt = p.dt_arr ? p.dt_arr[b] : p.dt;
@@ -128,7 +144,7 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
       double d = 0.0;
 #pragma unroll
       for (int i = 0; i < NP; ++i) d = fma(p.sl[i], u[i], d);
-      const double ux = (2.0 / h) * d;
+      const double ux = twoh * d;
       int br;
       const double slope = minmod3b(ux, (vp - v) / h, (v - vm) / h, &br);
 #pragma unroll
@@ -149,32 +165,41 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
 #pragma unroll 1
       for (int s = 0; s < 5; ++s) {
         // ---- exchange 1: traces and the mesh-wide max|u|
-        MaxLoc m = {-1.0, 0x7fffffff};
+        // (the value first: max is exact in any order; where it sits is settled afterwards by
+        // the few threads that hold it)
+        double m = -1.0;
         if (in) {
 #pragma unroll
-          for (int i = 0; i < NP; ++i) m = maxloc_better(m, MaxLoc{fabs(u[i]), i * K + k});
+          for (int i = 0; i < NP; ++i) m = fmax(m, fabs(u[i]));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          MaxLoc t = {__shfl_xor_sync(0xffffffffu, m.v, o), __shfl_xor_sync(0xffffffffu, m.idx, o)};
-          m = maxloc_better(m, t);
-        }
+        m = warp_max_nonneg(m);
         trL[par][tid] = u[0];
         trR[par][tid] = u[NP - 1];
-        if (lane == 0) {
-          wmax[par][wid] = m.v;
-          widx[par][wid] = m.idx;
-        }
+        if (lane == 0) wmax[par][wid] = m;
         __syncthreads();
-        MaxLoc best = {-1.0, 0x7fffffff};
-        for (int w = 0; w < nw; ++w) best = maxloc_better(best, MaxLoc{wmax[par][w], widx[par][w]});
-        const double maxvel = best.v;
-        if (p.amax && in && (best.idx % K) == k) {
-          const int i = best.idx / K;
-          double ui = 0.0;
+        if (pend) {   // argmax of the stage before: every candidate has voted by now
+          if (tid == 0) {
+            const int c = cand[par ^ 1];
+            *pend = (c & 1) ? -((c >> 1) + 1) : ((c >> 1) + 1);
+            cand[par ^ 1] = 0x7fffffff;
+          }
+          pend = nullptr;
+        }
+        const double maxvel = warp_max_nonneg((lane < nw) ? wmax[par][lane] : -1.0);
+        if (p.amax) {
+          // first occurrence in row-major order (i*K + k) of max|u|, and the sign of u there
+          if (in) {
+            int i0 = -1;
 #pragma unroll
-          for (int q = 0; q < NP; ++q) ui = (q == i) ? u[q] : ui;
-          p.amax[((size_t)b * p.S + n) * 5 + s] = (ui < 0.0) ? -(best.idx + 1) : (best.idx + 1);
+            for (int i = NP - 1; i >= 0; --i) i0 = (fabs(u[i]) == maxvel) ? i : i0;
+            if (i0 >= 0) {
+              double ui = 0.0;
+#pragma unroll
+              for (int q = 0; q < NP; ++q) ui = (q == i0) ? u[q] : ui;
+              atomicMin(&cand[par], ((i0 * K + k) << 1) | (ui < 0.0 ? 1 : 0));
+            }
+          }
+          pend = p.amax + ((size_t)b * p.S + n) * 5 + s;
         }
         double uL = trR[par][nbL], uR = trL[par][nbR];
         par ^= 1;
@@ -249,6 +274,14 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
       for (int i = 0; i < NP; ++i) p.uT[((size_t)b * NP + i) * K + k] = u[i];
     }
     __syncthreads();
+    if (pend) {   // the last stage's argmax
+      if (tid == 0) {
+        const int c = cand[par ^ 1];
+        *pend = (c & 1) ? -((c >> 1) + 1) : ((c >> 1) + 1);
+        cand[par ^ 1] = 0x7fffffff;
+      }
+      pend = nullptr;
+    }
   }
 }
 
@@ -262,7 +295,7 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_kernel(const __grid_constant_
 // including the rank-one term through C = max|u|, lk *= rka.
 // ---------------------------------------------------------------------------------------
 template <int NP, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) burgers_adjoint_kernel(const __grid_constant__ BurgersArgs p) {
+__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burgers_adjoint_kernel(const __grid_constant__ BurgersArgs p) {
   constexpr int HE = (NP + 1) / 2, HO = NP / 2;
   __shared__ double exA[2][MAXT], exB[2][MAXT];
   __shared__ double wsum[2][32];
@@ -275,6 +308,7 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_adjoint_kernel(const __grid_c
   const bool first = in && tid == 0, last = in && tid == K - 1;
   const double rx = in ? p.rxk[k] : 0.0, fs0 = in ? p.fs0[k] : 0.0, fs1 = in ? p.fs1[k] : 0.0;
   const double h = in ? p.hk[k] : 1.0;
+  const double twoh = 2.0 / h;
   double* ss = p.stage_scratch + (size_t)blockIdx.x * 5 * (NP + 2) * BD + tid;
   int par = 0;
   auto block_sum = [&](double v) -> double {   // deterministic: shuffle tree, then warps in order
@@ -312,7 +346,8 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_adjoint_kernel(const __grid_c
         a += lu[i];
         c = fma(in ? p.xc[(size_t)i * K + k] : 0.0, lu[i], c);
       }
-      const double ch = c / h;
+      double ch = 0.0;
+      if (br >= 2) ch = c / h;   // rare: keeps the division off the common path
       const double tr = (br == 2) ? ch : 0.0, tl = (br == 3) ? -ch : 0.0;
       __syncthreads();
       exA[0][tid] = tr;   // goes to cell k+1
@@ -326,7 +361,7 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_adjoint_kernel(const __grid_c
         if (first) fromR += tl;
       }
       double lv = (flag ? a : 0.0) + ((br == 2) ? -ch : ((br == 3) ? ch : 0.0)) + fromL + fromR;
-      const double cs = (br == 1) ? (2.0 / h) * c : 0.0;
+      const double cs = (br == 1) ? twoh * c : 0.0;
 #pragma unroll
       for (int i = 0; i < NP; ++i) lu[i] = (flag ? 0.0 : lu[i]) + p.aw[i] * lv + p.sl[i] * cs;
     };
@@ -421,7 +456,7 @@ __global__ void __launch_bounds__(MAXT, 1) burgers_adjoint_kernel(const __grid_c
             double d = 0.0;
 #pragma unroll
             for (int i = 0; i < NP; ++i) d = fma(p.sl[i], u[i], d);
-            const double slope = (br == 1) ? (2.0 / h) * d : ((br == 2) ? (vp - v) / h : ((br == 3) ? (v - vm) / h : 0.0));
+            const double slope = (br == 1) ? twoh * d : ((br == 2) ? (vp - v) / h : ((br == 3) ? (v - vm) / h : 0.0));
 #pragma unroll
             for (int i = 0; i < NP; ++i) u[i] = v + p.xc[(size_t)i * K + k] * slope;
           }

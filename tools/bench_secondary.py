@@ -72,7 +72,7 @@ def burgers(B=16384):
     x = torch.tensor(s.g.x, device=dev)[None]
     u0 = (c + A * torch.sin(math.pi * x + ph)).contiguous()
     dt = s.stable_dt(2.0)
-    S = 200
+    S = int(os.environ.get("SEC_S", 200))
     ms = timeit(lambda: s.forward(u0, dt, S, checkpoints=True), warm=2, reps=3)
     out = s.forward(u0, dt, S, checkpoints=True)
     ups = 5 * S * K * B
@@ -121,6 +121,7 @@ def tdg_fd(B=4096):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sweep", "burgers", "tdg_fd"]
     for w in which:
-        r = dict(sweep=sweep, burgers=burgers, tdg_fd=tdg_fd)[w]()
+        kw = dict(B=int(os.environ["SEC_B"])) if "SEC_B" in os.environ else {}
+        r = dict(sweep=sweep, burgers=burgers, tdg_fd=tdg_fd)[w](**kw)
         for line in (r if isinstance(r, list) else [r]):
             print(json.dumps(line), flush=True)
