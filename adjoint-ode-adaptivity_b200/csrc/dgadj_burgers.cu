@@ -61,11 +61,24 @@ struct BurgersArgs {
 
 // utils/minmod.m:7-11: s = sum(sign(v))/3; |s| == 1 -> s * min|v|, else 0.  |s| == 1 exactly when
 // the three arguments are all > 0 or all < 0, and then s * min|v| is min(v) resp. max(v) with
-// the same bits (a product with +-1 is exact): no division, no sign arithmetic.
-__device__ __forceinline__ double minmod3(double a, double b, double c) {
-  const bool pos = (a > 0.0) & (b > 0.0) & (c > 0.0), neg = (a < 0.0) & (b < 0.0) & (c < 0.0);
-  const double lo = fmin(a, fmin(b, c)), hi = fmax(a, fmax(b, c));
-  return pos ? lo : (neg ? hi : 0.0);
+// the same bits (a product with +-1 is exact): no division, no sign arithmetic.  The two calls
+// of SlopeLimitN.m:21-22 share their last two arguments (v - v_{k-1}, v_{k+1} - v).
+struct MinmodBC {
+  bool pos, neg;   // b, c both > 0 / both < 0
+  double lo, hi;   // min(b, c), max(b, c)
+};
+__device__ __forceinline__ MinmodBC minmod_bc(double b, double c) {
+  MinmodBC r;
+  r.pos = (b > 0.0) & (c > 0.0);
+  r.neg = (b < 0.0) & (c < 0.0);
+  const bool lt = b < c;
+  r.lo = lt ? b : c;
+  r.hi = lt ? c : b;
+  return r;
+}
+__device__ __forceinline__ double minmod3(double a, const MinmodBC& q) {
+  const double lo = (a < q.lo) ? a : q.lo, hi = (a > q.hi) ? a : q.hi;
+  return (q.pos & (a > 0.0)) ? lo : ((q.neg & (a < 0.0)) ? hi : 0.0);
 }
 
 // minmod of three with the index (1..3) of the winning argument (first smallest |v|, as
@@ -94,10 +107,72 @@ __device__ __forceinline__ double warp_max_nonneg(double m) {
   return __hiloint2double(mh, (int)ml);
 }
 
+// One LSERK4 stage update of an element, the step size folded into the thread's constants:
+//   c1 = -rx dt/4, k0 = -Fscale(1,k) dt/8, k1 = +Fscale(2,k) dt/8.
+// With F = u^2 (= 2f), C = max|u|:  dt/2 Fscale_f flux_f = k_f (u^- - u^+)(u^- + u^+ +- 2C), and in
+// the even/odd basis  dt rhs_i = E_i + O_i,  dt rhs_{N-i} = E_i - O_i,  dt rhs_mid = 2 E_mid  with
+//   E_i = c1 (DE Fo)_i + LS_i (G0 + G1),   O_i = c1 (DO Fe)_i + LA_i (G0 - G1).
+// Shared by the forward march and the adjoint's recomputation, so both see the same bits.
+struct BgCoef {
+  double c1, k0, k1;
+};
+template <int NP>
+__device__ __forceinline__ void burgers_stage_update(const BurgersArgs& p, const BgCoef& c, double (&u)[NP],
+                                                     double (&res)[NP], double uL, double uR, double maxvel,
+                                                     double rka, double rkb) {
+  constexpr int HE = (NP + 1) / 2, HO = NP / 2;
+  const double twoC = maxvel + maxvel;
+  const double G0 = (c.k0 * (u[0] - uL)) * ((u[0] + uL) + twoC);
+  const double G1 = (c.k1 * (u[NP - 1] - uR)) * ((u[NP - 1] + uR) - twoC);
+  const double ge = G0 + G1, go = G0 - G1;
+  double fe[HE], fo[HO > 0 ? HO : 1];
+#pragma unroll
+  for (int i = 0; i < NP / 2; ++i) {
+    const double ti = c.c1 * u[i], tj = c.c1 * u[NP - 1 - i];
+    const double a = ti * u[i];
+    fe[i] = fma(tj, u[NP - 1 - i], a);
+    fo[i] = fma(-tj, u[NP - 1 - i], a);
+  }
+  if (NP & 1) fe[NP / 2] = (c.c1 * u[NP / 2]) * u[NP / 2];
+  double E[HE], O[HO > 0 ? HO : 1];
+#pragma unroll
+  for (int i = 0; i < HE; ++i) {
+    const double2 l2 = p.so.LS2[i / 2];
+    double acc = ((i & 1) ? l2.y : l2.x) * ge;
+#pragma unroll
+    for (int j = 0; j < HO; ++j) {
+      const double2 c2 = p.so.DE2[i * HP + j / 2];
+      acc = fma((j & 1) ? c2.y : c2.x, fo[j], acc);
+    }
+    E[i] = acc;
+  }
+#pragma unroll
+  for (int i = 0; i < HO; ++i) {
+    const double2 l2 = p.so.LA2[i / 2];
+    double acc = ((i & 1) ? l2.y : l2.x) * go;
+#pragma unroll
+    for (int j = 0; j < HE; ++j) {
+      const double2 c2 = p.so.DO2[i * HP + j / 2];
+      acc = fma((j & 1) ? c2.y : c2.x, fe[j], acc);
+    }
+    O[i] = acc;
+  }
+#pragma unroll
+  for (int i = 0; i < NP / 2; ++i) {
+    res[i] = fma(rka, res[i], E[i] + O[i]);
+    res[NP - 1 - i] = fma(rka, res[NP - 1 - i], E[i] - O[i]);
+  }
+  if (NP & 1) res[NP / 2] = fma(rka, res[NP / 2], E[NP / 2] + E[NP / 2]);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) u[i] = fma(rkb, res[i], u[i]);
+}
+
+// Shared-memory exchanges alternate between two buffers (`par`): a buffer is rewritten two
+// exchanges later, and the barrier of the exchange in between orders that write after every
+// read of the earlier one -- one barrier per exchange.
 template <int NP, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burgers_kernel(const __grid_constant__ BurgersArgs p) {
-  constexpr int HE = (NP + 1) / 2, HO = NP / 2;
-  __shared__ double trL[2][MAXT], trR[2][MAXT], avg[MAXT];
+  __shared__ double trL[2][MAXT], trR[2][MAXT];   // traces; trL doubles as the cell-average buffer
   __shared__ double wmax[2][32];
   __shared__ int cand[2];
   const int tid = threadIdx.x, K = p.K;
@@ -112,34 +187,38 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
   const double twoh = 2.0 / h;
   if (tid < 2) cand[tid] = 0x7fffffff;
   int* pend = nullptr;   // where the argmax still being voted on goes (uniform over the CTA)
+  int par = 0;   // exchange buffer in use
+  int vs = 0;    // cand[] slot of the current stage's vote (alternates per stage: the slot is read and
+                 // reset one barrier after the vote, while the next stage already votes into the other)
   __syncthreads();
 
   for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
     const double dt = p.dt_arr ? p.dt_arr[b] : p.dt;
+    const BgCoef cf = {-rx * dt / 4.0, -fs0 * dt / 8.0, fs1 * dt / 8.0};
     double u[NP], res[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       u[i] = in ? p.u0[((size_t)b * NP + i) * K + k] : 0.0;
       res[i] = 0.0;
     }
-    int par = 0;
     // limiter applied to the element's current state; returns flag | branch << 1
     auto limiter = [&]() -> int {
-      double v = 0.0;
+      double v = p.aw[0] * u[0];
 #pragma unroll
-      for (int i = 0; i < NP; ++i) v = fma(p.aw[i], u[i], v);
+      for (int i = 1; i < NP; ++i) v = fma(p.aw[i], u[i], v);
+      trL[par][tid] = v;
       __syncthreads();
-      avg[tid] = v;
-      __syncthreads();
+      double vm = trL[par][nbL], vp = trL[par][nbR];
+      par ^= 1;
       if (!in) return 0;
-      double vm = avg[nbL], vp = avg[nbR];
       if (!p.periodic) {       // quirk C-16: ghost averages copy the end cells
         if (first) vm = v;
         if (last) vp = v;
       }
       const double ue1 = u[0], ue2 = u[NP - 1];
-      const double ve1 = v - minmod3(v - ue1, v - vm, vp - v);
-      const double ve2 = v + minmod3(ue2 - v, v - vm, vp - v);
+      const MinmodBC q = minmod_bc(v - vm, vp - v);
+      const double ve1 = v - minmod3(v - ue1, q);
+      const double ve2 = v + minmod3(ue2 - v, q);
       if (!(fabs(ve1 - ue1) > 1.0e-8 || fabs(ve2 - ue2) > 1.0e-8)) return 0;
       double d = 0.0;
 #pragma unroll
@@ -151,6 +230,16 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
       for (int i = 0; i < NP; ++i) u[i] = v + p.xc[(size_t)i * K + k] * slope;
       return 1 | (br << 1);
     };
+    auto flush_argmax = [&]() {   // after a barrier that follows the vote
+      if (pend) {
+        if (tid == 0) {
+          const int c = cand[vs ^ 1];
+          *pend = (c & 1) ? -((c >> 1) + 1) : ((c >> 1) + 1);
+          cand[vs ^ 1] = 0x7fffffff;
+        }
+        pend = nullptr;
+      }
+    };
     {
       const int c0 = p.limit ? limiter() : 0;
       if (p.lim0 && in) p.lim0[(size_t)b * K + k] = (unsigned char)c0;
@@ -160,33 +249,32 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
 #pragma unroll
       for (int i = 0; i < NP; ++i) hist[(size_t)i * K] = u[i];
     }
+    int* amax_b = p.amax ? p.amax + (size_t)b * p.S * 5 : nullptr;
+    double* maxvel_b = (p.maxvel && tid == 0) ? p.maxvel + (size_t)b * p.S * 5 : nullptr;
+    unsigned short* lim_b = (p.lim && in) ? p.lim + (size_t)b * p.S * K + k : nullptr;
     for (int n = 0; n < p.S; ++n) {
       unsigned fl = 0u;
 #pragma unroll 1
       for (int s = 0; s < 5; ++s) {
-        // ---- exchange 1: traces and the mesh-wide max|u|
-        // (the value first: max is exact in any order; where it sits is settled afterwards by
-        // the few threads that hold it)
+        // ---- exchange 1: traces and the mesh-wide max|u| (the value first: max is exact in any
+        // order; where it sits is settled afterwards by the few threads that hold it)
         double m = -1.0;
         if (in) {
+          m = fabs(u[0]);
 #pragma unroll
-          for (int i = 0; i < NP; ++i) m = fmax(m, fabs(u[i]));
+          for (int i = 1; i < NP; ++i) {
+            const double t = fabs(u[i]);
+            m = (t > m) ? t : m;
+          }
         }
         m = warp_max_nonneg(m);
         trL[par][tid] = u[0];
         trR[par][tid] = u[NP - 1];
         if (lane == 0) wmax[par][wid] = m;
         __syncthreads();
-        if (pend) {   // argmax of the stage before: every candidate has voted by now
-          if (tid == 0) {
-            const int c = cand[par ^ 1];
-            *pend = (c & 1) ? -((c >> 1) + 1) : ((c >> 1) + 1);
-            cand[par ^ 1] = 0x7fffffff;
-          }
-          pend = nullptr;
-        }
+        flush_argmax();   // the stage before: every candidate has voted by now
         const double maxvel = warp_max_nonneg((lane < nw) ? wmax[par][lane] : -1.0);
-        if (p.amax) {
+        if (amax_b) {
           // first occurrence in row-major order (i*K + k) of max|u|, and the sign of u there
           if (in) {
             int i0 = -1;
@@ -196,10 +284,11 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
               double ui = 0.0;
 #pragma unroll
               for (int q = 0; q < NP; ++q) ui = (q == i0) ? u[q] : ui;
-              atomicMin(&cand[par], ((i0 * K + k) << 1) | (ui < 0.0 ? 1 : 0));
+              atomicMin(&cand[vs], ((i0 * K + k) << 1) | (ui < 0.0 ? 1 : 0));
             }
           }
-          pend = p.amax + ((size_t)b * p.S + n) * 5 + s;
+          pend = amax_b + n * 5 + s;
+          vs ^= 1;
         }
         double uL = trR[par][nbL], uR = trL[par][nbR];
         par ^= 1;
@@ -207,62 +296,15 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
           if (first) uL = u[0];
           if (last) uR = u[NP - 1];
         }
-        if (p.maxvel && tid == 0) p.maxvel[((size_t)b * p.S + n) * 5 + s] = maxvel;
-        // flux = nx (u-^2 - u+^2)/4 - C/2 (u- - u+),  g_f = Fscale_f * flux_f
-        const double g0 = fs0 * (-((u[0] * u[0] - uL * uL) / 2.0) / 2.0 - maxvel / 2.0 * (u[0] - uL));
-        const double g1 = fs1 * (((u[NP - 1] * u[NP - 1] - uR * uR) / 2.0) / 2.0 - maxvel / 2.0 * (u[NP - 1] - uR));
-        const double ge = g0 + g1, go = g0 - g1;
-        // f = u^2/2 in the even/odd basis
-        double fe[HE], fo[HO > 0 ? HO : 1];
-#pragma unroll
-        for (int i = 0; i < NP / 2; ++i) {
-          const double a = u[i] * u[i] / 2.0, c = u[NP - 1 - i] * u[NP - 1 - i] / 2.0;
-          fe[i] = a + c;
-          fo[i] = a - c;
-        }
-        if (NP & 1) fe[NP / 2] = u[NP / 2] * u[NP / 2] / 2.0;
-        const double rka = p.rka[s], rkb = p.rkb[s];
-        // rows: even part E_i = -rx (DE fo)_i + LS_i ge, odd part O_i = -rx (DO fe)_i + LA_i go
-        double E[HE], O[HO > 0 ? HO : 1];
-#pragma unroll
-        for (int i = 0; i < HE; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < HO; ++j) {
-            const double2 c2 = p.so.DE2[i * HP + j / 2];
-            acc = fma((j & 1) ? c2.y : c2.x, fo[j], acc);
-          }
-          const double2 l2 = p.so.LS2[i / 2];
-          E[i] = fma(-rx, acc, ((i & 1) ? l2.y : l2.x) * ge);
-        }
-#pragma unroll
-        for (int i = 0; i < HO; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < HE; ++j) {
-            const double2 c2 = p.so.DO2[i * HP + j / 2];
-            acc = fma((j & 1) ? c2.y : c2.x, fe[j], acc);
-          }
-          const double2 l2 = p.so.LA2[i / 2];
-          O[i] = fma(-rx, acc, ((i & 1) ? l2.y : l2.x) * go);
-        }
-        // back to nodal: rhs_i = (E_i + O_i)/2, rhs_{N-i} = (E_i - O_i)/2, mid = E_mid
-#pragma unroll
-        for (int i = 0; i < NP / 2; ++i) {
-          const double r0 = 0.5 * (E[i] + O[i]), r1 = 0.5 * (E[i] - O[i]);
-          res[i] = fma(rka, res[i], dt * r0);
-          res[NP - 1 - i] = fma(rka, res[NP - 1 - i], dt * r1);
-        }
-        if (NP & 1) res[NP / 2] = fma(rka, res[NP / 2], dt * E[NP / 2]);
-#pragma unroll
-        for (int i = 0; i < NP; ++i) u[i] = fma(rkb, res[i], u[i]);
+        if (maxvel_b) maxvel_b[n * 5 + s] = maxvel;
+        burgers_stage_update<NP>(p, cf, u, res, uL, uR, maxvel, p.rka[s], p.rkb[s]);
         // ---- exchange 2: cell averages, limiter
         if (p.limit) {
           const int c = limiter();
           fl |= (unsigned)(c & 1) << s | (unsigned)(c >> 1) << (5 + 2 * s);
         }
       }
-      if (p.lim && in) p.lim[((size_t)b * p.S + n) * K + k] = (unsigned short)fl;
+      if (lim_b) lim_b[(size_t)n * K] = (unsigned short)fl;
       if (hist) {
         double* hn = hist + (size_t)(n + 1) * NP * K;
 #pragma unroll
@@ -274,14 +316,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
       for (int i = 0; i < NP; ++i) p.uT[((size_t)b * NP + i) * K + k] = u[i];
     }
     __syncthreads();
-    if (pend) {   // the last stage's argmax
-      if (tid == 0) {
-        const int c = cand[par ^ 1];
-        *pend = (c & 1) ? -((c >> 1) + 1) : ((c >> 1) + 1);
-        cand[par ^ 1] = 0x7fffffff;
-      }
-      pend = nullptr;
-    }
+    flush_argmax();   // the last stage's
   }
 }
 
@@ -296,7 +331,6 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
 // ---------------------------------------------------------------------------------------
 template <int NP, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burgers_adjoint_kernel(const __grid_constant__ BurgersArgs p) {
-  constexpr int HE = (NP + 1) / 2, HO = NP / 2;
   __shared__ double exA[2][MAXT], exB[2][MAXT];
   __shared__ double wsum[2][32];
   const int tid = threadIdx.x, K = p.K, BD = blockDim.x;
@@ -310,20 +344,22 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
   const double h = in ? p.hk[k] : 1.0;
   const double twoh = 2.0 / h;
   double* ss = p.stage_scratch + (size_t)blockIdx.x * 5 * (NP + 2) * BD + tid;
-  int par = 0;
-  auto block_sum = [&](double v) -> double {   // deterministic: shuffle tree, then warps in order
+  int par = 0;   // exchange buffer in use (see the note above burgers_kernel)
+  // deterministic CTA sum: shuffle tree, then the warps' partials in order
+  auto block_sum = [&](double v) -> double {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if (lane == 0) wsum[0][wid] = v;
+    if (lane == 0) wsum[par][wid] = v;
     __syncthreads();
     double t = 0.0;
-    for (int w = 0; w < nw; ++w) t += wsum[0][w];
+    for (int w = 0; w < nw; ++w) t += wsum[par][w];
+    par ^= 1;
     return t;
   };
 
   for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
     const double dt = p.dt_arr ? p.dt_arr[b] : p.dt;
+    const BgCoef cf = {-rx * dt / 4.0, -fs0 * dt / 8.0, fs1 * dt / 8.0};
     double lu[NP], lk[NP];
     {
       double jp = 0.0;
@@ -349,11 +385,11 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
       double ch = 0.0;
       if (br >= 2) ch = c / h;   // rare: keeps the division off the common path
       const double tr = (br == 2) ? ch : 0.0, tl = (br == 3) ? -ch : 0.0;
+      exA[par][tid] = tr;   // goes to cell k+1
+      exB[par][tid] = tl;   // goes to cell k-1
       __syncthreads();
-      exA[0][tid] = tr;   // goes to cell k+1
-      exB[0][tid] = tl;   // goes to cell k-1
-      __syncthreads();
-      double fromL = exA[0][nbL], fromR = exB[0][nbR];
+      double fromL = exA[par][nbL], fromR = exB[par][nbR];
+      par ^= 1;
       if (!p.periodic) {   // end cells see a copied ghost average: the term comes back to the cell
         if (first) fromL = 0.0;
         if (last) fromR = 0.0;
@@ -366,6 +402,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
       for (int i = 0; i < NP; ++i) lu[i] = (flag ? 0.0 : lu[i]) + p.aw[i] * lv + p.sl[i] * cs;
     };
 
+    const double* maxvel_b = p.maxvel + (size_t)b * p.S * 5;
+    const int* amax_b = p.amax + (size_t)b * p.S * 5;
     for (int n = p.S - 1; n >= 0; --n) {
       const unsigned code = in ? (unsigned)p.lim[((size_t)b * p.S + n) * K + k] : 0u;
       // ---- recompute the stage input states of step n
@@ -378,7 +416,6 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         }
 #pragma unroll 1
         for (int s = 0; s < 5; ++s) {
-          __syncthreads();
           exA[par][tid] = u[0];
           exB[par][tid] = u[NP - 1];
           __syncthreads();
@@ -393,57 +430,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
           ss[(size_t)(s * (NP + 2) + NP) * BD] = uL;
           ss[(size_t)(s * (NP + 2) + NP + 1) * BD] = uR;
           if (s == 4) break;   // the state after the last stage is u^{n+1}: not needed
-          const double maxvel = p.maxvel[((size_t)b * p.S + n) * 5 + s];
-          const double g0 = fs0 * (-((u[0] * u[0] - uL * uL) / 2.0) / 2.0 - maxvel / 2.0 * (u[0] - uL));
-          const double g1 = fs1 * (((u[NP - 1] * u[NP - 1] - uR * uR) / 2.0) / 2.0 - maxvel / 2.0 * (u[NP - 1] - uR));
-          const double ge = g0 + g1, go = g0 - g1;
-          double fe[HE], fo[HO > 0 ? HO : 1];
-#pragma unroll
-          for (int i = 0; i < NP / 2; ++i) {
-            const double a = u[i] * u[i] / 2.0, c = u[NP - 1 - i] * u[NP - 1 - i] / 2.0;
-            fe[i] = a + c;
-            fo[i] = a - c;
-          }
-          if (NP & 1) fe[NP / 2] = u[NP / 2] * u[NP / 2] / 2.0;
-          const double rka = p.rka[s], rkb = p.rkb[s];
-          double E[HE], O[HO > 0 ? HO : 1];
-#pragma unroll
-          for (int i = 0; i < HE; ++i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < HO; ++j) {
-              const double2 c2 = p.so.DE2[i * HP + j / 2];
-              acc = fma((j & 1) ? c2.y : c2.x, fo[j], acc);
-            }
-            const double2 l2 = p.so.LS2[i / 2];
-            E[i] = fma(-rx, acc, ((i & 1) ? l2.y : l2.x) * ge);
-          }
-#pragma unroll
-          for (int i = 0; i < HO; ++i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < HE; ++j) {
-              const double2 c2 = p.so.DO2[i * HP + j / 2];
-              acc = fma((j & 1) ? c2.y : c2.x, fe[j], acc);
-            }
-            const double2 l2 = p.so.LA2[i / 2];
-            O[i] = fma(-rx, acc, ((i & 1) ? l2.y : l2.x) * go);
-          }
-#pragma unroll
-          for (int i = 0; i < NP / 2; ++i) {
-            const double r0 = 0.5 * (E[i] + O[i]), r1 = 0.5 * (E[i] - O[i]);
-            res[i] = fma(rka, res[i], dt * r0);
-            res[NP - 1 - i] = fma(rka, res[NP - 1 - i], dt * r1);
-          }
-          if (NP & 1) res[NP / 2] = fma(rka, res[NP / 2], dt * E[NP / 2]);
-#pragma unroll
-          for (int i = 0; i < NP; ++i) u[i] = fma(rkb, res[i], u[i]);
+          burgers_stage_update<NP>(p, cf, u, res, uL, uR, maxvel_b[n * 5 + s], p.rka[s], p.rkb[s]);
           // limiter with the recorded decision
           const int flag = (code >> s) & 1, br = (code >> (5 + 2 * s)) & 3;
-          double v = 0.0;
+          double v = p.aw[0] * u[0];
 #pragma unroll
-          for (int i = 0; i < NP; ++i) v = fma(p.aw[i], u[i], v);
-          __syncthreads();
+          for (int i = 1; i < NP; ++i) v = fma(p.aw[i], u[i], v);
           exA[par][tid] = v;
           __syncthreads();
           double vm = exA[par][nbL], vp = exA[par][nbR];
@@ -473,7 +465,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
 #pragma unroll
         for (int i = 0; i < NP; ++i) us[i] = ss[(size_t)(s * (NP + 2) + i) * BD];
         const double uL = ss[(size_t)(s * (NP + 2) + NP) * BD], uR = ss[(size_t)(s * (NP + 2) + NP + 1) * BD];
-        const double mv = p.maxvel[((size_t)b * p.S + n) * 5 + s];
+        const double mv = maxvel_b[n * 5 + s];
         double G0 = 0.0, G1 = 0.0;
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
@@ -487,19 +479,18 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         double gam = in ? G0 * (-(us[0] - uL) / 2.0) + G1 * (-(us[NP - 1] - uR) / 2.0) : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gam += __shfl_xor_sync(0xffffffffu, gam, o);
-        __syncthreads();
         exA[par][tid] = d0p;   // belongs to the left neighbour's last node
         exB[par][tid] = d1p;   // belongs to the right neighbour's first node
-        if (lane == 0) wsum[1][wid] = gam;
+        if (lane == 0) wsum[par][wid] = gam;
         __syncthreads();
         double toN = exA[par][nbR], to0 = exB[par][nbL];
+        gam = 0.0;
+        for (int w = 0; w < nw; ++w) gam += wsum[par][w];
         par ^= 1;
         if (!p.periodic) {   // ghost = own trace
           if (last) toN = d1p;
           if (first) to0 = d0p;
         }
-        gam = 0.0;
-        for (int w = 0; w < nw; ++w) gam += wsum[1][w];
         double out[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
@@ -510,7 +501,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         }
         out[0] += d0m + to0;
         out[NP - 1] += d1m + toN;
-        const int am = p.amax[((size_t)b * p.S + n) * 5 + s];
+        const int am = amax_b[n * 5 + s];
         const int flat = (am < 0 ? -am : am) - 1;
         if (in && (flat % K) == k) {
           const int ii = flat / K;
@@ -530,7 +521,6 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
 #pragma unroll
       for (int i = 0; i < NP; ++i) p.lam0[((size_t)b * NP + i) * K + k] = lu[i];
     }
-    __syncthreads();
   }
 }
 
