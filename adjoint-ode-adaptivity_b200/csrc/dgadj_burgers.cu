@@ -329,8 +329,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
 // reverse: limiter^T (frozen flags / minmod branches), lk += rkb lu, lu += dt (dR/du)^T lk
 // including the rank-one term through C = max|u|, lk *= rka.
 // ---------------------------------------------------------------------------------------
-template <int NP, int MAXT>
+// The stage scratch (5 stage input states + neighbour traces per element) lives in dynamic shared
+// memory when the CTA is at most 256 threads (SS_SMEM; 5 (NP+2) 256 doubles = 70 KB at N = 4), in a
+// per-CTA global buffer (L2 resident) otherwise.
+template <int NP, int MAXT, bool SS_SMEM>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burgers_adjoint_kernel(const __grid_constant__ BurgersArgs p) {
+  extern __shared__ double ss_smem[];
   __shared__ double exA[2][MAXT], exB[2][MAXT];
   __shared__ double wsum[2][32];
   const int tid = threadIdx.x, K = p.K, BD = blockDim.x;
@@ -343,7 +347,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
   const double rx = in ? p.rxk[k] : 0.0, fs0 = in ? p.fs0[k] : 0.0, fs1 = in ? p.fs1[k] : 0.0;
   const double h = in ? p.hk[k] : 1.0;
   const double twoh = 2.0 / h;
-  double* ss = p.stage_scratch + (size_t)blockIdx.x * 5 * (NP + 2) * BD + tid;
+  double* const ss_g = SS_SMEM ? nullptr : p.stage_scratch + (size_t)blockIdx.x * 5 * (NP + 2) * BD + tid;
+  // slot (stage s, row i) of this thread's scratch column
+  auto ss = [&](int s, int i) -> double& {
+    if constexpr (SS_SMEM) return ss_smem[(s * (NP + 2) + i) * MAXT + tid];
+    else return ss_g[(size_t)(s * (NP + 2) + i) * BD];
+  };
   int par = 0;   // exchange buffer in use (see the note above burgers_kernel)
   // deterministic CTA sum: shuffle tree, then the warps' partials in order
   auto block_sum = [&](double v) -> double {
@@ -360,6 +369,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
   for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
     const double dt = p.dt_arr ? p.dt_arr[b] : p.dt;
     const BgCoef cf = {-rx * dt / 4.0, -fs0 * dt / 8.0, fs1 * dt / 8.0};
+    const double* hist_b = p.hist + (size_t)b * (p.S + 1) * NP * K + k;
     double lu[NP], lk[NP];
     {
       double jp = 0.0;
@@ -367,7 +377,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
       for (int i = 0; i < NP; ++i) {
         lu[i] = in ? p.jw[(size_t)i * K + k] : 0.0;
         lk[i] = 0.0;
-        const double uT = in ? p.hist[(((size_t)b * (p.S + 1) + p.S) * NP + i) * K + k] : 0.0;
+        const double uT = in ? hist_b[((size_t)p.S * NP + i) * K] : 0.0;
         jp = fma(lu[i], uT, jp);
       }
       const double J = block_sum(jp);
@@ -376,14 +386,15 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
     // limiter^T with a frozen decision code (flag | branch << 1)
     auto limiter_T = [&](int code) {
       const int flag = code & 1, br = code >> 1;
-      double a = 0.0, c = 0.0;
+      double a = 0.0, c = 0.0, ch = 0.0;
+      if (code) {   // rare (a limited cell): keeps the sums and the division off the common path
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        a += lu[i];
-        c = fma(in ? p.xc[(size_t)i * K + k] : 0.0, lu[i], c);
+        for (int i = 0; i < NP; ++i) {
+          a += lu[i];
+          c = fma(p.xc[(size_t)i * K + k], lu[i], c);
+        }
+        if (br >= 2) ch = c / h;
       }
-      double ch = 0.0;
-      if (br >= 2) ch = c / h;   // rare: keeps the division off the common path
       const double tr = (br == 2) ? ch : 0.0, tl = (br == 3) ? -ch : 0.0;
       exA[par][tid] = tr;   // goes to cell k+1
       exB[par][tid] = tl;   // goes to cell k-1
@@ -396,10 +407,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         if (last) fromL += tr;
         if (first) fromR += tl;
       }
-      double lv = (flag ? a : 0.0) + ((br == 2) ? -ch : ((br == 3) ? ch : 0.0)) + fromL + fromR;
-      const double cs = (br == 1) ? twoh * c : 0.0;
+      const double lv = (flag ? a : 0.0) + ((br == 2) ? -ch : ((br == 3) ? ch : 0.0)) + fromL + fromR;
+      if (code || lv != 0.0) {
+        const double cs = (br == 1) ? twoh * c : 0.0;
 #pragma unroll
-      for (int i = 0; i < NP; ++i) lu[i] = (flag ? 0.0 : lu[i]) + p.aw[i] * lv + p.sl[i] * cs;
+        for (int i = 0; i < NP; ++i) lu[i] = (flag ? 0.0 : lu[i]) + p.aw[i] * lv + p.sl[i] * cs;
+      }
     };
 
     const double* maxvel_b = p.maxvel + (size_t)b * p.S * 5;
@@ -411,7 +424,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         double u[NP], res[NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-          u[i] = in ? p.hist[(((size_t)b * (p.S + 1) + n) * NP + i) * K + k] : 0.0;
+          u[i] = in ? hist_b[((size_t)n * NP + i) * K] : 0.0;
           res[i] = 0.0;
         }
 #pragma unroll 1
@@ -426,9 +439,9 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
             if (last) uR = u[NP - 1];
           }
 #pragma unroll
-          for (int i = 0; i < NP; ++i) ss[(size_t)(s * (NP + 2) + i) * BD] = u[i];
-          ss[(size_t)(s * (NP + 2) + NP) * BD] = uL;
-          ss[(size_t)(s * (NP + 2) + NP + 1) * BD] = uR;
+          for (int i = 0; i < NP; ++i) ss(s, i) = u[i];
+          ss(s, NP) = uL;
+          ss(s, NP + 1) = uR;
           if (s == 4) break;   // the state after the last stage is u^{n+1}: not needed
           burgers_stage_update<NP>(p, cf, u, res, uL, uR, maxvel_b[n * 5 + s], p.rka[s], p.rkb[s]);
           // limiter with the recorded decision
@@ -463,8 +476,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         for (int i = 0; i < NP; ++i) lk[i] = fma(rkb, lu[i], lk[i]);
         double us[NP];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) us[i] = ss[(size_t)(s * (NP + 2) + i) * BD];
-        const double uL = ss[(size_t)(s * (NP + 2) + NP) * BD], uR = ss[(size_t)(s * (NP + 2) + NP + 1) * BD];
+        for (int i = 0; i < NP; ++i) us[i] = ss(s, i);
+        const double uL = ss(s, NP), uR = ss(s, NP + 1);
         const double mv = maxvel_b[n * 5 + s];
         double G0 = 0.0, G1 = 0.0;
 #pragma unroll
@@ -502,12 +515,11 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         out[0] += d0m + to0;
         out[NP - 1] += d1m + toN;
         const int am = amax_b[n * 5 + s];
-        const int flat = (am < 0 ? -am : am) - 1;
-        if (in && (flat % K) == k) {
-          const int ii = flat / K;
-          const double add = gam * (am < 0 ? -1.0 : 1.0);
+        const int rel = (am < 0 ? -am : am) - 1 - k;   // flat index i*K + k of max|u|, minus own k
+        if (in && rel >= 0) {
+          const double add = (am < 0) ? -gam : gam;
 #pragma unroll
-          for (int q = 0; q < NP; ++q) out[q] += (q == ii) ? add : 0.0;
+          for (int q = 0; q < NP; ++q) out[q] += (rel == q * K) ? add : 0.0;
         }
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
@@ -526,10 +538,14 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
 
 template <int NP>
 static cudaError_t burgers_adjoint_launch(int grid, int block, cudaStream_t st, const BurgersArgs& a) {
-  if (block <= 256)
-    burgers_adjoint_kernel<NP, 256><<<grid, block, 0, st>>>(a);
-  else
-    burgers_adjoint_kernel<NP, 1024><<<grid, block, 0, st>>>(a);
+  if (block <= 256) {
+    const int smem = 5 * (NP + 2) * 256 * (int)sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(burgers_adjoint_kernel<NP, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    burgers_adjoint_kernel<NP, 256, true><<<grid, block, smem, st>>>(a);
+  } else {
+    burgers_adjoint_kernel<NP, 1024, false><<<grid, block, 0, st>>>(a);
+  }
   return cudaGetLastError();
 }
 
@@ -671,7 +687,8 @@ extern "C" int dgadj_burgers_adjoint(dgadj_handle* h, int64_t B, int32_t S, doub
   const int block = (K + 31) / 32 * 32;
   const int per_sm = std::max(1, std::min(16, (block <= 256 ? 2048 : 1024) / block));
   const int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count * per_sm);
-  const size_t need = (size_t)grid * 5 * (Np + 2) * block * sizeof(double);
+  // stage scratch: shared memory for CTAs of at most 256 threads, a global per-CTA buffer beyond
+  const size_t need = block <= 256 ? 0 : (size_t)grid * 5 * (Np + 2) * block * sizeof(double);
   if (need > h->bgs_bytes) {
     CUDA_TRY(h, cudaDeviceSynchronize());
     cudaFree(h->bgs_scratch);
