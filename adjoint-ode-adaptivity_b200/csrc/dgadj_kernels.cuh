@@ -186,7 +186,9 @@ struct Ctx {
 // altogether (wrong results) the kernel is 12 % faster -- the ceiling for any scheme; point-to-point
 // variants (per-warp flags with a software spin; per-warp mbarrier pairs awaited only by the
 // edge lanes) were 30-50 % SLOWER: divergent waits and the extra live registers (spills at 254
-// registers/thread) cost more than the looser coupling gains.
+// registers/thread) cost more than the looser coupling gains.  Folding 1/sig_s and sga_s into
+// per-stage copies of p (three DMUL fewer per update) was 1.2 % slower: ten more constant loads
+// per stage and level outweigh the multiplies.
 // warp_local (a kernel parameter, hence uniform): every trajectory lives inside one warp, so
 // __syncwarp alone orders the exchange and the warps of a CTA never wait for one another.
 __device__ __forceinline__ void trace_arrive(Ctx& cx, int warp_local) {

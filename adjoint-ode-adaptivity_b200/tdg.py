@@ -48,6 +48,7 @@ class TimeDG:
         self.lib = _lib.load()
         self.linear, self.device, self.tol, self.maxit = bool(linear), device, float(tol), int(maxit)
         self._cache = {}                        # per-element constants by (kind, order, element end points)
+        self._mesh_cache = {}                   # padded whole-mesh blocks by (kind, orders, mesh)
         cfg = _lib.Config(device=device, N=1, K=1, bc=1, inflow=0, functional=0, scheme=0, reserved=0, alpha=0.0)
         self._h = C.c_void_p(0)
         rc = self.lib.dgadj_create(C.byref(cfg), C.byref(self._h))
@@ -125,6 +126,9 @@ class TimeDG:
         arrays, Np_max, nq_max)."""
         Ks = len(times) - 1
         Ns = self._orders(Ns, Ks)
+        mkey = ("M", Ns.tobytes(), np.asarray(times, dtype=np.float64).tobytes())
+        if mkey in self._mesh_cache:
+            return self._mesh_cache[mkey]
         els = [self._march_element(int(Ns[k]), times[k], times[k + 1]) for k in range(Ks)]
         NP = max(e["Np"] for e in els)
         nq = max(e["nq"] for e in els)
@@ -135,7 +139,14 @@ class TimeDG:
                 parts += [self._pad(e["Iq"], nq, NP), self._pad(e["Phi"], nq, NP), self._pad(e["w"], 1, nq)]
             parts += [[e["hk"], float(e["Np"])]]
             blocks.append(np.concatenate([np.asarray(p, dtype=np.float64) for p in parts]))
-        return np.ascontiguousarray(np.concatenate(blocks)), [e["x"] for e in els], NP, nq
+        out = (np.ascontiguousarray(np.concatenate(blocks)), [e["x"] for e in els], NP, nq)
+        self._remember(mkey, out)
+        return out
+
+    def _remember(self, key, value):
+        if len(self._mesh_cache) >= 8:          # whole-mesh blocks of the last few meshes only
+            self._mesh_cache.pop(next(iter(self._mesh_cache)))
+        self._mesh_cache[key] = value
 
     def _adjoint_element(self, Na, tk):
         key = ("a", Na, tk.tobytes())
@@ -171,6 +182,9 @@ class TimeDG:
         adj_march.m, padded to the mesh maxima.  Returns (blocks, node arrays, Npp_max, nq_max)."""
         Ks = len(t1)
         Nas = self._orders(Nas, Ks)
+        mkey = ("A", Nas.tobytes(), b"".join(np.asarray(t, dtype=np.float64).tobytes() for t in t1))
+        if mkey in self._mesh_cache:
+            return self._mesh_cache[mkey]
         els = [self._adjoint_element(int(Nas[k]), np.asarray(t1[k], dtype=np.float64)) for k in range(Ks)]
         for e in els:
             if e["Na"] != e["Npp"] + 1:
@@ -187,7 +201,9 @@ class TimeDG:
                 parts += [self._pad(e["Iq"], nq, NPP), self._pad(e["Phi"], nq, NA), self._pad(e["w"], 1, nq)]
             parts += [[e["hk"], float(e["Na"]), float(els[k - 1]["Npp"] - 1 if k > 0 else 0)]]
             blocks.append(np.concatenate([np.asarray(p, dtype=np.float64) for p in parts]))
-        return np.ascontiguousarray(np.concatenate(blocks)), [e["x"] for e in els], NPP, nq
+        out = (np.ascontiguousarray(np.concatenate(blocks)), [e["x"] for e in els], NPP, nq)
+        self._remember(mkey, out)
+        return out
 
     # ------------------------------------------------------------------ reference-named entry points
     def dg_march(self, Ns, Ks, times, y0, x_true=None, u_true=None):
