@@ -466,6 +466,7 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->tdg_scratch);
   cudaFree(h->bg_scratch);
   cudaFree(h->bgs_scratch);
+  cudaFree(h->nccl_scratch);
   if (h->pipe_init) {
     cudaStreamDestroy(h->s_in);
     cudaStreamDestroy(h->s_k);

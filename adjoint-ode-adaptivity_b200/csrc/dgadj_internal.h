@@ -46,6 +46,8 @@ struct dgadj_handle {
   size_t bg_bytes;
   double* bgs_scratch;  // dgadj_burgers_adjoint: per-CTA stage states
   size_t bgs_bytes;
+  double* nccl_scratch; // dgadj_allreduce_indicators: gathered partials [ranks][K+4]
+  size_t nccl_bytes;
   double Dr_nodal[MAXNP * MAXNP];  // host copies of the primal nodal Dr / LIFT
   double LIFT_nodal[MAXNP * 2];
   int sm_count, cc_major, cc_minor;

@@ -70,3 +70,18 @@ def batch_mean_refine(sums, B_global: int):
     K = s.size - 4
     mean_ind = s[:K] / float(B_global)
     return mean_ind, int(np.argmax(mean_ind))
+
+
+def allreduce_indicators_comm(solver, nccl_comm, sums):
+    """The same ordered combination through the C-ABI (`dgadj_allreduce_indicators`) on a raw
+    NCCL communicator (an `ncclComm_t` as an integer / ctypes pointer) -- what a C, C++ or MPI
+    host of the library calls; `sums` (float64 CUDA tensor [K+4]) is updated in place."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    K = sums.numel() - 4
+    rc = solver.lib.dgadj_allreduce_indicators(solver._h, C.c_void_p(int(nccl_comm)), K, C.c_void_p(sums.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream(sums.device).cuda_stream))
+    if rc != _lib.OK:
+        raise _lib.DgadjError(rc, solver.lib.dgadj_last_error(solver._h).decode())
+    return sums

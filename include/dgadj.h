@@ -172,6 +172,13 @@ int dgadj_rank(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev, int
 int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev,
                             const double* J_dev, double* sums_dev, void* stream);
 
+/* The cross-GPU step of that rule when the batch is sharded over ranks (one handle, one GPU, one
+ * NCCL rank each): sums_dev[K+4] (this rank's partials, in place) -> the combination over all
+ * ranks of nccl_comm (an ncclComm_t of the caller's NCCL): all-gather + sum in rank order, entry
+ * K+2 a maximum -- the same bits on every rank, independent of the number of GPUs a global batch
+ * is spread over.  Asynchronous on `stream`.  NCCL is resolved at run time from the process.  */
+int dgadj_allreduce_indicators(dgadj_handle* h, void* nccl_comm, int32_t K, double* sums_dev, void* stream);
+
 /* Finite-difference path of python/Main_finite_difference.py, batched over initial conditions
  * on a shared time mesh: forwardSolve (:34-51) -> adjSolve (:54-76, on the ref_factor-refined
  * mesh) -> errEst (:79-94) -> per-step window sums and argmax (:270-277, :337).

@@ -6,6 +6,7 @@ oracle/advec.py); refine flags / rankings bit-exact on identical indicator input
 import json
 import math
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -14,6 +15,7 @@ from oracle import advec
 from oracle import operators as ops
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1e-12
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -750,3 +752,16 @@ def test_matlab_named_entry_points(pkg, torch):
     t1, y1 = m.dg_march(tdg, np.ones(4, dtype=int), 4, times, torch.tensor(y0, device="cuda"))
     t2, v, err = m.adj_march(tdg, 2 * np.ones(4, dtype=int), 4, times, y1, t1)
     assert y1.shape == (3, 4, 2) and v.shape == (3, 4, 3) and err.shape == (3, 4)
+
+
+def test_nccl_c_abi_allreduce_two_gpus(torch):
+    """dgadj_allreduce_indicators on a raw ncclComm_t, one rank per GPU (tools/nccl_abi_check.py):
+    bit-identical to the torch.distributed path and to every other rank, equal to the unsharded
+    batch at 1e-12.  Needs two GPUs on the box."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "nccl_abi_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "nccl C-ABI all-reduce ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
