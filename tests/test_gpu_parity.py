@@ -654,6 +654,88 @@ def test_burgers_discrete_adjoint(pkg, torch, N, K, bc):
     assert rel(lim, ol.SlopeLimitN(rough, g, periodic=(bc == "periodic"))) < 1e-13
 
 
+def test_cfg3_size_properties(pkg, torch):
+    """BASELINE config 3 at its full size (Burgers + SlopeLimitN, N=4, K=256, B=16384, every
+    checkpoint written), where the oracle cannot go: parity on the first trajectories, and for all
+    of them mass conservation (periodic, conservative flux, mean-preserving limiter), results
+    independent of the batch a trajectory sits in, J of the adjoint sweep = the functional of
+    the forward state, and the adjoint identity  dJ/du0 . 1 = d(mass)/d(shift) = sum of weights."""
+    from oracle import burgers as ob
+    N, K, B, S = 4, 256, 16384, 60
+    s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc="periodic")
+    g = oracle_view(s.g)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1235)                       # SURVEY section 8(d), config 3
+    c = torch.rand((B, 1, 1), dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    A = torch.rand((B, 1, 1), dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    ph = torch.rand((B, 1, 1), dtype=torch.float64, device="cuda", generator=gen) * 2 * math.pi
+    x = torch.tensor(s.g.x, device="cuda")[None]
+    u0 = (c + A * torch.sin(math.pi * x + ph)).contiguous()
+    dt = s.stable_dt(2.0)
+    fwd = s.forward(u0, dt, S, checkpoints=True)
+    jw = torch.tensor(s.g.quad_weights(), device="cuda")
+    m0, mT = (jw * u0).sum((1, 2)), (jw * fwd["uT"]).sum((1, 2))
+    assert float((mT - m0).abs().max()) < 1e-12 * float((jw * u0.abs()).sum((1, 2)).max())
+    assert bool((fwd["lim"].int() & 31).any())                                        # limited cells exist
+    # oracle parity on the first two trajectories
+    ref, _, flags_r, mv_r = ob.burgers_march(u0[:2].cpu().numpy(), g, dt, S, bc="periodic", history=True)
+    assert rel(fwd["uT"][:2].cpu().numpy(), ref) < 1e-11
+    flags, _ = pkg.decode_limiter_record(fwd["lim"][:2])
+    assert np.array_equal(np.moveaxis(flags.cpu().numpy(), 2, 0), np.moveaxis(flags_r, (0, 1, 2), (2, 0, 1)))
+    # a trajectory's result does not depend on the batch around it (nor on the CTA it lands on)
+    pick = torch.tensor([0, 777, 9000, B - 1], device="cuda")
+    alone = s.forward(u0[pick].contiguous(), dt, S, checkpoints=True)
+    for k in ("uT", "lim", "amax", "maxvel"):
+        assert torch.equal(alone[k], fwd[k][pick]), k
+    adj = s.adjoint(fwd)
+    assert float((adj["J"] - mT).abs().max()) < 1e-12 * float((jw * fwd["uT"].abs()).sum((1, 2)).max())
+    # J = mass is conserved for every u0, so dJ/du0 = jw exactly in exact arithmetic: the frozen-branch
+    # discrete adjoint must reproduce it through 300 limited stages
+    dev = float((adj["lam0"] - jw).abs().max() / jw.abs().max())
+    assert dev < 1e-9, dev
+
+
+def test_cfg4_size_properties(pkg, torch):
+    """BASELINE config 4 at one GPU's share (131 072 trajectories, N=4, K=64, S=100, a speed and a CFL
+    step per trajectory): sampled trajectories against the oracle, the same bits when they run
+    alone, and the device reduction of the norms against torch's."""
+    N, K, S = 4, 64, 100
+    s = pkg.AdvecDG1D(N, K, domain=(0.0, 2 * math.pi), alpha=0.0, bc="periodic")
+    gc, gf = oracle_pair(s)
+    n1, n2 = 1024, 128
+    a = torch.linspace(0.5, 2.0, n1, dtype=torch.float64, device="cuda") * 2 * math.pi
+    sig = torch.linspace(0.02, 0.2, n2, dtype=torch.float64, device="cuda")
+    Aa, SG = torch.meshgrid(a, sig, indexing="ij")
+    Aa, SG = Aa.reshape(-1).contiguous(), SG.reshape(-1).contiguous()
+    B = Aa.numel()
+    x = torch.tensor(s.g.x, device="cuda")[None]
+    u0 = torch.exp(-(x - math.pi) ** 2 / (2 * SG[:, None, None] ** 2)).contiguous()
+    dt0, _ = s.cfl_dt(1.0)
+    dt = (dt0 * 2 * math.pi / Aa).contiguous()
+    out = s.fwd_adj(u0, Aa, dt, S, want_lam0=True)
+    pick = [0, 4321, 70000, B - 1]
+    pt = torch.tensor(pick, device="cuda")
+    ref = advec.fwd_adj_indicator(u0[pt].cpu().numpy(), gc, gf, Aa[pt].cpu().numpy(), dt[pt].cpu().numpy(), S, 0.0,
+                                  advec.BC_PERIODIC)
+    sub = {k: v[pt].cpu().numpy() for k, v in out.items()}
+    assert rel(sub["uT"], ref["uT"]) < TOL and rel(sub["lam0"], ref["lam0"]) < TOL
+    assert np.max(np.abs(sub["J"] - ref["J"])) <= TOL * max(1.0, np.max(np.abs(ref["J"])))
+    # the narrow pulses (sigma = 0.02 on h = 0.1) are zero to rounding away from the pulse: there the
+    # indicator and its own scale are both noise of the pulse's, so the yardstick is the
+    # trajectory's largest indicator scale
+    yard = ref["eta_scale"].max(axis=1, keepdims=True)
+    assert np.max(np.abs(sub["eta"] - ref["eta"]) / yard) <= TOL
+    alone = s.fwd_adj(u0[pt].contiguous(), Aa[pt].contiguous(), dt[pt].contiguous(), S, want_lam0=True)
+    for k in ("uT", "eta", "J", "lam0"):
+        assert torch.equal(alone[k], out[k][pt]), k
+    sums = s.reduce_indicators(out["eta"], out["J"])
+    eta = out["eta"]
+    assert float((sums[:K] - eta.abs().sum(0)).abs().max()) < 1e-12 * float(eta.abs().sum(0).max())
+    assert float(abs(sums[K] - eta.abs().sum())) < 1e-12 * float(eta.abs().sum())
+    assert float(abs(sums[K + 1] - (eta * eta).sum())) < 1e-12 * float((eta * eta).sum())
+    assert float(sums[K + 2]) == float(eta.abs().max())
+    assert float(abs(sums[K + 3] - out["J"].sum())) < 1e-12 * float(out["J"].abs().sum())
+
+
 def test_c_client_runs_on_gpu(tmp_path, torch):
     """The plain-C client (tests/c_abi_smoke.c) marches on the GPU through dgadj_forward_host."""
     import subprocess
