@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
   extern __shared__ double ss_smem[];
   __shared__ double exA[2][MAXT], exB[2][MAXT];
   __shared__ double wsum[2][32];
+  __shared__ double sm_mv[2][5];   // the step's recorded wave speeds / argmax (by step parity: fetched
+  __shared__ int sm_am[2][5];      // once per step, visible after the step's first exchange barrier)
   const int tid = threadIdx.x, K = p.K, BD = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = (BD + 31) >> 5;
   const bool in = tid < K;
@@ -419,6 +421,11 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
     const int* amax_b = p.amax + (size_t)b * p.S * 5;
     for (int n = p.S - 1; n >= 0; --n) {
       const unsigned code = in ? (unsigned)p.lim[((size_t)b * p.S + n) * K + k] : 0u;
+      const int np_ = n & 1;
+      if (tid < 5) {
+        sm_mv[np_][tid] = maxvel_b[n * 5 + tid];
+        sm_am[np_][tid] = amax_b[n * 5 + tid];
+      }
       // ---- recompute the stage input states of step n
       {
         double u[NP], res[NP];
@@ -443,7 +450,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
           ss(s, NP) = uL;
           ss(s, NP + 1) = uR;
           if (s == 4) break;   // the state after the last stage is u^{n+1}: not needed
-          burgers_stage_update<NP>(p, cf, u, res, uL, uR, maxvel_b[n * 5 + s], p.rka[s], p.rkb[s]);
+          burgers_stage_update<NP>(p, cf, u, res, uL, uR, sm_mv[np_][s], p.rka[s], p.rkb[s]);
           // limiter with the recorded decision
           const int flag = (code >> s) & 1, br = (code >> (5 + 2 * s)) & 3;
           double v = p.aw[0] * u[0];
@@ -478,7 +485,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
 #pragma unroll
         for (int i = 0; i < NP; ++i) us[i] = ss(s, i);
         const double uL = ss(s, NP), uR = ss(s, NP + 1);
-        const double mv = maxvel_b[n * 5 + s];
+        const double mv = sm_mv[np_][s];
         double G0 = 0.0, G1 = 0.0;
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         }
         out[0] += d0m + to0;
         out[NP - 1] += d1m + toN;
-        const int am = amax_b[n * 5 + s];
+        const int am = sm_am[np_][s];
         const int rel = (am < 0 ? -am : am) - 1 - k;   // flat index i*K + k of max|u|, minus own k
         if (in && rel >= 0) {
           const double add = (am < 0) ? -gam : gam;
