@@ -301,6 +301,23 @@ __global__ void tdg_adjrec_kernel(long long B, int Ks, double y0_hard, const dou
   }
 }
 
+// matlab/err_contribution.m:1-50 (unused by the reference, MAIN.m:50): err_i = int over element i of
+// a(t) (u_h - u_h')(t) dt with the exact adjoint a(t) = e^{1-t} - 1 of a' = -a - 1, a(1) = 0 (:23-25),
+// plus u(1) - 1 on the first element (:42-43).  u_h is the polyfit/polyval interpolant (:10-14), so
+// the integral is linear in the element's nodal values: err[b][k] = cvec_k . y[b][k][:], the weight
+// vectors built by the host (Gauss quadrature in place of MATLAB's adaptive `integral`).
+__global__ void tdg_errcon_kernel(long long B, int Ks, int Np, const double* __restrict__ cvec,
+                                  const double* __restrict__ y, double* __restrict__ err) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * Ks) return;
+  const int k = (int)(t % Ks);
+  const double* yk = y + (size_t)t * Np;
+  double e = 0.0;
+  for (int i = 0; i < Np; ++i) e = fma(cvec[(size_t)k * Np + i], yk[i], e);
+  if (k == 0) e += yk[0] - 1.0;
+  err[t] = e;
+}
+
 static int tdg_consts(dgadj_handle* h, const double* host, size_t n, cudaStream_t st) {
   const size_t need = n * sizeof(double);
   if (need > h->tdg_bytes) {
@@ -379,6 +396,23 @@ extern "C" int dgadj_tdg_adjoint_rec(dgadj_handle* h, int64_t B, int32_t Ks, int
 #define DGADJ_TDG_R(n) case n: tdg_adjrec_kernel<n><<<grid, block, 0, st>>>(B, Ks, y0_hard, h->tdg_scratch, y_dev, v_dev, err_dev); break;
   switch (Np_primal) { DGADJ_TDG_R(2) DGADJ_TDG_R(3) DGADJ_TDG_R(4) DGADJ_TDG_R(5) }
 #undef DGADJ_TDG_R
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_tdg_err_contribution(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np,
+                                          const double* cvec_host, const double* y_dev, double* err_dev,
+                                          void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || Ks <= 0 || Np < 2 || !cvec_host || !y_dev || !err_dev) return fail(h, DGADJ_ERR_INVALID, "bad tdg_err_contribution arguments");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = tdg_consts(h, cvec_host, (size_t)Ks * Np, st);
+  if (rc) return rc;
+  const int block = 128;
+  const long long n = (long long)B * Ks;
+  tdg_errcon_kernel<<<(unsigned)((n + block - 1) / block), block, 0, st>>>(B, Ks, Np, h->tdg_scratch, y_dev, err_dev);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return DGADJ_OK;

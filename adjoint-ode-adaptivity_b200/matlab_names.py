@@ -7,6 +7,7 @@ handles (argument order and meaning follow the .m files; batching adds a leading
     [t, v, err] = adj_march(tdg, Ns, Ks, times, y1, t1)           matlab/adj_march.m:1  (primal passed
                                                                   explicitly instead of the globals y1, t1)
     [t, v, err] = adj_rec(tdg, Ns, Ks, times, y1, t1)             matlab/adj_rec.m:1
+    [err, res]  = err_contribution(tdg, Ks, Ns, uh, t1)           matlab/err_contribution.m:1
     [t, y]      = fwd_euler_march(y0, times, ode)                 matlab/fwd_euler_march.m:1 (a broken stub in
                                                                   the reference; semantics of forwardSolve,
                                                                   python/Main_finite_difference.py:34-51)
@@ -37,6 +38,10 @@ def adj_march(tdg, Ns, Ks, times, y1, t1):
 
 def adj_rec(tdg, Ns, Ks, times, y1, t1):
     return tdg.adj_rec(Ns, Ks, times, y1, t1)
+
+
+def err_contribution(tdg, Ks, Ns, uh, t1):
+    return tdg.err_contribution(Ks, Ns, uh, t1), [None] * Ks
 
 
 def fwd_euler_march(y0, times, ode="sin", device=0):

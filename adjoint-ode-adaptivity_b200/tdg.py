@@ -309,6 +309,42 @@ class TimeDG:
         return nodes, v, err
 
 
+    # ------------------------------------------------------------------ err_contribution.m
+    def errcon_weights(self, Ns, t1, NP, nquad=64):
+        """cvec[Ks, NP]: err_i = cvec_i . u_i for matlab/err_contribution.m:10-39 -- the integral over
+        element i of a(t) (u_h - u_h')(t), a(t) = e^{1-t} - 1 (the dsolve result of :23-25), with u_h
+        the degree-Ns(i) polyfit interpolant (:10-14); Gauss quadrature (exact to rounding for a
+        polynomial times exp) in place of MATLAB's adaptive `integral` (:39)."""
+        Ks = len(t1)
+        Ns = self._orders(Ns, Ks)
+        xq, wq = np.polynomial.legendre.leggauss(nquad)
+        cvec = np.zeros((Ks, NP))
+        for i in range(Ks):
+            tu = np.asarray(t1[i], dtype=np.float64)
+            a, b = tu[0], tu[-1]
+            tq = 0.5 * (b - a) * xq + 0.5 * (a + b)
+            wa = 0.5 * (b - a) * wq * (np.exp(1.0 - tq) - 1.0)
+            eye = np.eye(len(tu))
+            for j in range(len(tu)):
+                pu = np.polyfit(tu, eye[j], int(Ns[i]))               # :10
+                cvec[i, j] = np.sum(wa * (np.polyval(pu, tq) - np.polyval(np.polyder(pu), tq)))   # :13-14,:30-31
+        return np.ascontiguousarray(cvec)
+
+    def err_contribution(self, Ks, Ns, uh, t1):
+        """[err, res] = err_contribution(Ks, Ns, uh, t1)  (matlab/err_contribution.m:1; unused by the
+        reference, MAIN.m:50): per-element error contributions against the exact adjoint of the linear
+        model problem.  uh = the [B, Ks, Np_max] array dg_march returned.  Returns err[B, Ks]
+        (`res` is an empty cell array in the reference, :4,:47)."""
+        torch = self.torch
+        B, _, NP = uh.shape
+        cvec = self.errcon_weights(Ns, t1, NP)
+        err = torch.empty((B, Ks), dtype=torch.float64, device=uh.device)
+        self._check(self.lib.dgadj_tdg_err_contribution(self._h, B, Ks, NP, C.c_void_p(cvec.ctypes.data),
+                                                        C.c_void_p(uh.contiguous().data_ptr()),
+                                                        C.c_void_p(err.data_ptr()), self._stream()))
+        return err
+
+
 def refine(times, Ns, err_mean, n):
     """matlab/MAIN.m:137-141: refine the element with the largest |err| (lowest index on ties,
     quirk C-10) by midpoint insertion; a new order entry n is appended."""

@@ -218,6 +218,13 @@ int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal,
 int dgadj_tdg_adjoint_rec(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, double y0_hard,
                           const double* elem_consts_host, const double* y_dev, double* v_dev,
                           double* err_dev, void* stream);
+/* matlab/err_contribution.m:1-50 (exact-adjoint error contributions of the linear model problem;
+ * unused by the reference, MAIN.m:50): err_dev[B][Ks] = cvec_k . y_dev[b][k][:] (+ u(1) - 1 on the
+ * first element, :42-43); cvec_host[Ks][Np] = the quadrature of a(t)(phi_j - phi_j')(t) over
+ * element k, built by the host.                                                             */
+int dgadj_tdg_err_contribution(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np,
+                               const double* cvec_host, const double* y_dev, double* err_dev,
+                               void* stream);
 
 /* Inviscid Burgers forward march (LSERK4) with SlopeLimitN (utils/SlopeLimitN.m:9-32,
  * SlopeLimitLin.m:10-18, minmod.m:6-12) applied to the initial state and after every stage,

@@ -507,6 +507,25 @@ def test_tdg_adj_rec(pkg, torch, orders):
     assert tn == [None] * Ks and vn == [None] * Ks and float(errn.abs().max()) == 0.0
 
 
+def test_tdg_err_contribution(pkg, torch):
+    """dgadj_tdg_err_contribution against the oracle's restatement of matlab/err_contribution.m, uniform
+    and mixed orders; and what the function is for: with the exact adjoint the contributions sum
+    to the error of J = int_0^1 u dt for u' = u ... the reference's model problem a' = -a - 1."""
+    from oracle import tdg as otdg
+    from adjoint_ode_adaptivity_b200 import matlab_names as m
+    rng = np.random.default_rng(3)
+    times = np.array([0.0, 0.2, 0.45, 0.7, 1.0])
+    y0 = np.concatenate(([1.0], rng.uniform(-2, 2, 31)))
+    s = pkg.TimeDG(linear=True)
+    for Ns in (np.array([1, 1, 1, 1]), np.array([2, 1, 3, 2])):
+        t1, y1, _ = s.dg_march(Ns, 4, times, torch.tensor(y0, device="cuda"))
+        err, res = m.err_contribution(s, 4, Ns, y1, t1)
+        t1r, y1r, _ = otdg.dg_march(Ns, 4, times, y0, linear=True)
+        ref = otdg.err_contribution_linear_exact(4, Ns, y1r, t1r)
+        assert np.max(np.abs(err.cpu().numpy() - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+        assert res == [None] * 4
+
+
 def test_tdg_reference_iteration0(pkg, torch):
     """matlab/MAIN.m iteration 0 on the GPU: the numbers of init_nonlin.png."""
     times, Ns = np.array([0.0, 1.0, 2.0]), np.array([1, 1])
