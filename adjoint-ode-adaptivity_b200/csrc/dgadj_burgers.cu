@@ -65,20 +65,18 @@ struct BurgersArgs {
 // of SlopeLimitN.m:21-22 share their last two arguments (v - v_{k-1}, v_{k+1} - v).
 struct MinmodBC {
   bool pos, neg;   // b, c both > 0 / both < 0
-  double lo, hi;   // min(b, c), max(b, c)
+  double t;        // min(b, c) if pos, max(b, c) otherwise: the bound the first argument competes with
 };
 __device__ __forceinline__ MinmodBC minmod_bc(double b, double c) {
   MinmodBC r;
   r.pos = (b > 0.0) & (c > 0.0);
   r.neg = (b < 0.0) & (c < 0.0);
-  const bool lt = b < c;
-  r.lo = lt ? b : c;
-  r.hi = lt ? c : b;
+  r.t = ((b < c) == r.pos) ? b : c;
   return r;
 }
 __device__ __forceinline__ double minmod3(double a, const MinmodBC& q) {
-  const double lo = (a < q.lo) ? a : q.lo, hi = (a > q.hi) ? a : q.hi;
-  return (q.pos & (a > 0.0)) ? lo : ((q.neg & (a < 0.0)) ? hi : 0.0);
+  const double r = ((a < q.t) == q.pos) ? a : q.t;   // min(a, t) if pos, max(a, t) if neg
+  return ((q.pos & (a > 0.0)) | (q.neg & (a < 0.0))) ? r : 0.0;
 }
 
 // minmod of three with the index (1..3) of the winning argument (first smallest |v|, as
@@ -172,16 +170,19 @@ __device__ __forceinline__ void burgers_stage_update(const BurgersArgs& p, const
 // read of the earlier one -- one barrier per exchange.
 template <int NP, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burgers_kernel(const __grid_constant__ BurgersArgs p) {
-  __shared__ double trL[2][MAXT], trR[2][MAXT];   // traces; trL doubles as the cell-average buffer
+  // traces; trL doubles as the cell-average buffer.  Slots MAXT / MAXT+1 are the ghosts of a
+  // non-periodic mesh: the end elements publish their own values there and point nbL / nbR at them
+  // (ghost state = own trace; ghost average = own average, SlopeLimitN.m:18)
+  __shared__ double trL[2][MAXT + 2], trR[2][MAXT + 2];
   __shared__ double wmax[2][32];
   __shared__ int cand[2];
   const int tid = threadIdx.x, K = p.K;
   const int lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
   const bool in = tid < K;
   const int k = in ? tid : 0;
-  const int nbL = in ? (tid == 0 ? K - 1 : tid - 1) : tid;
-  const int nbR = in ? (tid == K - 1 ? 0 : tid + 1) : tid;
-  const bool first = in && tid == 0, last = in && tid == K - 1;
+  const bool gfirst = in && tid == 0 && !p.periodic, glast = in && tid == K - 1 && !p.periodic;
+  const int nbL = in ? (tid == 0 ? (p.periodic ? K - 1 : MAXT) : tid - 1) : tid;
+  const int nbR = in ? (tid == K - 1 ? (p.periodic ? 0 : MAXT + 1) : tid + 1) : tid;
   const double rx = in ? p.rxk[k] : 0.0, fs0 = in ? p.fs0[k] : 0.0, fs1 = in ? p.fs1[k] : 0.0;
   const double h = in ? p.hk[k] : 1.0;
   const double twoh = 2.0 / h;
@@ -207,14 +208,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
 #pragma unroll
       for (int i = 1; i < NP; ++i) v = fma(p.aw[i], u[i], v);
       trL[par][tid] = v;
+      if (gfirst) trL[par][MAXT] = v;       // quirk C-16: ghost averages copy the end cells
+      if (glast) trL[par][MAXT + 1] = v;
       __syncthreads();
-      double vm = trL[par][nbL], vp = trL[par][nbR];
+      const double vm = trL[par][nbL], vp = trL[par][nbR];
       par ^= 1;
       if (!in) return 0;
-      if (!p.periodic) {       // quirk C-16: ghost averages copy the end cells
-        if (first) vm = v;
-        if (last) vp = v;
-      }
       const double ue1 = u[0], ue2 = u[NP - 1];
       const MinmodBC q = minmod_bc(v - vm, vp - v);
       const double ve1 = v - minmod3(v - ue1, q);
@@ -267,35 +266,33 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
             m = (t > m) ? t : m;
           }
         }
-        m = warp_max_nonneg(m);
+        const double mw = warp_max_nonneg(m);
         trL[par][tid] = u[0];
         trR[par][tid] = u[NP - 1];
-        if (lane == 0) wmax[par][wid] = m;
+        if (gfirst) trR[par][MAXT] = u[0];            // ghost state = own trace
+        if (glast) trL[par][MAXT + 1] = u[NP - 1];
+        if (lane == 0) wmax[par][wid] = mw;
         __syncthreads();
         flush_argmax();   // the stage before: every candidate has voted by now
         const double maxvel = warp_max_nonneg((lane < nw) ? wmax[par][lane] : -1.0);
         if (amax_b) {
           // first occurrence in row-major order (i*K + k) of max|u|, and the sign of u there
-          if (in) {
-            int i0 = -1;
+          if (m == maxvel) {   // (idle lanes hold -1.0: never equal)
+            int i0 = 0;
+            double ui = u[0];
 #pragma unroll
-            for (int i = NP - 1; i >= 0; --i) i0 = (fabs(u[i]) == maxvel) ? i : i0;
-            if (i0 >= 0) {
-              double ui = 0.0;
-#pragma unroll
-              for (int q = 0; q < NP; ++q) ui = (q == i0) ? u[q] : ui;
-              atomicMin(&cand[vs], ((i0 * K + k) << 1) | (ui < 0.0 ? 1 : 0));
+            for (int i = NP - 1; i >= 0; --i) {
+              const bool hit = fabs(u[i]) == maxvel;
+              i0 = hit ? i : i0;
+              ui = hit ? u[i] : ui;
             }
+            atomicMin(&cand[vs], ((i0 * K + k) << 1) | (ui < 0.0 ? 1 : 0));
           }
           pend = amax_b + n * 5 + s;
           vs ^= 1;
         }
-        double uL = trR[par][nbL], uR = trL[par][nbR];
+        const double uL = trR[par][nbL], uR = trL[par][nbR];
         par ^= 1;
-        if (!p.periodic) {
-          if (first) uL = u[0];
-          if (last) uR = u[NP - 1];
-        }
         if (maxvel_b) maxvel_b[n * 5 + s] = maxvel;
         burgers_stage_update<NP>(p, cf, u, res, uL, uR, maxvel, p.rka[s], p.rkb[s]);
         // ---- exchange 2: cell averages, limiter
