@@ -333,9 +333,11 @@ template <int NP, int MAXT, bool SS_SMEM>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burgers_adjoint_kernel(const __grid_constant__ BurgersArgs p) {
   extern __shared__ double ss_smem[];
   __shared__ double exA[2][MAXT], exB[2][MAXT];
-  __shared__ double wsum[2][32];
+  constexpr int NWMAX = MAXT / 32;
+  __shared__ __align__(16) double wsum[2][NWMAX];   // per-warp partials; slots of absent warps stay 0
   __shared__ double sm_mv[2][5];   // the step's recorded wave speeds / argmax (by step parity: fetched
-  __shared__ int sm_am[2][5];      // once per step, visible after the step's first exchange barrier)
+  __shared__ int sm_am[2][5];      // once per step, visible after the step's first exchange barrier);
+  __shared__ int sm_ak[2][5];      // sm_am = node index i of the argmax, negative-coded sign; sm_ak = its element
   const int tid = threadIdx.x, K = p.K, BD = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = (BD + 31) >> 5;
   const bool in = tid < K;
@@ -353,14 +355,21 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
     else return ss_g[(size_t)(s * (NP + 2) + i) * BD];
   };
   int par = 0;   // exchange buffer in use (see the note above burgers_kernel)
+  if (tid < 2 * NWMAX) wsum[tid / NWMAX][tid % NWMAX] = 0.0;
+  __syncthreads();
   // deterministic CTA sum: shuffle tree, then the warps' partials in order
+  auto warps_sum = [&]() -> double {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < NWMAX; ++w) t += wsum[par][w];
+    return t;
+  };
   auto block_sum = [&](double v) -> double {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) wsum[par][wid] = v;
     __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < nw; ++w) t += wsum[par][w];
+    const double t = warps_sum();
     par ^= 1;
     return t;
   };
@@ -419,16 +428,20 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
     for (int n = p.S - 1; n >= 0; --n) {
       const unsigned code = in ? (unsigned)p.lim[((size_t)b * p.S + n) * K + k] : 0u;
       const int np_ = n & 1;
-      if (tid < 5) {
+      const double* hist_n = hist_b + (size_t)n * NP * K;
+      if (tid < 5) {   // the recorded argmax decoded once per step: node, element, sign
         sm_mv[np_][tid] = maxvel_b[n * 5 + tid];
-        sm_am[np_][tid] = amax_b[n * 5 + tid];
+        const int am = amax_b[n * 5 + tid];
+        const int flat = (am < 0 ? -am : am) - 1;
+        sm_ak[np_][tid] = flat % K;
+        sm_am[np_][tid] = (am < 0) ? -(flat / K) - 1 : flat / K;
       }
       // ---- recompute the stage input states of step n
       {
         double u[NP], res[NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-          u[i] = in ? hist_b[((size_t)n * NP + i) * K] : 0.0;
+          u[i] = in ? hist_n[i * K] : 0.0;
           res[i] = 0.0;
         }
 #pragma unroll 1
@@ -501,8 +514,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         if (lane == 0) wsum[par][wid] = gam;
         __syncthreads();
         double toN = exA[par][nbR], to0 = exB[par][nbL];
-        gam = 0.0;
-        for (int w = 0; w < nw; ++w) gam += wsum[par][w];
+        gam = warps_sum();
         par ^= 1;
         if (!p.periodic) {   // ghost = own trace
           if (last) toN = d1p;
@@ -518,12 +530,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
         }
         out[0] += d0m + to0;
         out[NP - 1] += d1m + toN;
-        const int am = sm_am[np_][s];
-        const int rel = (am < 0 ? -am : am) - 1 - k;   // flat index i*K + k of max|u|, minus own k
-        if (in && rel >= 0) {
+        if (tid == sm_ak[np_][s]) {   // the element that held max|u|: the rank-one term of C
+          const int am = sm_am[np_][s];
+          const int ii = am < 0 ? -am - 1 : am;
           const double add = (am < 0) ? -gam : gam;
 #pragma unroll
-          for (int q = 0; q < NP; ++q) out[q] += (rel == q * K) ? add : 0.0;
+          for (int q = 0; q < NP; ++q) out[q] += (q == ii) ? add : 0.0;
         }
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
