@@ -505,6 +505,14 @@ def test_tdg_adj_rec(pkg, torch, orders):
     sn = pkg.TimeDG(linear=False)
     tn, vn, errn = sn.adj_rec(Ns, Ks, times, y1, t1)
     assert tn == [None] * Ks and vn == [None] * Ks and float(errn.abs().max()) == 0.0
+    # the reference tabulates Radau points up to m = 5 (utils/Globals1D.m:37-42): N = 5 has none
+    t5, y5, _ = s.dg_march(5 * np.ones(Ks, dtype=int), Ks, times, torch.tensor(y0, device="cuda"))
+    with pytest.raises(pkg.DgadjError):
+        s.adj_rec(5 * np.ones(Ks, dtype=int), Ks, times, y5, t5)
+    with pytest.raises(pkg.DgadjError):        # orders that are not the primal's
+        s.adj_rec(Ns + 1, Ks, times, y1, t1)
+    with pytest.raises(pkg.DgadjError):        # adj_march wants primal order + 1 on every element
+        s.adj_march(Ns, Ks, times, y1, t1)
 
 
 def test_tdg_err_contribution(pkg, torch):
