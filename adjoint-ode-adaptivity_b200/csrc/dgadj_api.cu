@@ -701,7 +701,7 @@ static int make_plan(dgadj_handle* h, int64_t B, int variant, LaunchPlan* pl) {
   pl->ngroups = (int)ngroups;
   pl->smem = march_smem_bytes(h->Np, ept, block, variant);
   if (pl->smem > 227 * 1024) return fail(h, DGADJ_ERR_UNSUPPORTED, "shared memory %zu B over budget", pl->smem);
-  int per_sm = std::max(1, std::min<int>(bdmax / block, (int)((227 * 1024) / pl->smem)));
+  int per_sm = std::max(1, std::min<int>(bdmax / block * march_min_ctas(h->Np, ept), (int)((227 * 1024) / pl->smem)));
   int grid = h->tune_grid ? h->tune_grid : h->sm_count * per_sm;
   pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ngroups));
   pl->tile = (size_t)h->NpF * ept * block;

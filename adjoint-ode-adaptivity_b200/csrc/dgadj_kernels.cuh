@@ -23,6 +23,10 @@ namespace dgadj {
 constexpr int MAXNP = 10;      // enriched space of N = 8
 constexpr int MAXSTAGES = 5;
 constexpr int MAXBD = 1024;
+// CTAs of MAXBD/EPT threads per SM the march kernels are compiled for: at N = 8 the state fills the
+// register file (1); N <= 2 fits 128 registers without spilling and gains 5-8 % from twice the warps
+// (measured, K = 64: N = 1 3.02 -> 3.27e11, N = 2 2.62 -> 2.77e11 updates/s; N = 4, 5 spill and lose 15-40 %)
+__host__ __device__ constexpr int march_min_ctas(int NP, int EPT) { return (NP <= 3 && EPT == 4) ? 2 : 1; }
 
 constexpr int HM = 5;  // max half dimension of the even/odd blocks ((MAXNP+1)/2)
 
@@ -413,7 +417,7 @@ __device__ __forceinline__ void apply_matrix(const double* M, const double (&x)[
 // immediate offsets); BDT = 0: any block size.
 // ---------------------------------------------------------------------------------------
 template <int NP, int EPT, int BDT, bool DO_FWD, bool RESID, bool DO_ADJ>
-__global__ void __launch_bounds__(MAXBD / EPT, 1) march_kernel(const __grid_constant__ KArgs ka) {
+__global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_kernel(const __grid_constant__ KArgs ka) {
   constexpr int NPF = NP + 1;
   const MarchParams& p = ka.p;
   const ConstOps& c = ka.c;
