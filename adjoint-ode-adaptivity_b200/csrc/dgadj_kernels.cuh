@@ -192,7 +192,9 @@ struct Ctx {
 // edge lanes) were 30-50 % SLOWER: divergent waits and the extra live registers (spills at 254
 // registers/thread) cost more than the looser coupling gains.  Folding 1/sig_s and sga_s into
 // per-stage copies of p (three DMUL fewer per update) was 1.2 % slower: ten more constant loads
-// per stage and level outweigh the multiplies.
+// per stage and level outweigh the multiplies.  Splitting the trace sums into two partial sums per
+// parity (shorter dependent DFMA chains, two more DADD per element-stage) was 1.2 % slower too: the
+// chains are not what the pipe waits for.
 // warp_local (a kernel parameter, hence uniform): every trajectory lives inside one warp, so
 // __syncwarp alone orders the exchange and the warps of a CTA never wait for one another.
 __device__ __forceinline__ void trace_arrive(Ctx& cx, int warp_local) {
