@@ -679,11 +679,16 @@ extern "C" int dgadj_set_tuning(dgadj_handle* h, int32_t ept, int32_t block, int
 static int make_plan(dgadj_handle* h, int64_t B, int variant, LaunchPlan* pl) {
   const int K = h->K;
   int ept = h->tune_ept ? h->tune_ept : ((K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1));
+  // K = 64 at N >= 3: two elements per thread put exactly one trajectory in a warp (every exchange a
+  // __syncwarp) and 16 warps on the SM -- measured 3-4 % faster than four per thread; at K = 256 and
+  // 1024 four per thread win by 4-8 % (profiles/r1_shape_sweep_fused.txt)
+  const bool warp_per_traj = !h->tune_ept && !h->tune_block && K == 64 && h->Np >= 4;
+  if (warp_per_traj) ept = 2;
   if (ept > 1 && (K % ept)) return fail(h, DGADJ_ERR_INVALID, "elems_per_thread=%d needs K divisible by it", ept);
   const int KT = K / ept;
   const int bdmax = MAXBD / ept;
   if (KT > bdmax) return fail(h, DGADJ_ERR_UNSUPPORTED, "K=%d does not fit one CTA", K);
-  int target = h->tune_block ? h->tune_block : bdmax / 2;
+  int target = h->tune_block ? h->tune_block : (warp_per_traj ? bdmax : bdmax / 2);
   target = std::max(std::min(target, bdmax), KT);
   int64_t tpc = std::max<int64_t>(1, std::min<int64_t>(target / KT, B));
   int block = (int)((tpc * KT + 31) / 32 * 32);
