@@ -874,3 +874,63 @@ def test_nccl_c_abi_allreduce_two_gpus(torch):
                         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "nccl_abi_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "nccl C-ABI all-reduce ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_randomised_secondary_paths(pkg, torch):
+    """Seeded random configurations of the three other paths against their oracles: the FD path
+    (mesh, ODE, functional, refinement factor), the time-DG march / adjoint / adj_rec (mesh, mixed
+    orders, linear or not) and the limited Burgers march (order, mesh size, boundary type)."""
+    from oracle import burgers as ob
+    from oracle import fd as ofd
+    from oracle import tdg as otdg
+    rng = np.random.default_rng(2026)
+    for case in range(10):                                        # FD path
+        n = int(rng.integers(1, 40))
+        times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.01, 1.99, n - 1))))
+        ode = ["sin", "linear"][int(rng.integers(2))]
+        functional = ["int_u", "u_N", "int_u2"][int(rng.integers(3))]
+        rf = int(rng.integers(3, 9))                              # the reference requires ref_factor > 2
+        u0 = rng.uniform(-3, 3, int(rng.integers(1, 300)))
+        ref = ofd.fd_awr(u0, np.diff(times), ref_factor=rf, functional=functional, ode=ode)
+        out = pkg.FDAdjoint(ode=ode, functional=functional, ref_factor=rf).solve(torch.tensor(u0, device="cuda"), np.diff(times))
+        for k in ("u", "v", "err_fine", "err_steps"):
+            a = out[k].cpu().numpy()
+            assert np.max(np.abs(a - ref[k])) <= 1e-12 * max(1.0, np.max(np.abs(ref[k]))), (case, k, n, ode, functional, rf)
+    for case in range(8):                                         # time-DG
+        Ks = int(rng.integers(1, 9))
+        times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.05, 1.95, Ks - 1))))
+        Ns = rng.integers(1, 5, Ks)
+        linear = bool(rng.integers(2))
+        y0 = rng.uniform(-3, 3, int(rng.integers(1, 100)))
+        s = pkg.TimeDG(linear=linear)
+        t1, y1, its = s.dg_march(Ns, Ks, times, torch.tensor(y0, device="cuda"))
+        t1r, y1r, itsr = otdg.dg_march(Ns, Ks, times, y0, linear=linear)
+        assert np.array_equal(its.cpu().numpy(), np.stack(itsr, axis=1)), (case, Ns, linear)
+        y1h = y1.cpu().numpy()
+        for k in range(Ks):
+            assert rel(y1h[:, k, :Ns[k] + 1], y1r[k]) < 1e-10, (case, k, Ns, linear)
+        _, v, err = s.adj_march(Ns + 1, Ks, times, y1, t1)
+        _, vr, errr = otdg.adj_march(Ns + 1, Ks, times, y1r, t1r, linear=linear)
+        vmax = max(np.max(np.abs(a)) for a in vr)
+        scale = max(1.0, vmax * max(np.max(np.abs(a)) for a in y1r))
+        assert np.max(np.abs(err.cpu().numpy() - errr)) < 1e-9 * scale, (case, Ns, linear)
+        if linear:
+            _, _, err3 = s.adj_rec(Ns, Ks, times, y1, t1)
+            _, _, err3r = otdg.adj_rec(Ns, Ks, times, y1r, t1r, linear=True)
+            assert np.max(np.abs(err3.cpu().numpy() - err3r)) < 1e-9 * scale, (case, Ns)
+    for case in range(6):                                         # Burgers + limiter
+        N, K = int(rng.integers(1, 7)), int(rng.integers(5, 80))
+        bc = ["periodic", "free"][int(rng.integers(2))]
+        s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc=bc)
+        g = oracle_view(s.g)
+        B = 5
+        c, A, ph = rng.uniform(-0.5, 0.5, (B, 1, 1)), rng.uniform(0.5, 1.5, (B, 1, 1)), rng.uniform(0, 2 * np.pi, (B, 1, 1))
+        u0 = c + A * np.sin(np.pi * g.x[None] + ph)
+        dt = s.stable_dt(2.0)
+        S = min(int(np.ceil(0.4 / dt)), 250)
+        ref, _, flags_r, mv_r = ob.burgers_march(u0, g, dt, S, bc=bc, history=True)
+        out = s.forward(torch.tensor(u0, device="cuda"), dt, S, checkpoints=True)
+        flags, _ = pkg.decode_limiter_record(out["lim"])
+        assert np.array_equal(np.moveaxis(flags.cpu().numpy(), 2, 0), np.moveaxis(flags_r, (0, 1, 2), (2, 0, 1))), (case, N, K, bc)
+        assert rel(out["uT"].cpu().numpy(), ref) < 1e-11, (case, N, K, bc)
+        assert rel(out["maxvel"].cpu().numpy(), np.moveaxis(mv_r, (0, 1, 2), (1, 2, 0))) < 1e-12
