@@ -37,6 +37,7 @@ struct BurgersArgs {
   const double* fs0;   // [K]
   const double* fs1;   // [K]
   const double* xc;    // [NP][K]  x - x0 (SlopeLimitLin.m:11-12)
+  double xcn[MAXNP];   // x - x0 of an element in units of h/2 (= the reference nodes r): the map is affine
   const double* hk;    // [K]      x(Np,k) - x(1,k)
   const double* u0;    // [B][NP][K]
   double* uT;          // [B][NP][K]
@@ -225,8 +226,9 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
       const double ux = twoh * d;
       int br;
       const double slope = minmod3b(ux, (vp - v) / h, (v - vm) / h, &br);
+      const double sh = slope * (0.5 * h);   // x - x0 = (h/2) r: no geometry loads on this path
 #pragma unroll
-      for (int i = 0; i < NP; ++i) u[i] = v + p.xc[(size_t)i * K + k] * slope;
+      for (int i = 0; i < NP; ++i) u[i] = fma(p.xcn[i], sh, v);
       return 1 | (br << 1);
     };
     auto flush_argmax = [&]() {   // after a barrier that follows the vote
@@ -399,8 +401,9 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
           a += lu[i];
-          c = fma(p.xc[(size_t)i * K + k], lu[i], c);
+          c = fma(p.xcn[i], lu[i], c);
         }
+        c *= 0.5 * h;
         if (br >= 2) ch = c / h;
       }
       const double tr = (br == 2) ? ch : 0.0, tl = (br == 3) ? -ch : 0.0;
@@ -479,8 +482,9 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_ADJ(NP) : 1) burge
 #pragma unroll
             for (int i = 0; i < NP; ++i) d = fma(p.sl[i], u[i], d);
             const double slope = (br == 1) ? twoh * d : ((br == 2) ? (vp - v) / h : ((br == 3) ? (v - vm) / h : 0.0));
+            const double sh = slope * (0.5 * h);
 #pragma unroll
-            for (int i = 0; i < NP; ++i) u[i] = v + p.xc[(size_t)i * K + k] * slope;
+            for (int i = 0; i < NP; ++i) u[i] = fma(p.xcn[i], sh, v);
           }
         }
       }
@@ -617,6 +621,8 @@ static int burgers_setup(dgadj_handle* h, BurgersArgs& a, int64_t B, int32_t S, 
       const double x0 = x_host[k] + hh / 2;
       hk[k] = hh;
       for (int i = 0; i < Np; ++i) xc[(size_t)i * K + k] = x_host[(size_t)i * K + k] - x0;
+      if (k == 0)
+        for (int i = 0; i < Np; ++i) a.xcn[i] = xc[(size_t)i * K] / (hh / 2);
     }
   }
   const size_t need = ((size_t)Np * K + K) * sizeof(double);
