@@ -166,6 +166,9 @@ __device__ __forceinline__ void burgers_stage_update(const BurgersArgs& p, const
   for (int i = 0; i < NP; ++i) u[i] = fma(rkb, res[i], u[i]);
 }
 
+// (Measured alternative: two trajectories interleaved per thread -- shared barriers / reductions /
+// address arithmetic, twice the independent chains, 128 registers, 2 CTAs per SM -- ran at the same
+// 7.9e10 updates/s as this one-trajectory form at 4 CTAs per SM: not kept.)
 // Shared-memory exchanges alternate between two buffers (`par`): a buffer is rewritten two
 // exchanges later, and the barrier of the exchange in between orders that write after every
 // read of the earlier one -- one barrier per exchange.
