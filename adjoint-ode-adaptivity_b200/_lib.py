@@ -62,8 +62,8 @@ PROTOTYPES = {
     "dgadj_tdg_march": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32,
                                   _P, _P, _P, _P, _P]),
     "dgadj_tdg_adjoint": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
-                                    _P, _P, _P, _P, _P]),
-    "dgadj_tdg_adjoint_rec": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P]),
+                                    _P, _P, _P, _P, _P, _P]),
+    "dgadj_tdg_adjoint_rec": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P]),
     "dgadj_tdg_err_contribution": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "dgadj_burgers_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, _P, C.c_int32, _P, _P, _P, _P, _P,
                                         _P, _P, _P, _P, _P, _P]),

@@ -59,16 +59,19 @@ def adapt_fd(u0, tspan=(0.0, 2.0), n_steps=2, iters=30, ode="sin", functional="i
     return hist
 
 
-def adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=30, linear=False, device=0, B_global=None):
+def adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=30, linear=False, device=0, B_global=None, quirks=True):
     """matlab/MAIN.m:19-166 (batched): Ks elements of order n, adjoint order n+1, refine the
-    element with the largest batch-mean |err| by midpoint insertion (:137-141)."""
-    s = TimeDG(linear=linear, device=device)
+    element with the largest batch-mean |err| by midpoint insertion (:137-141).  Every trajectory's
+    first-element residual is measured against its own initial value (the reference runs one
+    trajectory with y0 = 1 hard-coded in adj_march.m:9 -- identical for that case).  quirks=False:
+    see TimeDG."""
+    s = TimeDG(linear=linear, device=device, quirks=quirks)
     times = np.linspace(tspan[0], tspan[1], Ks + 1)
     Ns = n * np.ones(Ks, dtype=int)
     hist = []
     for it in range(iters + 1):
         t1, y1, its = s.dg_march(Ns, Ks, times, y0)                # MAIN.m:32
-        t2, v, err = s.adj_march(Ns + 1, Ks, times, y1, t1)        # MAIN.m:34
+        t2, v, err = s.adj_march(Ns + 1, Ks, times, y1, t1, y0=y0)  # MAIN.m:34
         mean_err = _batch_reduce(s, err, B_global)                 # mean_b |err| (MAIN.m:51 abs)
         times_new, Ns_new, ref_i = tdg_refine(times, Ns, mean_err, n)
         hist.append(dict(it=it, times=times.copy(), err=mean_err, ref_idx=ref_i, err_total=float(mean_err.sum()),

@@ -153,6 +153,7 @@ __global__ void tdg_march_kernel(long long B, int Ks, int nq, int linear, double
 // reverse march: v[b][k][:], err[b][k]
 template <int NPP>
 __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, double y0_hard,
+                                   const double* __restrict__ y0_arr,
                                    const double* __restrict__ ec, const double* __restrict__ y,
                                    double* __restrict__ v, double* __restrict__ err) {
   constexpr int NA = NPP + 1;
@@ -217,7 +218,7 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
       for (int j = 0; j < NPP; ++j) s = fma(Ix[i * NPP + j], Uk[j], s);
       uh[i] = s;
     }
-    const double f0 = (k == 0) ? y0_hard : y[((size_t)b * Ks + (k - 1)) * NPP + lastprev];
+    const double f0 = (k == 0) ? (y0_arr ? y0_arr[b] : y0_hard) : y[((size_t)b * Ks + (k - 1)) * NPP + lastprev];
     double e = 0.0;
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
@@ -238,7 +239,8 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
 //   block: A0[NP*NP] | f1[NP] | R[NP*NP] | H[NA*NA] | A2[NA*NA] | Ix[NA*NP] | np_k | last_{k-1}
 // (NA = NP + 1; same padding rules as above).  v[b][k][:] = [v at the Radau points; v at t_{k+1}].
 template <int NP>
-__global__ void tdg_adjrec_kernel(long long B, int Ks, double y0_hard, const double* __restrict__ ec,
+__global__ void tdg_adjrec_kernel(long long B, int Ks, double y0_hard, const double* __restrict__ y0_arr,
+                                  const double* __restrict__ ec,
                                   const double* __restrict__ y, double* __restrict__ v,
                                   double* __restrict__ err) {
   constexpr int NA = NP + 1;
@@ -275,7 +277,7 @@ __global__ void tdg_adjrec_kernel(long long B, int Ks, double y0_hard, const dou
     double Uk[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) Uk[i] = y[((size_t)b * Ks + k) * NP + i];
-    const double f0 = (k == 0) ? y0_hard : y[((size_t)b * Ks + (k - 1)) * NP + lastprev];
+    const double f0 = (k == 0) ? (y0_arr ? y0_arr[b] : y0_hard) : y[((size_t)b * Ks + (k - 1)) * NP + lastprev];
     double uh[NA];
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
@@ -357,8 +359,9 @@ extern "C" int dgadj_tdg_march(dgadj_handle* h, int64_t B, int32_t Ks, int32_t N
 }
 
 extern "C" int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, int32_t nq,
-                                 int32_t linear, double y0_hard, const double* elem_consts_host,
-                                 const double* y_dev, double* v_dev, double* err_dev, void* stream) {
+                                 int32_t linear, double y0_hard, const double* y0_dev,
+                                 const double* elem_consts_host, const double* y_dev, double* v_dev,
+                                 double* err_dev, void* stream) {
   if (!h) return DGADJ_ERR_INVALID;
   if (B <= 0 || Ks <= 0 || nq < 0 || !elem_consts_host || !y_dev) return fail(h, DGADJ_ERR_INVALID, "bad tdg_adjoint arguments");
   if (Np_primal < 2 || Np_primal > 6) return fail(h, DGADJ_ERR_UNSUPPORTED, "time-DG adjoint supports primal 1 <= N <= 5");
@@ -370,7 +373,7 @@ extern "C" int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t
   if (rc) return rc;
   const int block = 128;
   const unsigned grid = (unsigned)((B + block - 1) / block);
-#define DGADJ_TDG_A(n) case n: tdg_adjoint_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, y0_hard, h->tdg_scratch, y_dev, v_dev, err_dev); break;
+#define DGADJ_TDG_A(n) case n: tdg_adjoint_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, y0_hard, y0_dev, h->tdg_scratch, y_dev, v_dev, err_dev); break;
   switch (Np_primal) { DGADJ_TDG_A(2) DGADJ_TDG_A(3) DGADJ_TDG_A(4) DGADJ_TDG_A(5) DGADJ_TDG_A(6) }
 #undef DGADJ_TDG_A
   CUDA_TRY(h, cudaGetLastError());
@@ -379,8 +382,8 @@ extern "C" int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t
 }
 
 extern "C" int dgadj_tdg_adjoint_rec(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, double y0_hard,
-                                     const double* elem_consts_host, const double* y_dev, double* v_dev,
-                                     double* err_dev, void* stream) {
+                                     const double* y0_dev, const double* elem_consts_host, const double* y_dev,
+                                     double* v_dev, double* err_dev, void* stream) {
   if (!h) return DGADJ_ERR_INVALID;
   if (B <= 0 || Ks <= 0 || !elem_consts_host || !y_dev) return fail(h, DGADJ_ERR_INVALID, "bad tdg_adjoint_rec arguments");
   // utils/Globals1D.m:37-42 tabulates Radau points up to m = 5  =>  N <= 4
@@ -393,7 +396,7 @@ extern "C" int dgadj_tdg_adjoint_rec(dgadj_handle* h, int64_t B, int32_t Ks, int
   if (rc) return rc;
   const int block = 128;
   const unsigned grid = (unsigned)((B + block - 1) / block);
-#define DGADJ_TDG_R(n) case n: tdg_adjrec_kernel<n><<<grid, block, 0, st>>>(B, Ks, y0_hard, h->tdg_scratch, y_dev, v_dev, err_dev); break;
+#define DGADJ_TDG_R(n) case n: tdg_adjrec_kernel<n><<<grid, block, 0, st>>>(B, Ks, y0_hard, y0_dev, h->tdg_scratch, y_dev, v_dev, err_dev); break;
   switch (Np_primal) { DGADJ_TDG_R(2) DGADJ_TDG_R(3) DGADJ_TDG_R(4) DGADJ_TDG_R(5) }
 #undef DGADJ_TDG_R
   CUDA_TRY(h, cudaGetLastError());

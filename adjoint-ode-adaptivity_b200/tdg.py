@@ -42,11 +42,16 @@ RADAU = {
 
 
 class TimeDG:
-    def __init__(self, linear=False, device=0, tol=1e-7, maxit=500):
+    def __init__(self, linear=False, device=0, tol=1e-7, maxit=500, quirks=True):
         import torch
         self.torch = torch
         self.lib = _lib.load()
         self.linear, self.device, self.tol, self.maxit = bool(linear), device, float(tol), int(maxit)
+        # quirks=True: the reference bug for bug.  quirks=False switches off SURVEY quirk C-3 only: the
+        # adjoint linearises about the primal at quadrature points INSIDE the element instead of the
+        # mirrored interval of adj_march.m:72,78 -- with it the element indicators sum to the error of J
+        # (tools/cfg5_report.py); everything else is unchanged.
+        self.quirks = bool(quirks)
         self._cache = {}                        # per-element constants by (kind, order, element end points)
         self._mesh_cache = {}                   # padded whole-mesh blocks by (kind, orders, mesh)
         cfg = _lib.Config(device=device, N=1, K=1, bc=1, inflow=0, functional=0, scheme=0, reserved=0, alpha=0.0)
@@ -149,7 +154,7 @@ class TimeDG:
         self._mesh_cache[key] = value
 
     def _adjoint_element(self, Na, tk):
-        key = ("a", Na, tk.tobytes())
+        key = ("a", Na, self.quirks, tk.tobytes())
         if key not in self._cache:
             g = BaseGalerkin1D(n=Na, k=1, domain=(tk[0], tk[-1]), n_gq=1 if self.linear else 2 * Na)  # :17 / :71
             x = g.x[:, 0]
@@ -171,7 +176,7 @@ class TimeDG:
                 el["A0"] = -S.T + Bm                              # :86 without M_v (state dependent)
                 B2 = np.zeros((Np, Np)); B2[-1, -1] = -1.0        # :107
                 el["A2"] = -S.T - B2                              # :115
-                r_interp = tk[0] + (1 + g.r) * hk / 2             # :78 (mirrored interval)
+                r_interp = tk[0] + (1 + g.r) * (hk if self.quirks else -hk) / 2    # :78 (mirrored interval: C-3)
                 el["Iq"] = _polyfit_matrix(tk, deg, r_interp)
                 el["Phi"], el["w"], el["nq"] = g.phi, g.w, g.n_r
             self._cache[key] = el
@@ -182,7 +187,7 @@ class TimeDG:
         adj_march.m, padded to the mesh maxima.  Returns (blocks, node arrays, Npp_max, nq_max)."""
         Ks = len(t1)
         Nas = self._orders(Nas, Ks)
-        mkey = ("A", Nas.tobytes(), b"".join(np.asarray(t, dtype=np.float64).tobytes() for t in t1))
+        mkey = ("A", self.quirks, Nas.tobytes(), b"".join(np.asarray(t, dtype=np.float64).tobytes() for t in t1))
         if mkey in self._mesh_cache:
             return self._mesh_cache[mkey]
         els = [self._adjoint_element(int(Nas[k]), np.asarray(t1[k], dtype=np.float64)) for k in range(Ks)]
@@ -204,6 +209,18 @@ class TimeDG:
         out = (np.ascontiguousarray(np.concatenate(blocks)), [e["x"] for e in els], NPP, nq)
         self._remember(mkey, out)
         return out
+
+    def _y0_args(self, y0, B):
+        """(scalar, device pointer) for the initial value the first element's residual is measured
+        against: the reference hard-codes y0 = 1 (adj_march.m:9); a float64 CUDA tensor [B] gives every
+        trajectory of a batch its own."""
+        if isinstance(y0, self.torch.Tensor):
+            y0 = y0.contiguous().view(-1)
+            if y0.numel() != B or y0.dtype != self.torch.float64 or not y0.is_cuda:
+                raise _lib.DgadjError(_lib.ERR_INVALID, "y0 must be a float64 CUDA tensor [B]")
+            self._y0_keep = y0
+            return 0.0, C.c_void_p(y0.data_ptr())
+        return float(y0), C.c_void_p(0)
 
     # ------------------------------------------------------------------ reference-named entry points
     def dg_march(self, Ns, Ks, times, y0, x_true=None, u_true=None):
@@ -227,6 +244,7 @@ class TimeDG:
         """[t, v, err] = adj_march(Ns, Ks, times)  (matlab/adj_march.m:1); the primal the
         reference reads from globals (`y1`, `t1`, :4) is passed explicitly as dg_march returned it.
         Ns = adjoint orders, primal order + 1 on every element (matlab/MAIN.m:34 passes Ns+1).
+        y0 = the initial value(s): the reference's hard-coded 1 (adj_march.m:9) or a CUDA tensor [B].
         Returns (t, v[B, Ks, Na_max], err[B, Ks]) -- err signed, v zero beyond len(t[k])."""
         torch = self.torch
         B = y1.shape[0]
@@ -235,7 +253,8 @@ class TimeDG:
             raise _lib.DgadjError(_lib.ERR_INVALID, "y1 must be the [B, Ks, Np_max] array dg_march returned")
         v = torch.empty((B, Ks, NPP + 1), dtype=torch.float64, device=y1.device)
         err = torch.empty((B, Ks), dtype=torch.float64, device=y1.device)
-        self._check(self.lib.dgadj_tdg_adjoint(self._h, B, Ks, NPP, nq, int(self.linear), float(y0),
+        y0s, y0p = self._y0_args(y0, B)
+        self._check(self.lib.dgadj_tdg_adjoint(self._h, B, Ks, NPP, nq, int(self.linear), y0s, y0p,
                                                C.c_void_p(consts.ctypes.data), C.c_void_p(y1.contiguous().data_ptr()),
                                                C.c_void_p(v.data_ptr()), C.c_void_p(err.data_ptr()), self._stream()))
         return nodes, v, err
@@ -303,7 +322,8 @@ class TimeDG:
             raise _lib.DgadjError(_lib.ERR_INVALID, "y1 must be the [B, Ks, Np_max] array dg_march returned")
         v = torch.empty((B, Ks, NP + 1), dtype=torch.float64, device=y1.device)
         err = torch.empty((B, Ks), dtype=torch.float64, device=y1.device)
-        self._check(self.lib.dgadj_tdg_adjoint_rec(self._h, B, Ks, NP, float(y0), C.c_void_p(consts.ctypes.data),
+        y0s, y0p = self._y0_args(y0, B)
+        self._check(self.lib.dgadj_tdg_adjoint_rec(self._h, B, Ks, NP, y0s, y0p, C.c_void_p(consts.ctypes.data),
                                                    C.c_void_p(y1.contiguous().data_ptr()), C.c_void_p(v.data_ptr()),
                                                    C.c_void_p(err.data_ptr()), self._stream()))
         return nodes, v, err

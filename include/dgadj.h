@@ -204,7 +204,9 @@ int dgadj_fd_awr(dgadj_handle* h, int64_t B, int32_t n, int32_t ref_factor, int3
  * layout and padding rules in csrc/dgadj_tdg.cu) are built by the host.
  *   march:   y0_dev[B] -> y_dev[B][Ks][Np], its_dev[B][Ks] (Newton iterations; or NULL)
  *   adjoint: y_dev (primal, Np_primal) -> v_dev[B][Ks][Np_primal+1] (or NULL), err_dev[B][Ks]
- *            (signed; matlab/MAIN.m:51 takes abs); y0_hard = the `y0 = 1` of adj_march.m:9.
+ *            (signed; matlab/MAIN.m:51 takes abs); y0_hard = the `y0 = 1` of adj_march.m:9, the
+ *            initial value the first element's residual is measured against; y0_dev[B] (or NULL)
+ *            overrides it per trajectory -- a batch of initial values needs its own.
  *   adjoint_rec: matlab/adj_rec.m:18-71 (linear branch) -- the adjoint solved at the primal
  *            order and reconstructed to order N+1 through the Radau points of
  *            utils/Globals1D.m:37-42 (N <= 4); v_dev[B][Ks][Np_primal+1] = values at
@@ -213,11 +215,12 @@ int dgadj_tdg_march(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np, int32_t 
                     double tol, int32_t maxit, const double* elem_consts_host, const double* y0_dev,
                     double* y_dev, int32_t* its_dev, void* stream);
 int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, int32_t nq,
-                      int32_t linear, double y0_hard, const double* elem_consts_host,
-                      const double* y_dev, double* v_dev, double* err_dev, void* stream);
+                      int32_t linear, double y0_hard, const double* y0_dev,
+                      const double* elem_consts_host, const double* y_dev, double* v_dev,
+                      double* err_dev, void* stream);
 int dgadj_tdg_adjoint_rec(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np_primal, double y0_hard,
-                          const double* elem_consts_host, const double* y_dev, double* v_dev,
-                          double* err_dev, void* stream);
+                          const double* y0_dev, const double* elem_consts_host, const double* y_dev,
+                          double* v_dev, double* err_dev, void* stream);
 /* matlab/err_contribution.m:1-50 (exact-adjoint error contributions of the linear model problem;
  * unused by the reference, MAIN.m:50): err_dev[B][Ks] = cvec_k . y_dev[b][k][:] (+ u(1) - 1 on the
  * first element, :42-43); cvec_host[Ks][Np] = the quadrature of a(t)(phi_j - phi_j')(t) over

@@ -94,9 +94,11 @@ def dg_march(Ns, Ks, times, y0, linear=False, tol=1e-7, maxit=500):
     return t, y, its
 
 
-def adjoint_element(Na, tk_primal, linear=False):
+def adjoint_element(Na, tk_primal, linear=False, quirk_c3=True):
     """Per-element constants of adj_march.m for adjoint order Na on the element whose primal
-    nodes are tk_primal."""
+    nodes are tk_primal.  quirk_c3=False evaluates the primal at the quadrature points INSIDE the
+    element instead of the mirrored interval the reference uses (adj_march.m:78 with hk < 0);
+    everything else is unchanged."""
     tspan = (tk_primal[0], tk_primal[-1])
     g = ops.fem_setup(Na, 1, tspan, 1 if linear else 2 * Na)    # adj_march.m:17 / :71
     x = g.x[:, 0]
@@ -108,13 +110,13 @@ def adjoint_element(Na, tk_primal, linear=False):
     out = dict(g=g, x=x, hk=hk, Np=Np, S=S, Minv=Minv)
     out["Ix"] = _polyfit_matrix(tk_primal, deg, x)              # uh_k = polyval(pu, x)
     if not linear:
-        r_interp = tk_primal[0] + (1 + g.r) * hk / 2            # :78 (mirrored interval)
+        r_interp = tk_primal[0] + (1 + g.r) * (hk if quirk_c3 else -hk) / 2    # :78 (mirrored interval)
         out["Iq"] = _polyfit_matrix(tk_primal, deg, r_interp)
         out["Phi"], out["w"] = g.Phi, g.w
     return out
 
 
-def adj_march(Ns, Ks, times, y1, t1, linear=False, y0_hard=1.0):
+def adj_march(Ns, Ks, times, y1, t1, linear=False, y0_hard=1.0, quirk_c3=True):
     """matlab/adj_march.m:1-122.  Ns = adjoint orders (MAIN.m:34 passes Ns+1); y1 / t1 = primal
     from dg_march (lists over elements; y1[k] is (B, Np_primal)).  Returns (t, v, err) with
     v[k] (B, Np) and err (B, Ks) -- signed; MAIN.m:51 takes abs."""
@@ -123,7 +125,7 @@ def adj_march(Ns, Ks, times, y1, t1, linear=False, y0_hard=1.0):
     t, v = [None] * Ks, [None] * Ks
     err = np.zeros((B, Ks))
     for k in range(Ks - 1, -1, -1):
-        el = adjoint_element(int(Ns[k]), t1[k], linear)
+        el = adjoint_element(int(Ns[k]), t1[k], linear, quirk_c3)
         Np, S, Minv, hk = el["Np"], el["S"], el["Minv"], el["hk"]
         uh = y1[k] @ el["Ix"].T                                 # primal at the adjoint nodes
         F0 = np.zeros((B, Np))

@@ -584,13 +584,42 @@ def test_adaptive_loop_tdg(pkg, torch):
     times, Ns, Ks = np.linspace(0.0, 2.0, 3), np.ones(2, dtype=int), 2
     for it in range(13):
         t1, y1, _ = otdg.dg_march(Ns, Ks, times, y0)
-        _, _, err = otdg.adj_march(Ns + 1, Ks, times, y1, t1)
+        _, _, err = otdg.adj_march(Ns + 1, Ks, times, y1, t1, y0_hard=y0)
         mean_err = np.abs(err).mean(axis=0)
         assert np.array_equal(hist[it]["times"], times), it
         np.testing.assert_allclose(hist[it]["err"], mean_err, rtol=1e-8, atol=1e-12)
         times, Ns, ref_i = otdg.refine(times, Ns, mean_err, 1)
         assert hist[it]["ref_idx"] == ref_i
         Ks += 1
+
+
+def test_tdg_quirk_c3_switch(pkg, torch):
+    """TimeDG(quirks=False) switches off SURVEY quirk C-3 only (adjoint linearised inside the element
+    instead of the mirrored interval of adj_march.m:72,78): parity with the oracle's switch, and what
+    the switch buys -- with per-trajectory initial values the element indicators then sum to the
+    error of J = int_0^2 u dt (closed form of python/factory.py:130-131), which the bug-for-bug
+    indicator misses by orders of magnitude."""
+    from oracle import tdg as otdg
+    rng = np.random.default_rng(4)
+    y0 = rng.uniform(-3, 3, 96)
+    times = np.array([0.0, 0.25, 0.5, 0.75, 1.0, 1.25, 1.5, 1.75, 2.0])
+    Ks, Ns = 8, np.ones(8, dtype=int)
+    d_y0 = torch.tensor(y0, device="cuda")
+    xq, wq = np.polynomial.legendre.leggauss(200)
+    J_exact = (wq * 2.0 * np.arctan2(np.sin(y0[:, None] / 2) * np.exp(xq + 1.0), np.cos(y0[:, None] / 2))).sum(1)
+    gap = {}
+    for quirks in (True, False):
+        s = pkg.TimeDG(quirks=quirks)
+        t1, y1, _ = s.dg_march(Ns, Ks, times, d_y0)
+        _, v, err = s.adj_march(Ns + 1, Ks, times, y1, t1, y0=d_y0)
+        t1r, y1r, _ = otdg.dg_march(Ns, Ks, times, y0)
+        _, vr, errr = otdg.adj_march(Ns + 1, Ks, times, y1r, t1r, y0_hard=y0, quirk_c3=quirks)
+        assert rel(v.cpu().numpy(), np.stack(vr, axis=1)) < 1e-10
+        assert np.max(np.abs(err.cpu().numpy() - errr)) < 1e-10 * max(1.0, np.max(np.abs(errr)))
+        y1h = y1.cpu().numpy()
+        J_h = sum(0.5 * (times[k + 1] - times[k]) * (y1h[:, k, 0] + y1h[:, k, 1]) for k in range(Ks))
+        gap[quirks] = np.abs(err.cpu().numpy().sum(1) - (J_exact - J_h)).mean() / np.abs(J_exact - J_h).mean()
+    assert gap[False] < 0.05 and gap[True] > 1.0, gap
 
 
 # ------------------------------------------------------------------ Burgers + limiter (config 3)

@@ -305,7 +305,7 @@ def _tdg_host(pkg, linear):
     """A TimeDG with only its host-side constant builders (no device handle)."""
     from adjoint_ode_adaptivity_b200.tdg import TimeDG
     s = object.__new__(TimeDG)
-    s.linear, s._cache, s._mesh_cache, s._h = linear, {}, {}, None
+    s.linear, s.quirks, s._cache, s._mesh_cache, s._h = linear, True, {}, {}, None
     return s
 
 
