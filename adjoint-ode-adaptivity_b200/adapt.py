@@ -82,7 +82,7 @@ def adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=30, linear=False, device=0,
 
 
 def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic", inflow="zero", cfl=0.25, psi=None,
-                device=0, B_global=None):
+                device=0, B_global=None, ic_term=True):
     """Adjoint-driven h-refinement of the DG-in-space advection march (BASELINE config 5 for the
     PDE path: non-uniform h): per iteration the batch is marched forward and backward on the
     current mesh, the per-element indicators are reduced over the batch in a fixed order, and the
@@ -90,8 +90,13 @@ def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic",
     (matlab/MAIN.m:137-141 applied to space; batch rule python/Main_variable_params.py:340-341).
 
     u0_fn(x) -> float64 CUDA tensor [B, Np, K] of initial conditions at the nodes x[Np, K]
-    (re-evaluated on every mesh).  Returns the history (mesh, mean indicator, refined elements,
-    J mean) per iteration."""
+    (re-evaluated on every mesh).  ic_term: the march's indicator weighs the residual of the
+    *evolution* (coarse and enriched solutions start from the same interpolated data); with
+    ic_term the interpolation defect of the initial data enters too, weighted by the adjoint at
+    t = 0:  eta_k += lam0_k . (P u0(x_c) - u0(x_f))_k  -- so that sum_k eta_k is the whole difference
+    between the functional of the coarse solution and that of the order-N+1 solution of the true
+    initial data.  Returns the history (mesh, mean indicator, refined elements, J mean, the signed
+    batch-mean estimate) per iteration."""
     import torch
     v_x = np.asarray(v_x, dtype=np.float64)
     hist = []
@@ -101,14 +106,20 @@ def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic",
         S = int(np.ceil(T / (cfl * xmin / abs(a))))
         dt = T / S
         u0 = u0_fn(s.g.x)
-        out = s.fwd_adj(u0, a, dt, S, want_uT=False)
-        sums = allreduce_indicators(s.reduce_indicators(out["eta"], out["J"]), ordered=True)
+        out = s.fwd_adj(u0, a, dt, S, want_uT=False, want_lam0=ic_term)
+        eta = out["eta"]
+        if ic_term:
+            P = torch.tensor(s.P, device=u0.device)
+            defect = torch.einsum("ij,bjk->bik", P, u0) - u0_fn(s.gf.x)
+            eta = (eta + (out["lam0"] * defect).sum(1)).contiguous()
+        sums = allreduce_indicators(s.reduce_indicators(eta, out["J"]), ordered=True)
         Bg = B_global if B_global is not None else u0.shape[0]
         K = s.K
         mean_eta = (sums[:K] / float(Bg)).cpu().numpy()
         order = np.argsort(-mean_eta, kind="stable")[:topk]            # ties by lowest index
         hist.append(dict(it=it, v_x=v_x.copy(), K=K, S=S, mean_eta=mean_eta, refined=np.sort(order),
-                         eta_total=float(mean_eta.sum()), J_mean=float(sums[K + 3]) / float(Bg)))
+                         eta_total=float(mean_eta.sum()), J_mean=float(sums[K + 3]) / float(Bg),
+                         J=out["J"], estimate=eta.sum(1)))
         s.close()
         mids = 0.5 * (v_x[order] + v_x[order + 1])
         v_x = np.sort(np.concatenate([v_x, mids]))

@@ -853,7 +853,7 @@ def test_adaptive_loop_advection_nonuniform_h(pkg, torch):
     u0_fn = lambda x: torch.tensor(u0_np(x), device="cuda")
     v_x0 = np.linspace(0.0, 3.0, 13)
     a, T = 1.0, 0.6
-    hist = pkg.adapt_advec(u0_fn, N, v_x0, a, T, iters=6, topk=2, bc="inflow", inflow="zero", alpha=0.0)
+    hist = pkg.adapt_advec(u0_fn, N, v_x0, a, T, iters=6, topk=2, bc="inflow", inflow="zero", alpha=0.0, ic_term=False)
     assert [h["K"] for h in hist] == [12, 14, 16, 18, 20, 22, 24]
     for h in hist[:4]:                                    # oracle on the same (non-uniform) meshes
         gc, gf = ops.startup_mesh(N, h["v_x"]), ops.startup_mesh(N + 1, h["v_x"])
@@ -867,6 +867,17 @@ def test_adaptive_loop_advection_nonuniform_h(pkg, torch):
     assert widths.min() < 0.5 * widths.max()              # non-uniform h
     assert 0.5 < hist[-1]["v_x"][np.argmin(widths)] < 2.0   # refined where the pulses travel
     assert hist[-1]["eta_total"] < 0.5 * hist[0]["eta_total"]
+    # with the initial-data term the signed estimate is the whole coarse-vs-enriched difference:
+    #   sum_k eta_k = J_f(P u_c^S) - J_f(march of the enriched space from u0 at ITS nodes)
+    h2 = pkg.adapt_advec(u0_fn, N, v_x0, a, T, iters=1, topk=2, bc="inflow", inflow="zero", alpha=0.0)[1]
+    s = pkg.AdvecDG1D(N, v_x=h2["v_x"], alpha=0.0, bc="inflow", inflow="zero")
+    sf = pkg.AdvecDG1D(N + 1, v_x=h2["v_x"], alpha=0.0, bc="inflow", inflow="zero")
+    dt = T / h2["S"]
+    uc = s.forward(u0_fn(s.g.x), a, dt, h2["S"])
+    uf = sf.forward(u0_fn(s.gf.x), a, dt, h2["S"])
+    jw_f = torch.tensor(s.jw_f, device="cuda")
+    diff = (jw_f * (torch.einsum("ij,bjk->bik", torch.tensor(s.P, device="cuda"), uc) - uf)).sum((1, 2))
+    assert float((h2["estimate"] - diff).abs().max()) < 1e-11 * float((jw_f.abs() * uf.abs()).sum((1, 2)).max())
 
 
 def test_matlab_named_entry_points(pkg, torch):
