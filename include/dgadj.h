@@ -3,8 +3,9 @@
  *
  * The reference (wglao/Adjoint-ODE-Adaptivity) has NO native / FFI layer: its hot path is
  * MATLAB + NumPy source.  Each entry point below therefore cites the reference *source
- * routine* it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the
- * reference side (python/galerkin.py, python/Main_finite_difference.py).
+ * routine* it replaces; INTEGRATION.md shows the bindings a maintainer adds on the
+ * reference side: ctypes (python/galerkin.py, python/Main_finite_difference.py) and MATLAB
+ * loadlibrary (utils/, matlab/).
  *
  * Conventions
  *   - plain pointers and sizes only; no C++/torch types cross this boundary.
