@@ -1,5 +1,6 @@
 #!/usr/bin/env python
 """Secondary workloads of SURVEY section 8(d) (not the driver's headline; numbers go to profiles/):
+  forward the forward march alone (the reference's own workload), config 2 mesh
   sweep   config 4: parameter sweep, N=4, K=64, S=100, per-trajectory speed a and CFL dt
   burgers config 3: Burgers + SlopeLimitN, N=4, K=256, B=16384, forward + checkpoints
   tdg     config 5: DG-in-time march + adjoint (u' = sin u), B=4096 ICs, refined mesh
@@ -62,6 +63,27 @@ def sweep(B=131072):
                 plan=s.plan(B))
 
 
+def forward(B=32768):
+    """The reference's own workload (utils/One_code.mlx): the forward LSERK4 march alone, config 2 mesh."""
+    N, K, S = 8, 1024, 100
+    s = pkg.AdvecDG1D(N, K, domain=(0.0, TWO_PI), alpha=0.0, bc="periodic")
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    x = torch.tensor(s.g.x, device=dev)[None]
+    u0 = torch.zeros((B, N + 1, K), dtype=torch.float64, device=dev)
+    for m in range(1, 5):
+        A = torch.randn((B, 1, 1), dtype=torch.float64, device=dev, generator=g) / m
+        ph = torch.rand((B, 1, 1), dtype=torch.float64, device=dev, generator=g) * TWO_PI
+        u0 += A * torch.sin(m * x + ph)
+    dt, _ = s.cfl_dt(1.0)
+    ms = timeit(lambda: s.forward(u0, TWO_PI, dt, S), warm=2, reps=3)
+    ups = 5 * S * K * B
+    fl = 2 * 81 + 12 * 9 + 6                                   # SURVEY 8(d): forward stage, Np = 9
+    peak, _ = s.measure_dfma_peak(0.5)
+    return dict(workload="forward LSERK4 march only (One_code.mlx loop), N=8 K=1024 B=%d S=%d, periodic, upwind" % (B, S),
+                metric="DG element-stage updates/s (forward)", value=ups / (ms * 1e-3), ms=ms,
+                frac_fp64_peak=fl * ups / (ms * 1e-3) / 1e12 / peak, plan=s.plan(B, fused=False))
+
+
 def burgers(B=16384):
     N, K = 4, 256
     s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc="periodic")
@@ -119,9 +141,9 @@ def tdg_fd(B=4096):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sweep", "burgers", "tdg_fd"]
+    which = sys.argv[1:] or ["forward", "sweep", "burgers", "tdg_fd"]
     for w in which:
         kw = dict(B=int(os.environ["SEC_B"])) if "SEC_B" in os.environ else {}
-        r = dict(sweep=sweep, burgers=burgers, tdg_fd=tdg_fd)[w](**kw)
+        r = dict(forward=forward, sweep=sweep, burgers=burgers, tdg_fd=tdg_fd)[w](**kw)
         for line in (r if isinstance(r, list) else [r]):
             print(json.dumps(line), flush=True)
