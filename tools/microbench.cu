@@ -69,6 +69,41 @@ __global__ void __launch_bounds__(1024, 1) k_dmma(double* out, int iters, double
   for (int i = 0; i < NFMA; ++i) s += f[i];
   if (s == 123.456) out[0] = s;
 }
+// mode D: the march kernel's instruction mix without its dependencies: per 64 constants (1 LDCU : 4
+// DFMA = 256 DFMA) NLDS shared-memory loads whose values feed DFMAs, NSTS stores and NIMAD integer
+// multiply-adds -- is the fp64 pipe held back by the *mix* at 8 warps per SM, or by what the real
+// kernel waits for (barriers, exchange latencies)?
+template <int NCH, int NLDS, int NSTS, int NIMAD>
+__global__ void __launch_bounds__(256, 1) k_mix(const __grid_constant__ CB cb, double* out, int iters, double y) {
+  __shared__ double sm[4096];
+  double a[NCH];
+  int k = threadIdx.x;
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = 1e-9 * i;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) a[i] = threadIdx.x + i;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    const double* c = cb.c[it % 5];
+    double add[NLDS > 0 ? NLDS : 1];
+#pragma unroll
+    for (int l = 0; l < NLDS; ++l) add[l] = sm[(threadIdx.x + 64 * l + it) & 4095];
+#pragma unroll
+    for (int r = 0; r < 64; ++r) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = (r * 4 + u) % NCH;
+        a[q] = fma(a[q], c[r], (NLDS > 0 && (r * 4 + u) < NLDS) ? add[r * 4 + u] : y);
+      }
+      if (r < NIMAD) k = k * 3 + it;
+      if (r < NSTS) sm[(threadIdx.x + 2048 + 32 * r) & 4095] = a[r % NCH];
+    }
+  }
+  double s = k;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) s += a[i];
+  if (s == 123.456) out[0] = s;
+}
 template <typename F>
 double run(F launch, double flops_per_iter_per_thread, int threads, int iters) {
   cudaEvent_t e0, e1;
@@ -96,6 +131,11 @@ int main() {
   printf("cst 1:4 512thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,4><<<148,512>>>(cb,out,it,1e-9); }, 2.0*64*4, 512, IT));
   printf("cst 1:2 1024thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,2><<<148,1024>>>(cb,out,it,1e-9); }, 2.0*64*2, 1024, IT));
   printf("cst 1:1 1024thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,1><<<148,1024>>>(cb,out,it,1e-9); }, 2.0*64*1, 1024, IT));
+  printf("mix 256thr 32ch, DFMA + LDCU only (1:4)              : %.2f TF\n", run([&](int it){ k_mix<32,0,0,0><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS +9 STS +18 IMAD per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,9,18><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS               per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,0,0><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +44 LDS +18 STS +36 IMAD per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,44,18,36><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 8ch  +22 LDS +9 STS +18 IMAD per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<8,22,9,18><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
   // m8n8k4: 8*8*4*2 = 512 flop per warp instruction = 16 flop per thread
   printf("dmma 512thr 4ch       : %.2f TF (mma only)\n", run([&](int it){ k_dmma<4,0><<<148,512>>>(out,it,0.999,1e-9); }, 16.0*8*4, 512, IT));
   printf("dmma 1024thr 4ch      : %.2f TF (mma only)\n", run([&](int it){ k_dmma<4,0><<<148,1024>>>(out,it,0.999,1e-9); }, 16.0*8*4, 1024, IT));
