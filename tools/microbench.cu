@@ -73,11 +73,11 @@ __global__ void __launch_bounds__(1024, 1) k_dmma(double* out, int iters, double
 // DFMA = 256 DFMA) NLDS shared-memory loads whose values feed DFMAs, NSTS stores and NIMAD integer
 // multiply-adds -- is the fp64 pipe held back by the *mix* at 8 warps per SM, or by what the real
 // kernel waits for (barriers, exchange latencies)?
-template <int NCH, int NLDS, int NSTS, int NIMAD>
+template <int NCH, int NLDS, int NSTS, int NIMAD, int FRESH = 1, int KIND = 0>
 __global__ void __launch_bounds__(256, 1) k_mix(const __grid_constant__ CB cb, double* out, int iters, double y) {
   __shared__ double sm[4096];
   double a[NCH];
-  int k = threadIdx.x;
+  int k[4] = {(int)threadIdx.x, 1, 2, 3};
   for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = 1e-9 * i;
   __syncthreads();
 #pragma unroll
@@ -95,11 +95,19 @@ __global__ void __launch_bounds__(256, 1) k_mix(const __grid_constant__ CB cb, d
         const int q = (r * 4 + u) % NCH;
         a[q] = fma(a[q], c[r], (NLDS > 0 && (r * 4 + u) < NLDS) ? add[r * 4 + u] : y);
       }
-      if (r < NIMAD) k = k * 3 + it;
-      if (r < NSTS) sm[(threadIdx.x + 2048 + 32 * r) & 4095] = a[r % NCH];
+      if (r < NIMAD) {   // four independent integer chains; KIND picks the instruction class
+        int& kk = k[r & 3];
+        if (KIND == 0) kk = kk * 3 + it;                                   // IMAD
+        else if (KIND == 1) kk = kk ^ (it + r);                            // LOP3 (ALU)
+        else if (KIND == 2) kk = __funnelshift_l(kk, it, 3);               // SHF (ALU)
+        else if (KIND == 3) asm volatile("mov.b32 %0, %1;" : "=r"(kk) : "r"(k[(r + 1) & 3]));   // register move
+        else if (KIND == 4) kk = kk * it + r;                              // IMAD, register multiplier
+      }
+      // FRESH: store the accumulator the DFMA just above wrote; otherwise one written 16 DFMAs ago
+      if (r < NSTS) sm[(threadIdx.x + 2048 + 32 * r) & 4095] = a[(r * 4 + (FRESH ? 3 : 3 + NCH - 16)) % NCH];
     }
   }
-  double s = k;
+  double s = k[0] + k[1] + k[2] + k[3];
 #pragma unroll
   for (int i = 0; i < NCH; ++i) s += a[i];
   if (s == 123.456) out[0] = s;
@@ -132,10 +140,17 @@ int main() {
   printf("cst 1:2 1024thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,2><<<148,1024>>>(cb,out,it,1e-9); }, 2.0*64*2, 1024, IT));
   printf("cst 1:1 1024thr 8ch: %.2f TF\n", run([&](int it){ k_cst<8,1><<<148,1024>>>(cb,out,it,1e-9); }, 2.0*64*1, 1024, IT));
   printf("mix 256thr 32ch, DFMA + LDCU only (1:4)              : %.2f TF\n", run([&](int it){ k_mix<32,0,0,0><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
-  printf("mix 256thr 32ch +22 LDS +9 STS +18 IMAD per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,9,18><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS +9 STS +18 IMAD per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,9,18,1,4><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS +18 IMAD (dependent chains, imm) per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,0,18><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS +18 LOP3         per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,0,18,1,1><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS +18 SHF          per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,0,18,1,2><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS +18 MOV          per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,0,18,1,3><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS +18 IMAD (reg)   per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,0,18,1,4><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS +9 STS (stale)   per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,9,0,0><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +22 LDS +9 STS (fresh)   per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,9,0,1><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
   printf("mix 256thr 32ch +22 LDS               per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,22,0,0><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
-  printf("mix 256thr 32ch +44 LDS +18 STS +36 IMAD per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,44,18,36><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
-  printf("mix 256thr 8ch  +22 LDS +9 STS +18 IMAD per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<8,22,9,18><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 32ch +44 LDS +18 STS +36 IMAD per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<32,44,18,36,1,4><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
+  printf("mix 256thr 8ch  +22 LDS +9 STS +18 IMAD per 256 DFMA: %.2f TF\n", run([&](int it){ k_mix<8,22,9,18,1,4><<<148,256>>>(cb,out,it,1e-9); }, 2.0*64*4, 256, IT));
   // m8n8k4: 8*8*4*2 = 512 flop per warp instruction = 16 flop per thread
   printf("dmma 512thr 4ch       : %.2f TF (mma only)\n", run([&](int it){ k_dmma<4,0><<<148,512>>>(out,it,0.999,1e-9); }, 16.0*8*4, 512, IT));
   printf("dmma 1024thr 4ch      : %.2f TF (mma only)\n", run([&](int it){ k_dmma<4,0><<<148,1024>>>(out,it,0.999,1e-9); }, 16.0*8*4, 1024, IT));
