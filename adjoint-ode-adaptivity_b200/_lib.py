@@ -69,6 +69,7 @@ PROTOTYPES = {
                                         _P, _P, _P, _P, _P, _P]),
     "dgadj_burgers_adjoint": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                         _P, _P, _P, _P]),
+    "dgadj_ic_indicator": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "dgadj_rank": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "dgadj_reduce_indicators": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "dgadj_allreduce_indicators": (C.c_int, [_P, _P, C.c_int32, _P, _P]),

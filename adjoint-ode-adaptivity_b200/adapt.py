@@ -109,9 +109,7 @@ def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic",
         out = s.fwd_adj(u0, a, dt, S, want_uT=False, want_lam0=ic_term)
         eta = out["eta"]
         if ic_term:
-            P = torch.tensor(s.P, device=u0.device)
-            defect = torch.einsum("ij,bjk->bik", P, u0) - u0_fn(s.gf.x)
-            eta = (eta + (out["lam0"] * defect).sum(1)).contiguous()
+            s.ic_indicator(u0, u0_fn(s.gf.x), out["lam0"], eta)        # dgadj_ic_indicator, in place
         sums = allreduce_indicators(s.reduce_indicators(eta, out["J"]), ordered=True)
         Bg = B_global if B_global is not None else u0.shape[0]
         K = s.K

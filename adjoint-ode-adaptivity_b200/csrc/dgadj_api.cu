@@ -344,6 +344,27 @@ __global__ void __launch_bounds__(1024, 1) dfma_peak_cst_kernel(const __grid_con
 
 
 // ---------------------------------------------------------------------------------------
+// initial-data term of the indicator: eta[b][k] += sum_i lam0[b][i][k] ((P u0)[i][k] - u0f[b][i][k]).
+// One thread per (trajectory, element); memory-bound, once per march.
+__global__ void ic_indicator_kernel(long long B, int K, int Np, int NpF, const double* __restrict__ P,
+                                    const double* __restrict__ u0, const double* __restrict__ u0f,
+                                    const double* __restrict__ lam0, double* __restrict__ eta) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * K) return;
+  const long long b = t / K;
+  const int k = (int)(t - b * K);
+  double uc[MAXNP];
+  for (int j = 0; j < Np; ++j) uc[j] = u0[((size_t)b * Np + j) * K + k];
+  double e = 0.0;
+  for (int i = 0; i < NpF; ++i) {
+    double pu = 0.0;
+    for (int j = 0; j < Np; ++j) pu = fma(P[i * Np + j], uc[j], pu);
+    const size_t o = ((size_t)b * NpF + i) * K + k;
+    e = fma(lam0[o], pu - u0f[o], e);
+  }
+  eta[t] += e;
+}
+
 // single RHS evaluation in the plain nodal form of utils/AdvecRHS1D.m:8-19 (API parity and an
 // independent check of the even/odd march kernels; not a hot path).  One thread per element.
 // ---------------------------------------------------------------------------------------
@@ -457,6 +478,7 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   for (int lv = 0; lv < 2; ++lv)
     for (int i = 0; i < 2; ++i) cudaFree(h->d_nodal[lv][i]);
   cudaFree(h->d_jwc);
+  cudaFree(h->d_P);
   cudaFree(h->d_jwm_c);
   cudaFree(h->d_jwm_f);
   cudaFree(h->d_uin);
@@ -620,6 +642,8 @@ extern "C" int dgadj_set_enriched(dgadj_handle* h, int NpF, const double* DrF, c
   if (!(viol <= 1e-9))
     return fail(h, DGADJ_ERR_UNSUPPORTED,
                 "P is not the Legendre prolongation V_f(:,1:Np) inv(V_c) (deviation %.3e from the modal injection)", viol);
+  rc = upload(h, &h->d_P, P, (size_t)NpF * Np);
+  if (rc) return rc;
   h->enr_set = true;
   return DGADJ_OK;
 }
@@ -1077,6 +1101,22 @@ extern "C" int dgadj_forward_host(dgadj_handle* h, const dgadj_march_args* args,
 // ---------------------------------------------------------------------------------------
 // rank / reduce / peak / info
 // ---------------------------------------------------------------------------------------
+
+extern "C" int dgadj_ic_indicator(dgadj_handle* h, int64_t B, const double* u0_dev, const double* u0f_dev,
+                                  const double* lam0_dev, double* eta_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || !u0_dev || !u0f_dev || !lam0_dev || !eta_dev) return fail(h, DGADJ_ERR_INVALID, "bad ic_indicator arguments");
+  if (!h->enr_set) return fail(h, DGADJ_ERR_STATE, "dgadj_set_enriched has not been called");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)B * h->K;
+  const int block = 256;
+  ic_indicator_kernel<<<(unsigned)((n + block - 1) / block), block, 0, st>>>(B, h->K, h->Np, h->NpF, h->d_P, u0_dev, u0f_dev,
+                                                                             lam0_dev, eta_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}
 
 extern "C" int dgadj_rhs(dgadj_handle* h, int64_t B, int32_t level, const double* u_dev, double t, double a,
                          const double* a_dev, double* rhs_dev, void* stream) {

@@ -30,6 +30,7 @@ struct dgadj_handle {
   double* d_mesh[2][3];  // [level]{rx, fs0, fs1} each [K]
   double* d_nodal[2][2];  // [level]{Dr[Np*Np], LIFT[Np*2]} nodal copies (dgadj_rhs)
   double* d_jwc;          // nodal primal weights (Burgers adjoint)
+  double* d_P;            // nodal prolongation P[NpF][Np] (initial-data term of the indicator)
   double* d_jwm_c;        // modal weights V^T jw of the linear functional, primal / enriched
   double* d_jwm_f;
   double* d_uin;

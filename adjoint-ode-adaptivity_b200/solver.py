@@ -320,6 +320,19 @@ class AdvecDG1D:
                                         self._stream()))
         return order, flags
 
+    def ic_indicator(self, u0, u0f, lam0, eta):
+        """eta[b,k] += lam0[b,:,k] . ((P u0)[:,k] - u0f[b,:,k]): the initial-data term of the indicator
+        (`dgadj_ic_indicator`); u0 at the primal nodes [B,Np,K], u0f at the enriched nodes
+        [B,NpF,K], lam0 from fwd_adj(want_lam0=True); eta updated in place.  Device tensors."""
+        u0, u0f, lam0 = (_as_device_tensor(t).contiguous() for t in (u0, u0f, lam0))
+        if not eta.is_contiguous():
+            raise ValueError("eta must be contiguous (it is updated in place)")
+        B = u0.shape[0]
+        if u0f.shape != lam0.shape or lam0.shape[0] != B or eta.shape != (B, self.K):
+            raise ValueError("shapes: u0 [B,Np,K], u0f / lam0 [B,NpF,K], eta [B,K]")
+        self._check(self.lib.dgadj_ic_indicator(self._h, B, _ptr(u0), _ptr(u0f), _ptr(lam0), _ptr(eta), self._stream()))
+        return eta
+
     def reduce_indicators(self, eta, J=None):
         """sums[K+4] = [sum_b |eta[b,k]| ..., sum|eta|, sum eta^2, max|eta|, sum J] in a fixed
         order (the per-rank partial of the batch-mean indicator,

@@ -160,6 +160,15 @@ int dgadj_forward_host(dgadj_handle* h, const dgadj_march_args* args, const doub
 int dgadj_rhs(dgadj_handle* h, int64_t B, int32_t level, const double* u_dev, double t, double a,
               const double* a_dev, double* rhs_dev, void* stream);
 
+/* Initial-data term of the indicator.  The march's eta weighs the residual of the *evolution*:
+ * the coarse and the enriched solution both start from P u0.  Given the initial data at the
+ * enriched nodes too, u0f_dev[B][NpF][K], and the adjoint at t = 0 (lam0 of dgadj_fwd_adj /
+ * dgadj_adjoint), this adds   eta[b][k] += sum_i lam0[b][i][k] ((P u0)[i][k] - u0f[b][i][k]),
+ * after which sum_k eta[b][k] = J_f(P u_c(T)) - J_f(enriched march of the true initial data): the
+ * whole coarse-vs-enriched difference of the functional (SURVEY App. E.5 conventions).        */
+int dgadj_ic_indicator(dgadj_handle* h, int64_t B, const double* u0_dev, const double* u0f_dev,
+                       const double* lam0_dev, double* eta_dev, void* stream);
+
 /* Refine flag / ranking.  Replaces: ref_i = find(abs(err)==max(abs(err))) (matlab/MAIN.m:137),
  * np.argmax(err_steps) (Main_finite_difference.py:337) and sort(...,'descend') (MAIN.m:99).
  *   eta_dev[B][K] -> order_dev[B][K] int32 (elements by descending |eta|, ties by lowest
