@@ -974,3 +974,43 @@ def test_randomised_secondary_paths(pkg, torch):
         assert np.array_equal(np.moveaxis(flags.cpu().numpy(), 2, 0), np.moveaxis(flags_r, (0, 1, 2), (2, 0, 1))), (case, N, K, bc)
         assert rel(out["uT"].cpu().numpy(), ref) < 1e-11, (case, N, K, bc)
         assert rel(out["maxvel"].cpu().numpy(), np.moveaxis(mv_r, (0, 1, 2), (1, 2, 0))) < 1e-12
+
+
+def test_handles_release_device_memory_and_coexist(pkg, torch):
+    """Handles are independent (two on different streams give the results of one), and create /
+    march / destroy cycles return their device memory (ring, scratch, operator copies)."""
+    N, K, B, S = 4, 64, 512, 20
+    rng = np.random.default_rng(8)
+    s1 = pkg.AdvecDG1D(N, K, domain=(0.0, 2 * math.pi), alpha=0.0, bc="periodic")
+    u0 = torch.tensor(make_ics(oracle_view(s1.g), B, 2), device="cuda")
+    dt, _ = s1.cfl_dt(1.0)
+    ref = s1.fwd_adj(u0, 1.0, dt, S, want_lam0=True)
+    s2 = pkg.AdvecDG1D(N, K, domain=(0.0, 2 * math.pi), alpha=0.0, bc="periodic")
+    st1, st2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(st1):
+        o1 = s1.fwd_adj(u0, 1.0, dt, S, want_lam0=True)
+    with torch.cuda.stream(st2):
+        o2 = s2.fwd_adj(u0, 1.0, dt, S, want_lam0=True)
+    torch.cuda.synchronize()
+    for k in ("uT", "eta", "J", "lam0"):
+        assert torch.equal(o1[k], ref[k]) and torch.equal(o2[k], ref[k]), k
+    s1.close(); s2.close()
+    del ref, o1, o2
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(20):
+        s = pkg.AdvecDG1D(N, K, domain=(0.0, 2 * math.pi), alpha=0.0, bc="periodic")
+        s.fwd_adj(u0, 1.0, dt, S, want_uT=False)
+        b = pkg.BurgersDG1D(2, 32, domain=(-1.0, 1.0), bc="periodic")
+        b.adjoint(b.forward(torch.zeros((4, 3, 32), dtype=torch.float64, device="cuda") + 0.3, 1e-3, 5, checkpoints=True))
+        t = pkg.TimeDG()
+        t.dg_march(np.ones(3, dtype=int), 3, np.linspace(0, 1, 4), torch.ones(8, dtype=torch.float64, device="cuda"))
+        f = pkg.FDAdjoint()
+        f.solve(torch.ones(8, dtype=torch.float64, device="cuda"), np.full(4, 0.25))
+        for h in (s, b, t, f):
+            h.close()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 * 2**20, (free0 - free1) / 2**20        # nothing accumulates (MiB)
