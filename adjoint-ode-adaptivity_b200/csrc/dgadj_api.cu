@@ -866,7 +866,13 @@ static int ensure_ring(dgadj_handle* h, const LaunchPlan& pl, int S, cudaStream_
     h->ring = nullptr;
     h->ring_bytes = 0;
   }
-  CUDA_TRY(h, cudaMalloc((void**)&h->ring, need));
+  const cudaError_t e = cudaMalloc((void**)&h->ring, need);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // an allocation failure is not sticky: clear it, the handle stays usable
+    h->ring = nullptr;
+    return fail(h, DGADJ_ERR_NOMEM, "checkpoint ring of %.1f GB (%d CTAs x %d steps x %zu B) does not fit on the device",
+                need * 1e-9, pl.grid, S, pl.tile * sizeof(double));
+  }
   h->ring_bytes = need;
   return DGADJ_OK;
 }

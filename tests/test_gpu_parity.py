@@ -271,6 +271,10 @@ def test_edge_cases(pkg, torch):
         pkg.AdvecDG1D(2, 4, bc="inflow", inflow="table").forward(torch.zeros((1, 3, 4), dtype=torch.float64, device="cuda"), 1.0, 1e-3, 2)
     with pytest.raises(pkg.DgadjError):
         s._check(s.lib.dgadj_fwd_adj(s._h, None, None, None, None, None, None, None))
+    # a checkpoint ring that cannot fit (S = 10^9 steps) is refused cleanly and the handle stays usable
+    with pytest.raises(pkg.DgadjError, match="NOMEM|does not fit"):
+        s.fwd_adj(torch.tensor(u0, device="cuda"), 1.0, 1e-3, 10**9)
+    check_fused(s.fwd_adj(torch.tensor(u0, device="cuda"), 1.0, 1e-3, 10, want_lam0=True), ref, 3)
 
 
 # ------------------------------------------------------------------ config-2 size: properties
