@@ -55,6 +55,7 @@ PROTOTYPES = {
     "dgadj_ckpt_bytes": (C.c_int64, [_P, C.c_int64, C.c_int32]),
     "dgadj_adjoint": (C.c_int, [_P, C.POINTER(MarchArgs), _P, _P, _P, _P, _P, _P]),
     "dgadj_fwd_adj": (C.c_int, [_P, C.POINTER(MarchArgs), _P, _P, _P, _P, _P, _P]),
+    "dgadj_fwd_adj_windowed": (C.c_int, [_P, C.POINTER(MarchArgs), C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "dgadj_fwd_adj_host": (C.c_int, [_P, C.POINTER(MarchArgs), _P, _P, _P, _P, _P, _P, _P]),
     "dgadj_forward_host": (C.c_int, [_P, C.POINTER(MarchArgs), _P, _P, _P, _P, _P]),
     "dgadj_rhs": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_double, C.c_double, _P, _P, _P]),

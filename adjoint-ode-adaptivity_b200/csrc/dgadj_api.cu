@@ -902,6 +902,164 @@ extern "C" int dgadj_fwd_adj(dgadj_handle* h, const dgadj_march_args* args, cons
 }
 
 // ---------------------------------------------------------------------------------------
+// Windowed (two-level checkpointed) forward + adjoint + indicator for marches whose residual ring
+// does not fit the device (#CTAs x S x tile).  Per batch chunk:
+//   pass 1  the coarse march alone, window by window, keeping the state at every window start;
+//   pass 2  windows in reverse: the window's forward march again, now with the enriched one-step
+//           images (residual checkpoints of W steps only), then its adjoint sweep, which starts
+//           from the modal adjoint state the later window left, leaves its own, and continues the
+//           indicator sums in eta -- in the step order of the one-pass march, so for periodic or
+//           time-independent inflow data the results equal dgadj_fwd_adj's bit for bit.
+// Cost: one extra coarse march (about 1.3x the fused kernel's work); memory per chunk:
+// (S/W) states + W residual tiles + one adjoint state.
+// ---------------------------------------------------------------------------------------
+static int run_window(dgadj_handle* h, int variant, const dgadj_march_args* a, int n0, cudaStream_t st,
+                      void (*setup)(MarchParams&, void*), void* ctx) {
+  LaunchPlan pl;
+  int rc = make_plan(h, a->B, variant, &pl);
+  if (rc) return rc;
+  KArgs ka;
+  fill_params(h, a, pl, &ka);
+  ka.p.n0 = n0;
+  ka.p.ckpt_by_block = 0;
+  setup(ka.p, ctx);
+  return launch(h, variant, pl, st, &ka);
+}
+
+struct WinCtx {
+  int in_modal, out_modal;
+  const double* u_in;
+  double* u_out;
+  double* ckpt;
+  const double* uT_in;
+  const double* mu_in;
+  double* mu_out;
+  double *J, *lam0, *eta;
+  int eta_acc;
+};
+
+extern "C" int dgadj_fwd_adj_windowed(dgadj_handle* h, const dgadj_march_args* args, int32_t window,
+                                      int64_t batch_chunk, const double* u0_dev, double* uT_dev, double* J_dev,
+                                      double* lam0_dev, double* eta_dev, void* stream) {
+  int rc = check_args(h, args, true);
+  if (rc) return rc;
+  if (!u0_dev) return fail(h, DGADJ_ERR_INVALID, "u0_dev is null");
+  if (window < 1 || batch_chunk < 0) return fail(h, DGADJ_ERR_INVALID, "window must be >= 1 and batch_chunk >= 0");
+  const int S = args->S, W = window;
+  const int nwin = (S + W - 1) / W;
+  if (nwin <= 1) return dgadj_fwd_adj(h, args, u0_dev, uT_dev, J_dev, lam0_dev, eta_dev, stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Np = h->Np, NpF = h->NpF, K = h->K;
+  const size_t state = (size_t)Np * K, fstate = (size_t)NpF * K;
+  // chunk of the batch that fits: nwin states + W residual tiles + one adjoint state per trajectory
+  LaunchPlan pl1;
+  rc = make_plan(h, 1, VAR_FWD_RESID, &pl1);
+  if (rc) return rc;
+  const size_t per_traj = ((size_t)nwin * state + fstate + (size_t)W * pl1.tile / std::max(1, pl1.tpc) + fstate) * sizeof(double);
+  int64_t Bc = batch_chunk;
+  if (Bc == 0) {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
+    Bc = (int64_t)((double)free_b * 0.7 / (double)per_traj);
+    const int64_t wave = (int64_t)h->sm_count * 8;
+    if (Bc > wave) Bc -= Bc % wave;
+  }
+  Bc = std::max<int64_t>(1, std::min<int64_t>(Bc, args->B));
+  const int64_t ck_bytes = dgadj_ckpt_bytes(h, Bc, W);
+  if (ck_bytes < 0) return (int)ck_bytes;
+  double *states = nullptr, *mu = nullptr, *ck = nullptr;
+  auto release = [&]() {
+    cudaFree(states);
+    cudaFree(mu);
+    cudaFree(ck);
+  };
+  if (cudaMalloc((void**)&states, (size_t)nwin * Bc * state * sizeof(double)) != cudaSuccess ||
+      cudaMalloc((void**)&mu, (size_t)Bc * fstate * sizeof(double)) != cudaSuccess ||
+      cudaMalloc((void**)&ck, (size_t)ck_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    release();
+    return fail(h, DGADJ_ERR_NOMEM, "windowed march: %lld trajectories x (%d states + %d residual tiles) do not fit; "
+                "pass a smaller batch_chunk or window", (long long)Bc, nwin, W);
+  }
+  for (int64_t c0 = 0; c0 < args->B && rc == DGADJ_OK; c0 += Bc) {
+    const int64_t bc = std::min<int64_t>(Bc, args->B - c0);
+    dgadj_march_args a = *args;
+    a.B = bc;
+    if (a.a_dev) a.a_dev += c0;
+    if (a.dt_dev) a.dt_dev += c0;
+    auto st_ptr = [&](int j) -> double* { return states + (size_t)(j - 1) * Bc * state; };   // state at the start of window j >= 1; j = nwin: terminal
+    // pass 1: coarse march, window by window
+    for (int j = 0; j < nwin && rc == DGADJ_OK; ++j) {
+      a.S = std::min(W, S - j * W);
+      WinCtx cx = {};
+      cx.u_in = (j == 0) ? u0_dev + (size_t)c0 * state : st_ptr(j);
+      cx.in_modal = (j != 0);      // states are handed over as modal coefficients: no V^-1 V round trip
+      cx.out_modal = 1;
+      cx.u_out = st_ptr(j + 1);
+      rc = run_window(h, VAR_FWD, &a, j * W, st, [](MarchParams& p, void* v) {
+        WinCtx* c = (WinCtx*)v;
+        p.u0 = c->u_in;
+        p.uT = c->u_out;
+        p.in_modal = c->in_modal;
+        p.out_modal = c->out_modal;
+      }, &cx);
+    }
+    if (rc == DGADJ_OK && uT_dev) {   // nodal terminal state for the caller: a march of zero steps
+      a.S = 0;
+      WinCtx cx = {};
+      cx.u_in = st_ptr(nwin);
+      cx.u_out = uT_dev + (size_t)c0 * state;
+      rc = run_window(h, VAR_FWD, &a, S, st, [](MarchParams& p, void* v) {
+        WinCtx* c = (WinCtx*)v;
+        p.u0 = c->u_in;
+        p.uT = c->u_out;
+        p.in_modal = 1;
+      }, &cx);
+    }
+    // pass 2: windows in reverse
+    for (int j = nwin - 1; j >= 0 && rc == DGADJ_OK; --j) {
+      a.S = std::min(W, S - j * W);
+      WinCtx cx = {};
+      cx.u_in = (j == 0) ? u0_dev + (size_t)c0 * state : st_ptr(j);
+      cx.in_modal = (j != 0);
+      cx.ckpt = ck;
+      rc = run_window(h, VAR_FWD_RESID, &a, j * W, st, [](MarchParams& p, void* v) {
+        WinCtx* c = (WinCtx*)v;
+        p.u0 = c->u_in;
+        p.ckpt = c->ckpt;
+        p.in_modal = c->in_modal;
+      }, &cx);
+      if (rc != DGADJ_OK) break;
+      cx.uT_in = st_ptr(j + 1);
+      cx.mu_in = (j == nwin - 1) ? nullptr : mu;
+      cx.mu_out = (j == 0) ? nullptr : mu;
+      cx.J = (j == nwin - 1 && J_dev) ? J_dev + c0 : nullptr;
+      cx.lam0 = (j == 0 && lam0_dev) ? lam0_dev + (size_t)c0 * fstate : nullptr;
+      cx.eta = eta_dev ? eta_dev + (size_t)c0 * K : nullptr;
+      cx.eta_acc = (j != nwin - 1) && eta_dev;
+      rc = run_window(h, VAR_ADJ, &a, j * W, st, [](MarchParams& p, void* v) {
+        WinCtx* c = (WinCtx*)v;
+        p.uT_in = c->uT_in;
+        p.in_modal = 1;
+        p.ckpt = c->ckpt;
+        p.mu_in = c->mu_in;
+        p.mu_out = c->mu_out;
+        p.J = c->J;
+        p.lam0 = c->lam0;
+        p.eta = c->eta;
+        p.eta_acc = c->eta_acc;
+      }, &cx);
+    }
+  }
+  const cudaError_t e = cudaStreamSynchronize(st);   // the scratch is released: the call is synchronous
+  release();
+  if (rc != DGADJ_OK) return rc;
+  if (e != cudaSuccess) return fail(h, DGADJ_ERR_CUDA, "windowed march failed: %s", cudaGetErrorString(e));
+  return DGADJ_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // host-buffer pipeline: the batch is cut into chunks; chunk c+1's H2D copy and chunk c-1's
 // D2H copy overlap chunk c's kernel (three streams, two device buffer sets).  Pinned host
 // buffers are copied from / to directly; pageable ones go through pinned staging.

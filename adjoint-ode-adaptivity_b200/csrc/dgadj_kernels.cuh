@@ -104,6 +104,15 @@ struct MarchParams {
   double* J;
   double* lam0;
   double* eta;
+  // windowed marches (dgadj_fwd_adj_windowed): a window's adjoint sweep starts from the modal adjoint
+  // state the later window left (mu_in, [B][NPF][K]) instead of the functional's terminal condition,
+  // leaves its own (mu_out), continues the indicator sums already in `eta` (eta_acc), and counts
+  // its steps from n0 (time-dependent inflow data)
+  const double* mu_in;
+  double* mu_out;
+  int eta_acc;
+  int n0;
+  int in_modal, out_modal;   // the input state / uT are modal coefficients (window hand-over: no V^-1 V round trip)
 };
 
 struct KArgs {
@@ -225,7 +234,7 @@ static __device__ __noinline__ double inflow_value(const MarchParams& p, long lo
   switch (p.inflow) {
     case INFLOW_SIN_AT: return -sin(a * t);
     case INFLOW_SIN_AAT: return -sin(a * a * t);
-    case INFLOW_TABLE: return p.uin_table[n * p.nstages + s];
+    case INFLOW_TABLE: return p.uin_table[(n + p.n0) * p.nstages + s];
     default: return 0.0;
   }
 }
@@ -515,7 +524,12 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
         double u[NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) u[i] = active ? src[gofs + (size_t)i * K + e] : 0.0;
-        apply_matrix<NP, false>(c.iV, u, z[e].v);
+        if (p.in_modal) {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) z[e].v[i] = u[i];
+        } else {
+          apply_matrix<NP, false>(c.iV, u, z[e].v);
+        }
       }
     }
     if (DO_FWD) {
@@ -527,7 +541,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
           for (int i = 0; i < NP; ++i) hist[(size_t)i * K + e] = p.u0[gofs + (size_t)i * K + e];
         }
       }
-      double time = p.t0;
+      double time = p.t0 + (p.n0 ? p.n0 * (p.dt_arr ? p.dt_arr[bs] : p.dt) : 0.0);
       double* park = sm_big + tid;  // element e, row i at park[(i*EPT + e)*BD]
 #pragma unroll 1
       for (int n = 0; n < p.S; ++n) {
@@ -586,7 +600,12 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
           double u[NP];
-          apply_matrix<NP, false>(c.V, z[e].v, u);
+          if (p.out_modal) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) u[i] = z[e].v[i];
+          } else {
+            apply_matrix<NP, false>(c.V, z[e].v, u);
+          }
 #pragma unroll
           for (int i = 0; i < NP; ++i) p.uT[gofs + (size_t)i * K + e] = u[i];
         }
@@ -633,11 +652,15 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
       }
       const double Jtot = traj_sum(sm_tr, tid, KT, (cx.flags & CX_FIRST) != 0, jpart);
       if (p.J && active && (cx.flags & CX_FIRST)) p.J[b] = Jtot;
+      if (p.mu_in && active) {   // a window of a longer march: continue the later window's adjoint
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) mu[e].load(p.mu_in + (size_t)b * NPF * K + k0 + e, (size_t)K);
+      }
 
       MVec<NPF> w[EPT];
       double eta[EPT];
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) eta[e] = 0.0;
+      for (int e = 0; e < EPT; ++e) eta[e] = (p.eta_acc && active) ? p.eta[(size_t)b * K + k0 + e] : 0.0;
 #pragma unroll 1
       for (int n = p.S - 1; n >= 0; --n) {
         // eta[k] += lam^{n+1} . rho^n ; the tile is consumed at once, so one landing buffer
@@ -663,6 +686,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
           if (p.eta) p.eta[(size_t)b * K + k0 + e] = eta[e];
+          if (p.mu_out) mu[e].store(p.mu_out + (size_t)b * NPF * K + k0 + e, (size_t)K);
           if (p.lam0) {
             double lu[NPF];
             apply_matrix<NPF, true>(c.iVf, mu[e].v, lu);  // lam = V_f^-T mu

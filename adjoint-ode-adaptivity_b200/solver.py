@@ -209,14 +209,19 @@ class AdvecDG1D:
                                            C.c_void_p(0), self._stream()))
         return (uT, hist) if history else uT
 
-    def fwd_adj(self, u0, a, dt, S, t0=0.0, want_uT=True, want_lam0=False, out=None):
+    def fwd_adj(self, u0, a, dt, S, t0=0.0, want_uT=True, want_lam0=False, out=None, window=None, batch_chunk=0):
         """Fused forward + adjoint + indicator.  Returns dict(uT, J, eta[, lam0]):
         eta[B, K] is signed (consumers take abs, matlab/MAIN.m:51); lam0 = dJ/du0 in the
-        enriched space (B, Np+1, K).  `out` may carry preallocated outputs (same keys)."""
+        enriched space (B, Np+1, K).  `out` may carry preallocated outputs (same keys).
+        window (device tensors only): march in windows of that many steps with two-level
+        checkpointing (`dgadj_fwd_adj_windowed`) -- for step counts whose residual ring does not fit
+        the device; same results, about 1.3x the work."""
         a_s, a_v = self._split_scalar(a)
         dt_s, dt_v = self._split_scalar(dt)
         out = dict(out or {})
         if _is_host(u0):
+            if window is not None:
+                raise ValueError("window needs device tensors")
             u0 = self._shape_u(np.ascontiguousarray(u0, dtype=np.float64), self.Np)
             B = u0.shape[0]
             a_v = None if a_v is None else np.ascontiguousarray(a_v, dtype=np.float64)
@@ -241,8 +246,12 @@ class AdvecDG1D:
             eta = out.get("eta", torch.empty((B, self.K), **kw))
             lam0 = out.get("lam0", torch.empty((B, self.NpF, self.K), **kw) if want_lam0 else None)
             args = self._args(B, S, a_s, dt_s, t0, _ptr(a_v), _ptr(dt_v))
-            self._check(self.lib.dgadj_fwd_adj(self._h, C.byref(args), _ptr(u0), _ptr(uT), _ptr(J), _ptr(lam0),
-                                               _ptr(eta), self._stream()))
+            if window is not None:
+                self._check(self.lib.dgadj_fwd_adj_windowed(self._h, C.byref(args), int(window), int(batch_chunk), _ptr(u0),
+                                                            _ptr(uT), _ptr(J), _ptr(lam0), _ptr(eta), self._stream()))
+            else:
+                self._check(self.lib.dgadj_fwd_adj(self._h, C.byref(args), _ptr(u0), _ptr(uT), _ptr(J), _ptr(lam0),
+                                                   _ptr(eta), self._stream()))
         res = dict(J=J, eta=eta)
         if uT is not None:
             res["uT"] = uT

@@ -145,6 +145,17 @@ int dgadj_fwd_adj(dgadj_handle* h, const dgadj_march_args* args, const double* u
                   double* uT_dev, double* J_dev, double* lam0_dev, double* eta_dev,
                   void* stream);
 
+/* The same march for step counts whose residual ring does not fit the device (dgadj_fwd_adj needs
+ * #CTAs x S tiles; DGADJ_ERR_NOMEM beyond): two-level checkpointing.  Per chunk of `batch_chunk`
+ * trajectories (0 = as many as fit) the coarse march runs once keeping the state at the start of
+ * every `window` steps; then, windows in reverse, the window is marched again with its residual
+ * checkpoints and swept by the adjoint, which hands its state and the indicator sums to the
+ * earlier window.  About 1.3x the work of dgadj_fwd_adj; the results are the same (bit for bit
+ * with periodic or time-independent inflow data).  Synchronous (scratch is released on return). */
+int dgadj_fwd_adj_windowed(dgadj_handle* h, const dgadj_march_args* args, int32_t window,
+                           int64_t batch_chunk, const double* u0_dev, double* uT_dev, double* J_dev,
+                           double* lam0_dev, double* eta_dev, void* stream);
+
 /* Same as dgadj_fwd_adj with HOST buffers (chunked H2D, kernels, D2H, sync).
  * a_host / dt_host: [B] or NULL.                                                         */
 int dgadj_fwd_adj_host(dgadj_handle* h, const dgadj_march_args* args, const double* a_host,

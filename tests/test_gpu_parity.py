@@ -1018,3 +1018,30 @@ def test_handles_release_device_memory_and_coexist(pkg, torch):
     torch.cuda.empty_cache()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 64 * 2**20, (free0 - free1) / 2**20        # nothing accumulates (MiB)
+
+
+@pytest.mark.parametrize("N,K,bc,inflow,func", [(8, 1024, "periodic", "zero", "linear"), (3, 40, "inflow", "zero", "int_u2"),
+                                               (4, 66, "inflow", "sin_at", "linear"), (2, 7, "periodic", "zero", "linear")])
+def test_windowed_march_equals_the_one_pass_march(pkg, torch, N, K, bc, inflow, func):
+    """dgadj_fwd_adj_windowed (two-level checkpointing: coarse states per window, residuals recomputed per
+    window, adjoint state and indicator sums handed from window to window, batch in chunks) against the
+    fused one-pass kernel: bit for bit with periodic / time-independent inflow data, to rounding with
+    sin(a t) inflow (the window's clock starts at t0 + n0 dt instead of an accumulated sum); with
+    per-trajectory speeds and steps, ragged last window and ragged last chunk."""
+    rng = np.random.default_rng(N * 100 + K)
+    B, S, W = 37, 23, 5
+    s = pkg.AdvecDG1D(N, K, domain=(0.0, 2.0), alpha=0.0, bc=bc, inflow=inflow, functional=func)
+    u0 = torch.tensor(make_ics(oracle_view(s.g), B, 9), device="cuda")
+    a = torch.tensor(rng.uniform(0.5, 1.5, B), device="cuda")
+    dt0, _ = s.cfl_dt(1.0)
+    dt = (dt0 / a).contiguous()
+    one = s.fwd_adj(u0, a, dt, S, want_lam0=True)
+    for chunk in (0, 16):
+        win = s.fwd_adj(u0, a, dt, S, want_lam0=True, window=W, batch_chunk=chunk)
+        for k in ("uT", "J", "eta", "lam0"):
+            if inflow == "sin_at":
+                assert float((win[k] - one[k]).abs().max()) <= 1e-13 * max(1.0, float(one[k].abs().max())), (k, chunk)
+            else:
+                assert torch.equal(win[k], one[k]), (k, chunk)
+    same = s.fwd_adj(u0, a, dt, S, want_lam0=True, window=S + 3)            # one window: the fused kernel itself
+    assert torch.equal(same["eta"], one["eta"])

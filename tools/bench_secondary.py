@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Secondary workloads of SURVEY section 8(d) (not the driver's headline; numbers go to profiles/):
   forward the forward march alone (the reference's own workload), config 2 mesh
+  long_march  S = 20000 steps on the config 2 mesh through dgadj_fwd_adj_windowed
   sweep   config 4: parameter sweep, N=4, K=64, S=100, per-trajectory speed a and CFL dt
   burgers config 3: Burgers + SlopeLimitN, N=4, K=256, B=16384, forward + checkpoints
   tdg     config 5: DG-in-time march + adjoint (u' = sin u), B=4096 ICs, refined mesh
@@ -84,6 +85,29 @@ def forward(B=32768):
                 frac_fp64_peak=fl * ups / (ms * 1e-3) / 1e12 / peak, plan=s.plan(B, fused=False))
 
 
+def long_march(B=2368):
+    """A march too long for the one-pass kernel's residual ring: two-level checkpointing."""
+    N, K, S = 8, 1024, 20000
+    s = pkg.AdvecDG1D(N, K, domain=(0.0, TWO_PI), alpha=0.0, bc="periodic")
+    x = torch.tensor(s.g.x, device=dev)[None]
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    ph = torch.rand((B, 1, 1), dtype=torch.float64, device=dev, generator=g) * TWO_PI
+    u0 = torch.sin(x + ph).contiguous()
+    dt, _ = s.cfl_dt(1.0)
+    refused = ""
+    try:
+        s.fwd_adj(u0, TWO_PI, dt, S, want_uT=False)
+    except pkg.DgadjError as e:
+        refused = str(e)
+    W = int(math.ceil(math.sqrt(S)))
+    out = {}
+    ms = timeit(lambda: out.update(s.fwd_adj(u0, TWO_PI, dt, S, want_uT=False, window=W)), warm=0, reps=1)
+    ups = 2 * 5 * S * K * B
+    return dict(workload="long march N=8 K=1024 B=%d S=%d (T = %.3f): windows of %d steps, two-level checkpointing"
+                         % (B, S, S * dt, W), metric="DG element-stage updates/s (fwd+adjoint)", value=ups / (ms * 1e-3), ms=ms,
+                one_pass_kernel=refused or "ran", sum_abs_eta=float(out["eta"].abs().sum()), J_mean=float(out["J"].mean()))
+
+
 def burgers(B=16384):
     N, K = 4, 256
     s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc="periodic")
@@ -144,6 +168,6 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["forward", "sweep", "burgers", "tdg_fd"]
     for w in which:
         kw = dict(B=int(os.environ["SEC_B"])) if "SEC_B" in os.environ else {}
-        r = dict(forward=forward, sweep=sweep, burgers=burgers, tdg_fd=tdg_fd)[w](**kw)
+        r = dict(forward=forward, long_march=long_march, sweep=sweep, burgers=burgers, tdg_fd=tdg_fd)[w](**kw)
         for line in (r if isinstance(r, list) else [r]):
             print(json.dumps(line), flush=True)
