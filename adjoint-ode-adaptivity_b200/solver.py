@@ -213,7 +213,8 @@ class AdvecDG1D:
         """Fused forward + adjoint + indicator.  Returns dict(uT, J, eta[, lam0]):
         eta[B, K] is signed (consumers take abs, matlab/MAIN.m:51); lam0 = dJ/du0 in the
         enriched space (B, Np+1, K).  `out` may carry preallocated outputs (same keys).
-        window (device tensors only): march in windows of that many steps with two-level
+        window (device tensors only; an int, or "auto" = only when the one-pass kernel's residual ring
+        does not fit, with ceil(sqrt(S)) steps): march in windows with two-level
         checkpointing (`dgadj_fwd_adj_windowed`) -- for step counts whose residual ring does not fit
         the device; same results, about 1.3x the work."""
         a_s, a_v = self._split_scalar(a)
@@ -246,12 +247,18 @@ class AdvecDG1D:
             eta = out.get("eta", torch.empty((B, self.K), **kw))
             lam0 = out.get("lam0", torch.empty((B, self.NpF, self.K), **kw) if want_lam0 else None)
             args = self._args(B, S, a_s, dt_s, t0, _ptr(a_v), _ptr(dt_v))
-            if window is not None:
-                self._check(self.lib.dgadj_fwd_adj_windowed(self._h, C.byref(args), int(window), int(batch_chunk), _ptr(u0),
+            def windowed(W):
+                self._check(self.lib.dgadj_fwd_adj_windowed(self._h, C.byref(args), int(W), int(batch_chunk), _ptr(u0),
                                                             _ptr(uT), _ptr(J), _ptr(lam0), _ptr(eta), self._stream()))
+            if window is not None and window != "auto":
+                windowed(window)
             else:
-                self._check(self.lib.dgadj_fwd_adj(self._h, C.byref(args), _ptr(u0), _ptr(uT), _ptr(J), _ptr(lam0),
-                                                   _ptr(eta), self._stream()))
+                rc = self.lib.dgadj_fwd_adj(self._h, C.byref(args), _ptr(u0), _ptr(uT), _ptr(J), _ptr(lam0),
+                                            _ptr(eta), self._stream())
+                if rc == _lib.ERR_NOMEM and window == "auto":      # the residual ring does not fit: sqrt(S) windows
+                    windowed(int(math.ceil(math.sqrt(S))))
+                else:
+                    self._check(rc)
         res = dict(J=J, eta=eta)
         if uT is not None:
             res["uT"] = uT

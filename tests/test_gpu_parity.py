@@ -1045,3 +1045,5 @@ def test_windowed_march_equals_the_one_pass_march(pkg, torch, N, K, bc, inflow, 
                 assert torch.equal(win[k], one[k]), (k, chunk)
     same = s.fwd_adj(u0, a, dt, S, want_lam0=True, window=S + 3)            # one window: the fused kernel itself
     assert torch.equal(same["eta"], one["eta"])
+    auto = s.fwd_adj(u0, a, dt, S, want_lam0=True, window="auto")           # the ring fits: the fused kernel again
+    assert torch.equal(auto["eta"], one["eta"])

@@ -2,7 +2,7 @@
 # All secondary workloads at their configured sizes + the time-DG / FD pair at a
 # batch that fills the GPU.  usage: tools/gpu_secondary.sh [tag]
 TAG=${1:-r1sec}; OUT=gpurun_out/$TAG; mkdir -p $OUT
-timeout 900 python tools/bench_secondary.py forward sweep burgers tdg_fd > $OUT/secondary.jsonl 2> $OUT/secondary.err; echo "rc=$?"
+timeout 900 python tools/bench_secondary.py forward long_march sweep burgers tdg_fd > $OUT/secondary.jsonl 2> $OUT/secondary.err; echo "rc=$?"
 SEC_B=262144 timeout 600 python tools/bench_secondary.py tdg_fd > $OUT/secondary_bigB.jsonl 2>> $OUT/secondary.err; echo "rc=$?"
 python - <<PY
 import json
