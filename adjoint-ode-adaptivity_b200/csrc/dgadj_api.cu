@@ -905,13 +905,13 @@ extern "C" int dgadj_fwd_adj(dgadj_handle* h, const dgadj_march_args* args, cons
 // Windowed (two-level checkpointed) forward + adjoint + indicator for marches whose residual ring
 // does not fit the device (#CTAs x S x tile).  Per batch chunk:
 //   pass 1  the coarse march alone, window by window, keeping the state at every window start;
-//   pass 2  windows in reverse: the window's forward march again, now with the enriched one-step
-//           images (residual checkpoints of W steps only), then its adjoint sweep, which starts
+//   pass 2  windows in reverse, each one launch of the fused kernel: the window's forward march again,
+//           now with the enriched one-step images (a per-CTA ring of W residual tiles), then its adjoint sweep, which starts
 //           from the modal adjoint state the later window left, leaves its own, and continues the
 //           indicator sums in eta -- in the step order of the one-pass march, so for periodic or
 //           time-independent inflow data the results equal dgadj_fwd_adj's bit for bit.
 // Cost: one extra coarse march (about 1.3x the fused kernel's work); memory per chunk:
-// (S/W) states + W residual tiles + one adjoint state.
+// (S/W) states + one adjoint state per trajectory, W residual tiles per CTA.
 // ---------------------------------------------------------------------------------------
 static int run_window(dgadj_handle* h, int variant, const dgadj_march_args* a, int n0, cudaStream_t st,
                       void (*setup)(MarchParams&, void*), void* ctx) {
@@ -952,11 +952,8 @@ extern "C" int dgadj_fwd_adj_windowed(dgadj_handle* h, const dgadj_march_args* a
   cudaStream_t st = (cudaStream_t)stream;
   const int Np = h->Np, NpF = h->NpF, K = h->K;
   const size_t state = (size_t)Np * K, fstate = (size_t)NpF * K;
-  // chunk of the batch that fits: nwin states + W residual tiles + one adjoint state per trajectory
-  LaunchPlan pl1;
-  rc = make_plan(h, 1, VAR_FWD_RESID, &pl1);
-  if (rc) return rc;
-  const size_t per_traj = ((size_t)nwin * state + fstate + (size_t)W * pl1.tile / std::max(1, pl1.tpc) + fstate) * sizeof(double);
+  // chunk of the batch that fits: nwin states + one adjoint state per trajectory (+ the ring of W tiles per CTA)
+  const size_t per_traj = ((size_t)nwin * state + fstate) * sizeof(double);
   int64_t Bc = batch_chunk;
   if (Bc == 0) {
     size_t free_b = 0, total_b = 0;
@@ -966,17 +963,13 @@ extern "C" int dgadj_fwd_adj_windowed(dgadj_handle* h, const dgadj_march_args* a
     if (Bc > wave) Bc -= Bc % wave;
   }
   Bc = std::max<int64_t>(1, std::min<int64_t>(Bc, args->B));
-  const int64_t ck_bytes = dgadj_ckpt_bytes(h, Bc, W);
-  if (ck_bytes < 0) return (int)ck_bytes;
-  double *states = nullptr, *mu = nullptr, *ck = nullptr;
+  double *states = nullptr, *mu = nullptr;
   auto release = [&]() {
     cudaFree(states);
     cudaFree(mu);
-    cudaFree(ck);
   };
   if (cudaMalloc((void**)&states, (size_t)nwin * Bc * state * sizeof(double)) != cudaSuccess ||
-      cudaMalloc((void**)&mu, (size_t)Bc * fstate * sizeof(double)) != cudaSuccess ||
-      cudaMalloc((void**)&ck, (size_t)ck_bytes) != cudaSuccess) {
+      cudaMalloc((void**)&mu, (size_t)Bc * fstate * sizeof(double)) != cudaSuccess) {
     cudaGetLastError();
     release();
     return fail(h, DGADJ_ERR_NOMEM, "windowed march: %lld trajectories x (%d states + %d residual tiles) do not fit; "
@@ -991,6 +984,7 @@ extern "C" int dgadj_fwd_adj_windowed(dgadj_handle* h, const dgadj_march_args* a
     auto st_ptr = [&](int j) -> double* { return states + (size_t)(j - 1) * Bc * state; };   // state at the start of window j >= 1; j = nwin: terminal
     // pass 1: coarse march, window by window
     for (int j = 0; j < nwin && rc == DGADJ_OK; ++j) {
+      if (j == nwin - 1 && !uT_dev) break;   // the last window's end state is only the caller's u(T)
       a.S = std::min(W, S - j * W);
       WinCtx cx = {};
       cx.u_in = (j == 0) ? u0_dev + (size_t)c0 * state : st_ptr(j);
@@ -1017,32 +1011,30 @@ extern "C" int dgadj_fwd_adj_windowed(dgadj_handle* h, const dgadj_march_args* a
         p.in_modal = 1;
       }, &cx);
     }
-    // pass 2: windows in reverse
+    // pass 2: windows in reverse, each through the fused kernel (forward with residual tiles into the
+    // per-CTA ring of W steps, then the adjoint sweep over them)
     for (int j = nwin - 1; j >= 0 && rc == DGADJ_OK; --j) {
       a.S = std::min(W, S - j * W);
+      LaunchPlan pl;
+      rc = make_plan(h, a.B, VAR_FUSED, &pl);
+      if (rc == DGADJ_OK) rc = ensure_ring(h, pl, W, st);
+      if (rc != DGADJ_OK) break;
       WinCtx cx = {};
       cx.u_in = (j == 0) ? u0_dev + (size_t)c0 * state : st_ptr(j);
       cx.in_modal = (j != 0);
-      cx.ckpt = ck;
-      rc = run_window(h, VAR_FWD_RESID, &a, j * W, st, [](MarchParams& p, void* v) {
-        WinCtx* c = (WinCtx*)v;
-        p.u0 = c->u_in;
-        p.ckpt = c->ckpt;
-        p.in_modal = c->in_modal;
-      }, &cx);
-      if (rc != DGADJ_OK) break;
-      cx.uT_in = st_ptr(j + 1);
+      cx.ckpt = h->ring;
       cx.mu_in = (j == nwin - 1) ? nullptr : mu;
       cx.mu_out = (j == 0) ? nullptr : mu;
       cx.J = (j == nwin - 1 && J_dev) ? J_dev + c0 : nullptr;
       cx.lam0 = (j == 0 && lam0_dev) ? lam0_dev + (size_t)c0 * fstate : nullptr;
       cx.eta = eta_dev ? eta_dev + (size_t)c0 * K : nullptr;
       cx.eta_acc = (j != nwin - 1) && eta_dev;
-      rc = run_window(h, VAR_ADJ, &a, j * W, st, [](MarchParams& p, void* v) {
+      rc = run_window(h, VAR_FUSED, &a, j * W, st, [](MarchParams& p, void* v) {
         WinCtx* c = (WinCtx*)v;
-        p.uT_in = c->uT_in;
-        p.in_modal = 1;
+        p.u0 = c->u_in;
+        p.in_modal = c->in_modal;
         p.ckpt = c->ckpt;
+        p.ckpt_by_block = 1;
         p.mu_in = c->mu_in;
         p.mu_out = c->mu_out;
         p.J = c->J;
