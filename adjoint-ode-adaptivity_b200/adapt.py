@@ -106,7 +106,7 @@ def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic",
         S = int(np.ceil(T / (cfl * xmin / abs(a))))
         dt = T / S
         u0 = u0_fn(s.g.x)
-        out = s.fwd_adj(u0, a, dt, S, want_uT=False, want_lam0=ic_term)
+        out = s.fwd_adj(u0, a, dt, S, want_uT=False, want_lam0=ic_term, window="auto")   # windows only if the ring cannot fit
         eta = out["eta"]
         if ic_term:
             s.ic_indicator(u0, u0_fn(s.gf.x), out["lam0"], eta)        # dgadj_ic_indicator, in place
