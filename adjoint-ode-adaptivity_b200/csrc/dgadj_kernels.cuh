@@ -203,7 +203,10 @@ struct Ctx {
 // per-stage copies of p (three DMUL fewer per update) was 1.2 % slower: ten more constant loads
 // per stage and level outweigh the multiplies.  Splitting the trace sums into two partial sums per
 // parity (shorter dependent DFMA chains, two more DADD per element-stage) was 1.2 % slower too: the
-// chains are not what the pipe waits for.  Not built: a uniform-mesh variant with {m, q0, q1} as
+// chains are not what the pipe waits for.  Rotating the stage loop so that the outer elements' surface
+// update and traces come first and the arrive follows them at once (inner elements and the volume
+// terms after it: half the stretch between a warp's wait and its next arrive, same operations) was
+// 4 % slower: two elements at a time halve the independent chains in exactly those phases.  Not built: a uniform-mesh variant with {m, q0, q1} as
 // kernel constants instead of shared-memory columns (-3 LDS, -1 DMUL per element-stage) -- the
 // reference's rx / Fscale of a "uniform" mesh differ between elements by 1e-12..1e-11 (cancellation
 // noise of J = Dr*x), so one constant for all elements would leave the 1e-12 parity envelope.
