@@ -206,7 +206,9 @@ struct Ctx {
 // chains are not what the pipe waits for.  Rotating the stage loop so that the outer elements' surface
 // update and traces come first and the arrive follows them at once (inner elements and the volume
 // terms after it: half the stretch between a warp's wait and its next arrive, same operations) was
-// 4 % slower: two elements at a time halve the independent chains in exactly those phases.  Not built: a uniform-mesh variant with {m, q0, q1} as
+// 4 % slower: two elements at a time halve the independent chains in exactly those phases; moving one
+// diagonal of the volume terms in front of the trace sums and the last ones behind the exchange (so
+// that the scalar chains share a basic block with independent DFMA) was 1 % slower.  Not built: a uniform-mesh variant with {m, q0, q1} as
 // kernel constants instead of shared-memory columns (-3 LDS, -1 DMUL per element-stage) -- the
 // reference's rx / Fscale of a "uniform" mesh differ between elements by 1e-12..1e-11 (cancellation
 // noise of J = Dr*x), so one constant for all elements would leave the 1e-12 parity envelope.
