@@ -387,3 +387,40 @@ def test_tdg_padded_blocks_reproduce_mixed_orders(pkg, linear):
             assert np.all(vk[nak:] == 0.0)
             np.testing.assert_allclose(vk[:nak], vr[k][b], rtol=1e-9, atol=1e-11)
             np.testing.assert_allclose(e, errr[b, k], rtol=1e-9, atol=1e-11)
+
+
+# ---------------------------------------------------------------- property tests of the host logic
+def test_shard_range_partitions_any_batch(pkg):
+    from hypothesis import given, settings, strategies as st
+    from adjoint_ode_adaptivity_b200.sharding import shard_range
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 10**6), st.integers(1, 64))
+    def check(B, world):
+        cuts = [shard_range(B, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))            # contiguous, in rank order
+        sizes = [hi - lo for lo, hi in cuts]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    check()
+
+
+def test_refine_rules_insert_one_midpoint(pkg):
+    """matlab/MAIN.m:137-141 / Main_finite_difference.py:336-341 on the host side: exactly one new
+    point, the midpoint of the argmax element (lowest index on ties), everything else untouched."""
+    from hypothesis import given, settings, strategies as st
+    from adjoint_ode_adaptivity_b200.fd import refine_mesh
+    from adjoint_ode_adaptivity_b200.tdg import refine
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.lists(st.floats(0.01, 1.0), min_size=1, max_size=30), st.data())
+    def check(widths, data):
+        times = np.concatenate(([0.0], np.cumsum(widths)))
+        K = len(widths)
+        err = np.array(data.draw(st.lists(st.floats(-5, 5), min_size=K, max_size=K)))
+        t2, Ns2, ref_i = refine(times, np.ones(K, dtype=int), err, 1)
+        assert ref_i == int(np.argmax(np.abs(err))) and t2.size == times.size + 1 and Ns2.size == K + 1
+        assert t2[ref_i + 1] == 0.5 * (times[ref_i] + times[ref_i + 1])
+        assert np.array_equal(np.delete(t2, ref_i + 1), times) and np.all(np.diff(t2) > 0)
+        assert np.array_equal(refine_mesh(times, ref_i), t2)
+    check()
