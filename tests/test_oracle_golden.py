@@ -140,6 +140,18 @@ def test_adjoint_dot_product_and_effectivity(bc, alpha):
     Jf_c = advec.functional(P @ out["uT"], gf, advec.FUNC_INT_U)
     Jf_f = advec.functional(ufT, gf, advec.FUNC_INT_U)
     assert np.sum(out["eta"]) == pytest.approx(Jf_c - Jf_f, rel=1e-9, abs=1e-13)
+    # with the initial-data term eta0_k = lam0_k . (P u0 - u0_f)_k (dgadj_ic_indicator) the sum is the whole
+    # difference to the enriched march of the TRUE initial data
+    if bc == "periodic":
+        psi = lambda x: 1.0 + 0.5 * np.cos(x - 1.0)
+        u0c, u0f = np.exp(np.sin(3 * gc.x)), np.exp(np.sin(3 * gf.x))
+        out = advec.fwd_adj_indicator(u0c, gc, gf, a, dt, S, alpha, bc, advec.INFLOW_ZERO, psi=psi)
+        ufT, _ = advec.advec_march(u0f, gf, a, dt, S, alpha, bc, advec.INFLOW_ZERO)
+        eta0 = np.sum(out["lam0"] * (P @ u0c - u0f), axis=0)
+        Jf_c = advec.functional(P @ out["uT"], gf, advec.FUNC_INT_U, psi=psi)
+        Jf_f = advec.functional(ufT, gf, advec.FUNC_INT_U, psi=psi)
+        assert abs(Jf_c - Jf_f) > 1e-9
+        assert np.sum(out["eta"] + eta0) == pytest.approx(Jf_c - Jf_f, rel=1e-9, abs=1e-14)
 
 
 def test_rank_refine_semantics():
