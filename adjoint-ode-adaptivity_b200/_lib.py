@@ -66,7 +66,7 @@ PROTOTYPES = {
                                     _P, _P, _P, _P, _P, _P]),
     "dgadj_tdg_adjoint_rec": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P]),
     "dgadj_tdg_err_contribution": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
-    "dgadj_burgers_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, _P, C.c_int32, _P, _P, _P, _P, _P,
+    "dgadj_burgers_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, _P, C.c_int32, C.c_double, _P, _P, _P, _P, _P,
                                         _P, _P, _P, _P, _P, _P]),
     "dgadj_burgers_adjoint": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                         _P, _P, _P, _P]),

@@ -57,8 +57,12 @@ class BurgersDG1D:
         xmin = np.min(np.abs(self.g.x[0, :] - self.g.x[1, :]))
         return cfl * xmin / umax
 
-    def forward(self, u0, dt, S, limit=True, history=False, checkpoints=False):
+    LIMIT_CODES = {False: 0, None: 0, 0: 0, True: 1, 1: 1, "N": 1, "1": 2, "Pi1": 2, 2: 2}
+
+    def forward(self, u0, dt, S, limit=True, history=False, checkpoints=False, tvb_M=0.0):
         """u0: float64 CUDA tensor [B, Np, K]; dt scalar or CUDA tensor [B].
+        limit: True / "N" = SlopeLimitN after every stage (utils/SlopeLimitN.m), "1" = SlopeLimit1 (every
+        cell, utils/SlopeLimit1.m), False = none; tvb_M = the M of the TVB minmod (utils/minmodB.m), 0 = minmod.
         Returns dict(uT[, hist[B,S+1,Np,K]][, lim[B,S,K] int16, lim0[B,K] uint8, amax[B,S,5] int32,
         maxvel[B,S,5]]).  `checkpoints=True` writes everything `adjoint` consumes (incl. hist)."""
         torch = self.torch
@@ -84,8 +88,8 @@ class BurgersDG1D:
         o = self.ops
         p = lambda a: C.c_void_p(a.ctypes.data)
         self._check(self.lib.dgadj_burgers_forward(
-            self._h, B, S, dt_s, C.c_void_p(dt_v.data_ptr()) if dt_v is not None else C.c_void_p(0), int(limit),
-            p(o["invV"]), p(o["V"]), p(o["x"]), C.c_void_p(u0.data_ptr()), ptr("uT"), ptr("hist"), ptr("lim"),
+            self._h, B, S, dt_s, C.c_void_p(dt_v.data_ptr()) if dt_v is not None else C.c_void_p(0), self.LIMIT_CODES[limit],
+            float(tvb_M), p(o["invV"]), p(o["V"]), p(o["x"]), C.c_void_p(u0.data_ptr()), ptr("uT"), ptr("hist"), ptr("lim"),
             ptr("lim0"), ptr("amax"), ptr("maxvel"), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         out["dt"], out["S"] = dt, S
         return out
@@ -117,9 +121,10 @@ class BurgersDG1D:
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return dict(lam0=lam0, J=J)
 
-    def slope_limit(self, u):
-        """ulimit = SlopeLimitN(u)  (utils/SlopeLimitN.m:1): one limiter pass, no time steps."""
-        return self.forward(u, 0.0, 0, limit=True)["uT"]
+    def slope_limit(self, u, kind="N", tvb_M=0.0):
+        """ulimit = SlopeLimitN(u) (utils/SlopeLimitN.m:1) or, kind="1", SlopeLimit1(u)
+        (utils/SlopeLimit1.m:1): one limiter pass, no time steps; tvb_M > 0 uses minmodB."""
+        return self.forward(u, 0.0, 0, limit=kind, tvb_M=tvb_M)["uT"]
 
 
 def decode_limiter_record(lim):

@@ -30,7 +30,8 @@ namespace dgadj {
 
 struct BurgersArgs {
   long long B;
-  int K, S, periodic, limit;
+  int K, S, periodic, limit;   // limit: 0 none, 1 SlopeLimitN (detect, then limit), 2 SlopeLimit1 (every cell)
+  double tvbM;                 // M of minmodB (utils/minmodB.m:6-11) in the slope minmod; 0 = plain minmod
   double dt;
   const double* dt_arr;
   const double* rxk;   // [K]
@@ -222,13 +223,14 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
       const MinmodBC q = minmod_bc(v - vm, vp - v);
       const double ve1 = v - minmod3(v - ue1, q);
       const double ve2 = v + minmod3(ue2 - v, q);
-      if (!(fabs(ve1 - ue1) > 1.0e-8 || fabs(ve2 - ue2) > 1.0e-8)) return 0;
+      if (p.limit != 2 && !(fabs(ve1 - ue1) > 1.0e-8 || fabs(ve2 - ue2) > 1.0e-8)) return 0;
       double d = 0.0;
 #pragma unroll
       for (int i = 0; i < NP; ++i) d = fma(p.sl[i], u[i], d);
       const double ux = twoh * d;
-      int br;
-      const double slope = minmod3b(ux, (vp - v) / h, (v - vm) / h, &br);
+      int br = 1;
+      double slope = ux;   // minmodB: a slope below M h^2 passes (recorded as argument 1 winning)
+      if (!(p.tvbM > 0.0 && fabs(ux) <= p.tvbM * (h * h))) slope = minmod3b(ux, (vp - v) / h, (v - vm) / h, &br);
       const double sh = slope * (0.5 * h);   // x - x0 = (h/2) r: no geometry loads on this path
 #pragma unroll
       for (int i = 0; i < NP; ++i) u[i] = fma(p.xcn[i], sh, v);
@@ -594,7 +596,8 @@ static int burgers_setup(dgadj_handle* h, BurgersArgs& a, int64_t B, int32_t S, 
   a.K = K;
   a.S = S;
   a.periodic = (h->cfg.bc == DGADJ_BC_PERIODIC);
-  a.limit = limit ? 1 : 0;
+  a.limit = limit;
+  a.tvbM = 0.0;
   a.dt = dt;
   a.dt_arr = dt_dev;
   a.rxk = h->d_mesh[0][0];
@@ -646,7 +649,7 @@ static int burgers_setup(dgadj_handle* h, BurgersArgs& a, int64_t B, int32_t S, 
 }
 
 extern "C" int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, double dt, const double* dt_dev,
-                                     int32_t limit, const double* invV_host, const double* V_host,
+                                     int32_t limit, double tvb_M, const double* invV_host, const double* V_host,
                                      const double* x_host, const double* u0_dev, double* uT_dev,
                                      double* hist_dev, uint16_t* lim_dev, uint8_t* lim0_dev, int32_t* amax_dev,
                                      double* maxvel_dev, void* stream) {
@@ -659,8 +662,10 @@ extern "C" int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, doub
   cudaStream_t st = (cudaStream_t)stream;
   const int Np = h->Np, K = h->K;
   BurgersArgs a;
+  if (limit < 0 || limit > 2 || !(tvb_M >= 0.0)) return fail(h, DGADJ_ERR_INVALID, "limit must be 0, 1 or 2 and tvb_M >= 0");
   int rc = burgers_setup(h, a, B, S, dt, dt_dev, limit, invV_host, V_host, x_host, st);
   if (rc) return rc;
+  a.tvbM = tvb_M;
   a.u0 = u0_dev;
   a.uT = uT_dev;
   a.hist = hist_dev;

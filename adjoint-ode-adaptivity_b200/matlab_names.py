@@ -3,6 +3,7 @@ handles (argument order and meaning follow the .m files; batching adds a leading
 
     rhsu        = AdvecRHS1D(solver, u, timelocal, a)            utils/AdvecRHS1D.m:1
     ulimit      = SlopeLimitN(burgers_solver, u)                  utils/SlopeLimitN.m:1
+    ulimit      = SlopeLimit1(burgers_solver, u)                  utils/SlopeLimit1.m:1
     [t, y]      = dg_march(tdg, Ns, Ks, times, y0)                matlab/dg_march.m:1
     [t, v, err] = adj_march(tdg, Ns, Ks, times, y1, t1)           matlab/adj_march.m:1  (primal passed
                                                                   explicitly instead of the globals y1, t1)
@@ -25,6 +26,10 @@ def AdvecRHS1D(solver, u, timelocal, a):
 
 def SlopeLimitN(burgers_solver, u):
     return burgers_solver.slope_limit(u)
+
+
+def SlopeLimit1(burgers_solver, u):
+    return burgers_solver.slope_limit(u, kind="1")
 
 
 def dg_march(tdg, Ns, Ks, times, y0, x_true=None, u_true=None):

@@ -260,9 +260,12 @@ int dgadj_tdg_err_contribution(dgadj_handle* h, int64_t B, int32_t Ks, int32_t N
  *   lim_dev[B][S][K] uint16 (bits 0-4: cell limited after stage s; bits 5+2s, 6+2s: winning
  *   minmod argument), lim0_dev[B][K] uint8 (same code for the pass on the initial state),
  *   amax_dev[B][S][5] int32 (+-(flat index + 1) of max|u| per stage, sign of u there),
- *   maxvel_dev[B][S][5] (max|u| per stage).                                               */
+ *   maxvel_dev[B][S][5] (max|u| per stage).
+ *   limit: 0 none, 1 SlopeLimitN (detect troubled cells, limit those: utils/SlopeLimitN.m:9-32),
+ *   2 SlopeLimit1 (limit every cell: utils/SlopeLimit1.m:10-22); tvb_M: the M of the TVB minmod
+ *   (utils/minmodB.m:6-11) used for the slope in SlopeLimitLin; 0 = plain minmod, the reference's call. */
 int dgadj_burgers_forward(dgadj_handle* h, int64_t B, int32_t S, double dt, const double* dt_dev,
-                          int32_t limit, const double* invV_host, const double* V_host,
+                          int32_t limit, double tvb_M, const double* invV_host, const double* V_host,
                           const double* x_host, const double* u0_dev, double* uT_dev,
                           double* hist_dev, uint16_t* lim_dev, uint8_t* lim0_dev, int32_t* amax_dev,
                           double* maxvel_dev, void* stream);

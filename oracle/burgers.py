@@ -38,13 +38,19 @@ def BurgersRHS1D(u, g, bc=BC_PERIODIC):
     return -g.rx * (g.Dr @ (u ** 2 / 2.0)) + g.LIFT @ (g.Fscale * flux), maxvel
 
 
-def burgers_march(u0, g, dt, nsteps, bc=BC_PERIODIC, limit=True, history=False):
+def burgers_march(u0, g, dt, nsteps, bc=BC_PERIODIC, limit=True, history=False, tvb_M=0.0):
     """Returns (uT, hist, flags, maxvel): hist[n] = u^n (n = 0..S); flags[n, s] = cells limited
-    after stage s of step n; maxvel[n, s]."""
+    after stage s of step n; maxvel[n, s].  limit: True / "N" = SlopeLimitN, "1" = SlopeLimit1 (every
+    cell), False = none; tvb_M: the M of minmodB."""
     periodic = bc == BC_PERIODIC
     u = np.array(u0, dtype=float, copy=True)
+
+    def apply(u):
+        if limit == "1":
+            return limiter.SlopeLimit1(u, g, periodic, tvb_M), np.ones(u.shape[:-2] + (u.shape[-1],), dtype=bool)
+        return limiter.SlopeLimitN(u, g, periodic, return_flags=True, M=tvb_M)
     if limit:
-        u = limiter.SlopeLimitN(u, g, periodic)
+        u = apply(u)[0]
     resu = np.zeros_like(u)
     hist = [u.copy()] if history else None
     flags, mvs = [], []
@@ -55,7 +61,7 @@ def burgers_march(u0, g, dt, nsteps, bc=BC_PERIODIC, limit=True, history=False):
             resu = ops.rk4a[s] * resu + dt * rhs
             u = u + ops.rk4b[s] * resu
             if limit:
-                u, ids = limiter.SlopeLimitN(u, g, periodic, return_flags=True)
+                u, ids = apply(u)
             else:
                 ids = np.zeros(u.shape[:-2] + (u.shape[-1],), dtype=bool)
             fl.append(ids); mv.append(maxvel)

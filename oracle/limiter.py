@@ -39,13 +39,15 @@ def _neighbour_averages(v, periodic):
     return vkm1, vkp1
 
 
-def SlopeLimitLin(ul, xl, vm1, v0, vp1, g):
-    """utils/SlopeLimitLin.m:10-18."""
+def SlopeLimitLin(ul, xl, vm1, v0, vp1, g, M=0.0):
+    """utils/SlopeLimitLin.m:10-18.  M > 0: the TVB form -- minmodB(., M, h) (utils/minmodB.m:6-11) in
+    place of minmod at :18, the way minmodB is meant to be used; M = 0 is the reference's call."""
     Np = g.Np
     h = xl[Np - 1, :] - xl[0, :]
     x0 = xl[0, :] + h / 2
     ux = (2.0 / h) * (g.Dr @ ul)
-    slope = minmod(np.stack([ux[..., 0, :], (vp1 - v0) / h, (v0 - vm1) / h], axis=0))
+    args = np.stack([ux[..., 0, :], (vp1 - v0) / h, (v0 - vm1) / h], axis=0)
+    slope = minmodB(args, M, h) if M > 0.0 else minmod(args)
     return v0[..., None, :] + (xl - x0) * slope[..., None, :]
 
 
@@ -55,7 +57,7 @@ def cell_averages(u, g):
     return (g.V[0, 0] * uh0)[..., 0, :]
 
 
-def SlopeLimitN(u, g, periodic=False, return_flags=False):
+def SlopeLimitN(u, g, periodic=False, return_flags=False, M=0.0):
     """utils/SlopeLimitN.m:9-32 (Pi^N: detect, then limit the flagged cells)."""
     eps0 = 1.0e-8
     v = cell_averages(u, g)
@@ -69,13 +71,13 @@ def SlopeLimitN(u, g, periodic=False, return_flags=False):
         uhl = g.invV @ u
         uhl[..., 2:, :] = 0.0
         ul = g.V @ uhl
-        lim = SlopeLimitLin(ul, g.x, vkm1, v, vkp1, g)
+        lim = SlopeLimitLin(ul, g.x, vkm1, v, vkp1, g, M)
         mask = np.broadcast_to(ids[..., None, :], u.shape)
         ulimit[mask] = lim[mask]
     return (ulimit, ids) if return_flags else ulimit
 
 
-def SlopeLimit1(u, g, periodic=False):
+def SlopeLimit1(u, g, periodic=False, M=0.0):
     """utils/SlopeLimit1.m:10-22 (Pi^1: limit every cell)."""
     uh = g.invV @ u
     ul = uh.copy()
@@ -83,4 +85,4 @@ def SlopeLimit1(u, g, periodic=False):
     ul = g.V @ ul
     v = cell_averages(u, g)
     vkm1, vkp1 = _neighbour_averages(v, periodic)
-    return SlopeLimitLin(ul, g.x, vkm1, v, vkp1, g)
+    return SlopeLimitLin(ul, g.x, vkm1, v, vkp1, g, M)

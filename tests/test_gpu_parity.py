@@ -1047,3 +1047,53 @@ def test_windowed_march_equals_the_one_pass_march(pkg, torch, N, K, bc, inflow, 
     assert torch.equal(same["eta"], one["eta"])
     auto = s.fwd_adj(u0, a, dt, S, want_lam0=True, window="auto")           # the ring fits: the fused kernel again
     assert torch.equal(auto["eta"], one["eta"])
+
+
+@pytest.mark.parametrize("N,K,bc", [(4, 64, "periodic"), (2, 33, "free"), (1, 20, "periodic")])
+def test_limiter_variants_slopelimit1_and_tvb(pkg, torch, N, K, bc):
+    """The other limiters of utils/: SlopeLimit1 (every cell limited, SlopeLimit1.m:10-22) and the TVB
+    minmod (minmodB.m:6-11) in SlopeLimitLin -- stand-alone passes and fused into the Burgers march,
+    against oracle/limiter.py / oracle/burgers.py; the adjoint of a Pi^1-limited march against
+    finite differences (every cell carries a recorded branch)."""
+    from oracle import burgers as ob
+    from oracle import limiter as ol
+    from adjoint_ode_adaptivity_b200 import matlab_names as m
+    s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc=bc)
+    g = oracle_view(s.g)
+    periodic = bc == "periodic"
+    rng = np.random.default_rng(N + K)
+    B = 7
+    u = np.sin(np.pi * g.x[None] + rng.uniform(0, 6, (B, 1, 1))) + 0.4 * (g.x[None] > rng.uniform(-0.5, 0.5, (B, 1, 1)))
+    d_u = torch.tensor(u, device="cuda")
+    assert rel(m.SlopeLimit1(s, d_u).cpu().numpy(), ol.SlopeLimit1(u, g, periodic)) < 1e-13
+    h = g.x[-1, 0] - g.x[0, 0]
+    for M in (0.5 / h ** 2 * 0.05, 50.0):
+        assert rel(s.slope_limit(d_u, kind="N", tvb_M=M).cpu().numpy(), ol.SlopeLimitN(u, g, periodic, M=M)) < 1e-13
+        assert rel(s.slope_limit(d_u, kind="1", tvb_M=M).cpu().numpy(), ol.SlopeLimit1(u, g, periodic, M=M)) < 1e-13
+    # a large M switches the limiter off where the slopes are moderate: TVB keeps smooth extrema
+    smooth = np.sin(np.pi * g.x[None])
+    out = s.slope_limit(torch.tensor(smooth, device="cuda"), kind="1", tvb_M=1e6).cpu().numpy()
+    lin = ol.SlopeLimit1(smooth, g, periodic, M=1e6)
+    assert rel(out, lin) < 1e-13
+    # fused into the march
+    u0 = 0.2 + np.sin(np.pi * g.x[None] + rng.uniform(0, 6, (B, 1, 1)))
+    dt = s.stable_dt(1.5)
+    S = min(int(np.ceil(0.45 / dt)), 200)
+    for kind, M in (("1", 0.0), ("N", 20.0), ("1", 20.0)):
+        ref, _, flags_r, mv_r = ob.burgers_march(u0, g, dt, S, bc="periodic" if periodic else "free", limit=kind, tvb_M=M)
+        got = s.forward(torch.tensor(u0, device="cuda"), dt, S, limit=kind, tvb_M=M, checkpoints=True)
+        assert rel(got["uT"].cpu().numpy(), ref) < 1e-11, (kind, M)
+        flags, _ = pkg.decode_limiter_record(got["lim"])
+        assert np.array_equal(np.moveaxis(flags.cpu().numpy(), 2, 0), np.moveaxis(flags_r, (0, 1, 2), (2, 0, 1))), (kind, M)
+    # adjoint of the Pi^1-limited march (TVB on): finite differences through the GPU march
+    fwd = s.forward(torch.tensor(u0, device="cuda"), dt, S, limit="1", tvb_M=20.0, checkpoints=True)
+    adj = s.adjoint(fwd)
+    jw = torch.tensor(s.g.quad_weights(), device="cuda")
+    dvec = rng.standard_normal(u0.shape)
+    eps = 1e-7
+    Jp = (jw * s.forward(torch.tensor(u0 + eps * dvec, device="cuda"), dt, S, limit="1", tvb_M=20.0)["uT"]).sum((1, 2))
+    Jm = (jw * s.forward(torch.tensor(u0 - eps * dvec, device="cuda"), dt, S, limit="1", tvb_M=20.0)["uT"]).sum((1, 2))
+    fd = ((Jp - Jm) / (2 * eps)).cpu().numpy()
+    dual = np.sum(adj["lam0"].cpu().numpy() * dvec, axis=(1, 2))
+    good = np.abs(fd - dual) <= 1e-4 * np.maximum(np.abs(fd), 1e-3)
+    assert good.sum() >= B // 3, (fd, dual)

@@ -283,6 +283,12 @@ def test_limiter_kat_survey_b5():
     assert np.allclose(lx[:, 0], lx[0, 0])                  # quirk C-16: end cells see a copied ghost average -> flattened
     u1 = limiter.SlopeLimit1(u, g)
     assert np.max(np.abs(g.Dr @ (g.Dr @ u1))) < 1e-9                        # piecewise linear
+    # the TVB minmod in the limiter: an M large enough lets every slope pass -> the P1 part of u itself;
+    # M = 0 is the reference's plain minmod
+    uh = g.invV @ u; uh[2:] = 0.0
+    assert np.allclose(limiter.SlopeLimit1(u, g, M=1e9), g.V @ uh, rtol=0, atol=1e-13)
+    assert np.array_equal(limiter.SlopeLimit1(u, g, M=0.0), u1)
+    assert np.array_equal(limiter.SlopeLimitN(u, g, M=0.0), limiter.SlopeLimitN(u, g))
 
 
 def test_burgers_oracle_properties():
