@@ -32,6 +32,7 @@ struct BurgersArgs {
   long long B;
   int K, S, periodic, limit;   // limit: 0 none, 1 SlopeLimitN (detect, then limit), 2 SlopeLimit1 (every cell)
   double tvbM;                 // M of minmodB (utils/minmodB.m:6-11) in the slope minmod; 0 = plain minmod
+  double eps0;                 // detection threshold of SlopeLimitN.m:13 (1e-8); -1 in SlopeLimit1 mode: every cell
   double dt;
   const double* dt_arr;
   const double* rxk;   // [K]
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? BG_MINB_FWD(NP) : 1) burge
       const MinmodBC q = minmod_bc(v - vm, vp - v);
       const double ve1 = v - minmod3(v - ue1, q);
       const double ve2 = v + minmod3(ue2 - v, q);
-      if (p.limit != 2 && !(fabs(ve1 - ue1) > 1.0e-8 || fabs(ve2 - ue2) > 1.0e-8)) return 0;
+      if (!(fabs(ve1 - ue1) > p.eps0 || fabs(ve2 - ue2) > p.eps0)) return 0;
       double d = 0.0;
 #pragma unroll
       for (int i = 0; i < NP; ++i) d = fma(p.sl[i], u[i], d);
@@ -598,6 +599,7 @@ static int burgers_setup(dgadj_handle* h, BurgersArgs& a, int64_t B, int32_t S, 
   a.periodic = (h->cfg.bc == DGADJ_BC_PERIODIC);
   a.limit = limit;
   a.tvbM = 0.0;
+  a.eps0 = (limit == 2) ? -1.0 : 1.0e-8;
   a.dt = dt;
   a.dt_arr = dt_dev;
   a.rxk = h->d_mesh[0][0];
