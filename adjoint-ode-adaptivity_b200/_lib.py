@@ -74,6 +74,8 @@ PROTOTYPES = {
     "dgadj_rank": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "dgadj_reduce_indicators": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "dgadj_allreduce_indicators": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
+    "dgadj_reduce_indicator_blocks": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P, _P]),
+    "dgadj_allreduce_indicator_blocks": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "dgadj_measure_dfma_peak": (C.c_int, [_P, C.c_double, _D, _D]),
     "dgadj_device_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

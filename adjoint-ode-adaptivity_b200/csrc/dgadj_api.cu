@@ -294,6 +294,67 @@ __global__ void reduce_final_kernel(long long B, int K, const double* __restrict
   }
 }
 
+// Blocked form (count-independent): the batch is cut into blocks of R trajectories; block rb of the
+// grid's y axis reduces rows [rb R, (rb+1) R) exactly as above and leaves its own K+4 partials
+// parts[rb][.].  Combined in block order (combine_partials_kernel), the result does not depend on how
+// many ranks / launches the blocks were spread over.
+__global__ void reduce_blocks_cols_kernel(long long B, int K, long long R, const double* __restrict__ eta,
+                                          double* __restrict__ parts, double* __restrict__ colsq,
+                                          double* __restrict__ colmax) {
+  __shared__ double s1[8][33], s2[8][33], s3[8][33];
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const long long b0 = (long long)blockIdx.y * R, b1 = (b0 + R < B) ? b0 + R : B;
+  double a1 = 0, a2 = 0, a3 = 0;
+  if (k < K) {
+    for (long long b = b0 + threadIdx.y; b < b1; b += 8) {
+      const double v = fabs(eta[(size_t)b * K + k]);
+      a1 += v;
+      a2 = fma(v, v, a2);
+      a3 = fmax(a3, v);
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a1;
+  s2[threadIdx.y][threadIdx.x] = a2;
+  s3[threadIdx.y][threadIdx.x] = a3;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < K) {
+    for (int y = 1; y < 8; ++y) {
+      a1 += s1[y][threadIdx.x];
+      a2 += s2[y][threadIdx.x];
+      a3 = fmax(a3, s3[y][threadIdx.x]);
+    }
+    parts[(size_t)blockIdx.y * (K + 4) + k] = a1;
+    colsq[(size_t)blockIdx.y * K + k] = a2;
+    colmax[(size_t)blockIdx.y * K + k] = a3;
+  }
+}
+__global__ void reduce_blocks_final_kernel(long long B, int K, long long R, const double* __restrict__ colsq,
+                                           const double* __restrict__ colmax, const double* __restrict__ J,
+                                           double* __restrict__ parts) {
+  __shared__ double sj[256];
+  const long long b0 = (long long)blockIdx.x * R, b1 = (b0 + R < B) ? b0 + R : B;
+  double aj = 0;
+  if (J) {
+    for (long long b = b0 + threadIdx.x; b < b1; b += 256) aj += J[b];
+  }
+  sj[threadIdx.x] = aj;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* row = parts + (size_t)blockIdx.x * (K + 4);
+    double t1 = 0, t2 = 0, t3 = 0, tj = 0;
+    for (int k = 0; k < K; ++k) {
+      t1 += row[k];
+      t2 += colsq[(size_t)blockIdx.x * K + k];
+      t3 = fmax(t3, colmax[(size_t)blockIdx.x * K + k]);
+    }
+    for (int i = 0; i < 256; ++i) tj += sj[i];
+    row[K + 0] = t1;
+    row[K + 1] = t2;
+    row[K + 2] = t3;
+    row[K + 3] = tj;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // register-only DFMA peak microbenchmark (roofline denominator): 8 independent chains per
 // thread, 1024 threads per SM, 128 DFMA per loop trip.
@@ -395,7 +456,6 @@ __global__ void rhs_kernel(long long B, int K, int Np, int bc, int inflow, doubl
       double uin = 0.0;
       if (inflow == INFLOW_SIN_AT) uin = -sin(a * t);
       else if (inflow == INFLOW_SIN_AAT) uin = -sin(a * a * t);
-      else if (inflow == INFLOW_TABLE) uin = uin_table ? uin_table[0] : 0.0;
       du0 = (ul[0] - uin) * c0;  // :14-15
     }
   }
@@ -1165,6 +1225,9 @@ static int host_pipeline(dgadj_handle* h, const dgadj_march_args* args, bool fus
     return DGADJ_OK;
   };
 
+  // the chunk loop; on any error the three streams are drained before returning, so that no asynchronous
+  // copy into the caller's buffers (or the pinned staging) is still in flight after the call
+  auto run = [&]() -> int {
   while (done < B) {
     const int slot = c & 1;
     const int64_t nb = std::min<int64_t>(chunk, B - done);
@@ -1241,6 +1304,15 @@ static int host_pipeline(dgadj_handle* h, const dgadj_march_args* args, bool fus
   CUDA_TRY(h, cudaStreamSynchronize(h->s_out));
   CUDA_TRY(h, cudaStreamSynchronize(h->s_k));
   return DGADJ_OK;
+  };
+  const int rrc = run();
+  if (rrc != DGADJ_OK) {
+    cudaStreamSynchronize(h->s_in);
+    cudaStreamSynchronize(h->s_k);
+    cudaStreamSynchronize(h->s_out);
+    cudaGetLastError();
+  }
+  return rrc;
 }
 
 extern "C" int dgadj_fwd_adj_host(dgadj_handle* h, const dgadj_march_args* args, const double* a_host,
@@ -1279,6 +1351,10 @@ extern "C" int dgadj_rhs(dgadj_handle* h, int64_t B, int32_t level, const double
   if (!h) return DGADJ_ERR_INVALID;
   if (B <= 0 || !u_dev || !rhs_dev || level < 0 || level > 1) return fail(h, DGADJ_ERR_INVALID, "bad rhs arguments");
   if (!h->ops_set || (level == 1 && !h->enr_set)) return fail(h, DGADJ_ERR_STATE, "operators of level %d not set", level);
+  // a caller-supplied inflow table is indexed by (step, stage), which a stand-alone evaluation at a
+  // time t does not have: refuse instead of silently using the first entry
+  if (h->cfg.bc == DGADJ_BC_INFLOW && h->cfg.inflow == DGADJ_INFLOW_TABLE)
+    return fail(h, DGADJ_ERR_UNSUPPORTED, "dgadj_rhs cannot evaluate a tabulated inflow at a time t (the table is indexed by step and stage)");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const int Np = level ? h->NpF : h->Np;
   const long long n = (long long)B * h->K;
@@ -1338,6 +1414,34 @@ extern "C" int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, co
   reduce_cols_kernel<<<(K + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(B, K, eta_dev, sums_dev, colsq, colmax);
   CUDA_TRY(h, cudaGetLastError());
   reduce_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(B, K, colsq, colmax, J_dev, sums_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 2;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_reduce_indicator_blocks(dgadj_handle* h, int64_t B, int32_t K, int64_t rows_per_block,
+                                             const double* eta_dev, const double* J_dev, double* parts_dev,
+                                             void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || K <= 0 || rows_per_block <= 0 || !eta_dev || !parts_dev) return fail(h, DGADJ_ERR_INVALID, "bad reduce_indicator_blocks arguments");
+  const int64_t nblk = (B + rows_per_block - 1) / rows_per_block;
+  if (nblk > 65535) return fail(h, DGADJ_ERR_UNSUPPORTED, "more than 65535 blocks: use larger blocks");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t need = (size_t)2 * K * nblk * sizeof(double);
+  if (need > h->red_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->red_scratch);
+    h->red_scratch = nullptr;
+    h->red_bytes = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->red_scratch, need));
+    h->red_bytes = need;
+  }
+  double* colsq = h->red_scratch;
+  double* colmax = h->red_scratch + (size_t)K * nblk;
+  reduce_blocks_cols_kernel<<<dim3((K + 31) / 32, (unsigned)nblk), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      B, K, rows_per_block, eta_dev, parts_dev, colsq, colmax);
+  CUDA_TRY(h, cudaGetLastError());
+  reduce_blocks_final_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(B, K, rows_per_block, colsq, colmax, J_dev, parts_dev);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 2;
   return DGADJ_OK;

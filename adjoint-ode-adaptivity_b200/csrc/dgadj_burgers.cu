@@ -696,9 +696,11 @@ extern "C" int dgadj_burgers_adjoint(dgadj_handle* h, int64_t B, int32_t S, doub
                                      const uint8_t* lim0_dev, const int32_t* amax_dev, const double* maxvel_dev,
                                      double* lam0_dev, double* J_dev, void* stream) {
   if (!h) return DGADJ_ERR_INVALID;
-  if (B <= 0 || S < 0 || !jw_host || !hist_dev || !lim_dev || !lim0_dev || !amax_dev || !maxvel_dev)
+  // (a march of S = 0 steps has no per-step records: lim / amax / maxvel may be NULL then)
+  if (B <= 0 || S < 0 || !jw_host || !hist_dev || !lim0_dev || (S > 0 && (!lim_dev || !amax_dev || !maxvel_dev)))
     return fail(h, DGADJ_ERR_INVALID, "bad burgers_adjoint arguments (the forward checkpoints are all required)");
   if (!h->ops_set) return fail(h, DGADJ_ERR_STATE, "dgadj_set_operators has not been called");
+  if (h->nstages != 5) return fail(h, DGADJ_ERR_UNSUPPORTED, "the Burgers march is LSERK4 only");
   if (!invV_host || !V_host || !x_host) return fail(h, DGADJ_ERR_INVALID, "the limiter needs V, invV and x");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;

@@ -12,14 +12,19 @@ namespace dgadj {
 
 template <int NP, int EPT, int BDT, bool F, bool R, bool A>
 static cudaError_t launch_bd(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
-  static bool attr_set = false;  // per variant instantiation (function-local static per template)
+  // the opt-in shared-memory size is a per-device function attribute: remembered per (instantiation,
+  // device), so that a process with handles on several GPUs sets it on each of them
+  static bool attr_set[64] = {};
   if (block > MAXBD / EPT) return cudaErrorInvalidConfiguration;
   const size_t smem = march_smem_bytes(NP, EPT, block, variant);
   auto kern = march_kernel<NP, EPT, BDT, F, R, A>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   kern<<<grid, block, smem, stream>>>(*ka);
   return cudaGetLastError();

@@ -17,8 +17,10 @@ def shard_range(B: int, rank: int, world: int):
 def allreduce_indicators(sums, group=None, ordered=True):
     """Combine per-rank partials sums[K+4] = [sum_b|eta[b,k]| (K), sum|eta|, sum eta^2,
     max|eta|, sum J] across ranks.  ordered=True all-gathers the partials and adds them in
-    rank order on every rank, so 1/2/4/8-GPU runs of the same global batch rank elements
-    identically (SURVEY hard part 6); ordered=False is a plain all-reduce (sum + max)."""
+    rank order on every rank: the same bits on every rank whatever the reduction topology
+    (SURVEY hard part 6); ordered=False is a plain all-reduce (sum + max).  One partial per rank
+    still makes the batch sum depend on the number of ranks at rounding level -- use
+    `allreduce_indicator_blocks` for results that are bit-identical across 1/2/4/8 GPUs."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -40,6 +42,70 @@ def allreduce_indicators(sums, group=None, ordered=True):
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     out[K + 2] = mx[0]
     return out
+
+
+REDUCE_BLOCK = 4096   # trajectories per reduction block of the count-independent batch sums
+
+
+def combine_blocks(parts):
+    """Sum the rows of parts[nblk, K+4] in row order (entry K+2: a maximum).  CUDA tensors go through
+    the C-ABI (`dgadj_allreduce_indicator_blocks` without a communicator); CPU tensors (the gloo
+    tests of the host logic) are added row by row here -- same order, same bits."""
+    import torch
+    K = parts.shape[1] - 4
+    if parts.is_cuda:
+        from . import _lib
+        import ctypes as C
+        lib = _lib.load()
+        h = _any_handle(parts.device.index)
+        out = torch.empty(K + 4, dtype=torch.float64, device=parts.device)
+        parts = parts.contiguous()
+        rc = lib.dgadj_allreduce_indicator_blocks(h, C.c_void_p(0), K, parts.shape[0], C.c_void_p(parts.data_ptr()),
+                                                  C.c_void_p(out.data_ptr()),
+                                                  C.c_void_p(torch.cuda.current_stream(parts.device).cuda_stream))
+        if rc != _lib.OK:
+            raise _lib.DgadjError(rc, lib.dgadj_last_error(h).decode())
+        return out
+    out = parts[0].clone()
+    for r in range(1, parts.shape[0]):
+        mx = torch.maximum(out[K + 2], parts[r, K + 2])
+        out += parts[r]
+        out[K + 2] = mx
+    return out
+
+
+_HANDLES = {}
+
+
+def _any_handle(device):
+    """A minimal handle on `device` for calls that need none of a solver's state."""
+    import ctypes as C
+    from . import _lib
+    if device not in _HANDLES:
+        lib = _lib.load()
+        cfg = _lib.Config(device=device, N=1, K=1, bc=1, inflow=0, functional=0, scheme=0, reserved=0, alpha=0.0)
+        h = C.c_void_p(0)
+        rc = lib.dgadj_create(C.byref(cfg), C.byref(h))
+        if rc != _lib.OK:
+            raise _lib.DgadjError(rc, "dgadj_create failed (an sm_100 device is required; there is no CPU path)")
+        _HANDLES[device] = h
+    return _HANDLES[device]
+
+
+def allreduce_indicator_blocks(parts, group=None):
+    """Count-independent batch sums: `parts[nblk_local, K+4]` are this rank's block partials
+    (`AdvecDG1D.reduce_indicator_blocks`: fixed blocks of REDUCE_BLOCK trajectories); the rows of all
+    ranks are all-gathered in rank order (= global block order for `shard_range` shards) and added in
+    that order on every rank.  When every shard is a whole number of blocks the result has the same bits
+    on 1, 2, 4 or 8 GPUs, so near-ties of the batch-mean argmax refine the same element everywhere."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        rows = [torch.empty_like(parts) for _ in range(world)]
+        dist.all_gather(rows, parts.contiguous(), group=group)
+        parts = torch.cat(rows, dim=0)
+    return combine_blocks(parts)
 
 
 def gather_indicators(eta, group=None):

@@ -360,3 +360,18 @@ class AdvecDG1D:
         sums = torch.empty(K + 4, dtype=torch.float64, device=eta.device)
         self._check(self.lib.dgadj_reduce_indicators(self._h, B, K, _ptr(eta), _ptr(J), _ptr(sums), self._stream()))
         return sums
+
+    def reduce_indicator_blocks(self, eta, J=None, rows_per_block=None):
+        """parts[nblk, K+4]: the sums of `reduce_indicators` over fixed blocks of `rows_per_block`
+        trajectories (default sharding.REDUCE_BLOCK) -- the count-independent form that
+        `sharding.allreduce_indicator_blocks` combines in global block order.  Device tensors."""
+        from .sharding import REDUCE_BLOCK
+        torch = _torch()
+        eta = _as_device_tensor(eta)
+        B, K = eta.shape
+        R = int(rows_per_block or REDUCE_BLOCK)
+        J = None if J is None else _as_device_tensor(J)
+        nblk = (B + R - 1) // R
+        parts = torch.empty((nblk, K + 4), dtype=torch.float64, device=eta.device)
+        self._check(self.lib.dgadj_reduce_indicator_blocks(self._h, B, K, R, _ptr(eta), _ptr(J), _ptr(parts), self._stream()))
+        return parts

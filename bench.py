@@ -71,15 +71,19 @@ def synth_ics_np(x, B, seed):
     return u0
 
 
-def synth_ics_torch(torch, x, B, seed, device):
+def synth_ics_torch(torch, x, B, seed, device, first=None):
+    """The bench's ICs (same law as synth_ics_np, drawn on the device).  first=n: only the first n
+    trajectories of the B-trajectory draw are built (tests/test_gpu_parity.py checks those against
+    the oracle): the amplitudes / phases are always drawn for the whole batch."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     xt = torch.tensor(x, device=device)[None]
-    u0 = torch.zeros((B,) + tuple(x.shape), dtype=torch.float64, device=device)
+    n = B if first is None else min(first, B)
+    u0 = torch.zeros((n,) + tuple(x.shape), dtype=torch.float64, device=device)
     for m in range(1, 5):
         A = torch.randn((B, 1, 1), dtype=torch.float64, device=device, generator=g) / m
         ph = torch.rand((B, 1, 1), dtype=torch.float64, device=device, generator=g) * TWO_PI
-        u0 += A * torch.sin(m * xt + ph)
+        u0 += A[:n] * torch.sin(m * xt + ph[:n])
     return u0
 
 
@@ -169,6 +173,19 @@ def reference_arm(a):
     return 0
 
 
+def kernel_source_sha():
+    """sha256 (16 hex digits) of the march kernel's sources: the stamp tools/exec_inst.py and the ncu
+    traffic entry carry, so that a number measured on another build is reported as stale."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("dgadj_kernels.cuh", "dgadj_march_np.cu"):
+        try:
+            h.update(open(os.path.join(ROOT, "adjoint-ode-adaptivity_b200", "csrc", f), "rb").read())
+        except OSError:
+            return None
+    return h.hexdigest()[:16]
+
+
 def workload_config(a):
     return {"workload": f"linear advection N={a.N}, K={a.K}, batch {a.B} random ICs per GPU, LSERK4 S={a.S} steps, "
                         "fwd + adjoint (order N+1) + per-element indicator + refine flags, periodic, upwind",
@@ -251,7 +268,6 @@ def ours(a):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -360,32 +376,58 @@ def ours(a):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     ck_bytes = B * (2 * S * s.NpF * K * 8 + s.Np * K * 8 + K * 8 + 8)
-    traffic = None
+    # DRAM traffic of one launch from an `ncu --set full` capture (profiles/traffic.json); the entry names
+    # the kernel-source hash it was measured on, and is reported as stale if the source has changed since
+    src_sha = kernel_source_sha()
+    traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = f"N{N}_K{K}_S{S}_B{B}"
-        traffic = tj.get(key)
+        ent = tj.get(f"N{N}_K{K}_S{S}_B{B}")
+        if isinstance(ent, dict):
+            traffic = ent.get("bytes")
+            traffic_src = "%s; kernel source %s (%s)" % (ent.get("source"), ent.get("kernel_source_sha"),
+                                                         "current" if ent.get("kernel_source_sha") == src_sha else "STALE: source is now " + src_sha)
+        elif ent is not None:
+            traffic, traffic_src = ent, tj.get("_source")
     except Exception:
         pass
-    # fp64-pipe instructions the SASS actually executes per update (tools/sass_mix.py on the N = 8
-    # kernel: 57 coarse-forward + 65 fine-residual + 66 adjoint per element-stage, two updates):
-    # the modal / parity-sparse formulation needs about a third of the SURVEY 8(d) flop count,
-    # which is why `frac` (algorithmic flops / measured peak) can read above the pipe utilisation.
-    exec_inst = {8: 94.0}.get(N)
-    pipe_util = (exec_inst * 2 * 5 * S * K * B / (kern_ms * 1e-3)) / (148 * 64 * clocks["sm_mhz"] * 1e6) \
-        if exec_inst and clocks.get("sm_mhz") else None
+    # fp64-pipe instructions the SASS executes per update: counted from the built library by
+    # tools/exec_inst.py (the stage loops of the fused kernel; profiles/exec_inst.json, stamped with the
+    # kernel-source hash).  The modal / parity-sparse formulation needs about a third of the SURVEY 8(d)
+    # flop count, which is why the algorithmic fraction can read above 1: `frac` is therefore the
+    # EXECUTED fp64-pipe utilisation (thread instructions / (SMs x 64 lanes x clock)), the hardware
+    # figure ncu reports as sm__inst_executed_pipe_fp64; `frac_algorithmic` keeps the 8(d) number.
+    exec_inst, exec_src = None, None
+    try:
+        ej = json.load(open(os.path.join(ROOT, "profiles", "exec_inst.json")))
+        pl_ = s.plan(B)
+        ent = ej.get("np%d_ept%d_bd%d_fused" % (s.Np, pl_["elems_per_thread"], pl_["block"]))
+        if ent:
+            exec_inst = ent["fp64_inst_per_update"]
+            exec_src = "tools/exec_inst.py on libdgadj.so; kernel source %s (%s)" % (
+                ent["kernel_source_sha"], "current" if ent["kernel_source_sha"] == src_sha else "STALE: source is now " + src_sha)
+    except Exception:
+        pass
+    sm_clock = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    pipe_rate = 148 * 64 * sm_clock * 1e6            # fp64 thread-instructions per second the pipe can retire
+    pipe_util = (exec_inst * 2 * 5 * S * K * B / (kern_ms * 1e-3)) / pipe_rate if exec_inst else None
     roofline = {
         "bound": "fp64_fma", "kernel": "dgadj::march_kernel<NP=%d,EPT,fwd,resid,adj> (fused)" % s.Np,
-        "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
+        "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": pipe_util, "frac_kind": "executed fp64-pipe utilisation: executed fp64 instructions per update (SASS count) x updates/s "
+                                         "/ (148 SM x 64 lanes x SM clock under load)",
+        "frac_algorithmic": ach_tf / peak_tf if peak_tf else None,
+        "achieved_note": "`achieved` = SURVEY 8(d) algorithmic flops (277 per update at N=8) / kernel time; `frac_algorithmic` = achieved / peak",
         "peak_source": "measured live: best of two register-resident DFMA microbenchmarks (register and constant-bank operand forms, dgadj_measure_dfma_peak); "
                        "MEASURED_PEAKS.json has no fp64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
         "algorithmic_flops_per_update": flops_per_update(s.Np), "kernel_ms": kern_ms,
-        "executed_fp64_inst_per_update": exec_inst, "fp64_pipe_utilisation_from_sass_count": pipe_util,
+        "executed_fp64_inst_per_update": exec_inst, "executed_fp64_inst_source": exec_src,
+        "sm_clock_mhz_used": sm_clock,
         "kernel_share_of_step": kern_ms / ms_per_step if world == 1 else None,
         "hbm": {"achieved": ck_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ck_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                "frac": ck_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": ck_bytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"},
-        "traffic": traffic,
+        "traffic": traffic, "traffic_source": traffic_src,
     }
     cpu = None
     if not a.no_cpu and world == 1:

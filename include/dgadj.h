@@ -196,9 +196,24 @@ int dgadj_reduce_indicators(dgadj_handle* h, int64_t B, int32_t K, const double*
 /* The cross-GPU step of that rule when the batch is sharded over ranks (one handle, one GPU, one
  * NCCL rank each): sums_dev[K+4] (this rank's partials, in place) -> the combination over all
  * ranks of nccl_comm (an ncclComm_t of the caller's NCCL): all-gather + sum in rank order, entry
- * K+2 a maximum -- the same bits on every rank, independent of the number of GPUs a global batch
- * is spread over.  Asynchronous on `stream`.  NCCL is resolved at run time from the process.  */
+ * K+2 a maximum -- the same bits on every rank and for every reduction topology.  (Each rank's
+ * partial is summed over its own shard, so a different NUMBER of ranks changes the summation order
+ * of the batch sum at rounding level; dgadj_reduce_indicator_blocks / dgadj_allreduce_indicator_blocks
+ * below are the count-independent form.)  Asynchronous on `stream`.  NCCL is resolved at run time. */
 int dgadj_allreduce_indicators(dgadj_handle* h, void* nccl_comm, int32_t K, double* sums_dev, void* stream);
+
+/* Count-independent form of the two calls above (hard part 6: "fixed-order reduction
+ * for bit-stable ranking").  The batch is reduced in blocks of rows_per_block trajectories:
+ *   parts_dev[nblk][K+4], nblk = ceil(B / rows_per_block), row j = the sums of dgadj_reduce_indicators
+ *   over trajectories [j rows_per_block, (j+1) rows_per_block).
+ * dgadj_allreduce_indicator_blocks all-gathers the rows of every rank (nblk_local each; rank order =
+ * global block order for contiguous shards) and adds them in that order on every rank -> sums_dev[K+4].
+ * When every shard is a whole number of blocks, the result has the same bits for 1, 2, 4 or 8 GPUs (and
+ * for one GPU taking the batch in several calls).  nccl_comm may be NULL: the local rows only.      */
+int dgadj_reduce_indicator_blocks(dgadj_handle* h, int64_t B, int32_t K, int64_t rows_per_block,
+                                  const double* eta_dev, const double* J_dev, double* parts_dev, void* stream);
+int dgadj_allreduce_indicator_blocks(dgadj_handle* h, void* nccl_comm, int32_t K, int32_t nblk_local,
+                                     const double* parts_dev, double* sums_dev, void* stream);
 
 /* Finite-difference path of python/Main_finite_difference.py, batched over initial conditions
  * on a shared time mesh: forwardSolve (:34-51) -> adjSolve (:54-76, on the ref_factor-refined

@@ -315,6 +315,47 @@ def test_cfg2_size_properties(pkg, torch):
     assert float((out["eta"].sum(1) - (Jf_c - Jf_f)).abs().max()) < 1e-11 * scale
 
 
+def test_cfg2_bench_config_parity(pkg, torch):
+    """The bench configuration itself (BASELINE config 2 as bench.py runs it: N=8, K=1024, S=200 LSERK4
+    steps, periodic, upwind, a = 2 pi, dt of the mlx CFL rule): the first 64 trajectories of bench.py's
+    own batch (seed 1234, rank 0) against the oracle at the north-star tolerance -- SURVEY section 8(d)
+    'parity subset: first 64 trajectories vs oracle'.  utils/AdvecRHS1D.m:8-19 + the LSERK4 loop of
+    utils/One_code.mlx for the march; App. E.5 for adjoint and indicator."""
+    import bench
+    N, K, S, nsub, dom = 8, 1024, 200, 64, (0.0, 2 * math.pi)
+    s = pkg.AdvecDG1D(N, K, domain=dom, alpha=0.0, bc="periodic")
+    gc, gf = oracle_pair(s)
+    a = 2 * math.pi
+    dt, _ = s.cfl_dt(1.0)
+    d_u0 = bench.synth_ics_torch(torch, s.g.x, 65536, 1234, torch.device("cuda", 0), first=nsub)
+    u0 = d_u0.cpu().numpy()
+    out = s.fwd_adj(d_u0, a, dt, S, want_lam0=True)
+    _, flags = s.rank(out["eta"], topk=5, want_order=False)
+    ref = advec.fwd_adj_indicator(u0, gc, gf, a, dt, S, 0.0, advec.BC_PERIODIC)
+    eta = check_fused(out, ref, nsub)                         # 1e-12: uT, lam0, J; 1e-12 eta_scale: eta
+    # refine flags (top 5 of |eta|): exact away from ties -- where the oracle's 5th and 6th largest
+    # indicators are further apart than the rounding of the sums
+    order_ref, flags_ref = advec.rank_refine(ref["eta"], 5)
+    srt = np.sort(np.abs(ref["eta"]), axis=1)[:, ::-1]
+    clear = (srt[:, 4] - srt[:, 5]) > 1e-9 * np.max(ref["eta_scale"], axis=1)
+    assert clear.sum() >= nsub // 2
+    assert np.array_equal(flags.cpu().numpy()[clear], flags_ref[clear])
+    order_own, flags_own = advec.rank_refine(eta, 5)          # and exact on identical indicator input
+    assert np.array_equal(flags.cpu().numpy(), flags_own)
+    # against the reference's per-node rx (rx(i,k) = 1/(Dr x)(i,k), utils/GeometricFactors1D.m:6): the
+    # forward state still meets 1e-12; the deviation of adjoint and indicator from the element-constant
+    # rx the kernel uses is put on record (and bounded by noise x steps)
+    noise = max(np.max(np.abs(g.r_x / g.r_x[0:1, :] - 1.0)) for g in (s.g, s.gf))
+    gc.rx, gf.rx = s.g.r_x, s.gf.r_x
+    ref_node = advec.fwd_adj_indicator(u0, gc, gf, a, dt, S, 0.0, advec.BC_PERIODIC)
+    d_uT = rel(out["uT"].cpu().numpy(), ref_node["uT"])
+    d_lam = rel(out["lam0"].cpu().numpy(), ref_node["lam0"])
+    d_eta = float(np.max(np.abs(eta - ref_node["eta"]) / ref_node["eta_scale"]))
+    print(f"cfg2 parity vs per-node-rx oracle: rx noise {noise:.2e}; uT {d_uT:.2e}, lam0 {d_lam:.2e}, eta/eta_scale {d_eta:.2e}")
+    assert d_uT < 10 * TOL
+    assert d_lam < 50 * S * noise and d_eta < 50 * S * noise
+
+
 # ------------------------------------------------------------------ ranking / reduction
 def test_rank_and_reduce(pkg, torch):
     s = pkg.AdvecDG1D(2, 8)

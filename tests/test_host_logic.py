@@ -220,6 +220,20 @@ mean, idx = pkg.batch_mean_refine(tot, B)
 assert idx == int(np.argmax(np.abs(eta).sum(0)))
 full_eta = pkg.gather_indicators(torch.tensor(e))           # ragged slices (6 and 5 rows)
 assert torch.equal(full_eta, torch.tensor(eta))
+# count-independent form: block partials (4 trajectories per block here) combined in global block order
+# give the same bits as the one-rank combination of all blocks, whatever the number of ranks
+def block_parts(e, j, R):
+    rows = []
+    for b0 in range(0, len(e), R):
+        ee, jj = e[b0:b0 + R], j[b0:b0 + R]
+        rows.append(np.concatenate([np.abs(ee).sum(0), [np.abs(ee).sum(), (ee**2).sum(), np.abs(ee).max(), jj.sum()]]))
+    return torch.tensor(np.stack(rows))
+B2 = 16
+eta2 = rng.standard_normal((B2, K)); J2 = rng.standard_normal(B2)
+lo, hi = pkg.shard_range(B2, rank, world)          # 8 + 8: whole blocks per rank
+mine = pkg.allreduce_indicator_blocks(block_parts(eta2[lo:hi], J2[lo:hi], 4))
+one = pkg.combine_blocks(block_parts(eta2, J2, 4))  # what a single rank computes
+assert torch.equal(mine, one), (mine, one)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
