@@ -38,6 +38,14 @@ class MarchArgs(C.Structure):
                 ("a", C.c_double), ("dt", C.c_double), ("a_dev", C.c_void_p), ("dt_dev", C.c_void_p)]
 
 
+class BurgersArgs(C.Structure):
+    """dgadj_burgers_args (include/dgadj.h)"""
+    _fields_ = [("B", C.c_int64), ("S", C.c_int32), ("limit", C.c_int32), ("indicator", C.c_int32), ("reserved", C.c_int32),
+                ("dt", C.c_double), ("dt_dev", C.c_void_p), ("tvb_M", C.c_double),
+                ("invV_host", C.c_void_p), ("V_host", C.c_void_p), ("x_host", C.c_void_p), ("jw_host", C.c_void_p),
+                ("invVF_host", C.c_void_p), ("VF_host", C.c_void_p), ("xF_host", C.c_void_p), ("jwF_host", C.c_void_p)]
+
+
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
 # name -> (restype, argtypes); exactly the symbols include/dgadj.h declares
@@ -70,6 +78,9 @@ PROTOTYPES = {
                                         _P, _P, _P, _P, _P, _P]),
     "dgadj_burgers_adjoint": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                         _P, _P, _P, _P]),
+    "dgadj_burgers_fwd_adj": (C.c_int, [_P, C.POINTER(BurgersArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dgadj_burgers_plan": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dgadj_ic_indicator": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "dgadj_rank": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "dgadj_reduce_indicators": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),

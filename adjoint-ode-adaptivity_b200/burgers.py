@@ -121,6 +121,91 @@ class BurgersDG1D:
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return dict(lam0=lam0, J=J)
 
+    def _enriched(self):
+        """Operators of the enriched space (order N+1) for the indicator, set on first use."""
+        if getattr(self, "gf", None) is None:
+            if self.N + 2 > 10:
+                raise ValueError("the indicator needs N <= 8 (the enriched space is order N+1)")
+            g = self.g
+            self.gf = gf = BaseGalerkin1D(n=self.N + 1, k=self.K, domain=g.domain, v_x=g.v_x)
+            c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+            self.ops_f = dict(Dr=c(gf.d_r), LIFT=c(gf.lift), rx=c(gf.r_x), Fscale=c(gf.f_scale), V=c(gf.v),
+                              invV=c(gf.inv_v), x=c(gf.x))
+            self.P = c(g.prolongation_to(gf))
+            o = self.ops_f
+            p = lambda a: C.c_void_p(a.ctypes.data)
+            self._check(self.lib.dgadj_set_enriched(self._h, self.Np + 1, p(o["Dr"]), p(o["LIFT"]), p(o["V"]), p(o["rx"]),
+                                                    p(o["Fscale"]), p(self.P)))
+        return self.gf
+
+    def plan(self, B, indicator=True):
+        """Launch shape of the fused kernel: dict(elems_per_thread, block, grid, smem_bytes, ring_bytes_per_step)."""
+        if indicator:
+            self._enriched()
+        e, b, g = C.c_int32(), C.c_int32(), C.c_int32()
+        sm, rb = C.c_int64(), C.c_int64()
+        self._check(self.lib.dgadj_burgers_plan(self._h, int(B), int(bool(indicator)), C.byref(e), C.byref(b), C.byref(g),
+                                                C.byref(sm), C.byref(rb)))
+        return dict(elems_per_thread=e.value, block=b.value, grid=g.value, smem_bytes=sm.value, ring_bytes_per_step=rb.value)
+
+    def set_tuning(self, elems_per_thread=0, grid_ctas=0):
+        self._check(self.lib.dgadj_set_tuning(self._h, elems_per_thread, 0, grid_ctas))
+
+    def fwd_adj(self, u0, dt, S, limit=True, indicator=True, psi=None, tvb_M=0.0, want_uT=True, want_lam0=True):
+        """BASELINE config 3 in one call (`dgadj_burgers_fwd_adj`): the limited march, its discrete adjoint on
+        the frozen limiter / minmod / argmax branches and, with indicator=True, the per-element error indicator
+        (adjoint one order higher, matlab/MAIN.m:34; err(k) = v_k' * residual, matlab/adj_march.m:103-117).
+        Forward states go to a per-CTA ring on the device (no [B, S+1, Np, K] history), so marches past shock
+        formation fit at the full batch.  J = int psi(x) u(x,T) dx (psi = 1 by default).
+        Returns dict(uT, J[B], lam0, nlim[B] int32, status[B] int32[, eta[B, K]]):
+          indicator=False: lam0[B, Np, K] = dJ/du0 of the march (what `adjoint` gives);
+          indicator=True:  lam0[B, Np+1, K] = the enriched adjoint at t = 0, eta signed (consumers take abs)."""
+        torch = self.torch
+        if not (isinstance(u0, torch.Tensor) and u0.is_cuda and u0.dtype == torch.float64):
+            raise TypeError("u0 must be a float64 CUDA tensor")
+        if u0.ndim == 2:
+            u0 = u0[None]
+        if u0.shape[1:] != (self.Np, self.K):
+            raise ValueError(f"expected (B, {self.Np}, {self.K}), got {tuple(u0.shape)}")
+        u0 = u0.contiguous()
+        B = u0.shape[0]
+        dt_s, dt_v = (float(dt), None) if np.isscalar(dt) else (0.0, dt.contiguous())
+        jw = self.g.quad_weights()
+        if psi is not None:
+            jw = jw * psi(self.g.x)
+        jw = np.ascontiguousarray(jw, dtype=np.float64)
+        o = self.ops
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        a = _lib.BurgersArgs(B=B, S=int(S), limit=self.LIMIT_CODES[limit], indicator=int(bool(indicator)), reserved=0,
+                             dt=dt_s, dt_dev=C.c_void_p(dt_v.data_ptr()) if dt_v is not None else None, tvb_M=float(tvb_M),
+                             invV_host=p(o["invV"]), V_host=p(o["V"]), x_host=p(o["x"]), jw_host=p(jw))
+        keep = [jw]
+        NpX = self.Np
+        if indicator:
+            gf = self._enriched()
+            jwf = gf.quad_weights()
+            if psi is not None:
+                jwf = jwf * psi(gf.x)
+            jwf = np.ascontiguousarray(jwf, dtype=np.float64)
+            keep.append(jwf)
+            of = self.ops_f
+            a.invVF_host, a.VF_host, a.xF_host, a.jwF_host = p(of["invV"]), p(of["V"]), p(of["x"]), p(jwf)
+            NpX = self.Np + 1
+        kw = dict(dtype=torch.float64, device=u0.device)
+        out = dict(J=torch.empty(B, **kw), nlim=torch.empty(B, dtype=torch.int32, device=u0.device),
+                   status=torch.empty(B, dtype=torch.int32, device=u0.device))
+        if want_uT:
+            out["uT"] = torch.empty_like(u0)
+        if want_lam0:
+            out["lam0"] = torch.empty((B, NpX, self.K), **kw)
+        if indicator:
+            out["eta"] = torch.empty((B, self.K), **kw)
+        d = lambda k: C.c_void_p(out[k].data_ptr()) if k in out else C.c_void_p(0)
+        self._check(self.lib.dgadj_burgers_fwd_adj(
+            self._h, C.byref(a), C.c_void_p(u0.data_ptr()), d("uT"), d("J"), d("lam0"), d("eta"), d("nlim"), d("status"),
+            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out
+
     def slope_limit(self, u, kind="N", tvb_M=0.0):
         """ulimit = SlopeLimitN(u) (utils/SlopeLimitN.m:1) or, kind="1", SlopeLimit1(u)
         (utils/SlopeLimit1.m:1): one limiter pass, no time steps; tvb_M > 0 uses minmodB."""

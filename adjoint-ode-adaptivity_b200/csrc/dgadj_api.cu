@@ -16,7 +16,7 @@
 
 namespace dgadj {
 #define DGADJ_DECL_NP(n) \
-  cudaError_t march_launch_np##n(int, int, int, int, cudaStream_t, const KArgs*);
+  cudaError_t march_launch_np##n(int, int, int, int, size_t, cudaStream_t, const KArgs*);
 DGADJ_DECL_NP(2) DGADJ_DECL_NP(3) DGADJ_DECL_NP(4) DGADJ_DECL_NP(5)
 DGADJ_DECL_NP(6) DGADJ_DECL_NP(7) DGADJ_DECL_NP(8) DGADJ_DECL_NP(9) DGADJ_DECL_NP(10)
 // Np = 10 (N = 9) is forward-only: its enriched space would be Np = 11
@@ -548,6 +548,7 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->tdg_scratch);
   cudaFree(h->bg_scratch);
   cudaFree(h->bgs_scratch);
+  cudaFree(h->bgf_consts);
   cudaFree(h->nccl_scratch);
   if (h->pipe_init) {
     cudaStreamDestroy(h->s_in);
@@ -704,6 +705,9 @@ extern "C" int dgadj_set_enriched(dgadj_handle* h, int NpF, const double* DrF, c
                 "P is not the Legendre prolongation V_f(:,1:Np) inv(V_c) (deviation %.3e from the modal injection)", viol);
   rc = upload(h, &h->d_P, P, (size_t)NpF * Np);
   if (rc) return rc;
+  for (int i = 0; i < NpF * Np; ++i) h->P_host[i] = P[i];
+  for (int i = 0; i < NpF * NpF; ++i) h->Dr_nodal_f[i] = DrF[i];
+  for (int i = 0; i < NpF * 2; ++i) h->LIFT_nodal_f[i] = LIFTF[i];
   h->enr_set = true;
   return DGADJ_OK;
 }
@@ -791,6 +795,20 @@ static int make_plan(dgadj_handle* h, int64_t B, int variant, LaunchPlan* pl) {
   pl->smem = march_smem_bytes(h->Np, ept, block, variant);
   if (pl->smem > 227 * 1024) return fail(h, DGADJ_ERR_UNSUPPORTED, "shared memory %zu B over budget", pl->smem);
   int per_sm = std::max(1, std::min<int>(bdmax / block * march_min_ctas(h->Np, ept), (int)((227 * 1024) / pl->smem)));
+  // bulk-TMA checkpoint stores (a second park buffer): when the forward phase writes residual tiles, the
+  // stages synchronise through the CTA's trace barrier (not warp-local), and the larger footprint neither
+  // exceeds the SM nor costs a resident CTA.  DGADJ_TMA_STORE=0/1 forces the choice (A/B measurements).
+  pl->tma_store = 0;
+  if (variant == VAR_FUSED || variant == VAR_FWD_RESID) {
+    const bool warp_local = (KT <= 32 && 32 % KT == 0);
+    const size_t s2 = march_smem_bytes(h->Np, ept, block, variant, 2);
+    bool on = DGADJ_TMA_STORE_PATH && !warp_local && s2 <= 227 * 1024 && (int)((227 * 1024) / s2) >= per_sm;
+    if (const char* ev = getenv("DGADJ_TMA_STORE")) on = on && atoi(ev) != 0;
+    if (on) {
+      pl->tma_store = 1;
+      pl->smem = s2;
+    }
+  }
   int grid = h->tune_grid ? h->tune_grid : h->sm_count * per_sm;
   pl->grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ngroups));
   pl->tile = (size_t)h->NpF * ept * block;
@@ -864,12 +882,22 @@ static void fill_params(dgadj_handle* h, const dgadj_march_args* a, const Launch
   p.jw_c = h->d_jwm_c;
   p.jw_f = h->d_jwm_f;
   p.uin_table = h->d_uin;
+  p.tma_store = pl.tma_store;
 }
 
-static int launch(dgadj_handle* h, int variant, const LaunchPlan& pl, cudaStream_t st, const KArgs* ka) {
+// 128-bit state I/O when every [B][Np][K] pointer of the call is 16-byte aligned (K is a multiple of the
+// even EPT, so every row segment a thread touches then is)
+static void set_vec_io(KArgs* ka, const LaunchPlan& pl) {
+  const MarchParams& p = ka->p;
+  auto ok = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+  ka->p.vec_io = (pl.ept % 2 == 0) && ok(p.u0) && ok(p.uT) && ok(p.uT_in) && ok(p.lam0);
+}
+
+static int launch(dgadj_handle* h, int variant, const LaunchPlan& pl, cudaStream_t st, KArgs* ka) {
   march_launch_fn fn = launch_table[h->Np];
   if (!fn) return fail(h, DGADJ_ERR_UNSUPPORTED, "no kernel for Np=%d", h->Np);
-  cudaError_t e = fn(variant, pl.ept, pl.grid, pl.block, st, ka);
+  set_vec_io(ka, pl);
+  cudaError_t e = fn(variant, pl.ept, pl.grid, pl.block, pl.smem, st, ka);
   if (e != cudaSuccess) return fail(h, DGADJ_ERR_CUDA, "march kernel launch failed: %s", cudaGetErrorString(e));
   h->launches++;
   return DGADJ_OK;

@@ -17,6 +17,7 @@ struct LaunchPlan {
   int ept, KT, tpc, block, ngroups, grid;
   size_t smem;
   size_t tile;  // doubles per checkpoint tile
+  int tma_store;  // residual tiles leave through bulk-TMA from a double-buffered park (smem includes it)
 };
 
 struct dgadj_handle {
@@ -51,6 +52,11 @@ struct dgadj_handle {
   size_t nccl_bytes;
   double Dr_nodal[MAXNP * MAXNP];  // host copies of the primal nodal Dr / LIFT
   double LIFT_nodal[MAXNP * 2];
+  double Dr_nodal_f[MAXNP * MAXNP];  // ... and of the enriched space, and the nodal prolongation
+  double LIFT_nodal_f[MAXNP * 2];
+  double P_host[MAXNP * MAXNP];
+  double* bgf_consts;   // dgadj_burgers_fwd_adj: element widths + functional weights
+  size_t bgf_consts_bytes;
   int sm_count, cc_major, cc_minor;
   size_t total_mem;
   int tune_ept, tune_block, tune_grid;

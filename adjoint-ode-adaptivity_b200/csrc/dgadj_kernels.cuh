@@ -18,6 +18,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Checkpoint tiles leave the forward phase either as coalesced STG (0, the default) or through bulk-TMA
+// from a double-buffered park (1; see STORE_HOOK at fwd_step).  Compile-time, because even the untaken
+// hook costs issue slots in the stage loop; the host enables p.tma_store only in a build that has it.
+// MEASURED (B200, config 2, profiles/r2_march_fused_fullsize{,_tma_store_build}_ncu.json): the TMA build
+// removes the lg_throttle stalls as intended (2.9 % -> 0.07 % of the samples) but is 5 % SLOWER overall
+// (1038 ms vs 990 ms per launch; fp64 pipe 67.0 % vs 70.0 %): the residual now takes an STS per value (the
+// MIO queue the stage loop already leans on) instead of an STG, the hooks add 1.6 % executed instructions
+// to the stage loops, and the doubled park costs 4 registers of the 254.  The STG form stays the product.
+#ifndef DGADJ_TMA_STORE_PATH
+#define DGADJ_TMA_STORE_PATH 0
+#endif
+
 namespace dgadj {
 
 constexpr int MAXNP = 10;      // enriched space of N = 8
@@ -113,6 +125,8 @@ struct MarchParams {
   int eta_acc;
   int n0;
   int in_modal, out_modal;   // the input state / uT are modal coefficients (window hand-over: no V^-1 V round trip)
+  int tma_store;             // forward checkpoints leave through bulk-TMA from a double-buffered park (host: fits, not warp_local)
+  int vec_io;                // every [B][Np][K] pointer is 16-byte aligned and EPT is even: 128-bit state I/O
 };
 
 struct KArgs {
@@ -126,8 +140,9 @@ enum { FUNC_LINEAR = 0, FUNC_INT_U2 = 1 };
 enum { VAR_FWD = 0, VAR_FWD_RESID = 1, VAR_ADJ = 2, VAR_FUSED = 3 };
 
 // shared memory: 16-byte mbarrier header, then doubles tr[4][BD] coef[6*EPT][BD] big[nbig*EPT][BD]
-__host__ __device__ constexpr size_t march_smem_bytes(int NP, int EPT, int BD, int variant) {
-  const int nbig = (variant == VAR_FWD) ? 0 : NP + 1;
+// nbuf = 2: the park / residual tile is double buffered (bulk-TMA checkpoint stores, see march_kernel)
+__host__ __device__ constexpr size_t march_smem_bytes(int NP, int EPT, int BD, int variant, int nbuf = 1) {
+  const int nbig = (variant == VAR_FWD) ? 0 : (NP + 1) * nbuf;
   return 16 + sizeof(double) * (size_t)(4 + (6 + nbig) * EPT) * (size_t)BD;
 }
 
@@ -171,6 +186,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// shared -> global bulk copy (SASS UBLKCP.S.G... the store direction), tracked by bulk async-groups
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -186,6 +210,8 @@ struct Ctx {
   int flags;  // bit0 owns the first element, bit1 owns the last element, bit2 periodic
   uint64_t* trbar;    // mbarrier of the trace exchange (one arrival per warp)
   uint32_t trphase;   // its phase parity
+  double* ck;         // this CTA's checkpoint slot (tiles [S][NPF][EPT][BD])
+  double* big;        // park / residual tile area in shared memory
 };
 
 #ifndef DGADJ_SPLIT_BARRIER
@@ -281,7 +307,14 @@ __device__ __forceinline__ void traces(const double (&pv)[MAXNP], const MVec<NPX
 //     se = g1 + g0 (even modes), so = g1 - g0 (odd modes)
 // (the rka multiply is absorbed by the stage scaling described at ConstOps).
 // coef = this thread's smem column of the level: {m, q0, q1} x EPT, each a row of BD.
-template <int NPX, int LV, int EPT>
+// STORE_HOOK (bulk-TMA checkpoint stores, p.tma_store): the residual tile of step n-1 was completed in
+// the park buffer (n-1)&1 by every thread before it arrived at this step's first trace barrier, so
+//   LV = 1 (the fine step, first of a step): after the first wait, thread 0 hands that buffer to the TMA unit;
+//   LV = 0 (the coarse step, second):        before its first arrive, thread 0 waits until the TMA unit has
+//                                            read the buffer -- every thread that passes this barrier may
+//                                            overwrite it (it does at the top of step n+1).
+// No barrier is added: the store rides on the exchanges the stages need anyway.
+template <int NPX, int LV, int EPT, bool STORE_HOOK = false, int TILE_ELEMS = 0>
 __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __restrict__ tr,
                                          const double* __restrict__ coef, MVec<NPX> (&z)[EPT],
                                          MVec<NPX> (&r)[EPT], long long b, double time, int n) {
@@ -297,6 +330,7 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
     double* tB = tA + 2 * cx.BD;       // right-edge values u(+1) of the thread's last element
     tA[cx.tid] = uF[0];
     tB[cx.tid] = uB[EPT - 1];
+    if (DGADJ_TMA_STORE_PATH && STORE_HOOK && LV == 0 && s == 0 && ka.p.tma_store && cx.tid == 0) tma_store_wait_read();
     trace_arrive(cx, ka.p.warp_local);
     // volume terms (no neighbour data): r^_i += sum_{j = i+1, i+3, ...} D^_ij u^_j, walked by
     // diagonals (j - i = 1, 3, ...) so that consecutive DFMA hit different accumulators: no
@@ -311,6 +345,10 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
       }
     }
     trace_wait(cx, ka.p.warp_local);
+    if (DGADJ_TMA_STORE_PATH && STORE_HOOK && LV == 1 && s == 0 && n > 0 && ka.p.tma_store && cx.tid == 0) {
+      const size_t tile = (size_t)TILE_ELEMS * cx.BD;
+      tma_bulk_s2g(cx.ck + (size_t)(n - 1) * tile, cx.big + (size_t)((n - 1) & 1) * tile, (uint32_t)(tile * sizeof(double)));
+    }
     double uL = tB[cx.nbL];
     double uR = tA[cx.nbR];
     cx.par ^= 1;
@@ -409,6 +447,47 @@ static __device__ __noinline__ double traj_sum(double* red, int tid, int KT, boo
   }
   __syncthreads();
   return s;
+}
+
+// The thread's EPT adjacent elements of the rows of a [.][NPX][K] field: row i at base + i*K, elements
+// contiguous.  vec (uniform; host-checked 16-byte alignment, EPT even): 128-bit accesses -- a warp then
+// reads whole 128-byte lines instead of touching 32 sectors for 8 useful bytes each.
+template <int NPX, int EPT>
+__device__ __forceinline__ void load_rows(const double* base, size_t K, bool active, int vec, double (&u)[EPT][NPX]) {
+  if (EPT % 2 == 0 && vec) {
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+#pragma unroll
+      for (int e = 0; e < EPT; e += 2) {
+        const double2 t = active ? *reinterpret_cast<const double2*>(base + (size_t)i * K + e) : make_double2(0.0, 0.0);
+        u[e][i] = t.x;
+        u[e + 1 < EPT ? e + 1 : e][i] = t.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+      for (int i = 0; i < NPX; ++i) u[e][i] = active ? base[(size_t)i * K + e] : 0.0;
+    }
+  }
+}
+template <int NPX, int EPT>
+__device__ __forceinline__ void store_rows(double* base, size_t K, int vec, const double (&u)[EPT][NPX]) {
+  if (EPT % 2 == 0 && vec) {
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+#pragma unroll
+      for (int e = 0; e < EPT; e += 2)
+        *reinterpret_cast<double2*>(base + (size_t)i * K + e) = make_double2(u[e][i], u[e + 1 < EPT ? e + 1 : e][i]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+      for (int i = 0; i < NPX; ++i) base[(size_t)i * K + e] = u[e][i];
+    }
+  }
 }
 
 // dense Np x Np change of basis at the ends of a march (once per trajectory, not a hot loop)
@@ -517,6 +596,10 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
     }
     const size_t slot = p.ckpt_by_block ? (size_t)blockIdx.x : (size_t)g;
     double* ck = p.ckpt ? p.ckpt + slot * (size_t)p.S * tile : nullptr;
+    if (DGADJ_TMA_STORE_PATH) {
+      cx.ck = ck;
+      cx.big = sm_big;
+    }
     const size_t gofs = (size_t)bs * NP * K + k0;  // this thread's column in [B][NP][K]
 
     MVec<NP> z[EPT];  // primal modal state (at the end of the forward phase: u^(T))
@@ -524,16 +607,15 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
     {
       // nodal input (u0, or the terminal primal of an adjoint-only call) -> modal
       const double* src = DO_FWD ? p.u0 : p.uT_in;
+      double un[EPT][NP];
+      load_rows<NP, EPT>(src + gofs, (size_t)K, active, p.vec_io, un);
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
-        double u[NP];
-#pragma unroll
-        for (int i = 0; i < NP; ++i) u[i] = active ? src[gofs + (size_t)i * K + e] : 0.0;
         if (p.in_modal) {
 #pragma unroll
-          for (int i = 0; i < NP; ++i) z[e].v[i] = u[i];
+          for (int i = 0; i < NP; ++i) z[e].v[i] = un[e][i];
         } else {
-          apply_matrix<NP, false>(c.iV, u, z[e].v);
+          apply_matrix<NP, false>(c.iV, un[e], z[e].v);
         }
       }
     }
@@ -547,9 +629,11 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
         }
       }
       double time = p.t0 + (p.n0 ? p.n0 * (p.dt_arr ? p.dt_arr[bs] : p.dt) : 0.0);
-      double* park = sm_big + tid;  // element e, row i at park[(i*EPT + e)*BD]
 #pragma unroll 1
       for (int n = 0; n < p.S; ++n) {
+        // element e, row i at park[(i*EPT + e)*BD]; with bulk-TMA checkpoint stores the park alternates
+        // between two buffers: step n's residual tile leaves from buffer n&1 while step n+1 fills the other
+        double* park = sm_big + tid + ((DGADJ_TMA_STORE_PATH && RESID && p.tma_store && (n & 1)) ? tile : (size_t)0);
         if (RESID) {
           // fine one-step image of the injected coarse state: sigma = Phi_f(P u^n); in the modal
           // basis P u^n is (u^, 0).  The coarse state waits in the park meanwhile.
@@ -562,7 +646,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
             rf[e].zero();
             z[e].store(park + (size_t)e * BD, cstride);
           }
-          fwd_step<NPF, 1, EPT>(ka, cx, sm_tr, sm_coef + (size_t)3 * EPT * BD, f, rf, bs, time, n);
+          fwd_step<NPF, 1, EPT, true, NPF * EPT>(ka, cx, sm_tr, sm_coef + (size_t)3 * EPT * BD, f, rf, bs, time, n);
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
             z[e].load(park + (size_t)e * BD, cstride);
@@ -575,18 +659,32 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
           MVec<NP> r[EPT];
 #pragma unroll
           for (int e = 0; e < EPT; ++e) r[e].zero();
-          fwd_step<NP, 0, EPT>(ka, cx, sm_tr, sm_coef, z, r, bs, time, n);
+          fwd_step<NP, 0, EPT, RESID, NPF * EPT>(ka, cx, sm_tr, sm_coef, z, r, bs, time, n);
         }
         time += p.dt_arr ? p.dt_arr[bs] : p.dt;  // `time = time+dt` accumulation of the mlx
         if (RESID) {
-          // rho^n = P u^{n+1} - sigma  -> checkpoint tile [n][row][e][tid]  (coalesced)
-          double* dst = ck + (size_t)n * tile + tid;
+          // rho^n = P u^{n+1} - sigma  -> checkpoint tile [n][row][e][tid]
+          if (DGADJ_TMA_STORE_PATH && p.tma_store) {
+            // completed in place in the park (already the tile's layout); the TMA unit takes it to the ring
+            // after the next trace barrier (STORE_HOOK in fwd_step) -- no store instruction per value
 #pragma unroll
-          for (int e = 0; e < EPT; ++e) {
+            for (int e = 0; e < EPT; ++e) {
 #pragma unroll
-            for (int i = 0; i < NPF; ++i) {
-              const size_t o = (size_t)(i * EPT + e) * BD;
-              dst[o] = ((i < NP) ? z[e].v[i < NP ? i : 0] : 0.0) - park[o];
+              for (int i = 0; i < NPF; ++i) {
+                const size_t o = (size_t)(i * EPT + e) * BD;
+                park[o] = ((i < NP) ? z[e].v[i < NP ? i : 0] : 0.0) - park[o];
+              }
+            }
+            fence_proxy_async();   // generic-proxy writes -> visible to the async proxy (the TMA read)
+          } else {
+            double* dst = ck + (size_t)n * tile + tid;   // coalesced STG
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+              for (int i = 0; i < NPF; ++i) {
+                const size_t o = (size_t)(i * EPT + e) * BD;
+                dst[o] = ((i < NP) ? z[e].v[i < NP ? i : 0] : 0.0) - park[o];
+              }
             }
           }
         }
@@ -601,19 +699,26 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
           }
         }
       }
+      if (DGADJ_TMA_STORE_PATH && RESID && p.tma_store && p.S >= 1) {
+        // the last residual tile: no later trace barrier to ride on
+        __syncthreads();
+        if (tid == 0) {
+          tma_bulk_s2g(ck + (size_t)(p.S - 1) * tile, sm_big + (size_t)((p.S - 1) & 1) * tile, tile_bytes);
+          tma_store_wait_all();   // all tiles of this trajectory are in global memory (the adjoint phase /
+        }                         // the next group's park writes follow a __syncthreads)
+      }
       if (p.uT && active) {
+        double un[EPT][NP];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-          double u[NP];
           if (p.out_modal) {
 #pragma unroll
-            for (int i = 0; i < NP; ++i) u[i] = z[e].v[i];
+            for (int i = 0; i < NP; ++i) un[e][i] = z[e].v[i];
           } else {
-            apply_matrix<NP, false>(c.V, z[e].v, u);
+            apply_matrix<NP, false>(c.V, z[e].v, un[e]);
           }
-#pragma unroll
-          for (int i = 0; i < NP; ++i) p.uT[gofs + (size_t)i * K + e] = u[i];
         }
+        store_rows<NP, EPT>(p.uT + gofs, (size_t)K, p.vec_io, un);
       }
     }
 
@@ -692,13 +797,12 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
         for (int e = 0; e < EPT; ++e) {
           if (p.eta) p.eta[(size_t)b * K + k0 + e] = eta[e];
           if (p.mu_out) mu[e].store(p.mu_out + (size_t)b * NPF * K + k0 + e, (size_t)K);
-          if (p.lam0) {
-            double lu[NPF];
-            apply_matrix<NPF, true>(c.iVf, mu[e].v, lu);  // lam = V_f^-T mu
-            double* l0 = p.lam0 + (size_t)b * NPF * K + k0 + e;
+        }
+        if (p.lam0) {
+          double lu[EPT][NPF];
 #pragma unroll
-            for (int i = 0; i < NPF; ++i) l0[(size_t)i * K] = lu[i];
-          }
+          for (int e = 0; e < EPT; ++e) apply_matrix<NPF, true>(c.iVf, mu[e].v, lu[e]);  // lam = V_f^-T mu
+          store_rows<NPF, EPT>(p.lam0 + (size_t)b * NPF * K + k0, (size_t)K, p.vec_io, lu);
         }
       }
     }
@@ -708,7 +812,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
 #endif  // __CUDACC__ && DGADJ_DEVICE_CODE
 
 // host-callable launcher exported by each per-order object (dgadj_march_np.cu, -DDGADJ_NP=n)
-typedef cudaError_t (*march_launch_fn)(int variant, int ept, int grid, int block, cudaStream_t stream,
+typedef cudaError_t (*march_launch_fn)(int variant, int ept, int grid, int block, size_t smem, cudaStream_t stream,
                                        const KArgs* ka);
 
 }  // namespace dgadj

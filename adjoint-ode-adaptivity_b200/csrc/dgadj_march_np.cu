@@ -11,12 +11,12 @@
 namespace dgadj {
 
 template <int NP, int EPT, int BDT, bool F, bool R, bool A>
-static cudaError_t launch_bd(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
+static cudaError_t launch_bd(int variant, int grid, int block, size_t smem, cudaStream_t stream, const KArgs* ka) {
   // the opt-in shared-memory size is a per-device function attribute: remembered per (instantiation,
   // device), so that a process with handles on several GPUs sets it on each of them
   static bool attr_set[64] = {};
   if (block > MAXBD / EPT) return cudaErrorInvalidConfiguration;
-  const size_t smem = march_smem_bytes(NP, EPT, block, variant);
+  if (smem < march_smem_bytes(NP, EPT, block, variant)) return cudaErrorInvalidConfiguration;
   auto kern = march_kernel<NP, EPT, BDT, F, R, A>;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -35,32 +35,32 @@ static cudaError_t launch_bd(int variant, int grid, int block, cudaStream_t stre
 
 // the hot variants (forward, fused) also exist with the two common block sizes baked in
 template <int NP, int EPT, bool F, bool R, bool A>
-static cudaError_t launch_one(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
+static cudaError_t launch_one(int variant, int grid, int block, size_t smem, cudaStream_t stream, const KArgs* ka) {
   if (F && R == A) {
-    if (block == MAXBD / EPT) return launch_bd<NP, EPT, MAXBD / EPT, F, R, A>(variant, grid, block, stream, ka);
-    if (block == MAXBD / EPT / 2) return launch_bd<NP, EPT, MAXBD / EPT / 2, F, R, A>(variant, grid, block, stream, ka);
+    if (block == MAXBD / EPT) return launch_bd<NP, EPT, MAXBD / EPT, F, R, A>(variant, grid, block, smem, stream, ka);
+    if (block == MAXBD / EPT / 2) return launch_bd<NP, EPT, MAXBD / EPT / 2, F, R, A>(variant, grid, block, smem, stream, ka);
   }
-  return launch_bd<NP, EPT, 0, F, R, A>(variant, grid, block, stream, ka);
+  return launch_bd<NP, EPT, 0, F, R, A>(variant, grid, block, smem, stream, ka);
 }
 
 template <int EPT>
-static cudaError_t launch_ept(int variant, int grid, int block, cudaStream_t stream, const KArgs* ka) {
+static cudaError_t launch_ept(int variant, int grid, int block, size_t smem, cudaStream_t stream, const KArgs* ka) {
   switch (variant) {
-    case VAR_FWD: return launch_one<DGADJ_NP, EPT, true, false, false>(variant, grid, block, stream, ka);
+    case VAR_FWD: return launch_one<DGADJ_NP, EPT, true, false, false>(variant, grid, block, smem, stream, ka);
 #if DGADJ_NP + 1 <= 10  // the enriched space must fit MAXNP
-    case VAR_FWD_RESID: return launch_one<DGADJ_NP, EPT, true, true, false>(variant, grid, block, stream, ka);
-    case VAR_ADJ: return launch_one<DGADJ_NP, EPT, false, false, true>(variant, grid, block, stream, ka);
-    case VAR_FUSED: return launch_one<DGADJ_NP, EPT, true, true, true>(variant, grid, block, stream, ka);
+    case VAR_FWD_RESID: return launch_one<DGADJ_NP, EPT, true, true, false>(variant, grid, block, smem, stream, ka);
+    case VAR_ADJ: return launch_one<DGADJ_NP, EPT, false, false, true>(variant, grid, block, smem, stream, ka);
+    case VAR_FUSED: return launch_one<DGADJ_NP, EPT, true, true, true>(variant, grid, block, smem, stream, ka);
 #endif
     default: return cudaErrorInvalidValue;
   }
 }
 
-cudaError_t DGADJ_CAT(march_launch_np, DGADJ_NP)(int variant, int ept, int grid, int block,
+cudaError_t DGADJ_CAT(march_launch_np, DGADJ_NP)(int variant, int ept, int grid, int block, size_t smem,
                                                  cudaStream_t stream, const KArgs* ka) {
-  if (ept == 1) return launch_ept<1>(variant, grid, block, stream, ka);
-  if (ept == 2) return launch_ept<2>(variant, grid, block, stream, ka);
-  if (ept == 4) return launch_ept<4>(variant, grid, block, stream, ka);
+  if (ept == 1) return launch_ept<1>(variant, grid, block, smem, stream, ka);
+  if (ept == 2) return launch_ept<2>(variant, grid, block, smem, stream, ka);
+  if (ept == 4) return launch_ept<4>(variant, grid, block, smem, stream, ka);
   return cudaErrorInvalidValue;
 }
 

@@ -294,6 +294,47 @@ int dgadj_burgers_adjoint(dgadj_handle* h, int64_t B, int32_t S, double dt, cons
                           const uint8_t* lim0_dev, const int32_t* amax_dev, const double* maxvel_dev,
                           double* lam0_dev, double* J_dev, void* stream);
 
+/* BASELINE config 3 as ONE call: the limited Burgers march above, its reverse-time discrete adjoint and the
+ * per-element error indicator, fused in one persistent kernel (one CTA takes a trajectory forward and then
+ * immediately backward).  Forward states are checkpointed into a per-CTA ring owned by the handle
+ * (#CTAs x S x state -- never B x S, so T past shock formation fits at the full batch) and streamed back
+ * with bulk-TMA; nothing else is recorded: the adjoint phase takes each step again from its checkpoint
+ * with the same stage routine (the same bits, hence the same limiter flags, minmod branches, wave speeds
+ * and argmax) and transposes it.
+ *   indicator = 0: the adjoint of the march itself.  lam0_dev[B][Np][K] = dJ/du0 (what
+ *     dgadj_burgers_adjoint gives), J = sum jw o u(T); eta_dev must be NULL.
+ *   indicator = 1 (needs dgadj_set_enriched and the enriched-space arrays below): conventions of
+ *     matlab/MAIN.m:34 (adjoint one order higher), matlab/adj_march.m:103-117 (err(k) = v_k' * residual)
+ *     and errEst (python/Main_finite_difference.py:79-94), in the nonlinear form of SURVEY App. E.5:
+ *       rho^n = P u^{n+1} - Phi_f(P u^n)   (Phi_f: the same limited LSERK4 step at order N+1)
+ *       lam_f^n = Phi_f'(P u^n)^T lam_f^{n+1},  lam_f^S = jwF   (frozen branches of those steps)
+ *       eta_dev[b][k] = sum_n lam_f^{n+1}_k . rho^n_k   (signed);  lam0_dev[B][Np+1][K] = lam_f^0.
+ *   nlim_dev[B] (or NULL): limiter activations (cell, stage) of the forward march;
+ *   status_dev[B] (or NULL): per-trajectory status word, bit 0 = a non-finite value in u(T).
+ * Any output may be NULL.  Shapes whose stage states exceed shared memory (DGADJ_ERR_UNSUPPORTED) go
+ * through dgadj_burgers_forward / dgadj_burgers_adjoint.                                              */
+typedef struct {
+  int64_t B;              /* trajectories */
+  int32_t S;              /* LSERK4 steps */
+  int32_t limit;          /* 0 none, 1 SlopeLimitN, 2 SlopeLimit1 (as dgadj_burgers_forward) */
+  int32_t indicator;      /* 0 / 1, see above */
+  int32_t reserved;
+  double dt;              /* time step; dt_dev[B] overrides it per trajectory when not NULL */
+  const double* dt_dev;
+  double tvb_M;           /* M of utils/minmodB.m:6-11; 0 = plain minmod */
+  const double* invV_host; const double* V_host; const double* x_host;      /* primal StartUp1D arrays */
+  const double* jw_host;                                                     /* [Np*K] weights of J */
+  const double* invVF_host; const double* VF_host; const double* xF_host;   /* enriched space (indicator) */
+  const double* jwF_host;                                                    /* [(Np+1)*K] */
+} dgadj_burgers_args;
+int dgadj_burgers_fwd_adj(dgadj_handle* h, const dgadj_burgers_args* args, const double* u0_dev, double* uT_dev,
+                          double* J_dev, double* lam0_dev, double* eta_dev, int32_t* nlim_dev,
+                          uint32_t* status_dev, void* stream);
+/* Launch shape of that kernel for a batch of B: elements per thread, threads per CTA, CTAs, dynamic shared
+ * memory, bytes of the state ring per time step (ring = that x S).                                     */
+int dgadj_burgers_plan(dgadj_handle* h, int64_t B, int32_t indicator, int32_t* ept, int32_t* block,
+                       int32_t* grid, int64_t* smem_bytes, int64_t* ring_bytes_per_step);
+
 /* Register-only DFMA microbenchmark: sustained fp64 FMA-pipe peak of the handle's device
  * in TFLOP/s (the roofline denominator SURVEY section 8(d) asks to be measured).        */
 int dgadj_measure_dfma_peak(dgadj_handle* h, double seconds, double* tflops_out,

@@ -221,3 +221,86 @@ def burgers_adjoint(rec, g, dt, lamT, bc=BC_PERIODIC):
         lu = lu + dt * BurgersRHS1D_T(lk, st, g, bc)
         lk = ops.rk4a[s] * lk
     return limiter_T(lu, rec["ids0"], rec["br0"], g, periodic)
+
+
+# ----------------------------------------------------------------------------------
+# Per-element indicator of the limited Burgers march (build-specified; PARITY UNPINNED), the nonlinear
+# form of SURVEY App. E.5 and of the reference's estimators (matlab/MAIN.m:34 solves the adjoint at
+# order Ns+1; matlab/adj_march.m:103-117: err(k) = v_k' * residual; errEst,
+# python/Main_finite_difference.py:79-94: res[n] = u_f[n] - fwdUpdate(u_f, dt_f, n), err = res*v):
+#   rho^n   = P u^{n+1} - Phi_f(P u^n)          enriched-space (order N+1) one-step residual of the coarse
+#                                               march; Phi_f = the same limited LSERK4 step at order N+1;
+#                                               P = nodal prolongation V_f(:,1:Np) inv(V_c)
+#   lam_f^n = Phi_f'(P u^n)^T lam_f^{n+1}       enriched-space discrete adjoint, linearised at the prolonged
+#                                               coarse states on the frozen limiter / minmod / argmax
+#                                               branches of those steps;  lam_f^S = jw_f
+#   eta_k   = sum_n lam_f^{n+1}_k . rho^n_k
+# so that sum_k eta_k = J_f(P u_c^S) - J_f(u_f^S) to first order in the residuals (u_f = the enriched
+# march of P u_c^0) -- an identity for a linear problem (oracle/advec.py).  The coarse-space adjoint
+# (burgers_adjoint above: the exact gradient of the coarse march) does NOT give a usable estimate: it
+# differs from lam_f most in the modes the residual lives in (tests/test_oracle_golden.py).
+# ----------------------------------------------------------------------------------
+def burgers_step_record(u, g, dt, bc=BC_PERIODIC):
+    """One limited LSERK4 step from u (no limiter pass on u itself) keeping what its transpose
+    needs: per stage the input state, limiter flags / branches, location and sign of max|u|."""
+    periodic = bc == BC_PERIODIC
+    u = np.array(u, dtype=float, copy=True)
+    resu = np.zeros_like(u)
+    stages = []
+    for s in range(5):
+        flat = np.abs(u).reshape(u.shape[:-2] + (-1,))
+        am = np.argmax(flat, axis=-1)
+        sg = np.sign(np.take_along_axis(u.reshape(flat.shape), am[..., None], axis=-1))[..., 0]
+        rhs, maxvel = BurgersRHS1D(u, g, bc)
+        resu = ops.rk4a[s] * resu + dt * rhs
+        ut = u + ops.rk4b[s] * resu
+        un, ids, br = limit_with_branches(ut, g, periodic)
+        stages.append(dict(u=u, am=am, sg=sg, maxvel=maxvel, ids=ids, br=br, s=s))
+        u = un
+    return u, stages
+
+
+def burgers_step_T(lu, stages, g, dt, bc=BC_PERIODIC):
+    """Transpose of the linearised step recorded by burgers_step_record (the RK residual starts and
+    ends a step with weight zero: rk4a[0] = 0)."""
+    periodic = bc == BC_PERIODIC
+    lk = np.zeros_like(lu)
+    for st in reversed(stages):
+        s = st["s"]
+        lu = limiter_T(lu, st["ids"], st["br"], g, periodic)
+        lk = lk + ops.rk4b[s] * lu
+        lu = lu + dt * BurgersRHS1D_T(lk, st, g, bc)
+        lk = ops.rk4a[s] * lk
+    return lu
+
+
+def prolongation(gc, gf):
+    """P[NpF, Np] = V_f(:, 1:Np) inv(V_c)."""
+    return gf.V[:, :gc.Np] @ gc.invV
+
+
+def burgers_fwd_adj_indicator(u0, gc, gf, dt, nsteps, jw_c, jw_f, bc=BC_PERIODIC):
+    """One trajectory (u0: (Np, K)).  Returns dict(uT, J, lam0[NpF, K], eta[K], eta_scale[K], nlim,
+    fine=[per step: the enriched step's record]): coarse limited march (SlopeLimitN on the initial state
+    and after every stage, as burgers_march), J = sum jw_c o u(T), enriched adjoint and indicator as
+    specified above; nlim = number of (cell, stage) limiter activations of the coarse march."""
+    periodic = bc == BC_PERIODIC
+    P = prolongation(gc, gf)
+    u, ids0, _ = limit_with_branches(np.array(u0, dtype=float), gc, periodic)
+    states, nlim = [u], int(np.sum(ids0)) * 0
+    for _ in range(nsteps):
+        u, st = burgers_step_record(u, gc, dt, bc)
+        nlim += int(sum(int(np.sum(q["ids"])) for q in st))
+        states.append(u)
+    lam = np.array(jw_f, dtype=float, copy=True)
+    K = gc.K
+    eta, scale, fine = np.zeros(K), np.zeros(K), []
+    for n in range(nsteps - 1, -1, -1):
+        uf1, stf = burgers_step_record(P @ states[n], gf, dt, bc)
+        rho = P @ states[n + 1] - uf1
+        eta += np.sum(lam * rho, axis=0)
+        scale += np.sum(np.abs(lam) * np.abs(rho), axis=0)
+        lam = burgers_step_T(lam, stf, gf, dt, bc)
+        fine.append(stf)
+    return dict(uT=states[-1], J=float(np.sum(jw_c * states[-1])), lam0=lam, eta=eta,
+                eta_scale=scale + 1e-300, nlim=nlim, fine=fine[::-1], states=states)

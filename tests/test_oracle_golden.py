@@ -307,3 +307,53 @@ def test_burgers_oracle_properties():
     uA, _, flA, _ = burgers.burgers_march(u0, g, dt, 5, limit=True)
     uB, _, _, _ = burgers.burgers_march(u0, g, dt, 5, limit=False)
     assert flA.mean() < 0.1 and np.max(np.abs(uA - uB)) < 1e-2
+
+
+def test_burgers_indicator_effectivity_and_adjoint_identities():
+    """The Burgers indicator of oracle/burgers.py (build-specified, the nonlinear form of SURVEY App. E.5):
+    with the limiter out of the way the map is smooth and sum_k eta_k must equal J_f(P u_c^S) - J_f(u_f^S)
+    to first order in the residuals; with the COARSE adjoint in its place the estimate has the wrong
+    sign -- which is why the adjoint is taken one order higher (matlab/MAIN.m:34).  With the limiter on:
+    the step recorder reproduces burgers_march, and for J = mass (conserved by the enriched march) the
+    enriched adjoint stays the weight vector through the frozen-branch transposes."""
+    N, K = 2, 10
+    gc, gf = ops.startup_uniform(N, -1.0, 1.0, K), ops.startup_uniform(N + 1, -1.0, 1.0, K)
+    P = burgers.prolongation(gc, gf)
+    u0 = 0.2 + 0.5 * np.sin(np.pi * gc.x + 0.3)
+    dt = 0.25 * np.min(np.abs(gc.x[0] - gc.x[1])) / 2.0
+    wq = lambda g: (ops.mass_matrix(g.V) @ np.ones(g.Np))[:, None] * g.J
+    jc, jf = wq(gc) * np.cos(2 * gc.x), wq(gf) * np.cos(2 * gf.x)
+    saved = burgers.limit_with_branches
+    try:
+        burgers.limit_with_branches = lambda u, g, p: (u, np.zeros(u.shape[-1], bool), np.zeros(u.shape[-1], int))
+        for S in (5, 17, 37):
+            out = burgers.burgers_fwd_adj_indicator(u0, gc, gf, dt, S, jc, jf)
+            uf = P @ u0
+            for _ in range(S):
+                uf, _ = burgers.burgers_step_record(uf, gf, dt)
+            dJ = np.sum(jf * (P @ out["uT"])) - np.sum(jf * uf)
+            assert out["eta"].sum() == pytest.approx(dJ, rel=0.08)
+            # the coarse-space adjoint weighting the restricted residual: not an estimate of anything
+            if S == 5:
+                R = gc.V @ np.eye(gc.Np, gf.Np) @ gf.invV
+                lam, est = jc.copy(), 0.0
+                st = out["states"]
+                for n in range(S - 1, -1, -1):
+                    un1, stages = burgers.burgers_step_record(st[n], gc, dt)
+                    est += np.sum(lam * (st[n + 1] - R @ burgers.burgers_step_record(P @ st[n], gf, dt)[0]))
+                    lam = burgers.burgers_step_T(lam, stages, gc, dt)
+                ut = st[0]
+                for _ in range(S):
+                    ut = R @ burgers.burgers_step_record(P @ ut, gf, dt)[0]
+                dJ2 = np.sum(jc * out["uT"]) - np.sum(jc * ut)
+                assert est * dJ2 < 0
+    finally:
+        burgers.limit_with_branches = saved
+    # limiter on
+    S = 40
+    out = burgers.burgers_fwd_adj_indicator(u0, gc, gf, dt, S, wq(gc), wq(gf))
+    uT, _, flags, _ = burgers.burgers_march(u0, gc, dt, S)
+    assert np.array_equal(out["uT"], uT) and out["nlim"] == int(flags.sum()) and out["nlim"] > 0
+    assert np.max(np.abs(out["lam0"] - wq(gf))) < 1e-13
+    rec = burgers.burgers_record(u0, gc, dt, S)
+    assert np.array_equal(rec["uT"], uT)
