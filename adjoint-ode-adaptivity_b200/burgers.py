@@ -157,7 +157,8 @@ class BurgersDG1D:
         (adjoint one order higher, matlab/MAIN.m:34; err(k) = v_k' * residual, matlab/adj_march.m:103-117).
         Forward states go to a per-CTA ring on the device (no [B, S+1, Np, K] history), so marches past shock
         formation fit at the full batch.  J = int psi(x) u(x,T) dx (psi = 1 by default).
-        Returns dict(uT, J[B], lam0, nlim[B] int32, status[B] int32[, eta[B, K]]):
+        Returns dict(uT, J[B], lam0, nlim[B, 2] int32 (limiter activations of the march / of the steps the adjoint
+        phase takes again), status[B] int32[, eta[B, K]]):
           indicator=False: lam0[B, Np, K] = dJ/du0 of the march (what `adjoint` gives);
           indicator=True:  lam0[B, Np+1, K] = the enriched adjoint at t = 0, eta signed (consumers take abs)."""
         torch = self.torch
@@ -192,7 +193,7 @@ class BurgersDG1D:
             a.invVF_host, a.VF_host, a.xF_host, a.jwF_host = p(of["invV"]), p(of["V"]), p(of["x"]), p(jwf)
             NpX = self.Np + 1
         kw = dict(dtype=torch.float64, device=u0.device)
-        out = dict(J=torch.empty(B, **kw), nlim=torch.empty(B, dtype=torch.int32, device=u0.device),
+        out = dict(J=torch.empty(B, **kw), nlim=torch.empty((B, 2), dtype=torch.int32, device=u0.device),
                    status=torch.empty(B, dtype=torch.int32, device=u0.device))
         if want_uT:
             out["uT"] = torch.empty_like(u0)

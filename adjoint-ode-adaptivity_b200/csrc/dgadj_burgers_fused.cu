@@ -30,6 +30,18 @@
 
 #include "dgadj_internal.h"
 
+// resident CTAs per SM the kernels are compiled for (register budget = 65536 / (threads x CTAs))
+// Measured at config 3 (N = 4, K = 256, two elements per thread, 128 threads): the march with the adjoint in its
+// own space fits 128 registers with 80 B of spills and gains 8 % from the fourth CTA (4.71 -> 5.08e10
+// updates/s); the enriched step of indicator mode spills 336 B there and loses 10 % (4.09 -> 3.68e10).
+#ifndef BG_MINB128_IND
+#define BG_MINB128_IND 3
+#endif
+#ifndef BG_MINB128_PLAIN
+#define BG_MINB128_PLAIN 4
+#endif
+#define BG_MINB(BD, IND) ((BD) <= 128 ? ((IND) ? BG_MINB128_IND : BG_MINB128_PLAIN) : 1)
+
 namespace dgadj {
 
 struct BgLevel {               // one polynomial space: primal (order N) or enriched (order N+1)
@@ -56,7 +68,7 @@ struct BgFusedArgs {
   double* J;                   // [B] or null
   double* lam0;                // [B][NPX][K] or null
   double* eta;                 // [B][K] (IND) or null
-  int* nlim;                   // [B] limiter activations (cell, stage) of the coarse march, or null
+  int* nlim;                   // [B][2] limiter activations (cell, stage): the march; the steps taken again by the adjoint phase
   unsigned* status;            // [B] bit 0: non-finite state, or null
   double* ring;                // [grid][S][NP][EPT][BD]
   double rka[5], rkb[5];
@@ -100,6 +112,24 @@ __device__ __forceinline__ double warp_max_nn(double m) {   // values >= 0 or ex
   return __hiloint2double(mh, (int)ml);
 }
 
+// mbarrier wait that lets the hardware suspend the warp for up to `ns` before the test returns: fewer spin
+// iterations (each one costs issue slots of the scheduler the partner warps run on)
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(ns)
+        : "memory");
+  } while (!done);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // per-thread context
 // ------------------------------------------------------------------------------------------------------
@@ -123,9 +153,15 @@ struct BgCtx {
   }
   __device__ __forceinline__ void wait() {
     if (NW > 1) {
-      mbar_wait(bar, phase);
+      mbar_wait_suspend(bar, phase, 2000u);
       phase ^= 1u;
     }
+  }
+  // an exchange with nothing to do between publishing and reading: the hardware barrier parks the warp
+  // instead of spinning on the mbarrier (spin iterations cost issue slots the other warps can use)
+  __device__ __forceinline__ void sync() {
+    if (NW > 1) __syncthreads();
+    else __syncwarp();
   }
   __device__ __forceinline__ double* A() const { return exA + par * BDP; }
   __device__ __forceinline__ double* Bb() const { return exB + par * BDP; }
@@ -171,8 +207,7 @@ __device__ __forceinline__ void bg_limiter(const BgFusedArgs& p, const BgLevel& 
   eB[cx.tid] = v[EPT - 1];
   if (cx.gfirst) eB[BD] = v[0];             // quirk C-16: ghost averages copy the end cells (SlopeLimitN.m:18)
   if (cx.glast) eA[BD + 1] = v[EPT - 1];
-  cx.arrive();
-  cx.wait();
+  cx.sync();
   const double vmL = eB[cx.nbL], vpR = eA[cx.nbR];
   cx.par ^= 1;
 #pragma unroll
@@ -344,8 +379,7 @@ __device__ __forceinline__ double bg_block_sum(BgCtx<BD>& cx, double v) {
   if (NW == 1) return v;
   double* wr = cx.W();
   if (cx.lane == 0) wr[cx.wid] = v;
-  cx.arrive();
-  cx.wait();
+  cx.sync();
   double t = wr[0];
 #pragma unroll
   for (int w = 1; w < NW; ++w) t += wr[w];
@@ -379,8 +413,7 @@ __device__ __forceinline__ void bg_limiter_T(const BgFusedArgs& p, const BgLevel
   double* eB = cx.Bb();
   eA[cx.tid] = tl[0];         // for the left neighbour's last cell
   eB[cx.tid] = tr[EPT - 1];   // for the right neighbour's first cell
-  cx.arrive();
-  cx.wait();
+  cx.sync();
   double inL = eB[cx.nbL], inR = eA[cx.nbR];
   cx.par ^= 1;
   // end cells of a non-periodic mesh see a copied ghost average: the term comes back to the cell
@@ -400,10 +433,28 @@ __device__ __forceinline__ void bg_limiter_T(const BgFusedArgs& p, const BgLevel
   }
 }
 
+// P u as u_1 + P (u - u_1) (the rows of P sum to 1): a cell the limiter has flattened (all nodal values
+// bitwise equal) stays exactly flat in the enriched space, so the location of max|u| inside it follows the
+// lowest-index rule instead of rounding noise (oracle/burgers.py: prolong)
+template <int NP, int NPX>
+__device__ __forceinline__ void bg_prolong(const double* __restrict__ P, const double (&u)[NP], double (&x)[NPX]) {
+  double d[NP];
+#pragma unroll
+  for (int j = 1; j < NP; ++j) d[j] = u[j] - u[0];
+#pragma unroll
+  for (int i = 0; i < NPX; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 1; j < NP; ++j) acc = fma(P[i * NP + j], d[j], acc);
+    x[i] = u[0] + acc;
+  }
+}
+
 __host__ __device__ constexpr size_t bg_fused_smem(int NP, int NPX, int EPT, int BD) {
   // 16 B mbarriers | exA, exB [2][BD+2] | wred [2][8] | mv [5] (+pad) | cand [2], am [5] (+pad) |
-  // stage states ss [4][NPX][EPT][BD] | landing tile [NP][EPT][BD]
-  return 16 + sizeof(double) * ((size_t)4 * (BD + 2) + 16 + 6 + 4 + (size_t)4 * NPX * EPT * BD + (size_t)NP * EPT * BD);
+  // stage states ss [4][NPX][EPT][BD]; the checkpoint tile [NP][EPT][BD] of the next step lands in ss[3]
+  // while that slot is idle (between the transposes of stage 3 and the next step's stage 3)
+  return 16 + sizeof(double) * ((size_t)4 * (BD + 2) + 16 + 6 + 4 + (size_t)4 * NPX * EPT * BD);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -411,7 +462,7 @@ __host__ __device__ constexpr size_t bg_fused_smem(int NP, int NPX, int EPT, int
 // enriched adjoint + indicator (lam0 = lam_f^0, [NP+1][K]; eta[K]).
 // ------------------------------------------------------------------------------------------------------
 template <int NP, int EPT, int BD, bool IND>
-__global__ void __launch_bounds__(BD, BD <= 128 ? 3 : 1) burgers_fused_kernel(const __grid_constant__ BgFusedArgs p) {
+__global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(const __grid_constant__ BgFusedArgs p) {
   constexpr int NPX = IND ? NP + 1 : NP;
   constexpr int LX = IND ? 1 : 0;
   using Ctx = BgCtx<BD>;
@@ -427,7 +478,7 @@ __global__ void __launch_bounds__(BD, BD <= 128 ? 3 : 1) burgers_fused_kernel(co
   cx.cand = reinterpret_cast<int*>(cx.mv + 6);
   cx.am = cx.cand + 2;
   double* ss = cx.mv + 6 + 4;                                   // [4][NPX][EPT][BD]
-  double* land = ss + (size_t)4 * NPX * EPT * BD;               // [NP][EPT][BD]
+  double* land = ss + (size_t)3 * NPX * EPT * BD;               // [NP][EPT][BD] inside ss[3]
   constexpr size_t tile = (size_t)NP * EPT * BD;
   constexpr uint32_t tile_bytes = (uint32_t)(tile * sizeof(double));
   constexpr size_t sstride = (size_t)NPX * EPT * BD;
@@ -523,7 +574,7 @@ __global__ void __launch_bounds__(BD, BD <= 128 ? 3 : 1) burgers_fused_kernel(co
       if (p.J && tid == 0) p.J[b] = Jt;
       if (p.nlim) {
         const double nl = bg_block_sum<BD>(cx, (double)nlim);
-        if (tid == 0) p.nlim[b] = (int)nl;
+        if (tid == 0) p.nlim[2 * b] = (int)nl;
       }
       if (p.status) {
         const int anybad = __syncthreads_or(bad ? 1 : 0);
@@ -540,21 +591,19 @@ __global__ void __launch_bounds__(BD, BD <= 128 ? 3 : 1) burgers_fused_kernel(co
       tma_bulk_g2s(land, ck + (size_t)(p.S - 1) * tile, tile_bytes, &mbar[0]);
     }
     double lu[EPT][NPX], eta[EPT];
-    // P u^{n+1} of the step being transposed sits in ss[0] of the step done before it; for n = S-1 it is P u^S
-    double pun[EPT][IND ? NPX : 1];
+    int nlim2 = 0;   // limiter activations of the steps taken again (the enriched ones in indicator mode)
+    // P u^{n+1} of the step being transposed sits in ss[0] (left there by the step done before it; P u^S for
+    // n = S-1): a thread's own column, so no exchange is involved
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       eta[e] = 0.0;
 #pragma unroll
       for (int i = 0; i < NPX; ++i) lu[e][i] = cx.in ? p.jw[LX][(size_t)i * K + k0 + e] : 0.0;
       if (IND) {
+        double px[NPX];
+        bg_prolong<NP, NPX>(p.P, u[e], px);
 #pragma unroll
-        for (int i = 0; i < NPX; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < NP; ++j) acc = fma(p.P[i * NP + j], u[e][j], acc);
-          pun[e][i] = acc;
-        }
+        for (int i = 0; i < NPX; ++i) ss[(size_t)(i * EPT + e) * BD + tid] = px[i];
       }
     }
 #pragma unroll 1
@@ -562,6 +611,16 @@ __global__ void __launch_bounds__(BD, BD <= 128 ? 3 : 1) burgers_fused_kernel(co
       double x[EPT][NPX], res[EPT][NPX];
       BgCoef cf[EPT];
       int codes[EPT];   // the step's limiter decisions, 3 bits per stage
+      if (IND) {
+        // eta_k += lam_f^{n+1}_k . rho^n_k with rho^n = P u^{n+1} - Phi_f(P u^n), in two parts: the first
+        // now (P u^{n+1} is about to be overwritten), the second once the step has been taken again
+        const double* s0 = ss + tid;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+          for (int i = 0; i < NPX; ++i) eta[e] = fma(lu[e][i], s0[(size_t)(i * EPT + e) * BD], eta[e]);
+        }
+      }
       mbar_wait(&mbar[0], land_phase & 1u);
       ++land_phase;
       {
@@ -575,13 +634,7 @@ __global__ void __launch_bounds__(BD, BD <= 128 ? 3 : 1) burgers_fused_kernel(co
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
           if (IND) {
-#pragma unroll
-            for (int i = 0; i < NPX; ++i) {
-              double acc = 0.0;
-#pragma unroll
-              for (int j = 0; j < NP; ++j) acc = fma(p.P[i * NP + j], un[e][j], acc);
-              x[e][i] = acc;
-            }
+            bg_prolong<NP, NPX>(p.P, un[e], x[e]);
           } else {
 #pragma unroll
             for (int i = 0; i < NPX; ++i) x[e][i] = un[e][i < NP ? i : 0];
@@ -614,27 +667,17 @@ __global__ void __launch_bounds__(BD, BD <= 128 ? 3 : 1) burgers_fused_kernel(co
         }
         int code[EPT];
         bg_stage<NPX, EPT, BD, true>(p, LXv, cx, k0, cf, x, res, s, code, pend);
-        if (s == 0 && tid == 0 && n >= 1) {
-          // every thread has passed the stage's exchanges, hence consumed the landing tile: refill it
-          // for step n-1; the copy flies during the rest of this step
-          mbar_expect_tx(&mbar[0], tile_bytes);
-          tma_bulk_g2s(land, ck + (size_t)(n - 1) * tile, tile_bytes, &mbar[0]);
-        }
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) codes[e] |= code[e] << (3 * s);
+        for (int e = 0; e < EPT; ++e) {
+          codes[e] |= code[e] << (3 * s);
+          nlim2 += code[e] & 1;
+        }
       }
       if (IND) {
-        // rho^n = P u^{n+1} - Phi_f(P u^n);  eta_k += lam_f^{n+1}_k . rho^n_k;  then P u^n for the next step
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
 #pragma unroll
-          for (int i = 0; i < NPX; ++i) eta[e] = fma(lu[e][i], pun[e][i] - x[e][i], eta[e]);
-        }
-        const double* s0 = ss + tid;
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-#pragma unroll
-          for (int i = 0; i < NPX; ++i) pun[e][i] = s0[(size_t)(i * EPT + e) * BD];
+          for (int i = 0; i < NPX; ++i) eta[e] = fma(-lu[e][i], x[e][i], eta[e]);
         }
       }
       // ---- transpose the stages in reverse
@@ -651,6 +694,13 @@ __global__ void __launch_bounds__(BD, BD <= 128 ? 3 : 1) burgers_fused_kernel(co
         for (int e = 0; e < EPT; ++e) code[e] = (codes[e] >> (3 * s)) & 7;
         bg_limiter_T<NPX, EPT, BD>(p, LXv, cx, k0, code, lu);
         bg_flush_vote<BD>(cx, pend);   // (after an exchange that follows the last stage's vote)
+        if (s == 2 && tid == 0 && n >= 1) {
+          // every thread is past the transpose of stage 3, the last reader of ss[3]: the state tile of step
+          // n-1 lands there while stages 2..0 are transposed
+          fence_proxy_async();
+          mbar_expect_tx(&mbar[0], tile_bytes);
+          tma_bulk_g2s(land, ck + (size_t)(n - 1) * tile, tile_bytes, &mbar[0]);
+        }
         const double rka = p.rka[s], rkb = p.rkb[s];
         double us[EPT][NPX];
         double uLL, uRR;
@@ -777,6 +827,10 @@ __global__ void __launch_bounds__(BD, BD <= 128 ? 3 : 1) burgers_fused_kernel(co
       // (NPX == NP here)
       bg_limiter_T<NPX, EPT, BD>(p, LXv, cx, k0, code, lu);
     }
+    if (p.nlim) {
+      const double nl = bg_block_sum<BD>(cx, (double)nlim2);
+      if (tid == 0) p.nlim[2 * b + 1] = (int)nl;
+    }
     if (cx.in) {
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
@@ -894,7 +948,11 @@ extern "C" int dgadj_burgers_plan(dgadj_handle* h, int64_t B, int32_t indicator,
                 "dgadj_burgers_forward / dgadj_burgers_adjoint", smem);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   per_sm = std::max(1, std::min(per_sm, std::min(32, 2048 / bd)));
-  if (bd <= 128) per_sm = std::min(per_sm, std::max(3, 65536 / (bd * 168)));   // registers: compiled for 3 CTAs of <= 128 threads
+  {   // registers: what __launch_bounds__(bd, BG_MINB) lets a thread use
+    const int minb = BG_MINB(bd, indicator ? 1 : 0);
+    const int regs = std::min(255, (65536 / (bd * minb)) / 8 * 8);
+    per_sm = std::min(per_sm, std::max(minb, 65536 / (bd * regs)));
+  }
   int g = h->tune_grid ? h->tune_grid : h->sm_count * per_sm;
   g = (int)std::max<int64_t>(1, std::min<int64_t>(g, B));
   if (ept) *ept = e;

@@ -54,6 +54,7 @@ def parse_args():
     p.add_argument("--grid", type=int, default=0)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-secondary", action="store_true", help="skip the bounded runs of configs 3, 4 and 5")
     p.add_argument("--cpu-B", type=int, default=48, help="CPU sample: trajectories per worker")
     p.add_argument("--cpu-S", type=int, default=8)
     return p.parse_args()
@@ -360,6 +361,38 @@ def ours(a):
         # host path and device path run the same kernels on the same inputs
         assert torch.equal(h_eta.to(dev), out["eta"]), "host-path indicators differ from device-path"
 
+    # ---- configs 3, 4, 5 (bounded; outside the headline's timed region).  Config 4 is the GLOBAL sweep sharded
+    # over all ranks (every rank takes part); configs 3 and 5 run on rank 0.  CPU legs at N = 1 only.
+    secondary = None
+    if not a.no_secondary:
+        try:
+            del out, sums, flags
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import secondary as sec
+
+        class _Pool:
+            def __init__(self, op):
+                self.workers, self.map = op.workers, op.pool.map
+        opool = OraclePool(cpu_workers()) if (world == 1 and not a.no_cpu) else None
+        spool = _Pool(opool) if opool else None
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        secondary = {}
+        for name, fn in (("cfg4_sweep_global", lambda: sec.cfg4(pkg, torch, dist, rank, world, dev, sm_mhz, pool=spool)),
+                         ("cfg3_burgers", lambda: sec.cfg3(pkg, torch, dev, sm_mhz, pool=spool) if rank == 0 else None),
+                         ("cfg5_adaptive", lambda: sec.cfg5(pkg, torch, dev, pool=spool) if rank == 0 else None)):
+            try:
+                secondary[name] = fn()
+            except Exception as e:      # a secondary workload must not take the headline line down
+                if name == "cfg4_sweep_global" and world > 1:
+                    raise               # (a rank dropping out of a collective would hang the others)
+                secondary[name] = {"error": repr(e)[:300]}
+        if opool:
+            opool.close()
+        barrier()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -443,7 +476,7 @@ def ours(a):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(a), "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "plan": s.plan(B), "refine_element_batch_mean": refine_idx,
+        "plan": s.plan(B), "refine_element_batch_mean": refine_idx, "secondary": secondary,
         "frac_of_fp64_peak_whole_step": flops_per_update(s.Np) * updates_per_step / world / (ms_per_step * 1e-3) / 1e12 / peak_tf if peak_tf else None,
     }
     emit(line)

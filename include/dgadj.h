@@ -309,7 +309,8 @@ int dgadj_burgers_adjoint(dgadj_handle* h, int64_t B, int32_t S, double dt, cons
  *       rho^n = P u^{n+1} - Phi_f(P u^n)   (Phi_f: the same limited LSERK4 step at order N+1)
  *       lam_f^n = Phi_f'(P u^n)^T lam_f^{n+1},  lam_f^S = jwF   (frozen branches of those steps)
  *       eta_dev[b][k] = sum_n lam_f^{n+1}_k . rho^n_k   (signed);  lam0_dev[B][Np+1][K] = lam_f^0.
- *   nlim_dev[B] (or NULL): limiter activations (cell, stage) of the forward march;
+ *   nlim_dev[B][2] (or NULL): limiter activations (cell, stage) of the forward march, and of the steps the
+ *     adjoint phase takes again (indicator = 0: the same steps, the same number; 1: the enriched steps);
  *   status_dev[B] (or NULL): per-trajectory status word, bit 0 = a non-finite value in u(T).
  * Any output may be NULL.  Shapes whose stage states exceed shared memory (DGADJ_ERR_UNSUPPORTED) go
  * through dgadj_burgers_forward / dgadj_burgers_adjoint.                                              */

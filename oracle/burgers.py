@@ -279,8 +279,18 @@ def prolongation(gc, gf):
     return gf.V[:, :gc.Np] @ gc.invV
 
 
+def prolong(P, u):
+    """P u in the form u_1 + P (u - u_1) (u_1 = the element's first nodal value; the rows of P sum to 1):
+    a cell the limiter has flattened (minmod = 0 at an extremum: all nodal values bitwise equal) stays exactly
+    flat in the enriched space.  With a plain matrix product its nodes would differ by rounding, and the
+    location of max|u| inside such a cell -- which the frozen-branch adjoint records -- would be decided by
+    that noise instead of the lowest-index rule."""
+    u1 = u[..., 0:1, :]
+    return u1 + P @ (u - u1)
+
+
 def burgers_fwd_adj_indicator(u0, gc, gf, dt, nsteps, jw_c, jw_f, bc=BC_PERIODIC):
-    """One trajectory (u0: (Np, K)).  Returns dict(uT, J, lam0[NpF, K], eta[K], eta_scale[K], nlim,
+    """One trajectory (u0: (Np, K)).  Returns dict(uT, J, lam0[NpF, K], eta[K], eta_scale[K] (see below), nlim,
     fine=[per step: the enriched step's record]): coarse limited march (SlopeLimitN on the initial state
     and after every stage, as burgers_march), J = sum jw_c o u(T), enriched adjoint and indicator as
     specified above; nlim = number of (cell, stage) limiter activations of the coarse march."""
@@ -296,10 +306,13 @@ def burgers_fwd_adj_indicator(u0, gc, gf, dt, nsteps, jw_c, jw_f, bc=BC_PERIODIC
     K = gc.K
     eta, scale, fine = np.zeros(K), np.zeros(K), []
     for n in range(nsteps - 1, -1, -1):
-        uf1, stf = burgers_step_record(P @ states[n], gf, dt, bc)
-        rho = P @ states[n + 1] - uf1
+        uf1, stf = burgers_step_record(prolong(P, states[n]), gf, dt, bc)
+        pu1 = prolong(P, states[n + 1])
+        rho = pu1 - uf1
         eta += np.sum(lam * rho, axis=0)
-        scale += np.sum(np.abs(lam) * np.abs(rho), axis=0)
+        # magnitude before the cancellation in rho (a difference of two O(|u|) states that agree to the
+        # one-step residual): any two fp64 evaluations of eta agree to eps * scale, not to eps * |eta|
+        scale += np.sum(np.abs(lam) * (np.abs(pu1) + np.abs(uf1)), axis=0)
         lam = burgers_step_T(lam, stf, gf, dt, bc)
         fine.append(stf)
     return dict(uT=states[-1], J=float(np.sum(jw_c * states[-1])), lam0=lam, eta=eta,

@@ -783,7 +783,7 @@ def test_burgers_fused_fwd_adj_indicator(pkg, torch, N, K, bc, ept):
     d_u0 = torch.tensor(u0, device="cuda")
     plain = s.fwd_adj(d_u0, dt, S, indicator=False, psi=psi)
     ind = s.fwd_adj(d_u0, dt, S, indicator=True, psi=psi)
-    assert torch.equal(plain["uT"], ind["uT"]) and torch.equal(plain["J"], ind["J"]) and torch.equal(plain["nlim"], ind["nlim"])
+    assert torch.equal(plain["uT"], ind["uT"]) and torch.equal(plain["J"], ind["J"]) and torch.equal(plain["nlim"][:, 0], ind["nlim"][:, 0])
     assert int(plain["status"].abs().max()) == 0
     gf = oracle_view(s.gf)
     jwf = s.gf.quad_weights() * psi(s.gf.x)
@@ -795,14 +795,19 @@ def test_burgers_fused_fwd_adj_indicator(pkg, torch, N, K, bc, ept):
         ref = ob.burgers_adjoint(rec, g, dt, jw, obc)
         nl = sum(int(np.sum(st["ids"])) for st in rec["stages"])
         some_limited |= nl > 0
-        assert int(plain["nlim"][b]) == nl
+        assert plain["nlim"][b].tolist() == [nl, nl]          # the march, and the same steps taken again
         assert rel(plain["uT"][b].cpu().numpy(), rec["uT"]) < 1e-11
         assert rel(plain["lam0"][b].cpu().numpy(), ref) < 1e-10
         assert abs(float(plain["J"][b]) - np.sum(jw * rec["uT"])) < 1e-12
         o = ob.burgers_fwd_adj_indicator(u0[b], g, gf, dt, S, jw, jwf, obc)
-        assert rel(ind["lam0"][b].cpu().numpy(), o["lam0"]) < 1e-10
+        nlf = sum(int(np.sum(q["ids"])) for stf in o["fine"] for q in stf)
+        assert ind["nlim"][b].tolist() == [nl, nlf], (b, ind["nlim"][b].tolist(), nl, nlf)   # the enriched steps: same decisions
+        assert rel(ind["lam0"][b].cpu().numpy(), o["lam0"]) < 1e-10, b
+        # eta cancels: rho is the difference of two O(|u|) states that agree to the one-step residual; eta_scale
+        # is the magnitude before that cancellation (as for the advection indicator).  The states themselves
+        # carry the 1e-11 of the march, hence the same bound here.
         dev = np.max(np.abs(ind["eta"][b].cpu().numpy() - o["eta"]) / o["eta_scale"])
-        assert dev < 1e-10, dev
+        assert dev < 1e-11, dev
     assert some_limited
     # S = 0: no steps -- J of the limited initial state, lam0 = the limiter's transpose of jw, eta = 0
     z = s.fwd_adj(d_u0, dt, 0, indicator=True, psi=psi)
@@ -835,9 +840,13 @@ def test_cfg3_full_size_post_shock(pkg, torch):
     m0, mT = (jw * u0).sum((1, 2)), (jw * out["uT"]).sum((1, 2))
     assert float((mT - m0).abs().max()) < 1e-11 * float((jw * u0.abs()).sum((1, 2)).max())      # conservative, periodic
     assert float((out["J"] - mT).abs().max()) < 1e-12 * float((jw * out["uT"].abs()).sum((1, 2)).max())
-    frac = float(out["nlim"].double().mean()) / (5 * S * K)
+    frac = float(out["nlim"][:, 0].double().mean()) / (5 * S * K)
     print(f"cfg3 full size: S = {S}, T = {S * dt:.3f}, limited fraction {frac:.4f}, max |eta| {float(out['eta'].abs().max()):.3e}")
-    assert frac > 0.02                                                                 # shocks have formed: the limiter is busy
+    assert frac > 0.005                                                                # the limiter is at work (extrema, then shocks)
+    # shocks have formed: the steepest cell-to-cell jump of the means is O(1) of the amplitude in most trajectories
+    v = out["uT"].mean(1)
+    jump = (v - torch.roll(v, 1, dims=1)).abs().max(1).values
+    assert float((jump > 0.1).double().mean()) > 0.5
     # J = mass is conserved by the enriched march too: its adjoint is the weight vector for every n, so
     # lam_f^0 = jw_f through ~12 000 limited stages (frozen-branch transposes preserve it exactly up to rounding)
     jwf = torch.tensor(s.gf.quad_weights(), device="cuda")
@@ -851,10 +860,10 @@ def test_cfg3_full_size_post_shock(pkg, torch):
     # oracle parity on the first trajectory (the NumPy oracle takes ~1 min for one post-shock trajectory)
     gf = oracle_view(s.gf)
     o = ob.burgers_fwd_adj_indicator(u0[0].cpu().numpy(), g, gf, dt, S, s.g.quad_weights(), s.gf.quad_weights(), "periodic")
-    assert int(out["nlim"][0]) == o["nlim"]
+    assert int(out["nlim"][0, 0]) == o["nlim"]
     assert rel(out["uT"][0].cpu().numpy(), o["uT"]) < 1e-10
     assert rel(out["lam0"][0].cpu().numpy(), o["lam0"]) < 1e-9
-    assert np.max(np.abs(out["eta"][0].cpu().numpy() - o["eta"]) / o["eta_scale"]) < 1e-9
+    assert np.max(np.abs(out["eta"][0].cpu().numpy() - o["eta"]) / o["eta_scale"]) < 1e-10
 
 
 def test_cfg3_size_properties(pkg, torch):

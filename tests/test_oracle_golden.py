@@ -328,7 +328,7 @@ def test_burgers_indicator_effectivity_and_adjoint_identities():
         burgers.limit_with_branches = lambda u, g, p: (u, np.zeros(u.shape[-1], bool), np.zeros(u.shape[-1], int))
         for S in (5, 17, 37):
             out = burgers.burgers_fwd_adj_indicator(u0, gc, gf, dt, S, jc, jf)
-            uf = P @ u0
+            uf = burgers.prolong(P, u0)
             for _ in range(S):
                 uf, _ = burgers.burgers_step_record(uf, gf, dt)
             dJ = np.sum(jf * (P @ out["uT"])) - np.sum(jf * uf)

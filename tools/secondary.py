@@ -1,0 +1,356 @@
+"""Bounded runs of BASELINE configs 3, 4 and 5 for bench.py's `secondary` key (SURVEY section 8(d);
+BASELINE.md section 4 rows: GPU value, fraction of the fp64 pipe, achieved HBM GB/s, CPU baseline on the
+box's host cores, max relative difference GPU vs oracle).  Each function returns one dict; the CPU legs
+are the only callers of oracle/ here (bench.py's `cpu_baseline` role).
+
+  cfg3  Burgers + SlopeLimitN, N=4, K=256, B=16384 per GPU, T = 0.4 (past shock formation): the fused
+        forward + adjoint + indicator kernel (rank 0)
+  cfg4  the GLOBAL 1024 x 1024 parameter sweep (advection speed x pulse width), N=4, K=64, S=100, sharded
+        over the ranks; batch norms / mean indicator through the count-independent block reduction
+        (+ all-gather over NCCL): the sha256 of the reduced vector is the same for 1, 2, 4 and 8 GPUs
+  cfg5  adjoint-driven refinement loops, B=4096 ICs, 30 refinements: DG-in-time (matlab/MAIN.m) and the
+        finite-difference path (python/Main_finite_difference.py), device-side mesh updates (rank 0)
+"""
+import hashlib
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+TWO_PI = 2.0 * math.pi
+
+
+def _events(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _exec_inst(key):
+    """Executed fp64 instructions per update of a kernel from profiles/exec_inst.json (tools/exec_inst.py),
+    with the stamp of the kernel source it was counted on."""
+    try:
+        ej = json.load(open(os.path.join(ROOT, "profiles", "exec_inst.json")))
+        ent = ej.get(key)
+        if ent:
+            return ent["fp64_inst_per_update"], ent.get("kernel_source_sha")
+    except Exception:
+        pass
+    return None, None
+
+
+def _pipe_frac(exec_inst, updates_per_s, sm_mhz):
+    if not exec_inst:
+        return None
+    return exec_inst * updates_per_s / (148 * 64 * sm_mhz * 1e6)
+
+
+# --------------------------------------------------------------------------------------------- config 3
+def _cfg3_ics(torch, s, B, dev, seed=1235):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    c = torch.rand((B, 1, 1), dtype=torch.float64, device=dev, generator=g) - 0.5
+    A = torch.rand((B, 1, 1), dtype=torch.float64, device=dev, generator=g) + 0.5
+    ph = torch.rand((B, 1, 1), dtype=torch.float64, device=dev, generator=g) * TWO_PI
+    x = torch.tensor(s.g.x, device=dev)[None]
+    return (c + A * torch.sin(math.pi * x + ph)).contiguous()
+
+
+def _cfg3_cpu_worker(args):
+    S, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import numpy as np
+    from oracle import burgers as ob
+    from oracle import operators as ops
+    N, K = 4, 256
+    gc, gf = ops.startup_uniform(N, -1.0, 1.0, K), ops.startup_uniform(N + 1, -1.0, 1.0, K)
+    rng = np.random.default_rng(seed)
+    u0 = rng.uniform(-0.5, 0.5) + rng.uniform(0.5, 1.5) * np.sin(np.pi * gc.x + rng.uniform(0, TWO_PI))
+    dt = 0.25 * np.min(np.abs(gc.x[0] - gc.x[1])) / 2.0
+    wq = lambda g: (ops.mass_matrix(g.V) @ np.ones(g.Np))[:, None] * g.J
+    t0 = time.perf_counter()
+    ob.burgers_fwd_adj_indicator(u0, gc, gf, dt, S, wq(gc), wq(gf))
+    return 2 * 5 * S * K, time.perf_counter() - t0
+
+
+def cfg3(pkg, torch, dev, sm_mhz, pool=None, B=16384, T=0.4, parity=True):
+    import numpy as np
+    N, K = 4, 256
+    s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc="periodic", device=dev.index)
+    u0 = _cfg3_ics(torch, s, B, dev)
+    dt = s.stable_dt(2.0)
+    S = int(math.ceil(T / dt))
+    out = s.fwd_adj(u0, dt, S, indicator=True, want_uT=False, want_lam0=False)      # warm-up: allocates the ring
+    torch.cuda.synchronize()
+    e0, e1 = _events(torch)
+    e0.record()
+    out = s.fwd_adj(u0, dt, S, indicator=True, want_uT=False, want_lam0=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ups = 2 * 5 * S * K * B
+    val = ups / (ms * 1e-3)
+    plan = s.plan(B, True)
+    ring_bytes = plan["ring_bytes_per_step"] * S
+    hbm_bytes = B * (2 * S * (N + 1) * K * 8 + (N + 1) * K * 8 + K * 8)
+    ei, sha = _exec_inst("burgers_fused_np5_ind")
+    res = dict(
+        workload="config 3: Burgers + SlopeLimitN after every stage, N=4 K=256 B=%d, T=%.2f (S=%d LSERK4 steps, past shock "
+                 "formation), fused forward + enriched adjoint + per-element indicator, per-CTA state ring (%.1f GB)"
+                 % (B, S * dt, S, ring_bytes * 1e-9),
+        metric="DG element-stage updates/s (fwd+adjoint)", value=val, unit="updates/s", ms=ms,
+        limited_fraction=float(out["nlim"][:, 0].double().mean()) / (5 * S * K), status_max=int(out["status"].max()),
+        plan=plan,
+        roofline=dict(bound="fp64_fma", frac=_pipe_frac(ei, val, sm_mhz), executed_fp64_inst_per_update=ei,
+                      frac_kind="executed fp64-pipe utilisation (instructions per update from an ncu capture of this kernel, "
+                                "profiles/exec_inst.json, kernel source %s)" % sha,
+                      hbm_gbs=hbm_bytes / (ms * 1e-3) / 1e9, algorithmic_hbm_bytes=hbm_bytes))
+    if parity:
+        from oracle import burgers as ob
+        from oracle import operators as ops
+        from types import SimpleNamespace
+
+        def view(g):
+            rx = np.broadcast_to(g.r_x.sum(axis=0, keepdims=True) / g.r_x.shape[0], g.r_x.shape).copy()
+            return SimpleNamespace(N=g.n, Np=g.n_p, K=g.k, Dr=g.d_r, LIFT=g.lift, rx=rx, J=g.j_mat, Fscale=g.f_scale,
+                                   x=g.x, V=g.v, invV=g.inv_v, VX=g.v_x)
+        Sp = 300
+        small = s.fwd_adj(u0[:2].contiguous(), dt, Sp, indicator=True)
+        gc, gf = view(s.g), view(s.gf)
+        worst = dict(uT=0.0, lam0=0.0, eta_over_scale=0.0, nlim_mismatch=0)
+        for b in range(2):
+            o = ob.burgers_fwd_adj_indicator(u0[b].cpu().numpy(), gc, gf, dt, Sp, s.g.quad_weights(), s.gf.quad_weights())
+            rel = lambda a, r: float(np.max(np.abs(a - r)) / np.max(np.abs(r)))
+            worst["uT"] = max(worst["uT"], rel(small["uT"][b].cpu().numpy(), o["uT"]))
+            worst["lam0"] = max(worst["lam0"], rel(small["lam0"][b].cpu().numpy(), o["lam0"]))
+            worst["eta_over_scale"] = max(worst["eta_over_scale"], float(np.max(np.abs(small["eta"][b].cpu().numpy() - o["eta"]) / o["eta_scale"])))
+            worst["nlim_mismatch"] += int(int(small["nlim"][b, 0]) != o["nlim"])
+        res["max_rel_diff_vs_oracle"] = dict(worst, sample="first 2 trajectories, S=%d" % Sp)
+    if pool is not None:
+        t0 = time.perf_counter()
+        r = pool.map(_cfg3_cpu_worker, [(40, 100 + i) for i in range(pool.workers)])
+        sec = time.perf_counter() - t0
+        res["cpu_baseline"] = dict(value=sum(x[0] for x in r) / sec, unit="updates/s", cores=pool.workers, kind="port",
+                                   sample="%d workers x 1 trajectory x S=40 steps of the same workload (oracle/burgers.py, NumPy fp64), %.1f s wall"
+                                          % (pool.workers, sec))
+    s.close()
+    return res
+
+
+# --------------------------------------------------------------------------------------------- config 4
+NA, NSIG = 1024, 1024
+
+
+def _cfg4_params(torch, idx):
+    ia = torch.div(idx, NSIG, rounding_mode="floor").double()
+    isg = (idx % NSIG).double()
+    a = (0.5 + 1.5 * ia / (NA - 1)) * TWO_PI
+    sig = 0.02 + 0.18 * isg / (NSIG - 1)
+    return a, sig
+
+
+def _cfg4_cpu_worker(args):
+    i0, n = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import numpy as np
+    from oracle import advec
+    from oracle import operators as ops
+    N, K, S = 4, 64, 100
+    gc, gf = ops.startup_uniform(N, 0.0, TWO_PI, K), ops.startup_uniform(N + 1, 0.0, TWO_PI, K)
+    idx = np.arange(i0, i0 + n)
+    a = (0.5 + 1.5 * (idx // NSIG) / (NA - 1)) * TWO_PI
+    sig = 0.02 + 0.18 * (idx % NSIG) / (NSIG - 1)
+    u0 = np.exp(-(gc.x[None] - math.pi) ** 2 / (2 * sig[:, None, None] ** 2))
+    dt0, _ = advec.cfl_dt(gc, 1.0)
+    t0 = time.perf_counter()
+    advec.fwd_adj_indicator(u0, gc, gf, a, dt0 * TWO_PI / a, S, alpha=0.0, bc=advec.BC_PERIODIC)
+    return 2 * 5 * S * K * n, time.perf_counter() - t0
+
+
+def cfg4(pkg, torch, dist, rank, world, dev, sm_mhz, pool=None, chunk=131072, parity=True):
+    import numpy as np
+    N, K, S = 4, 64, 100
+    NG = NA * NSIG
+    s = pkg.AdvecDG1D(N, K, domain=(0.0, TWO_PI), alpha=0.0, bc="periodic", device=dev.index)
+    per_rank = NG // world
+    lo = rank * per_rank
+    assert per_rank % pkg.REDUCE_BLOCK == 0
+    x = torch.tensor(s.g.x, device=dev)[None]
+    dt0, _ = s.cfl_dt(1.0)
+    batches = []
+    for c0 in range(lo, lo + per_rank, chunk):
+        idx = torch.arange(c0, min(c0 + chunk, lo + per_rank), device=dev)
+        a, sig = _cfg4_params(torch, idx)
+        u0 = torch.exp(-(x - math.pi) ** 2 / (2 * sig[:, None, None] ** 2)).contiguous()
+        batches.append((u0, a.contiguous(), (dt0 * TWO_PI / a).contiguous()))
+
+    def run():
+        parts = []
+        for u0, a, dt in batches:
+            out = s.fwd_adj(u0, a, dt, S, want_uT=False)
+            parts.append(s.reduce_indicator_blocks(out["eta"], out["J"]))
+        return pkg.allreduce_indicator_blocks(torch.cat(parts, dim=0)), out
+
+    sums, out = run()       # warm-up
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = _events(torch)
+    e0.record()
+    sums, out = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    h = sums.cpu().numpy()
+    digest = hashlib.sha256(h.tobytes()).hexdigest()
+    if dist is not None:       # the same bits on every rank
+        allh = [None] * world
+        dist.all_gather_object(allh, digest)
+        assert all(d == digest for d in allh), allh
+    if rank != 0:
+        s.close()
+        return None
+    ups = 2 * 5 * S * K * NG
+    val = ups / (ms * 1e-3)
+    pl = s.plan(chunk)
+    ei, sha = _exec_inst("np%d_ept%d_bd%d_fused" % (N + 1, pl["elems_per_thread"], pl["block"]))
+    res = dict(
+        workload="config 4: the global %d x %d parameter sweep (advection speed a in [0.5, 2] 2pi x Gaussian pulse width sigma in "
+                 "[0.02, 0.2]), N=4 K=64 S=100, per-trajectory a and CFL dt, %d trajectories per GPU on %d GPU(s); batch norms and "
+                 "mean indicator reduced in blocks of %d trajectories + ordered all-gather combination" % (NA, NSIG, per_rank, world, pkg.REDUCE_BLOCK),
+        metric="DG element-stage updates/s (fwd+adjoint)", value=val, unit="updates/s", ms=ms, n_gpus=world, scaling="strong",
+        norms=dict(sum_abs_eta=float(h[K]), sum_eta2=float(h[K + 1]), max_abs_eta=float(h[K + 2]), sum_J=float(h[K + 3]),
+                   refine_element=int(np.argmax(h[:K]))),
+        norms_sha256=digest, norms_sha256_note="sha256 of the reduced [K+4] fp64 vector: identical for 1, 2, 4, 8 GPUs (count-independent reduction)",
+        plan=pl,
+        roofline=dict(bound="fp64_fma", frac=_pipe_frac(ei, val / world, sm_mhz), executed_fp64_inst_per_update=ei,
+                      frac_kind="executed fp64-pipe utilisation per GPU (SASS count of the N=4 fused kernel, tools/exec_inst.py, kernel source %s)" % sha,
+                      hbm_gbs=(NG // world) * (2 * S * (N + 2) * K * 8 + (N + 1) * K * 8) / (ms * 1e-3) / 1e9))
+    if parity:
+        from oracle import advec
+        from types import SimpleNamespace
+
+        def view(g):
+            rx = np.broadcast_to(g.r_x.sum(axis=0, keepdims=True) / g.r_x.shape[0], g.r_x.shape).copy()
+            return SimpleNamespace(N=g.n, Np=g.n_p, K=g.k, Dr=g.d_r, LIFT=g.lift, rx=rx, J=g.j_mat, Fscale=g.f_scale,
+                                   x=g.x, V=g.v, invV=g.inv_v, VX=g.v_x)
+        u0, a, dt = batches[0]
+        pick = torch.tensor([0, 1, 517, 1023, 70000, 131071][: 6], device=dev)
+        pick = pick[pick < u0.shape[0]]
+        got = s.fwd_adj(u0[pick].contiguous(), a[pick].contiguous(), dt[pick].contiguous(), S, want_lam0=True)
+        ref = advec.fwd_adj_indicator(u0[pick].cpu().numpy(), view(s.g), view(s.gf), a[pick].cpu().numpy(), dt[pick].cpu().numpy(), S,
+                                      alpha=0.0, bc=advec.BC_PERIODIC)
+        rel = lambda x_, r: float(np.max(np.abs(x_ - r)) / np.max(np.abs(r)))
+        res["max_rel_diff_vs_oracle"] = dict(uT=rel(got["uT"].cpu().numpy(), ref["uT"]), lam0=rel(got["lam0"].cpu().numpy(), ref["lam0"]),
+                                             eta_over_scale=float(np.max(np.abs(got["eta"].cpu().numpy() - ref["eta"]) / ref["eta_scale"])),
+                                             sample="%d trajectories of rank 0's first chunk" % int(pick.numel()))
+    if pool is not None:
+        t0 = time.perf_counter()
+        r = pool.map(_cfg4_cpu_worker, [(i * 4099, 64) for i in range(pool.workers)])
+        sec = time.perf_counter() - t0
+        res["cpu_baseline"] = dict(value=sum(x_[0] for x_ in r) / sec, unit="updates/s", cores=pool.workers, kind="port",
+                                   sample="%d workers x 64 trajectories of the sweep (oracle/advec.py, NumPy fp64), %.1f s wall" % (pool.workers, sec))
+    s.close()
+    return res
+
+
+# --------------------------------------------------------------------------------------------- config 5
+def _reference_fd():
+    """The reference's own python/Main_finite_difference.py, imported unmodified, when /root/reference is
+    present (this container; the GPU box does not have it) -- as tests/golden/make_fd_golden.py does."""
+    path = "/root/reference/python/Main_finite_difference.py"
+    if not os.path.isfile(path):
+        return None
+    try:
+        import importlib.util
+        from unittest.mock import MagicMock
+        for m in ("cv2", "matplotlib", "matplotlib.pyplot", "matplotlib.patches"):
+            sys.modules.setdefault(m, MagicMock())
+        spec = importlib.util.spec_from_file_location("ref_fd", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)      # the driver loop is under __main__ and does not run
+        mod.ref_factor = 4                # interpU reads a module global (quirk C-12)
+        return mod
+    except Exception:
+        return None
+
+
+def _cfg5_fd_cpu_worker(args):
+    """One trajectory of the FD loop (Main_finite_difference.py:263-343: forwardSolve, adjSolve, errEst,
+    window sums, argmax, midpoint insertion), u' = sin u, J = int u^2, ref_factor 4."""
+    u0, iters = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import numpy as np
+    mod = _reference_fd()
+    units = 0
+    t0 = time.perf_counter()
+    times = np.linspace(0.0, 2.0, 3)
+    if mod is not None:
+        kind = "reference"
+        # problem functions of the reference's __main__ block (:131-140, :225-227), restated as closures
+        fwdUpdate = lambda u, dt, n: u[n - 1] + np.sin(u[n - 1]) * dt[n - 1]
+        getJF = lambda u, dt: np.diag(1 + np.cos(u[:-1]) * dt, -1)
+        getK = lambda dt, u: np.concatenate((2 * u[:-1] * dt, 0), axis=None)
+        for it in range(iters + 1):
+            dt_n = np.diff(times)
+            u = mod.forwardSolve(fwdUpdate, dt_n, u0)
+            v = mod.adjSolve(getK, getJF, dt_n, u, 4)
+            e = np.abs(mod.errEst(fwdUpdate, u, v, dt_n, 4))[2:]
+            n = dt_n.size
+            err_steps = np.array([e[4 * r:4 * r + 3].sum() for r in range(n)])
+            ref_idx = int(np.argmax(err_steps))
+            times = np.insert(times, ref_idx + 1, 0.5 * (times[ref_idx] + times[ref_idx + 1]))
+            units += n + 2 * 4 * n
+    else:
+        from oracle import fd as ofd
+        kind = "port"
+        for it in range(iters + 1):
+            dt_n = np.diff(times)
+            r = ofd.fd_awr(np.array([u0]), dt_n, ref_factor=4, functional="int_u2", ode="sin")
+            ref_idx = int(r["ref_idx"][0])
+            times = np.insert(times, ref_idx + 1, 0.5 * (times[ref_idx] + times[ref_idx + 1]))
+            units += dt_n.size + 2 * 4 * dt_n.size
+    return units, time.perf_counter() - t0, kind
+
+
+def cfg5(pkg, torch, dev, pool=None, B=4096, iters=30):
+    import numpy as np
+    rng = np.random.default_rng(0)
+    y0 = torch.tensor(rng.uniform(-3, 3, B), device=dev)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = fn()
+        torch.cuda.synchronize()
+        return h, time.perf_counter() - t0
+    h_dg, t_dg = timed(lambda: pkg.adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=iters, device=dev.index))
+    h_fd, t_fd = timed(lambda: pkg.adapt_fd(y0, tspan=(0.0, 2.0), n_steps=2, iters=iters, functional="int_u2", device=dev.index))
+    solves = sum(2 * (h["times"].size - 1) for h in h_dg) * B
+    fine = sum((h["times"].size - 1) * 9 for h in h_fd) * B
+    res = dict(
+        workload="config 5: adjoint-driven refinement loops, B=%d ICs u0 ~ U(-3,3), u' = sin u on [0,2], shared mesh, batch-mean "
+                 "indicator, %d argmax refinements from 2 elements / steps (matlab/MAIN.m:29-166; Main_finite_difference.py:263-343)" % (B, iters),
+        tdg=dict(metric="element-solves/s (Newton march or adjoint solve + indicator), whole loop incl. mesh updates", value=solves / t_dg,
+                 unit="element-solves/s", ms_per_iteration=1e3 * t_dg / (iters + 1), final_elements=int(h_dg[-1]["times"].size - 1),
+                 refined_first=[int(h["ref_idx"]) for h in h_dg[:3]], max_newton_its=int(max(h["max_newton_its"] for h in h_dg))),
+        fd=dict(metric="fine-step updates/s (forward, adjoint recurrence, residual), whole loop incl. mesh updates", value=fine / t_fd,
+                unit="fine-step updates/s", ms_per_iteration=1e3 * t_fd / (iters + 1), final_steps=int(h_fd[-1]["times"].size - 1),
+                refined_first=[int(h["ref_idx"]) for h in h_fd[:3]]))
+    if pool is not None:
+        t0 = time.perf_counter()
+        r = pool.map(_cfg5_fd_cpu_worker, [(float(v), iters) for v in rng.uniform(-3, 3, pool.workers * 4)])
+        sec = time.perf_counter() - t0
+        res["fd"]["cpu_baseline"] = dict(value=sum(x[0] for x in r) / sec, unit="fine-step updates/s", cores=pool.workers, kind=r[0][2],
+                                         sample="%d single-trajectory loops (%d iterations each) over %d workers, %s, %.1f s wall"
+                                                % (len(r), iters + 1, pool.workers,
+                                                   "the reference's own python/Main_finite_difference.py functions (imported)" if r[0][2] == "reference"
+                                                   else "oracle/fd.py (the reference tree is not on this box)", sec))
+    return res
