@@ -46,6 +46,15 @@ class BurgersArgs(C.Structure):
                 ("invVF_host", C.c_void_p), ("VF_host", C.c_void_p), ("xF_host", C.c_void_p), ("jwF_host", C.c_void_p)]
 
 
+class TdgLoopArgs(C.Structure):
+    """dgadj_tdg_loop_args (include/dgadj.h)"""
+    _fields_ = [("B", C.c_int64), ("iters", C.c_int32), ("Ks0", C.c_int32), ("Np", C.c_int32), ("nq_march", C.c_int32),
+                ("nq_adj", C.c_int32), ("linear", C.c_int32), ("maxit", C.c_int32), ("y0_per_trajectory", C.c_int32),
+                ("tol", C.c_double), ("y0_hard", C.c_double), ("times0_host", C.c_void_p),
+                ("march_T0_host", C.c_void_p), ("march_T1_host", C.c_void_p), ("adj_T0_host", C.c_void_p),
+                ("adj_T1_host", C.c_void_p)]
+
+
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
 # name -> (restype, argtypes); exactly the symbols include/dgadj.h declares
@@ -78,6 +87,8 @@ PROTOTYPES = {
                                         _P, _P, _P, _P, _P, _P]),
     "dgadj_burgers_adjoint": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                         _P, _P, _P, _P]),
+    "dgadj_tdg_adapt_loop": (C.c_int, [_P, C.POINTER(TdgLoopArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dgadj_fd_adapt_loop": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "dgadj_burgers_fwd_adj": (C.c_int, [_P, C.POINTER(BurgersArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
     "dgadj_burgers_plan": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

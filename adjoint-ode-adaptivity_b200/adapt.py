@@ -37,14 +37,53 @@ def _batch_reduce(obj, eta, B_global=None):
     return (sums[:K] / float(Bg)).cpu().numpy()
 
 
+def _distributed():
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:
+        return False
+
+
+def _fd_device_loop(s, u0, times, iters):
+    """dgadj_fd_adapt_loop: every iteration enqueued by one call, the mesh lives on the device."""
+    torch = s.torch
+    u0 = u0.contiguous().view(-1)
+    B, n0 = u0.numel(), times.size - 1
+    nmax, W = n0 + iters, n0 + iters + 2
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    th = torch.zeros((iters + 1, W), dtype=torch.float64, device=u0.device)
+    eh = torch.zeros((iters + 1, nmax), dtype=torch.float64, device=u0.device)
+    ri = torch.zeros(iters + 1, dtype=torch.int32, device=u0.device)
+    tot = torch.zeros(iters + 1, dtype=torch.float64, device=u0.device)
+    rc = s.lib.dgadj_fd_adapt_loop(s._h, B, iters, n0, s.ref_factor, _lib.FD_ODE[s.ode], _lib.FD_FUNCTIONAL[s.functional],
+                                   C.c_void_p(times.ctypes.data), C.c_void_p(u0.data_ptr()), C.c_void_p(th.data_ptr()),
+                                   C.c_void_p(eh.data_ptr()), C.c_void_p(ri.data_ptr()), C.c_void_p(tot.data_ptr()),
+                                   C.c_void_p(torch.cuda.current_stream(s.device).cuda_stream))
+    if rc != _lib.OK:
+        raise _lib.DgadjError(rc, s.lib.dgadj_last_error(s._h).decode())
+    th, eh, ri, tot = th.cpu().numpy(), eh.cpu().numpy(), ri.cpu().numpy(), tot.cpu().numpy()   # the one read-back
+    return [dict(it=it, times=th[it, :n0 + it + 1].copy(), err_steps=eh[it, :n0 + it].copy(), ref_idx=int(ri[it]),
+                 err_total=float(tot[it])) for it in range(iters + 1)]
+
+
 def adapt_fd(u0, tspan=(0.0, 2.0), n_steps=2, iters=30, ode="sin", functional="int_u2", ref_factor=4,
-             tol=None, device=0, B_global=None):
+             tol=None, device=0, B_global=None, device_loop=None):
     """python/Main_finite_difference.py:263-343 (batched): start from n_steps uniform steps,
     refine the step with the largest batch-mean indicator `iters` times (or until the summed
     indicator drops below tol, :263).  Returns the history: one dict per iteration with
-    times, err_steps (batch mean), ref_idx (0-based element refined), err_total."""
+    times, err_steps (batch mean), ref_idx (0-based element refined), err_total.
+    device_loop (default: whenever there is no tolerance to test and no other rank to meet): the whole loop
+    is one C-ABI call (`dgadj_fd_adapt_loop`) -- mesh, tables, argmax and midpoint insertion on the device,
+    one read-back at the end; otherwise the host drives it iteration by iteration."""
     s = FDAdjoint(ode=ode, functional=functional, ref_factor=ref_factor, device=device)
     times = np.linspace(tspan[0], tspan[1], n_steps + 1)
+    if device_loop is None:
+        device_loop = tol is None and B_global is None and not _distributed()
+    if device_loop:
+        hist = _fd_device_loop(s, u0, times, iters)
+        s.close()
+        return hist
     hist = []
     for it in range(iters + 1):
         out = s.solve(u0, np.diff(times), want=("err_steps",))
@@ -59,14 +98,74 @@ def adapt_fd(u0, tspan=(0.0, 2.0), n_steps=2, iters=30, ode="sin", functional="i
     return hist
 
 
-def adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=30, linear=False, device=0, B_global=None, quirks=True):
+def _tdg_templates(s, n):
+    """Element blocks of the time-DG march / adjoint as affine functions of the element width,
+    block(h) = T0 + h T1: the host builds the blocks of the second element of the meshes [0, 1, 2] and
+    [0, 2, 4] (fem_setup operators, the polyfit/polyval matrices, the mirrored quadrature interval: everything
+    `TimeDG.march_constants` / `adjoint_constants` produce) and differences them."""
+    out = {}
+    for kind in ("m", "a"):
+        blocks = []
+        for hh in (1.0, 2.0):
+            times = np.array([0.0, hh, 2 * hh])
+            Ns = n * np.ones(2, dtype=int)
+            cm, nodes, NP, nqm = s.march_constants(Ns, times)
+            if kind == "m":
+                blocks.append(cm.reshape(2, -1)[1].copy())
+                out["nq_m"] = nqm
+            else:
+                ca, _, _, nqa = s.adjoint_constants(Ns + 1, nodes)
+                blocks.append(ca.reshape(2, -1)[1].copy())
+                out["nq_a"] = nqa
+        out[kind + "1"] = np.ascontiguousarray(blocks[1] - blocks[0])
+        out[kind + "0"] = np.ascontiguousarray(2.0 * blocks[0] - blocks[1])
+    return out
+
+
+def _tdg_device_loop(s, y0, times, n, iters):
+    """dgadj_tdg_adapt_loop: every iteration enqueued by one call, the mesh lives on the device."""
+    torch = s.torch
+    y0 = y0.contiguous().view(-1)
+    B, Ks0 = y0.numel(), times.size - 1
+    Kmax, W, Np = Ks0 + iters, Ks0 + iters + 2, n + 1
+    tp = _tdg_templates(s, n)
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    args = _lib.TdgLoopArgs(B=B, iters=iters, Ks0=Ks0, Np=Np, nq_march=tp["nq_m"], nq_adj=tp["nq_a"], linear=int(s.linear),
+                            maxit=s.maxit, y0_per_trajectory=1, tol=s.tol, y0_hard=1.0, times0_host=p(times),
+                            march_T0_host=p(tp["m0"]), march_T1_host=p(tp["m1"]), adj_T0_host=p(tp["a0"]), adj_T1_host=p(tp["a1"]))
+    kw = dict(dtype=torch.float64, device=y0.device)
+    th, eh = torch.zeros((iters + 1, W), **kw), torch.zeros((iters + 1, Kmax), **kw)
+    ri = torch.zeros(iters + 1, dtype=torch.int32, device=y0.device)
+    st, ist = torch.zeros((iters + 1, 2), **kw), torch.zeros((iters + 1, 3), dtype=torch.int32, device=y0.device)
+    d = lambda t: C.c_void_p(t.data_ptr())
+    rc = s.lib.dgadj_tdg_adapt_loop(s._h, C.byref(args), d(y0), d(th), d(eh), d(ri), d(st), d(ist), C.c_void_p(0), s._stream())
+    if rc != _lib.OK:
+        raise _lib.DgadjError(rc, s.lib.dgadj_last_error(s._h).decode())
+    th, eh, ri, st, ist = (t.cpu().numpy() for t in (th, eh, ri, st, ist))        # the one read-back
+    return [dict(it=it, times=th[it, :Ks0 + it + 1].copy(), err=eh[it, :Ks0 + it].copy(), ref_idx=int(ri[it]),
+                 err_total=float(st[it, 1]), max_newton_its=int(ist[it, 0]), yT_mean=float(st[it, 0]),
+                 not_converged=int(ist[it, 1]), non_finite=int(ist[it, 2])) for it in range(iters + 1)]
+
+
+def adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=30, linear=False, device=0, B_global=None, quirks=True,
+              device_loop=None):
     """matlab/MAIN.m:19-166 (batched): Ks elements of order n, adjoint order n+1, refine the
     element with the largest batch-mean |err| by midpoint insertion (:137-141).  Every trajectory's
     first-element residual is measured against its own initial value (the reference runs one
     trajectory with y0 = 1 hard-coded in adj_march.m:9 -- identical for that case).  quirks=False:
-    see TimeDG."""
+    see TimeDG.
+    device_loop (default: whenever no other rank has to be met): the whole loop is one C-ABI call
+    (`dgadj_tdg_adapt_loop`): element blocks, march, adjoint, batch mean, argmax and midpoint insertion on
+    the device, one read-back at the end; otherwise the host drives it iteration by iteration."""
     s = TimeDG(linear=linear, device=device, quirks=quirks)
     times = np.linspace(tspan[0], tspan[1], Ks + 1)
+    if device_loop is None:
+        device_loop = B_global is None and not _distributed()
+    if device_loop:
+        hist = _tdg_device_loop(s, y0, times, n, iters)
+        s.close()
+        return hist
     Ns = n * np.ones(Ks, dtype=int)
     hist = []
     for it in range(iters + 1):

@@ -189,3 +189,151 @@ extern "C" int dgadj_fd_awr(dgadj_handle* h, int64_t B, int32_t n, int32_t ref_f
   h->launches++;
   return DGADJ_OK;
 }
+
+// =======================================================================================================
+// Device-resident adaptive loop of python/Main_finite_difference.py:263-343, batched
+// with the batch-mean rule of python/Main_variable_params.py:340-341: per iteration the interpolation
+// tables of the current mesh (refineAll :16-21, np.interp's interval search :24-31 -- the host routine of
+// dgadj_fd_awr above, restated for one device thread: the meshes have at most a few hundred nodes),
+// forwardSolve / adjSolve / errEst / window sums (:266-277), batch mean, argmax step and midpoint
+// insertion (:336-341).  One call enqueues every iteration; nothing is read back in between.
+// =======================================================================================================
+namespace dgadj {
+
+struct FdTablesRW {
+  int* jc;
+  double* dx;
+  double* den;
+  double* dtf;
+  double* dtn;
+  unsigned char* exact;
+};
+
+__global__ void fd_tables_kernel(int n, int rf, const double* __restrict__ times, FdTablesRW t, double* __restrict__ tc,
+                                 double* __restrict__ tf) {
+  // thread 0: the sequential sums (np.diff, np.cumsum); then all threads: the interval search per fine node
+  const int nf = n * rf;
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < n; ++j) t.dtn[j] = times[j + 1] - times[j];                 // dt_n = np.diff(times)
+    for (int j = 0; j < n; ++j)
+      for (int f = 0; f < rf; ++f) t.dtf[j * rf + f] = t.dtn[j] / rf;              // refineAll
+    tc[0] = 0.0;
+    for (int j = 0; j < n; ++j) tc[j + 1] = tc[j] + t.dtn[j];
+    tf[0] = 0.0;
+    for (int i = 0; i < nf; ++i) tf[i + 1] = tf[i] + t.dtf[i];
+    for (int j = 0; j < n; ++j) t.den[j] = tc[j + 1] - tc[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= nf; i += blockDim.x) {
+    const double x = tf[i];
+    int j;
+    if (x >= tc[n]) {
+      j = n;
+    } else {
+      int lo = 0, hi = n;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        if (tc[mid] <= x) lo = mid; else hi = mid - 1;
+      }
+      j = lo;
+    }
+    t.jc[i] = j;
+    t.dx[i] = x - tc[j];
+    t.exact[i] = (j >= n || tc[j] == x) ? 1 : 0;
+  }
+}
+
+// batch mean of err_steps[b][r] per coarse step (fixed-order tree)
+__global__ void fd_loop_mean_kernel(long long B, int n, const double* __restrict__ steps, double* __restrict__ mean) {
+  __shared__ double sm[256];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  double acc = 0.0;
+  for (long long b = tid; b < B; b += 256) acc += steps[(size_t)b * n + r];
+  sm[tid] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) sm[tid] += sm[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) mean[r] = sm[0] / (double)B;
+}
+
+__global__ void fd_refine_kernel(int n, const double* __restrict__ ind, const double* __restrict__ times,
+                                 double* __restrict__ times_next, int* __restrict__ ref_idx, double* __restrict__ total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int best = 0;
+  double bv = ind[0], tot = 0.0;
+  for (int k = 0; k < n; ++k) {       // np.argmax: first maximum
+    const double v = ind[k];
+    tot += v;
+    if (v > bv) {
+      bv = v;
+      best = k;
+    }
+  }
+  *ref_idx = best;
+  if (total) *total = tot;
+  if (times_next) {
+    for (int j = 0; j <= best; ++j) times_next[j] = times[j];
+    times_next[best + 1] = (times[best] + times[best + 1]) / 2.0;
+    for (int j = best + 1; j <= n; ++j) times_next[j + 1] = times[j];
+  }
+}
+
+}  // namespace dgadj
+
+extern "C" int dgadj_fd_adapt_loop(dgadj_handle* h, int64_t B, int32_t iters, int32_t n0, int32_t ref_factor, int32_t ode,
+                                   int32_t functional, const double* times0_host, const double* u0_dev,
+                                   double* times_hist_dev, double* err_hist_dev, int32_t* ref_idx_dev,
+                                   double* total_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || iters < 0 || n0 < 1 || !times0_host || !u0_dev || !times_hist_dev || !err_hist_dev || !ref_idx_dev)
+    return fail(h, DGADJ_ERR_INVALID, "bad fd_adapt_loop arguments");
+  if (ref_factor < 3 || ref_factor > FD_MAX_REF)
+    return fail(h, DGADJ_ERR_UNSUPPORTED, "ref_factor must be in [3, %d] (the reference requires > 2)", FD_MAX_REF);
+  if (ode != FD_ODE_SIN && ode != FD_ODE_LINEAR) return fail(h, DGADJ_ERR_INVALID, "unknown ode %d", ode);
+  if (functional < FD_FUNC_INT_U || functional > FD_FUNC_INT_U2) return fail(h, DGADJ_ERR_INVALID, "unknown functional %d", functional);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nmax = n0 + iters, nfmax = nmax * ref_factor, W = nmax + 2;
+  // scratch: tables (sized for the last mesh) | tc | tf | mean | coarse states [nmax+1][B] | err_steps [B][nmax]
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_dx = 0, o_den = o_dx + al(sizeof(double) * (nfmax + 1)), o_dtf = o_den + al(sizeof(double) * nmax),
+               o_dtn = o_dtf + al(sizeof(double) * nfmax), o_tc = o_dtn + al(sizeof(double) * nmax),
+               o_tf = o_tc + al(sizeof(double) * (nmax + 1)), o_jc = o_tf + al(sizeof(double) * (nfmax + 1)),
+               o_ex = o_jc + al(sizeof(int) * (nfmax + 1)), o_uc = o_ex + al(nfmax + 1),
+               o_steps = o_uc + al(sizeof(double) * (size_t)(nmax + 1) * (size_t)B),
+               need = o_steps + al(sizeof(double) * (size_t)nmax * (size_t)B);
+  if (need > h->fd_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->fd_scratch);
+    h->fd_scratch = nullptr;
+    h->fd_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->fd_scratch, need));
+    h->fd_bytes = need;
+  }
+  unsigned char* base = (unsigned char*)h->fd_scratch;
+  FdTablesRW tw = {(int*)(base + o_jc), (double*)(base + o_dx), (double*)(base + o_den), (double*)(base + o_dtf),
+                   (double*)(base + o_dtn), base + o_ex};
+  FdTables t = {tw.jc, tw.dx, tw.den, tw.dtf, tw.dtn, tw.exact};
+  double* tc = (double*)(base + o_tc);
+  double* tf = (double*)(base + o_tf);
+  double* uc = (double*)(base + o_uc);
+  double* steps = (double*)(base + o_steps);
+  CUDA_TRY(h, cudaMemcpyAsync(times_hist_dev, times0_host, (size_t)(n0 + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+  const int block = (B <= 16384) ? 32 : 128;   // small batches: spread the trajectories over more SMs
+  for (int it = 0; it <= iters; ++it) {
+    const int n = n0 + it;
+    const double* times = times_hist_dev + (size_t)it * W;
+    fd_tables_kernel<<<1, 128, 0, st>>>(n, ref_factor, times, tw, tc, tf);
+    fd_awr_kernel<<<(unsigned)((B + block - 1) / block), block, 0, st>>>(B, n, ref_factor, ode, functional, t, u0_dev, uc,
+                                                                        nullptr, nullptr, nullptr, steps, nullptr);
+    double* mrow = err_hist_dev + (size_t)it * nmax;
+    fd_loop_mean_kernel<<<n, 256, 0, st>>>(B, n, steps, mrow);
+    fd_refine_kernel<<<1, 32, 0, st>>>(n, mrow, times, it == iters ? nullptr : times_hist_dev + (size_t)(it + 1) * W,
+                                       ref_idx_dev + it, total_dev ? total_dev + it : nullptr);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 4;
+  }
+  return DGADJ_OK;
+}

@@ -150,6 +150,103 @@ __global__ void tdg_march_kernel(long long B, int Ks, int nq, int linear, double
   }
 }
 
+// The same march with one WARP per trajectory (small batches: config 5 has 4096 initial values, a handful
+// of warps for the whole device in the thread-per-trajectory form).  The lanes share the quadrature points
+// of an element (30 N + 1 of them, dg_march.m:29: the sin / cos evaluations are what a Newton iteration
+// costs), the partial sums meet in a butterfly of shuffles -- every lane ends with the same bits -- and each
+// lane then repeats the small dense solve.  Same stopping rule; the quadrature sums are associated
+// differently from the sequential kernel (rounding-level differences in U).
+template <int NP>
+__global__ void tdg_march_warp_kernel(long long B, int Ks, int nq, double tol, int maxit,
+                                      const double* __restrict__ ec, const double* __restrict__ y0,
+                                      double* __restrict__ y, int* __restrict__ its) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;   // whole warps leave together
+  const int blk = NP * NP + 2 * nq * NP + nq + 2;
+  double uR = y0[b];
+  for (int k = 0; k < Ks; ++k) {
+    const double* A = ec + (size_t)k * blk;
+    const double* Iq = A + NP * NP;
+    const double* Phi = Iq + nq * NP;
+    const double* w = Phi + nq * NP;
+    const double hk2 = 0.5 * w[nq];
+    const int npk = (int)w[nq + 1];
+    double U[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) U[i] = (i < npk) ? uR : 0.0;
+    int it = 0;
+    double err = 1.0;
+    while (it <= maxit && err > tol) {   // uniform over the warp: every lane holds the same err
+      double Mt[NP], J[NP][NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        Mt[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) J[i][j] = 0.0;
+      }
+      for (int q = lane; q < nq; q += 32) {
+        double ur = 0.0, ph[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          ur = fma(Iq[q * NP + i], U[i], ur);
+          ph[i] = Phi[q * NP + i];
+        }
+        double sn, cs;
+        sincos(ur, &sn, &cs);
+        const double ws = w[q] * sn, wc = w[q] * cs;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          Mt[i] = fma(ph[i], ws, Mt[i]);
+          const double pw = ph[i] * wc;
+#pragma unroll
+          for (int j = i; j < NP; ++j) J[i][j] = fma(pw, ph[j], J[i][j]);   // symmetric: upper triangle
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          Mt[i] += __shfl_xor_sync(0xffffffffu, Mt[i], o);
+#pragma unroll
+          for (int j = i; j < NP; ++j) J[i][j] += __shfl_xor_sync(0xffffffffu, J[i][j], o);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+#pragma unroll
+        for (int j = 0; j < i; ++j) J[i][j] = J[j][i];
+      }
+      double R[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        double r = fma(hk2, Mt[i], (i == 0) ? uR : 0.0);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          r = fma(A[i * NP + j], U[j], r);
+          J[i][j] = fma(hk2, J[i][j], A[i * NP + j]);
+        }
+        R[i] = r;
+      }
+      solve_dense<NP>(J, R);
+      double e2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        U[i] -= R[i];
+        e2 = fma(R[i], R[i], e2);
+      }
+      err = sqrt(e2);
+      ++it;
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      if (i == npk - 1) uR = U[i];
+      if (lane == 0) y[((size_t)b * Ks + k) * NP + i] = U[i];
+    }
+    if (its && lane == 0) its[(size_t)b * Ks + k] = it;
+  }
+}
+
 // reverse march: v[b][k][:], err[b][k]
 template <int NPP>
 __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, double y0_hard,
@@ -335,6 +432,42 @@ static int tdg_consts(dgadj_handle* h, const double* host, size_t n, cudaStream_
   return DGADJ_OK;
 }
 
+// One warp per trajectory below this batch size (nonlinear branch): the thread-per-trajectory kernel needs
+// ~150k trajectories to fill the device.  dgadj_set_tuning(block_threads = 1 / 32) forces either form.
+constexpr long long TDG_WARP_BATCH = 16384;
+static int tdg_launch_march(dgadj_handle* h, long long B, int Ks, int Np, int nq, int linear, double tol, int maxit,
+                            const double* ec_dev, const double* y0_dev, double* y_dev, int* its_dev, cudaStream_t st) {
+  const bool warp = !linear && (h->tune_block == 32 || (h->tune_block != 1 && B <= TDG_WARP_BATCH));
+  if (warp) {
+    const int block = 128;
+    const unsigned grid = (unsigned)((B * 32 + block - 1) / block);
+#define DGADJ_TDG_W(n) case n: tdg_march_warp_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, tol, maxit, ec_dev, y0_dev, y_dev, its_dev); break;
+    switch (Np) { DGADJ_TDG_W(2) DGADJ_TDG_W(3) DGADJ_TDG_W(4) DGADJ_TDG_W(5) DGADJ_TDG_W(6) }
+#undef DGADJ_TDG_W
+  } else {
+    const int block = 128;
+    const unsigned grid = (unsigned)((B + block - 1) / block);
+#define DGADJ_TDG_M(n) case n: tdg_march_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, tol, maxit, ec_dev, y0_dev, y_dev, its_dev); break;
+    switch (Np) { DGADJ_TDG_M(2) DGADJ_TDG_M(3) DGADJ_TDG_M(4) DGADJ_TDG_M(5) DGADJ_TDG_M(6) }
+#undef DGADJ_TDG_M
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return DGADJ_OK;
+}
+
+static int tdg_launch_adjoint(dgadj_handle* h, long long B, int Ks, int Npp, int nq, int linear, double y0_hard,
+                              const double* y0_dev, const double* ec_dev, const double* y_dev, double* v_dev,
+                              double* err_dev, cudaStream_t st) {
+  // small batches: 32 threads per CTA spread the trajectories over four times as many SMs
+  const int block = (B <= TDG_WARP_BATCH) ? 32 : 128;
+  const unsigned grid = (unsigned)((B + block - 1) / block);
+#define DGADJ_TDG_A(n) case n: tdg_adjoint_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, y0_hard, y0_dev, ec_dev, y_dev, v_dev, err_dev); break;
+  switch (Npp) { DGADJ_TDG_A(2) DGADJ_TDG_A(3) DGADJ_TDG_A(4) DGADJ_TDG_A(5) DGADJ_TDG_A(6) }
+#undef DGADJ_TDG_A
+  CUDA_TRY(h, cudaGetLastError());
+  return DGADJ_OK;
+}
+
 }  // namespace dgadj
 
 extern "C" int dgadj_tdg_march(dgadj_handle* h, int64_t B, int32_t Ks, int32_t Np, int32_t nq, int32_t linear,
@@ -348,12 +481,8 @@ extern "C" int dgadj_tdg_march(dgadj_handle* h, int64_t B, int32_t Ks, int32_t N
   const size_t blk = (size_t)Np * Np + 2 * (size_t)nq * Np + nq + 2;
   int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
   if (rc) return rc;
-  const int block = 128;
-  const unsigned grid = (unsigned)((B + block - 1) / block);
-#define DGADJ_TDG_M(n) case n: tdg_march_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, tol, maxit, h->tdg_scratch, y0_dev, y_dev, its_dev); break;
-  switch (Np) { DGADJ_TDG_M(2) DGADJ_TDG_M(3) DGADJ_TDG_M(4) DGADJ_TDG_M(5) DGADJ_TDG_M(6) }
-#undef DGADJ_TDG_M
-  CUDA_TRY(h, cudaGetLastError());
+  rc = tdg_launch_march(h, B, Ks, Np, nq, linear, tol, maxit, h->tdg_scratch, y0_dev, y_dev, its_dev, st);
+  if (rc) return rc;
   h->launches++;
   return DGADJ_OK;
 }
@@ -371,12 +500,8 @@ extern "C" int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t
   const size_t blk = Na * Na + Na + Na * Na + Na * Np_primal + (size_t)nq * Np_primal + (size_t)nq * Na + nq + 3;
   int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
   if (rc) return rc;
-  const int block = 128;
-  const unsigned grid = (unsigned)((B + block - 1) / block);
-#define DGADJ_TDG_A(n) case n: tdg_adjoint_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, y0_hard, y0_dev, h->tdg_scratch, y_dev, v_dev, err_dev); break;
-  switch (Np_primal) { DGADJ_TDG_A(2) DGADJ_TDG_A(3) DGADJ_TDG_A(4) DGADJ_TDG_A(5) DGADJ_TDG_A(6) }
-#undef DGADJ_TDG_A
-  CUDA_TRY(h, cudaGetLastError());
+  rc = tdg_launch_adjoint(h, B, Ks, Np_primal, nq, linear, y0_hard, y0_dev, h->tdg_scratch, y_dev, v_dev, err_dev, st);
+  if (rc) return rc;
   h->launches++;
   return DGADJ_OK;
 }
@@ -419,4 +544,179 @@ extern "C" int dgadj_tdg_err_contribution(dgadj_handle* h, int64_t B, int32_t Ks
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return DGADJ_OK;
+}
+
+// =======================================================================================================
+// Device-resident adaptive refinement loop of matlab/MAIN.m:29-166, batched over the
+// initial values on a shared mesh with the batch-mean indicator of python/Main_variable_params.py:340-341:
+//   per iteration  build the element blocks of the current mesh -> dg_march (MAIN.m:32) -> adj_march at order
+//                  n+1 with the indicator (MAIN.m:34) -> batch mean of |err| (MAIN.m:51) -> argmax element,
+//                  lowest index on ties, midpoint insertion (MAIN.m:137-141)
+// all enqueued on the caller's stream by ONE call: the mesh lives on the device, the number of elements of
+// iteration `it` is Ks0 + it whatever gets refined, so no launch shape depends on a result and nothing is
+// read back inside the loop.
+// Element blocks: every entry of a block is affine in the element width h (fem_setup.m:27-39 operators are
+// those of the reference element; M_k = h/2 M, hk = +-h; the polyfit/polyval interpolation matrices of
+// dg_march.m:47-49 / adj_march.m:75-79 are invariant under the affine map of an element), so the host hands
+// over two template blocks T0, T1 per kind and the device forms block_k = T0 + h_k T1.
+// =======================================================================================================
+namespace dgadj {
+
+__global__ void tdg_build_blocks_kernel(int Ks, const double* __restrict__ times, int blk_m, const double* __restrict__ m0,
+                                        const double* __restrict__ m1, double* __restrict__ out_m, int blk_a,
+                                        const double* __restrict__ a0, const double* __restrict__ a1,
+                                        double* __restrict__ out_a) {
+  const int k = blockIdx.x;
+  if (k >= Ks) return;
+  const double h = times[k + 1] - times[k];
+  for (int i = threadIdx.x; i < blk_m; i += blockDim.x) out_m[(size_t)k * blk_m + i] = fma(h, m1[i], m0[i]);
+  for (int i = threadIdx.x; i < blk_a; i += blockDim.x) {
+    double v = fma(h, a1[i], a0[i]);
+    if (i == blk_a - 1 && k == 0) v = 0.0;   // last_{k-1}: there is no element before the first
+    out_a[(size_t)k * blk_a + i] = v;
+  }
+}
+
+// batch mean of |err[b][k]| per element (block k; fixed-order tree: the same bits for every launch), the mean
+// terminal value, the largest Newton count, and the status of the solve:
+//   stats[0] = mean_b y[b][Ks-1][Np-1];  istats[0] = max its;  istats[1] = #elements-solves that hit maxit
+//   without converging;  istats[2] = #non-finite values in err
+__global__ void tdg_loop_reduce_kernel(long long B, int Ks, int Np, int maxit, const double* __restrict__ err,
+                                       const double* __restrict__ y, const int* __restrict__ its,
+                                       double* __restrict__ mean_err, double* __restrict__ stats, int* __restrict__ istats) {
+  __shared__ double sm[256];
+  __shared__ int smi[3][256];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  double acc = 0.0;
+  int mx = 0, nc = 0, bad = 0;
+  if (k < Ks) {
+    for (long long b = tid; b < B; b += 256) {
+      const double e = err[(size_t)b * Ks + k];
+      acc += fabs(e);
+      bad += !isfinite(e);
+      const int it = its[(size_t)b * Ks + k];
+      mx = max(mx, it);
+      nc += (it > maxit);
+    }
+  } else {   // block Ks: the terminal value of the primal
+    for (long long b = tid; b < B; b += 256) acc += y[((size_t)b * Ks + (Ks - 1)) * Np + (Np - 1)];
+  }
+  sm[tid] = acc;
+  smi[0][tid] = mx;
+  smi[1][tid] = nc;
+  smi[2][tid] = bad;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      sm[tid] += sm[tid + o];
+      smi[0][tid] = max(smi[0][tid], smi[0][tid + o]);
+      smi[1][tid] += smi[1][tid + o];
+      smi[2][tid] += smi[2][tid + o];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (k < Ks) {
+      mean_err[k] = sm[0] / (double)B;
+      atomicMax(&istats[0], smi[0][0]);
+      atomicAdd(&istats[1], smi[1][0]);
+      atomicAdd(&istats[2], smi[2][0]);
+    } else {
+      stats[0] = sm[0] / (double)B;
+    }
+  }
+}
+
+// argmax element (lowest index on ties: find(abs(err)==max(abs(err))) of MAIN.m:137 taken as its first
+// entry, np.argmax of Main_finite_difference.py:337) and midpoint insertion (MAIN.m:138-141 /
+// Main_finite_difference.py:338-341) into the next row of the mesh history
+__global__ void refine_shared_kernel(int K, const double* __restrict__ ind, const double* __restrict__ times,
+                                     double* __restrict__ times_next, int* __restrict__ ref_idx, double* __restrict__ total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int best = 0;
+  double bv = ind[0], tot = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double v = ind[k];
+    tot += v;
+    if (v > bv) {
+      bv = v;
+      best = k;
+    }
+  }
+  *ref_idx = best;
+  if (total) *total = tot;
+  if (times_next) {
+    for (int j = 0; j <= best; ++j) times_next[j] = times[j];
+    times_next[best + 1] = (times[best] + times[best + 1]) / 2.0;
+    for (int j = best + 1; j <= K; ++j) times_next[j + 1] = times[j];
+  }
+}
+
+}  // namespace dgadj
+
+extern "C" int dgadj_tdg_adapt_loop(dgadj_handle* h, const dgadj_tdg_loop_args* a, const double* y0_dev,
+                                    double* times_hist_dev, double* err_hist_dev, int32_t* ref_idx_dev,
+                                    double* stats_dev, int32_t* istats_dev, double* y_last_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (!a || a->B <= 0 || a->iters < 0 || a->Ks0 < 1 || !a->times0_host || !a->march_T0_host || !a->march_T1_host ||
+      !a->adj_T0_host || !a->adj_T1_host || !y0_dev || !times_hist_dev || !err_hist_dev || !ref_idx_dev)
+    return fail(h, DGADJ_ERR_INVALID, "bad tdg_adapt_loop arguments");
+  const int Np = a->Np, Na = Np + 1;
+  if (Np < 2 || Np > 6) return fail(h, DGADJ_ERR_UNSUPPORTED, "time-DG loop supports 1 <= N <= 5 (Np = %d)", Np);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nqm = a->nq_march, nqa = a->nq_adj;
+  const size_t blk_m = (size_t)Np * Np + 2 * (size_t)nqm * Np + nqm + 2;
+  const size_t blk_a = (size_t)Na * Na + Na + (size_t)Na * Na + (size_t)Na * Np + (size_t)nqa * Np + (size_t)nqa * Na + nqa + 3;
+  const int Kmax = a->Ks0 + a->iters;          // elements of the last solve
+  const int W = Kmax + 2;                      // row stride of the mesh history
+  const long long B = a->B;
+  // scratch: templates | blocks of the current mesh | y | its | err | mean
+  const size_t n_tmpl = 2 * blk_m + 2 * blk_a;
+  const size_t n_d = n_tmpl + (size_t)Kmax * (blk_m + blk_a) + (size_t)B * Kmax * Np + (size_t)B * Kmax + (size_t)Kmax + 8;
+  const size_t need = n_d * sizeof(double) + (size_t)B * Kmax * sizeof(int) + 64;
+  if (need > h->tdg_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->tdg_scratch);
+    h->tdg_scratch = nullptr;
+    h->tdg_bytes = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->tdg_scratch, need));
+    h->tdg_bytes = need;
+  }
+  double* d = h->tdg_scratch;
+  double *m0 = d, *m1 = m0 + blk_m, *a0 = m1 + blk_m, *a1 = a0 + blk_a;
+  double* bm = a1 + blk_a;
+  double* ba = bm + (size_t)Kmax * blk_m;
+  double* y = ba + (size_t)Kmax * blk_a;
+  double* err = y + (size_t)B * Kmax * Np;
+  double* mean = err + (size_t)B * Kmax;
+  int* its = (int*)(mean + Kmax + 8);
+  CUDA_TRY(h, cudaMemcpyAsync(m0, a->march_T0_host, blk_m * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(m1, a->march_T1_host, blk_m * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(a0, a->adj_T0_host, blk_a * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(a1, a->adj_T1_host, blk_a * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(times_hist_dev, a->times0_host, (size_t)(a->Ks0 + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (istats_dev) CUDA_TRY(h, cudaMemsetAsync(istats_dev, 0, (size_t)(a->iters + 1) * 3 * sizeof(int32_t), st));
+  int rc = DGADJ_OK;
+  for (int it = 0; it <= a->iters && rc == DGADJ_OK; ++it) {
+    const int Ks = a->Ks0 + it;
+    const double* times = times_hist_dev + (size_t)it * W;
+    tdg_build_blocks_kernel<<<Ks, 128, 0, st>>>(Ks, times, (int)blk_m, m0, m1, bm, (int)blk_a, a0, a1, ba);
+    const bool last = (it == a->iters);
+    double* yo = (last && y_last_dev) ? y_last_dev : y;
+    rc = tdg_launch_march(h, B, Ks, Np, nqm, a->linear, a->tol, a->maxit, bm, y0_dev, yo, its, st);
+    if (rc) break;
+    rc = tdg_launch_adjoint(h, B, Ks, Np, nqa, a->linear, a->y0_hard, a->y0_per_trajectory ? y0_dev : nullptr, ba, yo, nullptr, err, st);
+    if (rc) break;
+    double* mrow = err_hist_dev + (size_t)it * Kmax;
+    int* ist = istats_dev ? istats_dev + (size_t)it * 3 : (int*)(mean + Kmax);   // (scratch when not wanted)
+    if (!istats_dev) CUDA_TRY(h, cudaMemsetAsync(ist, 0, 3 * sizeof(int), st));
+    tdg_loop_reduce_kernel<<<Ks + 1, 256, 0, st>>>(B, Ks, Np, a->maxit, err, yo, its, mrow,
+                                                    stats_dev ? stats_dev + (size_t)it * 2 : mean + Kmax + 4, ist);
+    refine_shared_kernel<<<1, 32, 0, st>>>(Ks, mrow, times, last ? nullptr : times_hist_dev + (size_t)(it + 1) * W,
+                                            ref_idx_dev + it, stats_dev ? stats_dev + (size_t)it * 2 + 1 : nullptr);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 5;
+  }
+  return rc;
 }

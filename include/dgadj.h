@@ -265,6 +265,44 @@ int dgadj_tdg_err_contribution(dgadj_handle* h, int64_t B, int32_t Ks, int32_t N
                                const double* cvec_host, const double* y_dev, double* err_dev,
                                void* stream);
 
+/* The adaptive refinement loop of matlab/MAIN.m:29-166 with the mesh on the device, batched
+ * over initial values on a shared mesh with the batch-mean indicator (python/Main_variable_params.py:340-341):
+ * per iteration dg_march (MAIN.m:32), adj_march at order n+1 with the indicator (MAIN.m:34), mean_b |err|
+ * (MAIN.m:51), argmax element (lowest index on ties) and midpoint insertion (MAIN.m:137-141).  ONE call
+ * enqueues all iters+1 solves on `stream`; nothing is read back in between (iteration `it` has Ks0 + it
+ * elements whatever gets refined).  Uniform order n = Np - 1.  Element blocks (layout of dgadj_tdg_march /
+ * dgadj_tdg_adjoint) are affine in the element width h: block_k = T0 + h_k T1, the two templates per kind
+ * built by the host.
+ *   times_hist_dev[(iters+1)][Ks0+iters+2]: row `it` = the mesh of iteration `it` (Ks0+it+1 entries);
+ *   err_hist_dev[(iters+1)][Ks0+iters]:     row `it` = mean_b |err[b][k]|;
+ *   ref_idx_dev[iters+1]:                   element refined after iteration `it` (0-based);
+ *   stats_dev[(iters+1)][2] (or NULL):      {mean_b y(T), sum_k mean|err|};
+ *   istats_dev[(iters+1)][3] (or NULL):     {max Newton iterations, element solves that hit maxit without
+ *                                            converging (dg_march.m:69-73 prints those), non-finite indicators}
+ *   y_last_dev[B][Ks0+iters][Np] (or NULL): the primal of the last solve.                                    */
+typedef struct {
+  int64_t B;
+  int32_t iters, Ks0, Np, nq_march, nq_adj, linear, maxit;
+  int32_t y0_per_trajectory;   /* 1: every trajectory's first-element residual is measured against its own y0;
+                                  0: against y0_hard (the `y0 = 1` of adj_march.m:9) */
+  double tol, y0_hard;
+  const double* times0_host;                               /* [Ks0+1] */
+  const double* march_T0_host; const double* march_T1_host;
+  const double* adj_T0_host; const double* adj_T1_host;
+} dgadj_tdg_loop_args;
+int dgadj_tdg_adapt_loop(dgadj_handle* h, const dgadj_tdg_loop_args* args, const double* y0_dev,
+                         double* times_hist_dev, double* err_hist_dev, int32_t* ref_idx_dev, double* stats_dev,
+                         int32_t* istats_dev, double* y_last_dev, void* stream);
+
+/* The same for the finite-difference loop of python/Main_finite_difference.py:263-343: per iteration the
+ * interpolation tables of the current mesh, forwardSolve / adjSolve / errEst / window sums (dgadj_fd_awr),
+ * batch mean of err_steps, argmax step (np.argmax, :337) and midpoint insertion (:338-341) -- all on the device.
+ *   times_hist_dev[(iters+1)][n0+iters+2], err_hist_dev[(iters+1)][n0+iters], ref_idx_dev[iters+1],
+ *   total_dev[iters+1] (or NULL) = sum of the mean step indicators (the loop's `err`, :263).              */
+int dgadj_fd_adapt_loop(dgadj_handle* h, int64_t B, int32_t iters, int32_t n0, int32_t ref_factor, int32_t ode,
+                        int32_t functional, const double* times0_host, const double* u0_dev, double* times_hist_dev,
+                        double* err_hist_dev, int32_t* ref_idx_dev, double* total_dev, void* stream);
+
 /* Inviscid Burgers forward march (LSERK4) with SlopeLimitN (utils/SlopeLimitN.m:9-32,
  * SlopeLimitLin.m:10-18, minmod.m:6-12) applied to the initial state and after every stage,
  * on the handle's primal operators (dgadj_set_operators) and boundary type (periodic, or

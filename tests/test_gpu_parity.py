@@ -623,6 +623,14 @@ def test_adaptive_loop_fd_vs_reference_semantics(pkg, torch):
     hist = pkg.adapt_fd(torch.tensor([1.0], dtype=torch.float64, device="cuda"), iters=2)
     assert [h["ref_idx"] for h in hist] == [0, 0, 3]
     np.testing.assert_allclose(hist[0]["err_steps"], [0.436375956067089, 0.125822589823601], rtol=1e-12)
+    # the loops above ran on the device (dgadj_fd_adapt_loop: one call, the mesh never leaves the GPU); the
+    # host-driven loop (one dgadj_fd_awr per iteration) walks the same meshes
+    u0 = torch.tensor(np.random.default_rng(3).uniform(-3, 3, 512), device="cuda")
+    h_dev = pkg.adapt_fd(u0, iters=30, device_loop=True)
+    h_host = pkg.adapt_fd(u0, iters=30, device_loop=False)
+    for a_, b_ in zip(h_dev, h_host):
+        assert np.array_equal(a_["times"], b_["times"]) and a_["ref_idx"] == b_["ref_idx"]
+        np.testing.assert_allclose(a_["err_steps"], b_["err_steps"], rtol=1e-12, atol=1e-16)
 
 
 def test_adaptive_loop_tdg(pkg, torch):
@@ -640,6 +648,39 @@ def test_adaptive_loop_tdg(pkg, torch):
         times, Ns, ref_i = otdg.refine(times, Ns, mean_err, 1)
         assert hist[it]["ref_idx"] == ref_i
         Ks += 1
+    assert all(h["not_converged"] == 0 and h["non_finite"] == 0 for h in hist) and max(h["max_newton_its"] for h in hist) <= 6
+    # that loop ran on the device (dgadj_tdg_adapt_loop); the host-driven loop walks the same meshes
+    h_host = pkg.adapt_tdg(torch.tensor(y0, device="cuda"), iters=12, device_loop=False)
+    for a_, b_ in zip(hist, h_host):
+        assert np.array_equal(a_["times"], b_["times"]) and a_["ref_idx"] == b_["ref_idx"]
+        np.testing.assert_allclose(a_["err"], b_["err"], rtol=1e-9, atol=1e-13)
+        assert a_["max_newton_its"] == b_["max_newton_its"]
+        assert abs(a_["yT_mean"] - b_["yT_mean"]) < 1e-12
+    # config 5's size: 4096 initial values, 30 refinements, second order -- device loop against host loop
+    y0b = torch.tensor(np.random.default_rng(0).uniform(-3, 3, 4096), device="cuda")
+    for n in (1, 2):
+        hd = pkg.adapt_tdg(y0b, iters=30 if n == 1 else 8, n=n)
+        hh = pkg.adapt_tdg(y0b, iters=30 if n == 1 else 8, n=n, device_loop=False)
+        assert [h["ref_idx"] for h in hd] == [h["ref_idx"] for h in hh]
+        assert np.array_equal(hd[-1]["times"], hh[-1]["times"])
+
+
+def test_tdg_warp_march_equals_thread_march(pkg, torch):
+    """The warp-per-trajectory Newton march (small batches) against the thread-per-trajectory one: the same
+    Newton iteration counts, states equal to rounding (the quadrature sums are associated differently)."""
+    rng = np.random.default_rng(11)
+    y0 = torch.tensor(rng.uniform(-3, 3, 777), device="cuda")
+    times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.05, 1.95, 9))))
+    Ks = times.size - 1
+    for n in (1, 2, 3):
+        res = {}
+        for form, blk in (("thread", 1), ("warp", 32)):
+            s = pkg.TimeDG()
+            s._check(s.lib.dgadj_set_tuning(s._h, 0, blk, 0))
+            res[form] = s.dg_march(n * np.ones(Ks, dtype=int), Ks, times, y0)
+            s.close()
+        assert torch.equal(res["thread"][2], res["warp"][2])                      # Newton iteration counts
+        assert float((res["thread"][1] - res["warp"][1]).abs().max()) < 1e-13
 
 
 def test_tdg_quirk_c3_switch(pkg, torch):

@@ -6,7 +6,7 @@ SASS of the built library (no GPU needed):
 
 The kernel's time loops are `step loop { stage loop x nstages }` (forward phase: a fine and a coarse
 stage loop per step; adjoint phase: one stage loop per step).  Loops are recognised by their backward
-branches; a stage loop is a loop of > 150 instructions without another such loop inside, a step loop
+branches; a stage loop is a loop with >= 20 fp64 instructions and no other such loop inside, a step loop
 its smallest enclosing loop.  Per thread and step the count is  nstages x body(stage loops) (the rest of
 a step-loop body is left out: see analyse());  per update it is that over EPT elements x nstages stages
 x 2 (one forward and one adjoint update per element-stage).  fp64-pipe opcodes: DFMA DMUL DADD DSETP (and DMNMX / F2F.F64 if any).
@@ -62,7 +62,8 @@ def count(ins, lo, hi, ops=FP64):
 
 def analyse(ins, ept, nstages=5):
     loops = loops_of(ins)
-    big = [(lo, hi) for lo, hi in loops if (hi - lo) // 16 + 1 > 150]
+    # candidates: loops that hold real arithmetic (>= 20 fp64 instructions) -- not the spin loops of the waits
+    big = [(lo, hi) for lo, hi in loops if count(ins, lo, hi)[0] >= 20]
     # spin loops of mbarrier waits branch back from an out-of-line tail: they "contain" later code; drop loops
     # that contain the start of another big loop's *enclosing* step loop by keeping only properly nested ones
     stage = [l for l in big if not any(o != l and l[0] <= o[0] and o[1] <= l[1] for o in big)]

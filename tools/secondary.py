@@ -130,10 +130,10 @@ def cfg3(pkg, torch, dev, sm_mhz, pool=None, B=16384, T=0.4, parity=True):
         res["max_rel_diff_vs_oracle"] = dict(worst, sample="first 2 trajectories, S=%d" % Sp)
     if pool is not None:
         t0 = time.perf_counter()
-        r = pool.map(_cfg3_cpu_worker, [(40, 100 + i) for i in range(pool.workers)])
+        r = pool.map(_cfg3_cpu_worker, [(600, 100 + i) for i in range(pool.workers)])
         sec = time.perf_counter() - t0
         res["cpu_baseline"] = dict(value=sum(x[0] for x in r) / sec, unit="updates/s", cores=pool.workers, kind="port",
-                                   sample="%d workers x 1 trajectory x S=40 steps of the same workload (oracle/burgers.py, NumPy fp64), %.1f s wall"
+                                   sample="%d workers x 1 trajectory x S=600 steps of the same workload (oracle/burgers.py, NumPy fp64), %.1f s wall"
                                           % (pool.workers, sec))
     s.close()
     return res
@@ -247,15 +247,18 @@ def cfg4(pkg, torch, dist, rank, world, dev, sm_mhz, pool=None, chunk=131072, pa
         ref = advec.fwd_adj_indicator(u0[pick].cpu().numpy(), view(s.g), view(s.gf), a[pick].cpu().numpy(), dt[pick].cpu().numpy(), S,
                                       alpha=0.0, bc=advec.BC_PERIODIC)
         rel = lambda x_, r: float(np.max(np.abs(x_ - r)) / np.max(np.abs(r)))
+        # (the narrow pulses are zero to rounding away from the pulse: there the indicator and its own scale are both
+        #  noise of the pulse's, so the yardstick is the trajectory's largest indicator scale -- as in tests/test_gpu_parity.py)
+        yard = ref["eta_scale"].max(axis=1, keepdims=True)
         res["max_rel_diff_vs_oracle"] = dict(uT=rel(got["uT"].cpu().numpy(), ref["uT"]), lam0=rel(got["lam0"].cpu().numpy(), ref["lam0"]),
-                                             eta_over_scale=float(np.max(np.abs(got["eta"].cpu().numpy() - ref["eta"]) / ref["eta_scale"])),
+                                             eta_over_scale=float(np.max(np.abs(got["eta"].cpu().numpy() - ref["eta"]) / yard)),
                                              sample="%d trajectories of rank 0's first chunk" % int(pick.numel()))
     if pool is not None:
         t0 = time.perf_counter()
-        r = pool.map(_cfg4_cpu_worker, [(i * 4099, 64) for i in range(pool.workers)])
+        r = pool.map(_cfg4_cpu_worker, [(i * 4099, 1024) for i in range(pool.workers)])
         sec = time.perf_counter() - t0
         res["cpu_baseline"] = dict(value=sum(x_[0] for x_ in r) / sec, unit="updates/s", cores=pool.workers, kind="port",
-                                   sample="%d workers x 64 trajectories of the sweep (oracle/advec.py, NumPy fp64), %.1f s wall" % (pool.workers, sec))
+                                   sample="%d workers x 1024 trajectories of the sweep (oracle/advec.py, NumPy fp64), %.1f s wall" % (pool.workers, sec))
     s.close()
     return res
 
@@ -346,7 +349,7 @@ def cfg5(pkg, torch, dev, pool=None, B=4096, iters=30):
                 refined_first=[int(h["ref_idx"]) for h in h_fd[:3]]))
     if pool is not None:
         t0 = time.perf_counter()
-        r = pool.map(_cfg5_fd_cpu_worker, [(float(v), iters) for v in rng.uniform(-3, 3, pool.workers * 4)])
+        r = pool.map(_cfg5_fd_cpu_worker, [(float(v), iters) for v in rng.uniform(-3, 3, pool.workers * 160)])
         sec = time.perf_counter() - t0
         res["fd"]["cpu_baseline"] = dict(value=sum(x[0] for x in r) / sec, unit="fine-step updates/s", cores=pool.workers, kind=r[0][2],
                                          sample="%d single-trajectory loops (%d iterations each) over %d workers, %s, %.1f s wall"
