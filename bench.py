@@ -269,8 +269,10 @@ def ours(a):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # (a short collective timeout: a rank that drops out must fail the run quickly, not hold the box)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     N, K, B, S = a.N, a.K, a.B, a.S
     s = pkg.AdvecDG1D(N, K, domain=(0.0, TWO_PI), alpha=0.0, bc="periodic", device=local)

@@ -1100,17 +1100,20 @@ def test_matlab_named_entry_points(pkg, torch):
     assert y1.shape == (3, 4, 2) and v.shape == (3, 4, 3) and err.shape == (3, 4)
 
 
-def test_nccl_c_abi_allreduce_two_gpus(torch):
-    """dgadj_allreduce_indicators on a raw ncclComm_t, one rank per GPU (tools/nccl_abi_check.py):
-    bit-identical to the torch.distributed path and to every other rank, equal to the unsharded
-    batch at 1e-12.  Needs two GPUs on the box."""
+@pytest.mark.parametrize("ranks", [2, 8])
+def test_nccl_c_abi_allreduce_multi_gpu(torch, ranks):
+    """dgadj_allreduce_indicators / dgadj_allreduce_indicator_blocks on a raw ncclComm_t, one rank per GPU
+    (tools/nccl_abi_check.py): bit-identical to the torch.distributed path and to every other rank; the
+    one-partial-per-rank form equal to the unsharded batch at 1e-12, the blocked form BIT-IDENTICAL to it.
+    Self-skips on a box with fewer GPUs (logs of the 2- and 8-rank runs are kept under profiles/)."""
     import subprocess
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "nccl_abi_check.py")],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "nccl C-ABI all-reduce ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    if torch.cuda.device_count() < ranks:
+        pytest.skip(f"needs {ranks} GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks),
+                        "--master-addr", "127.0.0.1", "--master-port", str(29541 + ranks), os.path.join(ROOT, "tools", "nccl_abi_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "nccl C-ABI all-reduce ok" in r.stdout and "blocked all-reduce ok" in r.stdout, \
+        r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_randomised_secondary_paths(pkg, torch):

@@ -64,8 +64,25 @@ assert int(got[:K].argmax()) == int(whole[:K].argmax())
 gathered = [None] * world
 dist.all_gather_object(gathered, got.cpu().numpy().tobytes())
 assert all(g == gathered[0] for g in gathered)          # the same bits on every rank
+# count-independent form: block partials (125 trajectories per block: whole blocks per rank for 2, 4 or 8 ranks)
+# all-gathered and combined in global block order through the C-ABI on the raw communicator -- the SAME BITS as
+# the unsharded batch reduced on one GPU, and as the torch.distributed path
+R = 125
+parts = s.reduce_indicator_blocks(out["eta"], out["J"], rows_per_block=R)
+tot = torch.empty(K + 4, dtype=torch.float64, device="cuda")
+rc = s.lib.dgadj_allreduce_indicator_blocks(s._h, C.c_void_p(comm.value), K, parts.shape[0], C.c_void_p(parts.data_ptr()),
+                                            C.c_void_p(tot.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+assert rc == 0, s.lib.dgadj_last_error(s._h)
+torch.cuda.synchronize()
+one = pkg.combine_blocks(s.reduce_indicator_blocks(full["eta"], full["J"], rows_per_block=R))
+assert torch.equal(tot, one), (tot - one).abs().max()
+assert torch.equal(pkg.allreduce_indicator_blocks(parts), one)
+import hashlib
+digest = hashlib.sha256(tot.cpu().numpy().tobytes()).hexdigest()
 nccl.ncclCommDestroy(comm)
 if rank == 0:
     print("nccl C-ABI all-reduce ok: world %d, K+4 = %d, vs torch.distributed bit-identical, vs unsharded rel %.1e, refine element %d"
           % (world, K + 4, relerr, int(got[:K].argmax())))
+    print("nccl C-ABI blocked all-reduce ok: world %d, %d blocks per rank, BIT-IDENTICAL to the unsharded batch; sha256 %s"
+          % (world, parts.shape[0], digest))
 dist.destroy_process_group()
