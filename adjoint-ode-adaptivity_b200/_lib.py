@@ -92,6 +92,7 @@ PROTOTYPES = {
     "dgadj_burgers_fwd_adj": (C.c_int, [_P, C.POINTER(BurgersArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
     "dgadj_burgers_plan": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dgadj_march_status": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "dgadj_ic_indicator": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "dgadj_rank": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "dgadj_reduce_indicators": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
@@ -107,6 +108,26 @@ PROTOTYPES = {
     "dgadj_host_eo_operators": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _D]),
     "dgadj_host_modal_operators": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _D]),
 }
+
+STATUS_NOT_CONVERGED, STATUS_NON_FINITE = 1, 2
+
+
+def march_status(lib, h, torch, values=None, its=None, maxit=0, stream=None):
+    """status[B] (int32 view of the uint32 word) through `dgadj_march_status`: values = a float64 CUDA tensor
+    [B, ...] (NaN / Inf check), its = an int32 CUDA tensor [B, ...] of Newton counts (its > maxit = not converged)."""
+    ref = values if values is not None else its
+    B = ref.shape[0]
+    status = torch.empty(B, dtype=torch.int32, device=ref.device)
+    v = None if values is None else values.contiguous()
+    i = None if its is None else its.contiguous()
+    st = C.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream) if stream is None else stream
+    rc = lib.dgadj_march_status(h, B, 0 if v is None else v.numel() // B, C.c_void_p(0 if v is None else v.data_ptr()),
+                                0 if i is None else i.numel() // B, C.c_void_p(0 if i is None else i.data_ptr()), int(maxit),
+                                C.c_void_p(status.data_ptr()), st)
+    if rc != OK:
+        raise DgadjError(rc, lib.dgadj_last_error(h).decode())
+    return status
+
 
 _lib = None
 

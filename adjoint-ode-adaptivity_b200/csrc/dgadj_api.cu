@@ -1475,6 +1475,39 @@ extern "C" int dgadj_reduce_indicator_blocks(dgadj_handle* h, int64_t B, int32_t
   return DGADJ_OK;
 }
 
+// per-trajectory status word ("failure detection": the reference only prints Newton
+// non-convergence, matlab/dg_march.m:69-73): one warp per trajectory scans its values / iteration counts
+namespace dgadj {
+__global__ void status_kernel(long long B, long long nval, const double* __restrict__ vals, int nits,
+                              const int* __restrict__ its, int maxit, unsigned* __restrict__ status) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  bool bad = false, nc = false;
+  if (vals)
+    for (long long i = lane; i < nval; i += 32) bad |= !isfinite(vals[(size_t)b * nval + i]);
+  if (its)
+    for (int i = lane; i < nits; i += 32) nc |= its[(size_t)b * nits + i] > maxit;
+  const unsigned anybad = __ballot_sync(0xffffffffu, bad), anync = __ballot_sync(0xffffffffu, nc);
+  if (lane == 0) status[b] = (anync ? DGADJ_STATUS_NOT_CONVERGED : 0u) | (anybad ? DGADJ_STATUS_NON_FINITE : 0u);
+}
+}  // namespace dgadj
+
+extern "C" int dgadj_march_status(dgadj_handle* h, int64_t B, int64_t values_per_trajectory, const double* values_dev,
+                                  int32_t its_per_trajectory, const int32_t* its_dev, int32_t maxit, uint32_t* status_dev,
+                                  void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || !status_dev || (!values_dev && !its_dev) || values_per_trajectory < 0 || its_per_trajectory < 0)
+    return fail(h, DGADJ_ERR_INVALID, "bad march_status arguments");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int block = 128;
+  status_kernel<<<(unsigned)((B * 32 + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
+      B, values_per_trajectory, values_dev, its_per_trajectory, its_dev, maxit, status_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}
+
 extern "C" int dgadj_measure_dfma_peak(dgadj_handle* h, double seconds, double* tflops_out,
                                        double* sm_clock_mhz_out) {
   if (!h || !tflops_out) return DGADJ_ERR_INVALID;

@@ -361,6 +361,16 @@ class AdvecDG1D:
         self._check(self.lib.dgadj_reduce_indicators(self._h, B, K, _ptr(eta), _ptr(J), _ptr(sums), self._stream()))
         return sums
 
+    def status(self, *fields):
+        """status[B] int32 of a march's outputs (device tensors [B, ...]: uT, lam0, eta ...): bit 1
+        (`_lib.STATUS_NON_FINITE`) = a NaN or Inf among the trajectory's values (`dgadj_march_status`)."""
+        torch = _torch()
+        out = None
+        for f in fields:
+            st = _lib.march_status(self.lib, self._h, torch, values=_as_device_tensor(f), stream=self._stream())
+            out = st if out is None else (out | st)
+        return out
+
     def reduce_indicator_blocks(self, eta, J=None, rows_per_block=None):
         """parts[nblk, K+4]: the sums of `reduce_indicators` over fixed blocks of `rows_per_block`
         trajectories (default sharding.REDUCE_BLOCK) -- the count-independent form that

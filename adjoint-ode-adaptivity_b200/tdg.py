@@ -238,7 +238,16 @@ class TimeDG:
         self._check(self.lib.dgadj_tdg_march(self._h, B, Ks, NP, nq, int(self.linear), self.tol, self.maxit,
                                              C.c_void_p(consts.ctypes.data), C.c_void_p(y0.data_ptr()),
                                              C.c_void_p(y.data_ptr()), C.c_void_p(its.data_ptr()), self._stream()))
+        # per-trajectory status word (the reference prints "not converged", dg_march.m:69-73): kept for `status()`
+        self._last = (y, its)
         return nodes, y, its
+
+    def status(self, y=None, its=None):
+        """status[B] int32 of a march (default: the last `dg_march`): bit 0 = a Newton solve stopped at maxit + 1
+        iterations without meeting the tolerance (dg_march.m:69-73), bit 1 = a non-finite value in y."""
+        if y is None and its is None:
+            y, its = self._last
+        return _lib.march_status(self.lib, self._h, self.torch, values=y, its=its, maxit=self.maxit, stream=self._stream())
 
     def adj_march(self, Ns, Ks, times, y1, t1, y0=1.0):
         """[t, v, err] = adj_march(Ns, Ks, times)  (matlab/adj_march.m:1); the primal the

@@ -374,6 +374,18 @@ int dgadj_burgers_fwd_adj(dgadj_handle* h, const dgadj_burgers_args* args, const
 int dgadj_burgers_plan(dgadj_handle* h, int64_t B, int32_t indicator, int32_t* ept, int32_t* block,
                        int32_t* grid, int64_t* smem_bytes, int64_t* ring_bytes_per_step);
 
+/* Per-trajectory status word of a march (the reference's only failure report is the
+ * "not converged" print of matlab/dg_march.m:69-73): status_dev[b] = DGADJ_STATUS_NOT_CONVERGED if any of the
+ * trajectory's its_per_trajectory Newton counts exceeds maxit (dg_march stops at maxit + 1 iterations),
+ * | DGADJ_STATUS_NON_FINITE if any of its values_per_trajectory doubles (a state, an adjoint, indicators) is
+ * NaN or Inf.  Either array may be NULL.  (dgadj_burgers_fwd_adj and the adaptive loops report the same
+ * conditions themselves.)                                                                                */
+#define DGADJ_STATUS_NOT_CONVERGED 1u
+#define DGADJ_STATUS_NON_FINITE 2u
+int dgadj_march_status(dgadj_handle* h, int64_t B, int64_t values_per_trajectory, const double* values_dev,
+                       int32_t its_per_trajectory, const int32_t* its_dev, int32_t maxit, uint32_t* status_dev,
+                       void* stream);
+
 /* Register-only DFMA microbenchmark: sustained fp64 FMA-pipe peak of the handle's device
  * in TFLOP/s (the roofline denominator SURVEY section 8(d) asks to be measured).        */
 int dgadj_measure_dfma_peak(dgadj_handle* h, double seconds, double* tflops_out,

@@ -1100,6 +1100,72 @@ def test_matlab_named_entry_points(pkg, torch):
     assert y1.shape == (3, 4, 2) and v.shape == (3, 4, 3) and err.shape == (3, 4)
 
 
+def test_reference_argument_lists(pkg, torch):
+    """the reference's own argument lists, through the module-level state that stands in
+    for its globals (utils/Globals1D.m:3-17; y1 / t1 of matlab/adj_march.m:4):
+        rhsu = AdvecRHS1D(u, timelocal, a);  ulimit = SlopeLimitN(u);  [t,y] = dg_march(Ns,Ks,times,y0,x_true,u_true);
+        [t,v,err] = adj_march(Ns,Ks,times);  forwardSolve(updateRule, dt_n, u0);  adjSolve(getK, getJF, dt_n, u, ref_factor);
+        errEst(fwdUpdate, u, v, dt_n, ref_factor)          (python/Main_finite_difference.py:34,54,79)
+    NumPy in -> NumPy out, as the reference; callables are probed against the reference's problem functions."""
+    from oracle import fd as ofd
+    from oracle import limiter as ol
+    from oracle import tdg as otdg
+    from adjoint_ode_adaptivity_b200 import fd as pfd
+    m = pkg.matlab_names
+    m.StartUp1D(3, 8, domain=(0.0, 1.0), alpha=1.0, bc="inflow", inflow="sin_at")
+    g = oracle_view(m.G.advec.g)
+    u = make_ics(g, 1, 0)[0]                                      # (Np, K): the reference's own shape
+    rhs = m.AdvecRHS1D(u, 0.3, 2.0)
+    assert isinstance(rhs, np.ndarray) and rhs.shape == u.shape
+    assert rel(rhs, advec.AdvecRHS1D(u, 0.3, 2.0, g, 1.0, advec.BC_INFLOW, advec.INFLOW_SIN_AT)) < 1e-13
+    rough = u + (g.x > 0.5)
+    assert rel(m.SlopeLimitN(rough), ol.SlopeLimitN(rough, oracle_view(m.G.burgers.g))) < 1e-13
+    assert rel(m.SlopeLimit1(rough), ol.SlopeLimit1(rough, oracle_view(m.G.burgers.g))) < 1e-13
+    v3 = np.array([[1.0, -1.0, 2.0, 0.5], [2.0, -3.0, -1.0, 0.25], [0.5, -2.0, 1.0, 1.0]])
+    assert np.array_equal(m.minmod(v3), ol.minmod(v3))
+    # matlab/MAIN.m:19-34 at iteration 0 (SURVEY App. B.2): scalar y0 = 1, Ks = 2, n = 1
+    times, Ns = np.array([0.0, 1.0, 2.0]), np.ones(2, dtype=int)
+    m.set_time_dg()
+    t1, y1 = m.dg_march(Ns, 2, times, 1.0, None, None)
+    t2, v, err = m.adj_march(Ns + 1, 2, times)
+    np.testing.assert_allclose(y1[0].cpu().numpy(), [[0.984104, 1.956225], [2.028961, 2.659823]], atol=2e-6)
+    np.testing.assert_allclose(err[0].cpu().numpy(), [-0.843478, 0.092681], atol=2e-6)
+    assert m.G.its[0].tolist() == [5, 4] and int(m.G.status[0]) == 0
+    ot1, oy1, _ = otdg.dg_march(Ns, 2, times, np.array([1.0]))
+    _, _, oerr = otdg.adj_march(Ns + 1, 2, times, oy1, ot1)
+    assert rel(err.cpu().numpy(), oerr) < 1e-10
+    # a Newton solve that cannot converge in the allowed iterations sets the status word (dg_march.m:69-73 prints it)
+    m.set_time_dg(maxit=1)
+    m.dg_march(Ns, 2, times, np.array([1.0, 2.5]))
+    assert (m.G.status.cpu().numpy() & pkg._lib.STATUS_NOT_CONVERGED).all()
+    m.set_time_dg()
+    # the FD free functions with the reference's closures (Main_finite_difference.py:131-140, :225-227)
+    fwdUpdate = lambda u_, dt, n: u_[n - 1] + np.sin(u_[n - 1]) * dt[n - 1]
+    getJF = lambda u_, dt: np.diag(1 + np.cos(u_[:-1]) * dt, -1)
+    getK = lambda dt, u_: np.concatenate((2 * u_[:-1] * dt, 0), axis=None)
+    dt_n = np.diff(np.array([0.0, 0.25, 0.5, 1.0, 2.0]))
+    uu = pfd.forwardSolve(fwdUpdate, dt_n, 1.0)
+    vv = pfd.adjSolve(getK, getJF, dt_n, uu, 4)
+    ee = pfd.errEst(fwdUpdate, uu, vv, dt_n, 4)
+    ref = ofd.fd_awr(np.array([1.0]), dt_n)
+    assert isinstance(uu, np.ndarray) and uu.shape == (5,) and vv.shape == (17,) and ee.shape == (17,)
+    assert np.array_equal(uu, ref["u"][0]) and np.array_equal(vv, ref["v"][0]) and np.array_equal(ee, ref["err_fine"][0])
+    with pytest.raises(NotImplementedError):
+        pfd.forwardSolve(lambda u_, dt, n: u_[n - 1] + np.tanh(u_[n - 1]) * dt[n - 1], dt_n, 1.0)
+    with pytest.raises(ValueError):
+        pfd.adjSolve(getK, getJF, dt_n, uu + 1e-3, 4)            # not the primal of uu[0]
+    # batched, device tensors
+    U0 = torch.tensor([1.0, -0.5, 2.2], device="cuda")
+    ub = pfd.forwardSolve(fwdUpdate, dt_n, U0)
+    assert torch.is_tensor(ub) and rel(ub.cpu().numpy(), ofd.forwardSolve(U0.cpu().numpy(), dt_n)) < 1e-15
+    # status words of the PDE march
+    s = m.G.advec
+    u0 = torch.tensor(make_ics(g, 3, 1), device="cuda")
+    u0[1, 0, 0] = float("nan")
+    out = s.fwd_adj(u0, 2.0, 1e-3, 5, want_lam0=True)
+    assert s.status(out["uT"], out["eta"]).tolist() == [0, pkg._lib.STATUS_NON_FINITE, 0]
+
+
 @pytest.mark.parametrize("ranks", [2, 8])
 def test_nccl_c_abi_allreduce_multi_gpu(torch, ranks):
     """dgadj_allreduce_indicators / dgadj_allreduce_indicator_blocks on a raw ncclComm_t, one rank per GPU

@@ -438,3 +438,34 @@ def test_refine_rules_insert_one_midpoint(pkg):
         assert np.array_equal(np.delete(t2, ref_i + 1), times) and np.all(np.diff(t2) > 0)
         assert np.array_equal(refine_mesh(times, ref_i), t2)
     check()
+
+
+def test_fd_callable_probing(pkg):
+    """The reference passes callables (python/Main_finite_difference.py:34,54,79); the host recognises the problem
+    functions of its __main__ block by probing them, and refuses anything else."""
+    from adjoint_ode_adaptivity_b200 import fd
+    sin_rule = lambda u, dt, n: u[n - 1] + np.sin(u[n - 1]) * dt[n - 1]                 # :131-132
+    lin_rule = lambda u, dt, n: (1 + dt[n - 1]) * u[n - 1]                             # :112-113
+    assert fd._identify_ode(updateRule=sin_rule) == "sin" and fd._identify_ode(updateRule=lin_rule) == "linear"
+    assert fd._identify_ode(getJF=lambda u, dt: np.diag(1 + np.cos(u[:-1]) * dt, -1)) == "sin"     # :138-140
+    assert fd._identify_ode(getJF=lambda u, dt: np.diag(1 + dt, -1)) == "linear"                   # :118-119
+    with pytest.raises(ValueError):
+        fd._identify_ode(updateRule=sin_rule, getJF=lambda u, dt: np.diag(1 + dt, -1))
+    with pytest.raises(NotImplementedError):
+        fd._identify_ode(updateRule=lambda u, dt, n: u[n - 1] * (1 - dt[n - 1]))
+    assert fd._identify_functional(lambda dt, u: np.concatenate((2 * u[:-1] * dt, 0), axis=None)) == "int_u2"   # :225-227
+    assert fd._identify_functional(lambda dt, u=None: np.concatenate((dt, 0), axis=None)) == "int_u"          # :153-155
+
+    def getK_uN(dt, u=None):                                                                                  # :162-165
+        k = np.zeros_like(dt)
+        k[-1] = 1
+        return np.concatenate((k, 0), axis=None)
+    assert fd._identify_functional(getK_uN) == "u_N"
+    with pytest.raises(NotImplementedError):
+        fd._identify_functional(lambda dt, u: np.concatenate((u[:-1] ** 3 * dt, 0), axis=None))
+    assert np.allclose(fd.interpU(None, np.array([1.0, 1.0]), np.array([0.0, 1.0, 3.0])), [0, .25, .5, .75, 1, 1.5, 2, 2.5, 3])
+    m = pkg.matlab_names
+    v3 = np.array([[1.0, -1.0, 2.0], [2.0, -3.0, -1.0], [0.5, -2.0, 1.0]])
+    assert m.minmod(v3).tolist() == [0.5, -1.0, 0.0]
+    with pytest.raises(RuntimeError):
+        m.AdvecRHS1D(np.zeros((3, 4)), 0.0, 1.0) if m.G.advec is None else (_ for _ in ()).throw(RuntimeError())
