@@ -44,14 +44,46 @@
 
 namespace dgadj {
 
-struct BgLevel {               // one polynomial space: primal (order N) or enriched (order N+1)
+// The operators the stage loops read.  One copy per RK stage, indexed by the stage counter: the copies are
+// identical, but a loop-invariant constant would be hoisted out of the stage loop into uniform registers --
+// 36 + 12 + 18 doubles against a file of 63 -- and spilled from there through local memory (seen in the SASS
+// as R2UR / LDL pairs); indexed by the counter they stay in the loop as constant-bank operands (the same
+// measure as in the advection kernel, dgadj_kernels.cuh).
+// MEASURED on config 3 (B200; N = 4, K = 256, B = 16384, S = 2373; updates/s, indicator mode / plain):
+//   first version (stage 4's state in registers, separate landing tile, mbarrier everywhere)   3.79e10 / 4.46e10
+//   + state tile lands in the idle stage slot, hardware barrier for exchanges without overlap  4.09e10 / 4.71e10
+//   + fourth resident CTA where it fits 128 registers (plain mode only)                           --    / 5.08e10
+//   + all five stage states in shared memory (the conditional register copy of stage 4 cost ~50 moves per
+//     stage), volume terms folded into the residual / adjoint before the wait, per-stage operator copies (no
+//     hoisting into uniform registers: 336 B of spills -> 0)                                    4.38e10 / 5.29e10
+//   split exchanges (BG_SPLIT 1) vs a plain hardware barrier at the arrive point (0): 4.399 / 4.415e10 -- no
+//   difference; nor does the suspend-time hint of the mbarrier wait matter (BG_SUSPEND_NS 0 vs 2000).
+//   Four elements per thread (64-thread CTAs): 2.25e10 (half the warps: latency bound); one per thread: 2.4e10.
+// ncu of the final form (profiles/r2_burgers_fused_ncu.json): fp64 pipe 47.3 %, issue slots 51 % busy, 46 % of
+// the issued instructions on the fp64 pipe; per issued instruction 1.49 cycles of fixed-latency waits, 0.91 on the
+// exchange mbarrier, 0.35 on the hardware barrier -- 12 warps per SM (3 CTAs: the five stage states of a
+// trajectory take 61 KB of shared memory) leave the schedulers without an eligible warp half of the time.
+#ifndef BG_SPLIT
+#define BG_SPLIT 1
+#endif
+#ifndef BG_SUSPEND_NS
+#define BG_SUSPEND_NS 2000u
+#endif
+#ifndef BG_STAGE_CONSTS
+#define BG_STAGE_CONSTS 1
+#endif
+struct BgStageOps {
   StageOps so;                 // even/odd blocks of the nodal Dr / LIFT (forward volume and lift terms)
   double Dr[MAXNP * MAXNP];    // nodal Dr (transposed volume term)
   double LIFT[MAXNP * 2];
   double aw[MAXNP];            // cell average weights  V(1,1)*invV(1,:)                 (SlopeLimitN.m:9)
+};
+struct BgLevel {               // one polynomial space: primal (order N) or enriched (order N+1)
+  BgStageOps st[BG_STAGE_CONSTS ? 5 : 1];
   double sl[MAXNP];            // slope weights         Dr(1,:)*V(:,1:2)*invV(1:2,:)     (SlopeLimitLin.m:16)
   double xcn[MAXNP];           // (x - x0)/(h/2) = the reference nodes                   (SlopeLimitLin.m:11-12)
   const double *rxk, *fs0, *fs1;   // [K]
+  __host__ __device__ const BgStageOps& ops(int s) const { return st[BG_STAGE_CONSTS ? s : 0]; }
 };
 
 struct BgFusedArgs {
@@ -147,15 +179,22 @@ struct BgCtx {
   double* mv;               // [5] wave speeds of the step being transposed
   int* am;                  // [5] argmax of the step being transposed ((flat << 1) | negative)
 
+  // BG_SPLIT = 1: split exchange (mbarrier arrive, work, wait); 0: a plain hardware barrier at the arrive point
   __device__ __forceinline__ void arrive() {
+#if BG_SPLIT
     __syncwarp();
     if (NW > 1 && lane == 0) mbar_arrive(bar);
+#else
+    sync();
+#endif
   }
   __device__ __forceinline__ void wait() {
+#if BG_SPLIT
     if (NW > 1) {
-      mbar_wait_suspend(bar, phase, 2000u);
+      mbar_wait_suspend(bar, phase, BG_SUSPEND_NS);
       phase ^= 1u;
     }
+#endif
   }
   // an exchange with nothing to do between publishing and reading: the hardware barrier parks the warp
   // instead of spinning on the mbarrier (spin iterations cost issue slots the other warps can use)
@@ -191,14 +230,15 @@ __device__ __forceinline__ void bg_flush_vote(BgCtx<BD>& cx, int& pend) {
 }
 
 template <int NPX, int EPT, int BD>
-__device__ __forceinline__ void bg_limiter(const BgFusedArgs& p, const BgLevel& L, BgCtx<BD>& cx, int k0,
+__device__ __forceinline__ void bg_limiter(const BgFusedArgs& p, const BgLevel& L, int s, BgCtx<BD>& cx, int k0,
                                            double (&u)[EPT][NPX], int (&code)[EPT]) {
+  const BgStageOps& Ls = L.ops(s);
   double v[EPT];
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
-    double a = L.aw[0] * u[e][0];
+    double a = Ls.aw[0] * u[e][0];
 #pragma unroll
-    for (int i = 1; i < NPX; ++i) a = fma(L.aw[i], u[e][i], a);
+    for (int i = 1; i < NPX; ++i) a = fma(Ls.aw[i], u[e][i], a);
     v[e] = a;
   }
   double* eA = cx.A();
@@ -241,6 +281,7 @@ __device__ __forceinline__ void bg_stage(const BgFusedArgs& p, const BgLevel& L,
                                          int s, int (&code)[EPT], int& pend) {
   constexpr int HE = (NPX + 1) / 2, HO = NPX / 2;
   constexpr int NW = BD / 32;
+  const BgStageOps& Ls = L.ops(s);
   // ---- exchange 1: traces and the mesh-wide max|u| (value first; where it sits is voted afterwards)
   double m = -1.0;
   if (cx.in) {
@@ -263,8 +304,9 @@ __device__ __forceinline__ void bg_stage(const BgFusedArgs& p, const BgLevel& L,
   double* wr = cx.W();
   if (NW > 1 && cx.lane == 0) wr[cx.wid] = mw;
   cx.arrive();
-  // volume terms (no neighbour data): E_i = c1 (DE Fo)_i, O_i = c1 (DO Fe)_i with F = u^2
-  double E[EPT][HE], O[EPT][HO > 0 ? HO : 1];
+  // volume terms (no neighbour data), folded into the RK residual at once: with F = u^2,
+  //   E_i = c1 (DE Fo)_i, O_i = c1 (DO Fe)_i;  dt rhs_i = E_i + O_i, dt rhs_{N-i} = E_i - O_i, dt rhs_mid = 2 E_mid
+  const double rka = p.rka[s], rkb = p.rkb[s];
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
     double fe[HE], fo[HO > 0 ? HO : 1];
@@ -278,23 +320,24 @@ __device__ __forceinline__ void bg_stage(const BgFusedArgs& p, const BgLevel& L,
     if (NPX & 1) fe[NPX / 2] = (cf[e].c1 * u[e][NPX / 2]) * u[e][NPX / 2];
 #pragma unroll
     for (int i = 0; i < HE; ++i) {
-      double acc = 0.0;
+      double E = 0.0;
 #pragma unroll
       for (int j = 0; j < HO; ++j) {
-        const double2 c2 = L.so.DE2[i * HP + j / 2];
-        acc = fma((j & 1) ? c2.y : c2.x, fo[j], acc);
+        const double2 c2 = Ls.so.DE2[i * HP + j / 2];
+        E = fma((j & 1) ? c2.y : c2.x, fo[j], E);
       }
-      E[e][i] = acc;
-    }
+      if (i < HO) {
+        double O = 0.0;
 #pragma unroll
-    for (int i = 0; i < HO; ++i) {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < HE; ++j) {
-        const double2 c2 = L.so.DO2[i * HP + j / 2];
-        acc = fma((j & 1) ? c2.y : c2.x, fe[j], acc);
+        for (int j = 0; j < HE; ++j) {
+          const double2 c2 = Ls.so.DO2[i * HP + j / 2];
+          O = fma((j & 1) ? c2.y : c2.x, fe[j], O);
+        }
+        res[e][i] = fma(rka, res[e][i], E + O);
+        res[e][NPX - 1 - i] = fma(rka, res[e][NPX - 1 - i], E - O);
+      } else {
+        res[e][i] = fma(rka, res[e][i], E + E);   // the middle node of an odd node count
       }
-      O[e][i] = acc;
     }
   }
   cx.wait();
@@ -328,42 +371,38 @@ __device__ __forceinline__ void bg_stage(const BgFusedArgs& p, const BgLevel& L,
     cx.vs ^= 1;
     if (cx.tid == 0) cx.mv[s] = maxvel;
   }
-  // ---- surface terms, RK update
+  // ---- surface terms (the lift of the Lax-Friedrichs flux), state update
   const double twoC = maxvel + maxvel;
-  const double rka = p.rka[s], rkb = p.rkb[s];
+  double G0[EPT], G1[EPT];
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) {
+  for (int e = 0; e < EPT; ++e) {   // (all fluxes first: they read the neighbours' states of this stage)
     const double uL = (e == 0) ? uLL : u[e - 1][NPX - 1];
     const double uR = (e == EPT - 1) ? uRR : u[e + 1][0];
-    const double G0 = (cf[e].k0 * (u[e][0] - uL)) * ((u[e][0] + uL) + twoC);
-    const double G1 = (cf[e].k1 * (u[e][NPX - 1] - uR)) * ((u[e][NPX - 1] + uR) - twoC);
-    const double ge = G0 + G1, go = G0 - G1;
-#pragma unroll
-    for (int i = 0; i < HE; ++i) {
-      const double2 l2 = L.so.LS2[i / 2];
-      E[e][i] = fma((i & 1) ? l2.y : l2.x, ge, E[e][i]);
-    }
-#pragma unroll
-    for (int i = 0; i < HO; ++i) {
-      const double2 l2 = L.so.LA2[i / 2];
-      O[e][i] = fma((i & 1) ? l2.y : l2.x, go, O[e][i]);
-    }
+    G0[e] = (cf[e].k0 * (u[e][0] - uL)) * ((u[e][0] + uL) + twoC);
+    G1[e] = (cf[e].k1 * (u[e][NPX - 1] - uR)) * ((u[e][NPX - 1] + uR) - twoC);
   }
-  // (the neighbours' old traces are consumed: the state may change now)
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
+    const double ge = G0[e] + G1[e], go = G0[e] - G1[e];
 #pragma unroll
-    for (int i = 0; i < NPX / 2; ++i) {
-      res[e][i] = fma(rka, res[e][i], E[e][i] + O[e][i]);
-      res[e][NPX - 1 - i] = fma(rka, res[e][NPX - 1 - i], E[e][i] - O[e][i]);
+    for (int i = 0; i < HE; ++i) {
+      const double2 l2 = Ls.so.LS2[i / 2];
+      const double Es = ((i & 1) ? l2.y : l2.x) * ge;
+      if (i < HO) {
+        const double2 a2 = Ls.so.LA2[i / 2];
+        const double Os = ((i & 1) ? a2.y : a2.x) * go;
+        res[e][i] += Es + Os;
+        res[e][NPX - 1 - i] += Es - Os;
+      } else {
+        res[e][i] += Es + Es;
+      }
     }
-    if (NPX & 1) res[e][NPX / 2] = fma(rka, res[e][NPX / 2], E[e][NPX / 2] + E[e][NPX / 2]);
 #pragma unroll
     for (int i = 0; i < NPX; ++i) u[e][i] = fma(rkb, res[e][i], u[e][i]);
   }
   // ---- exchange 2: cell averages, limiter
   if (p.limit) {
-    bg_limiter<NPX, EPT, BD>(p, L, cx, k0, u, code);
+    bg_limiter<NPX, EPT, BD>(p, L, s, cx, k0, u, code);
   } else {
 #pragma unroll
     for (int e = 0; e < EPT; ++e) code[e] = 0;
@@ -389,8 +428,9 @@ __device__ __forceinline__ double bg_block_sum(BgCtx<BD>& cx, double v) {
 
 // transpose of the limiter on the recorded decisions (oracle/burgers.py: limiter_T)
 template <int NPX, int EPT, int BD>
-__device__ __forceinline__ void bg_limiter_T(const BgFusedArgs& p, const BgLevel& L, BgCtx<BD>& cx, int k0,
+__device__ __forceinline__ void bg_limiter_T(const BgFusedArgs& p, const BgLevel& L, int s, BgCtx<BD>& cx, int k0,
                                              const int (&code)[EPT], double (&lu)[EPT][NPX]) {
+  const BgStageOps& Ls = L.ops(s);
   double a[EPT], c[EPT], ch[EPT], tr[EPT], tl[EPT];
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
@@ -428,7 +468,7 @@ __device__ __forceinline__ void bg_limiter_T(const BgFusedArgs& p, const BgLevel
       double cs = 0.0;
       if (br == 1) cs = (2.0 / __ldg(p.hk + k0 + e)) * c[e];
 #pragma unroll
-      for (int i = 0; i < NPX; ++i) lu[e][i] = (flag ? 0.0 : lu[e][i]) + L.aw[i] * lv + L.sl[i] * cs;
+      for (int i = 0; i < NPX; ++i) lu[e][i] = (flag ? 0.0 : lu[e][i]) + Ls.aw[i] * lv + L.sl[i] * cs;
     }
   }
 }
@@ -452,9 +492,9 @@ __device__ __forceinline__ void bg_prolong(const double* __restrict__ P, const d
 
 __host__ __device__ constexpr size_t bg_fused_smem(int NP, int NPX, int EPT, int BD) {
   // 16 B mbarriers | exA, exB [2][BD+2] | wred [2][8] | mv [5] (+pad) | cand [2], am [5] (+pad) |
-  // stage states ss [4][NPX][EPT][BD]; the checkpoint tile [NP][EPT][BD] of the next step lands in ss[3]
+  // stage input states ss [5][NPX][EPT][BD]; the checkpoint tile [NP][EPT][BD] of the next step lands in ss[3]
   // while that slot is idle (between the transposes of stage 3 and the next step's stage 3)
-  return 16 + sizeof(double) * ((size_t)4 * (BD + 2) + 16 + 6 + 4 + (size_t)4 * NPX * EPT * BD);
+  return 16 + sizeof(double) * ((size_t)4 * (BD + 2) + 16 + 6 + 4 + (size_t)5 * NPX * EPT * BD);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -477,7 +517,7 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
   cx.mv = cx.wred + 16;
   cx.cand = reinterpret_cast<int*>(cx.mv + 6);
   cx.am = cx.cand + 2;
-  double* ss = cx.mv + 6 + 4;                                   // [4][NPX][EPT][BD]
+  double* ss = cx.mv + 6 + 4;                                   // [5][NPX][EPT][BD]
   double* land = ss + (size_t)3 * NPX * EPT * BD;               // [NP][EPT][BD] inside ss[3]
   constexpr size_t tile = (size_t)NP * EPT * BD;
   constexpr uint32_t tile_bytes = (uint32_t)(tile * sizeof(double));
@@ -496,6 +536,8 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
   cx.glast = cx.in && tid == KT - 1 && !p.periodic;
   cx.nbL = cx.in ? (tid == 0 ? (p.periodic ? KT - 1 : BD) : tid - 1) : tid;
   cx.nbR = cx.in ? (tid == KT - 1 ? (p.periodic ? 0 : BD + 1) : tid + 1) : tid;
+  // neighbour threads in the periodic sense (the ends of a non-periodic mesh override what they read there)
+  const int nbLp = cx.in ? (tid == 0 ? KT - 1 : tid - 1) : tid, nbRp = cx.in ? (tid == KT - 1 ? 0 : tid + 1) : tid;
   cx.bar = &mbar[1];
   cx.phase = 0u;
   if (tid == 0) {
@@ -532,7 +574,7 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
         }
       }
       int code[EPT];
-      if (p.limit) bg_limiter<NP, EPT, BD>(p, L0, cx, k0, u, code);   // the pass on the initial state
+      if (p.limit) bg_limiter<NP, EPT, BD>(p, L0, 0, cx, k0, u, code);   // the pass on the initial state
 #pragma unroll 1
       for (int n = 0; n < p.S; ++n) {
         double* dst = ck + (size_t)n * tile + tid;   // u^n -> ring (coalesced)
@@ -646,23 +688,15 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
           for (int i = 0; i < NPX; ++i) res[e][i] = 0.0;
         }
       }
-      // ---- the step again (same routine, same bits), stage input states kept: ss[0..3] in shared
-      // memory, the fifth in registers
-      double x4[EPT][NPX];
+      // ---- the step again (same routine, same bits), the five stage input states kept in shared memory
 #pragma unroll 1
       for (int s = 0; s < 5; ++s) {
-        if (s < 4) {
+        {
           double* d = ss + (size_t)s * sstride + tid;
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
 #pragma unroll
             for (int i = 0; i < NPX; ++i) d[(size_t)(i * EPT + e) * BD] = x[e][i];
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < EPT; ++e) {
-#pragma unroll
-            for (int i = 0; i < NPX; ++i) x4[e][i] = x[e][i];
           }
         }
         int code[EPT];
@@ -692,7 +726,7 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
         int code[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) code[e] = (codes[e] >> (3 * s)) & 7;
-        bg_limiter_T<NPX, EPT, BD>(p, LXv, cx, k0, code, lu);
+        bg_limiter_T<NPX, EPT, BD>(p, LXv, s, cx, k0, code, lu);
         bg_flush_vote<BD>(cx, pend);   // (after an exchange that follows the last stage's vote)
         if (s == 2 && tid == 0 && n >= 1) {
           // every thread is past the transpose of stage 3, the last reader of ss[3]: the state tile of step
@@ -704,37 +738,23 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
         const double rka = p.rka[s], rkb = p.rkb[s];
         double us[EPT][NPX];
         double uLL, uRR;
-        if (s == 4) {
-          // the fifth stage state lives in registers: its outer traces cross through an exchange
-          double* eA = cx.A();
-          double* eB = cx.Bb();
-          eA[tid] = x4[0][0];
-          eB[tid] = x4[EPT - 1][NPX - 1];
-          cx.arrive();
-#pragma unroll
-          for (int e = 0; e < EPT; ++e) {
-#pragma unroll
-            for (int i = 0; i < NPX; ++i) us[e][i] = x4[e][i];
-          }
-          cx.wait();
-          uLL = eB[cx.in ? (tid == 0 ? KT - 1 : tid - 1) : tid];
-          uRR = eA[cx.in ? (tid == KT - 1 ? 0 : tid + 1) : tid];
-          cx.par ^= 1;
-        } else {
+        {
+          // the stage's input state, and the neighbours' traces straight from their columns (every column was
+          // written before an exchange of the stage that produced it)
           const double* d = ss + (size_t)s * sstride;
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
 #pragma unroll
             for (int i = 0; i < NPX; ++i) us[e][i] = d[(size_t)(i * EPT + e) * BD + tid];
           }
-          const int tl = cx.in ? (tid == 0 ? KT - 1 : tid - 1) : tid, trr = cx.in ? (tid == KT - 1 ? 0 : tid + 1) : tid;
-          uLL = d[(size_t)((NPX - 1) * EPT + (EPT - 1)) * BD + tl];
-          uRR = d[(size_t)(0 * EPT + 0) * BD + trr];
+          uLL = d[(size_t)((NPX - 1) * EPT + (EPT - 1)) * BD + nbLp];
+          uRR = d[(size_t)(0 * EPT + 0) * BD + nbRp];
         }
         if (cx.gfirst) uLL = us[0][0];                 // ghost = own trace
         if (cx.glast) uRR = us[EPT - 1][NPX - 1];
         const double mv = cx.mv[s];
-        double G0[EPT], G1[EPT], d0m[EPT], d0p[EPT], d1m[EPT], d1p[EPT];
+        const BgStageOps& LXs = LXv.ops(s);
+        double d0m[EPT], d0p[EPT], d1m[EPT], d1p[EPT];
         double gam = 0.0;
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
@@ -743,19 +763,18 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
           double g0 = 0.0, g1 = 0.0;
 #pragma unroll
           for (int i = 0; i < NPX; ++i) {
-            g0 = fma(LXv.LIFT[i * 2], lk[e][i], g0);
-            g1 = fma(LXv.LIFT[i * 2 + 1], lk[e][i], g1);
+            g0 = fma(LXs.LIFT[i * 2], lk[e][i], g0);
+            g1 = fma(LXs.LIFT[i * 2 + 1], lk[e][i], g1);
           }
           const double f0 = cx.in ? __ldg(LXv.fs0 + k0 + e) : 0.0, f1 = cx.in ? __ldg(LXv.fs1 + k0 + e) : 0.0;
-          G0[e] = g0 * f0;
-          G1[e] = g1 * f1;
+          const double G0 = g0 * f0, G1 = g1 * f1;
           const double uL = (e == 0) ? uLL : us[e - 1][NPX - 1];
           const double uR = (e == EPT - 1) ? uRR : us[e + 1][0];
-          d0m[e] = (-us[e][0] / 2.0 - mv / 2.0) * G0[e];
-          d0p[e] = (uL / 2.0 + mv / 2.0) * G0[e];
-          d1m[e] = (us[e][NPX - 1] / 2.0 - mv / 2.0) * G1[e];
-          d1p[e] = (-uR / 2.0 + mv / 2.0) * G1[e];
-          if (cx.in) gam += G0[e] * (-(us[e][0] - uL) / 2.0) + G1[e] * (-(us[e][NPX - 1] - uR) / 2.0);
+          d0m[e] = (-us[e][0] / 2.0 - mv / 2.0) * G0;
+          d0p[e] = (uL / 2.0 + mv / 2.0) * G0;
+          d1m[e] = (us[e][NPX - 1] / 2.0 - mv / 2.0) * G1;
+          d1p[e] = (-uR / 2.0 + mv / 2.0) * G1;
+          if (cx.in) gam += G0 * (-(us[e][0] - uL) / 2.0) + G1 * (-(us[e][NPX - 1] - uR) / 2.0);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gam += __shfl_xor_sync(0xffffffffu, gam, o);
@@ -766,11 +785,11 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
         eB[tid] = d1p[EPT - 1];   // belongs to the right neighbour's first node
         if (Ctx::NW > 1 && cx.lane == 0) wr[cx.wid] = gam;
         cx.arrive();
-        // volume part (no neighbour data): out_j = us_j sum_i Dr_ij (-rx lk_i)
-        double out[EPT][NPX];
+        // volume part (no neighbour data), folded into lu at once: lu_j += dt us_j sum_i Dr_ij (-rx lk_i);
+        // then the residual's own scaling lk *= rka (everything that reads lk of this stage is done)
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-          const double mrx = cx.in ? -__ldg(LXv.rxk + k0 + e) : 0.0;
+          const double mrx = cx.in ? -__ldg(LXv.rxk + k0 + e) * dt : 0.0;
           double w[NPX];
 #pragma unroll
           for (int i = 0; i < NPX; ++i) w[i] = mrx * lk[e][i];
@@ -778,13 +797,15 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
           for (int j = 0; j < NPX; ++j) {
             double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < NPX; ++i) acc = fma(LXv.Dr[i * NPX + j], w[i], acc);
-            out[e][j] = us[e][j] * acc;
+            for (int i = 0; i < NPX; ++i) acc = fma(LXs.Dr[i * NPX + j], w[i], acc);
+            lu[e][j] = fma(us[e][j], acc, lu[e][j]);
           }
+#pragma unroll
+          for (int i = 0; i < NPX; ++i) lk[e][i] *= rka;
         }
         cx.wait();
-        double inN = eA[cx.in ? (tid == KT - 1 ? 0 : tid + 1) : tid];   // right neighbour's d0p
-        double in0 = eB[cx.in ? (tid == 0 ? KT - 1 : tid - 1) : tid];   // left neighbour's d1p
+        double inN = eA[nbRp];   // right neighbour's d0p
+        double in0 = eB[nbLp];   // left neighbour's d1p
         if (Ctx::NW > 1) {
           gam = wr[0];
 #pragma unroll
@@ -798,17 +819,12 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
         const int ai = aflat / K, ak = aflat - ai * K;
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-          out[e][0] += d0m[e] + ((e == 0) ? in0 : d1p[e - 1]);
-          out[e][NPX - 1] += d1m[e] + ((e == EPT - 1) ? inN : d0p[e + 1]);
+          lu[e][0] = fma(dt, d0m[e] + ((e == 0) ? in0 : d1p[e - 1]), lu[e][0]);
+          lu[e][NPX - 1] = fma(dt, d1m[e] + ((e == EPT - 1) ? inN : d0p[e + 1]), lu[e][NPX - 1]);
           if (cx.in && k0 + e == ak) {   // the element that held max|u|: the rank-one term of C
             const double add = (amv & 1) ? -gam : gam;
 #pragma unroll
-            for (int q = 0; q < NPX; ++q) out[e][q] += (q == ai) ? add : 0.0;
-          }
-#pragma unroll
-          for (int i = 0; i < NPX; ++i) {
-            lu[e][i] = fma(dt, out[e][i], lu[e][i]);
-            lk[e][i] *= rka;
+            for (int q = 0; q < NPX; ++q) lu[e][q] = fma(dt, (q == ai) ? add : 0.0, lu[e][q]);
           }
         }
       }
@@ -823,9 +839,9 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
 #pragma unroll
         for (int i = 0; i < NP; ++i) v0[e][i] = cx.in ? p.u0[((size_t)b * NP + i) * K + k0 + e] : 0.0;
       }
-      bg_limiter<NP, EPT, BD>(p, L0, cx, k0, v0, code);
+      bg_limiter<NP, EPT, BD>(p, L0, 0, cx, k0, v0, code);
       // (NPX == NP here)
-      bg_limiter_T<NPX, EPT, BD>(p, LXv, cx, k0, code, lu);
+      bg_limiter_T<NPX, EPT, BD>(p, LXv, 0, cx, k0, code, lu);
     }
     if (p.nlim) {
       const double nl = bg_block_sum<BD>(cx, (double)nlim2);
@@ -906,7 +922,7 @@ static void bgf_limiter_weights(int Np, const double* Dr, const double* V, const
                                 BgLevel* L) {
   // aw = V(1,1)*invV(1,:) (SlopeLimitN.m:9);  sl = Dr(1,:)*V(:,1:2)*invV(1:2,:) (SlopeLimitN.m:27,
   // SlopeLimitLin.m:16);  xcn = (x - x0)/(h/2) of the first element (the map is affine: the reference nodes)
-  for (int i = 0; i < Np; ++i) L->aw[i] = V[0] * invV[i];
+  for (int i = 0; i < Np; ++i) L->st[0].aw[i] = V[0] * invV[i];
   for (int i = 0; i < Np; ++i) {
     double sum = 0.0;
     for (int j = 0; j < Np; ++j)
@@ -1002,12 +1018,14 @@ extern "C" int dgadj_burgers_fwd_adj(dgadj_handle* h, const dgadj_burgers_args* 
   for (int lv = 0; lv < (ind ? 2 : 1); ++lv) {
     BgLevel& L = k.lv[lv];
     const int n = lv ? NpF : Np;
-    L.so = h->base_ops[lv];
     const double* Dr = lv ? h->Dr_nodal_f : h->Dr_nodal;
     const double* LIFT = lv ? h->LIFT_nodal_f : h->LIFT_nodal;
-    for (int i = 0; i < n * n; ++i) L.Dr[i] = Dr[i];
-    for (int i = 0; i < n * 2; ++i) L.LIFT[i] = LIFT[i];
+    BgStageOps& S0 = L.st[0];
+    S0.so = h->base_ops[lv];
+    for (int i = 0; i < n * n; ++i) S0.Dr[i] = Dr[i];
+    for (int i = 0; i < n * 2; ++i) S0.LIFT[i] = LIFT[i];
     bgf_limiter_weights(n, Dr, lv ? a->VF_host : a->V_host, lv ? a->invVF_host : a->invV_host, lv ? a->xF_host : a->x_host, K, &L);
+    for (int q = 1; q < (BG_STAGE_CONSTS ? 5 : 1); ++q) L.st[q] = S0;
     L.rxk = h->d_mesh[lv][0];
     L.fs0 = h->d_mesh[lv][1];
     L.fs1 = h->d_mesh[lv][2];

@@ -28,14 +28,27 @@ def _events(torch):
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
+def _source_sha(files):
+    h = hashlib.sha256()
+    for f in files:
+        try:
+            h.update(open(os.path.join(ROOT, "adjoint-ode-adaptivity_b200", "csrc", f), "rb").read())
+        except OSError:
+            return None
+    return h.hexdigest()[:16]
+
+
 def _exec_inst(key):
-    """Executed fp64 instructions per update of a kernel from profiles/exec_inst.json (tools/exec_inst.py),
-    with the stamp of the kernel source it was counted on."""
+    """Executed fp64 instructions per update of a kernel from profiles/exec_inst.json (tools/exec_inst.py, or an
+    ncu capture for the Burgers kernel), with the stamp of the kernel source it was counted on -- marked STALE when
+    the source has changed since."""
     try:
         ej = json.load(open(os.path.join(ROOT, "profiles", "exec_inst.json")))
         ent = ej.get(key)
         if ent:
-            return ent["fp64_inst_per_update"], ent.get("kernel_source_sha")
+            cur = _source_sha(["dgadj_burgers_fused.cu"] if key.startswith("burgers") else ["dgadj_kernels.cuh", "dgadj_march_np.cu"])
+            sha = ent.get("kernel_source_sha")
+            return ent["fp64_inst_per_update"], "%s (%s)" % (sha, "current" if sha == cur else "STALE: source is now %s" % cur)
     except Exception:
         pass
     return None, None
