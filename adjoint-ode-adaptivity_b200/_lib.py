@@ -94,6 +94,7 @@ PROTOTYPES = {
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dgadj_march_status": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "dgadj_ic_indicator": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "dgadj_refine_shared": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "dgadj_rank": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "dgadj_reduce_indicators": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "dgadj_allreduce_indicators": (C.c_int, [_P, _P, C.c_int32, _P, _P]),

@@ -181,7 +181,7 @@ def adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=30, linear=False, device=0,
 
 
 def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic", inflow="zero", cfl=0.25, psi=None,
-                device=0, B_global=None, ic_term=True):
+                device=0, B_global=None, ic_term=True, keep_indicators=True):
     """Adjoint-driven h-refinement of the DG-in-space advection march (BASELINE config 5 for the
     PDE path: non-uniform h): per iteration the batch is marched forward and backward on the
     current mesh, the per-element indicators are reduced over the batch in a fixed order, and the
@@ -199,8 +199,17 @@ def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic",
     import torch
     v_x = np.asarray(v_x, dtype=np.float64)
     hist = []
+    # ONE handle for the whole loop (capacity = the last mesh); the vertex list also lives on the device, where the
+    # refinement rule runs (`dgadj_refine_shared`: argmax / top-k + midpoint insertion).  The march length of the
+    # next iteration follows the CFL rule of the refined mesh, so the host mirrors the mesh from the indices of the
+    # split elements -- 4 topk bytes, the one read-back per iteration.
+    s = AdvecDG1D(N, v_x=v_x, alpha=alpha, bc=bc, inflow=inflow, psi=psi, device=device, capacity=v_x.size - 1 + iters * topk)
+    dev = torch.device("cuda", device)
+    d_vx = torch.zeros(s.capacity + topk + 1, dtype=torch.float64, device=dev)
+    d_vx[:v_x.size] = torch.as_tensor(v_x, device=dev)
     for it in range(iters + 1):
-        s = AdvecDG1D(N, v_x=v_x, alpha=alpha, bc=bc, inflow=inflow, psi=psi, device=device)
+        if it:
+            s.set_mesh(v_x)
         xmin = np.min(np.abs(s.g.x[0, :] - s.g.x[1, :]))
         S = int(np.ceil(T / (cfl * xmin / abs(a))))
         dt = T / S
@@ -212,12 +221,16 @@ def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic",
         sums = allreduce_indicators(s.reduce_indicators(eta, out["J"]), ordered=True)
         Bg = B_global if B_global is not None else u0.shape[0]
         K = s.K
-        mean_eta = (sums[:K] / float(Bg)).cpu().numpy()
-        order = np.argsort(-mean_eta, kind="stable")[:topk]            # ties by lowest index
-        hist.append(dict(it=it, v_x=v_x.copy(), K=K, S=S, mean_eta=mean_eta, refined=np.sort(order),
-                         eta_total=float(mean_eta.sum()), J_mean=float(sums[K + 3]) / float(Bg),
+        refined = s.refine_shared(sums[:K], d_vx, topk)                # device: argmax / top-k, midpoint insertion
+        order = np.sort(refined.cpu().numpy())                         # the read-back: which elements were split
+        mean_eta = (sums[:K] / float(Bg)).cpu().numpy() if keep_indicators else None
+        hist.append(dict(it=it, v_x=v_x.copy(), K=K, S=S, mean_eta=mean_eta, refined=order,
+                         eta_total=float(sums[K]) / float(Bg) if keep_indicators else None,
+                         J_mean=float(sums[K + 3]) / float(Bg) if keep_indicators else None,
                          J=out["J"], estimate=eta.sum(1)))
-        s.close()
-        mids = 0.5 * (v_x[order] + v_x[order + 1])
+        mids = 0.5 * (v_x[order] + v_x[order + 1])                     # host mirror of the device mesh (same arithmetic)
         v_x = np.sort(np.concatenate([v_x, mids]))
+    if not np.array_equal(d_vx[:v_x.size].cpu().numpy(), v_x):       # the device mesh and its host mirror
+        raise RuntimeError("adapt_advec: the host mirror of the mesh has left the device mesh")
+    s.close()
     return hist

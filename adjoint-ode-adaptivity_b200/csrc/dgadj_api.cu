@@ -670,7 +670,15 @@ static int set_level(dgadj_handle* h, int lv, int Np, const double* Dr, const do
 extern "C" int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double* Dr, const double* LIFT,
                                    const double* V, const double* rx, const double* Fscale) {
   if (!h) return DGADJ_ERR_INVALID;
-  if (Np != h->Np || K != h->K) return fail(h, DGADJ_ERR_INVALID, "Np/K (%d,%d) differ from the handle's (%d,%d)", Np, K, h->Np, h->K);
+  // K may be any mesh size up to the capacity the handle was created with (cfg.K): a refinement loop keeps
+  // one handle and sets the operators of each refined mesh (matlab/MAIN.m:138-141 applied to space)
+  if (Np != h->Np || K < 1 || K > h->cfg.K)
+    return fail(h, DGADJ_ERR_INVALID, "Np/K (%d,%d) do not fit the handle's (%d, capacity %d)", Np, K, h->Np, h->cfg.K);
+  if (K != h->K) {   // a new mesh size: the enriched operators and the functional weights of the old mesh are void
+    h->K = K;
+    h->enr_set = false;
+    h->jw_set = false;
+  }
   if (!Dr || !LIFT || !V || !rx || !Fscale) return fail(h, DGADJ_ERR_INVALID, "null operator pointer");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   int rc = set_level(h, 0, Np, Dr, LIFT, V, rx, Fscale);
@@ -1503,6 +1511,65 @@ extern "C" int dgadj_march_status(dgadj_handle* h, int64_t B, int64_t values_per
   const int block = 128;
   status_kernel<<<(unsigned)((B * 32 + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
       B, values_per_trajectory, values_dev, its_per_trajectory, its_dev, maxit, status_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// shared-mesh refinement on the device: the topk elements with the largest indicator (lowest index on
+// ties: np.argmax, python/Main_finite_difference.py:337; find(abs(err)==max(abs(err))), matlab/MAIN.m:137)
+// are split at their midpoints (MAIN.m:138-141); the vertex array grows in place.
+// ---------------------------------------------------------------------------------------
+namespace dgadj {
+__global__ void refine_topk_kernel(int K, const double* __restrict__ ind, int topk, double* __restrict__ vx,
+                                   int* __restrict__ refined, double* __restrict__ scratch) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // selection: topk rounds of "largest remaining, lowest index" (K <= 1024, topk small)
+  unsigned char* mark = reinterpret_cast<unsigned char*>(scratch + (K + 1));
+  for (int k = 0; k < K; ++k) mark[k] = 0;
+  for (int t = 0; t < topk && t < K; ++t) {
+    int best = -1;
+    double bv = 0.0;
+    for (int k = 0; k < K; ++k) {
+      if (mark[k]) continue;
+      const double v = fabs(ind[k]);
+      if (best < 0 || v > bv) {
+        bv = v;
+        best = k;
+      }
+    }
+    mark[best] = 1;
+  }
+  for (int j = 0; j <= K; ++j) scratch[j] = vx[j];
+  int o = 0, r = 0;
+  for (int k = 0; k < K; ++k) {
+    vx[o++] = scratch[k];
+    if (mark[k]) {
+      vx[o++] = (scratch[k] + scratch[k + 1]) / 2.0;
+      if (refined) refined[r] = k;
+      ++r;
+    }
+  }
+  vx[o] = scratch[K];
+}
+}  // namespace dgadj
+
+extern "C" int dgadj_refine_shared(dgadj_handle* h, int32_t K, const double* ind_dev, int32_t topk, double* v_x_dev,
+                                   int32_t* refined_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (K < 1 || topk < 1 || topk > K || !ind_dev || !v_x_dev) return fail(h, DGADJ_ERR_INVALID, "bad refine_shared arguments");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t need = ((size_t)(K + 1) + (size_t)(K + 7) / 8 + 1) * sizeof(double);
+  if (need > h->red_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->red_scratch);
+    h->red_scratch = nullptr;
+    h->red_bytes = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->red_scratch, need));
+    h->red_bytes = need;
+  }
+  refine_topk_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(K, ind_dev, topk, v_x_dev, refined_dev, h->red_scratch);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return DGADJ_OK;

@@ -633,6 +633,8 @@ static int burgers_setup(dgadj_handle* h, BurgersArgs& a, int64_t B, int32_t S, 
         for (int i = 0; i < Np; ++i) a.xcn[i] = xc[(size_t)i * K] / (hh / 2);
     }
   }
+  // (xc is kept in the argument struct for reference; no kernel reads it: the limited path reconstructs
+  //  through the affine map, xcn)
   const size_t need = ((size_t)Np * K + K) * sizeof(double);
   if (need > h->bg_bytes) {
     CUDA_TRY(h, cudaDeviceSynchronize());

@@ -63,14 +63,16 @@ class AdvecDG1D:
 
     def __init__(self, N: int, K: Optional[int] = None, domain=(0.0, 1.0), v_x=None, alpha: float = 1.0,
                  bc: str = "inflow", inflow: str = "sin_at", functional: str = "int_u",
-                 scheme: str = "lserk4", device: int = 0, psi=None):
+                 scheme: str = "lserk4", device: int = 0, psi=None, capacity: Optional[int] = None):
+        """capacity: the largest mesh (elements) this handle will ever hold (default: the initial mesh); a
+        refinement loop creates the handle once and moves it from mesh to mesh with `set_mesh`."""
         self.lib = _lib.load()
-        self.g = BaseGalerkin1D(n=N, k=K, domain=domain, v_x=v_x)
-        self.gf = BaseGalerkin1D(n=N + 1, k=K, domain=domain, v_x=v_x)
-        self.N, self.Np, self.NpF, self.K = N, N + 1, N + 2, self.g.k
+        g0 = BaseGalerkin1D(n=N, k=K, domain=domain, v_x=v_x)
+        self.N, self.Np, self.NpF = N, N + 1, N + 2
         self.alpha, self.bc, self.inflow, self.functional, self.scheme = alpha, bc, inflow, functional, scheme
         self.device = device
-        cfg = _lib.Config(device=device, N=N, K=self.K, bc=_lib.BC[bc], inflow=_lib.INFLOW[inflow],
+        self.capacity = max(int(capacity or 0), g0.k)
+        cfg = _lib.Config(device=device, N=N, K=self.capacity, bc=_lib.BC[bc], inflow=_lib.INFLOW[inflow],
                           functional=_lib.FUNCTIONAL[functional], scheme=_lib.SCHEME[scheme], reserved=0,
                           alpha=float(alpha))
         self._h = C.c_void_p(0)
@@ -78,7 +80,21 @@ class AdvecDG1D:
         if rc != _lib.OK:
             self._h = C.c_void_p(0)
             raise _lib.DgadjError(rc, "dgadj_create failed (an sm_100 device is required; there is no CPU path)")
+        self._psi = psi
+        self.set_mesh(g=g0)
+
+    def set_mesh(self, v_x=None, g=None):
+        """Move the handle to the mesh with vertices v_x (at most `capacity` elements): the operators of both
+        spaces (StartUp1D chain, host) and the functional weights are set again on the SAME device handle
+        (matlab/MAIN.m:138-141 applied to space: the refined mesh of the next iteration)."""
+        N = self.N
+        self.g = g if g is not None else BaseGalerkin1D(n=N, v_x=np.asarray(v_x, dtype=np.float64))
+        self.gf = BaseGalerkin1D(n=N + 1, v_x=self.g.v_x)
+        self.K = self.g.k
+        if self.K > self.capacity:
+            raise ValueError(f"mesh of {self.K} elements exceeds the handle's capacity {self.capacity}")
         g, gf = self.g, self.gf
+        psi = self._psi
         c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         # keep the contiguous copies alive across the ctypes calls (and for inspection)
         self.ops_c = dict(Dr=c(g.d_r), LIFT=c(g.lift), V=c(g.v), rx=c(g.r_x), Fscale=c(g.f_scale))
@@ -154,6 +170,7 @@ class AdvecDG1D:
     def set_linear_functional(self, psi=None):
         """J = int psi(x) u(x,T) dx  (psi = 1: 'J = int u', cf. getK in
         python/Main_finite_difference.py:153-155).  Nodal weights in both spaces."""
+        self._psi = psi
         jw_c, jw_f = self.g.quad_weights(), self.gf.quad_weights()
         if psi is not None:
             jw_c, jw_f = jw_c * psi(self.g.x), jw_f * psi(self.gf.x)
@@ -370,6 +387,18 @@ class AdvecDG1D:
             st = _lib.march_status(self.lib, self._h, torch, values=_as_device_tensor(f), stream=self._stream())
             out = st if out is None else (out | st)
         return out
+
+    def refine_shared(self, ind, v_x_dev, topk=1):
+        """Split the `topk` elements with the largest |ind[k]| (lowest index on ties) of the mesh v_x_dev[:K+1]
+        (a float64 CUDA tensor with room for K+topk+1 vertices) at their midpoints, on the device
+        (`dgadj_refine_shared`; matlab/MAIN.m:137-141).  Returns the int32 CUDA tensor of the split elements."""
+        torch = _torch()
+        ind = _as_device_tensor(ind)
+        refined = torch.empty(topk, dtype=torch.int32, device=ind.device)
+        if v_x_dev.numel() < self.K + topk + 1:
+            raise ValueError("v_x_dev has no room for the refined mesh")
+        self._check(self.lib.dgadj_refine_shared(self._h, self.K, _ptr(ind), int(topk), _ptr(v_x_dev), _ptr(refined), self._stream()))
+        return refined
 
     def reduce_indicator_blocks(self, eta, J=None, rows_per_block=None):
         """parts[nblk, K+4]: the sums of `reduce_indicators` over fixed blocks of `rows_per_block`

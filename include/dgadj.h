@@ -87,6 +87,10 @@ const char* dgadj_last_error(const dgadj_handle* h);
 int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double* Dr, const double* LIFT,
                         const double* V, const double* rx, const double* Fscale);
 
+/* (A refinement loop keeps ONE handle: K may be any mesh size up to cfg.K, the capacity the handle was created
+ * with; setting the operators of a mesh of another size voids the enriched operators and functional weights of
+ * the old one, which are then set again.)                                                                  */
+
 /* Operators of the enriched space (order N+1; matlab/MAIN.m:34 solves the adjoint at Ns+1)
  * plus the nodal prolongation P[NpF*Np] = V_{N+1}(:,1:Np) inv(V_N).                      */
 int dgadj_set_enriched(dgadj_handle* h, int NpF, const double* DrF, const double* LIFTF,
@@ -186,6 +190,14 @@ int dgadj_ic_indicator(dgadj_handle* h, int64_t B, const double* u0_dev, const d
  *   index; or NULL), flags_dev[B][K] uint8 (1 on the topk elements; or NULL).            */
 int dgadj_rank(dgadj_handle* h, int64_t B, int32_t K, const double* eta_dev, int32_t topk,
                int32_t* order_dev, uint8_t* flags_dev, void* stream);
+
+/* Shared-mesh refinement on the device (matlab/MAIN.m:137-141; python/Main_finite_difference.py:336-341; the
+ * batch rule of python/Main_variable_params.py:340-341 feeds it the batch-reduced indicator): the `topk`
+ * elements with the largest |ind_dev[k]| (lowest index on ties) are split at their midpoints.
+ *   v_x_dev[K+1] -> [K+topk+1] in place (the array must have room); refined_dev[topk] (or NULL) = the
+ *   elements that were split, ascending.                                                                  */
+int dgadj_refine_shared(dgadj_handle* h, int32_t K, const double* ind_dev, int32_t topk, double* v_x_dev,
+                        int32_t* refined_dev, void* stream);
 
 /* Batch reduction feeding the cross-GPU all-reduce (python/Main_variable_params.py:340,
  * jnp.mean(err_refine, axis=0)): sums_dev[K+4] = { sum_b |eta[b][k]| (k<K), sum|eta|,

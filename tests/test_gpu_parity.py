@@ -1029,6 +1029,16 @@ def test_fused_randomised_configurations(pkg, torch):
             dev = lambda v: v if np.isscalar(v) else torch.tensor(v, device="cuda")
             out = s.fwd_adj(torch.tensor(u0, device="cuda"), dev(a), dev(dt), S, want_lam0=True)
             check_fused(out, ref, B)
+            # schedule fuzz (no racecheck on this pool): a trajectory's arithmetic depends on the elements per
+            # thread only -- any other block size / grid / trajectories per CTA / ring slot must give the SAME BITS
+            plan_ept = s.plan(B)["elems_per_thread"]
+            for _ in range(2):
+                s.set_tuning(plan_ept, int(rng.choice([0, 32, 64, 128, 256, 512])), int(rng.choice([0, 1, 2, 5, 11])))
+                if s.plan(B)["elems_per_thread"] != plan_ept:
+                    continue
+                out2 = s.fwd_adj(torch.tensor(u0, device="cuda"), dev(a), dev(dt), S, want_lam0=True)
+                for key in ("uT", "J", "eta", "lam0"):
+                    assert torch.equal(out[key], out2[key]), f"{key} differs between launch shapes {s.plan(B)}"
         except AssertionError as e:
             raise AssertionError(f"trial {trial}: N={N} K={K} bc={bc} alpha={alpha} inflow={inflow} B={B} S={S} "
                                  f"tuning=({ept},{block},{grid}) plan={s.plan(B)}: {e}")
@@ -1060,6 +1070,17 @@ def test_adaptive_loop_advection_nonuniform_h(pkg, torch):
         mean_ref = np.abs(ref["eta"]).mean(axis=0)
         np.testing.assert_allclose(h["mean_eta"], mean_ref, rtol=1e-6, atol=1e-9 * mean_ref.max())
         assert np.array_equal(h["refined"], np.sort(np.argsort(-mean_ref, kind="stable")[:2]))
+    # the loop keeps ONE handle (capacity = the last mesh) and moves it from mesh to mesh: the same bits as a
+    # handle created for that mesh
+    one = pkg.AdvecDG1D(N, v_x=hist[0]["v_x"], alpha=0.0, bc="inflow", inflow="zero", capacity=24)
+    one.fwd_adj(u0_fn(one.g.x), a, T / hist[0]["S"], hist[0]["S"])
+    one.set_mesh(hist[3]["v_x"])
+    fresh = pkg.AdvecDG1D(N, v_x=hist[3]["v_x"], alpha=0.0, bc="inflow", inflow="zero")
+    o1 = one.fwd_adj(u0_fn(one.g.x), a, T / hist[3]["S"], hist[3]["S"], want_lam0=True)
+    o2 = fresh.fwd_adj(u0_fn(fresh.g.x), a, T / hist[3]["S"], hist[3]["S"], want_lam0=True)
+    assert all(torch.equal(o1[k], o2[k]) for k in ("uT", "J", "eta", "lam0"))
+    with pytest.raises(ValueError):
+        one.set_mesh(np.linspace(0.0, 3.0, 40))           # beyond the capacity
     widths = np.diff(hist[-1]["v_x"])
     assert widths.min() < 0.5 * widths.max()              # non-uniform h
     assert 0.5 < hist[-1]["v_x"][np.argmin(widths)] < 2.0   # refined where the pulses travel
