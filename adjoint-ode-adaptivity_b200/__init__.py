@@ -12,10 +12,10 @@ from .solver import AdvecDG1D
 from .fd import FDAdjoint, refine_mesh
 from .tdg import TimeDG
 from .burgers import BurgersDG1D, decode_limiter_record
-from .adapt import adapt_fd, adapt_tdg, adapt_advec
+from .adapt import adapt_fd, adapt_tdg, adapt_advec, adapt_fd_per_trajectory, adapt_tdg_per_trajectory
 from . import matlab_names
 from .sharding import (shard_range, allreduce_indicators, batch_mean_refine, gather_indicators,
                        allreduce_indicator_blocks, combine_blocks, REDUCE_BLOCK)
 
-__all__ = ["AdvecDG1D", "BaseGalerkin1D", "DgadjError", "FDAdjoint", "refine_mesh", "TimeDG", "BurgersDG1D", "decode_limiter_record", "adapt_fd", "adapt_tdg", "adapt_advec", "shard_range", "allreduce_indicators",
+__all__ = ["AdvecDG1D", "BaseGalerkin1D", "DgadjError", "FDAdjoint", "refine_mesh", "TimeDG", "BurgersDG1D", "decode_limiter_record", "adapt_fd", "adapt_tdg", "adapt_advec", "adapt_fd_per_trajectory", "adapt_tdg_per_trajectory", "shard_range", "allreduce_indicators",
            "batch_mean_refine", "gather_indicators", "allreduce_indicator_blocks", "combine_blocks", "REDUCE_BLOCK", "_lib"]

@@ -89,6 +89,8 @@ PROTOTYPES = {
                                         _P, _P, _P, _P]),
     "dgadj_tdg_adapt_loop": (C.c_int, [_P, C.POINTER(TdgLoopArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
     "dgadj_fd_adapt_loop": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "dgadj_tdg_adapt_loop_pt": (C.c_int, [_P, C.POINTER(TdgLoopArgs), _P, _P, _P, _P, _P, _P, _P]),
+    "dgadj_fd_adapt_loop_pt": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "dgadj_burgers_fwd_adj": (C.c_int, [_P, C.POINTER(BurgersArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
     "dgadj_burgers_plan": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -67,6 +67,60 @@ def _fd_device_loop(s, u0, times, iters):
                  err_total=float(tot[it])) for it in range(iters + 1)]
 
 
+def adapt_fd_per_trajectory(u0, tspan=(0.0, 2.0), n_steps=2, iters=30, ode="sin", functional="int_u2", ref_factor=4, device=0):
+    """python/Main_finite_difference.py:263-343 for every trajectory of a batch at once, each on ITS OWN mesh (the
+    reference's single-trajectory loop, no batch rule): `dgadj_fd_adapt_loop_pt`, one kernel, each thread runs the whole
+    loop.  Returns dict(times[B, n_steps+iters+1], ref_idx[B, iters+1], err_total[B, iters+1]) as NumPy arrays."""
+    s = FDAdjoint(ode=ode, functional=functional, ref_factor=ref_factor, device=device)
+    torch = s.torch
+    u0 = u0.contiguous().view(-1)
+    B = u0.numel()
+    times0 = np.ascontiguousarray(np.linspace(tspan[0], tspan[1], n_steps + 1))
+    to = torch.zeros((B, n_steps + iters + 1), dtype=torch.float64, device=u0.device)
+    ri = torch.zeros((B, iters + 1), dtype=torch.int32, device=u0.device)
+    tot = torch.zeros((B, iters + 1), dtype=torch.float64, device=u0.device)
+    rc = s.lib.dgadj_fd_adapt_loop_pt(s._h, B, iters, n_steps, s.ref_factor, _lib.FD_ODE[s.ode], _lib.FD_FUNCTIONAL[s.functional],
+                                      C.c_void_p(times0.ctypes.data), C.c_void_p(u0.data_ptr()), C.c_void_p(to.data_ptr()),
+                                      C.c_void_p(ri.data_ptr()), C.c_void_p(tot.data_ptr()),
+                                      C.c_void_p(torch.cuda.current_stream(s.device).cuda_stream))
+    if rc != _lib.OK:
+        raise _lib.DgadjError(rc, s.lib.dgadj_last_error(s._h).decode())
+    out = dict(times=to.cpu().numpy(), ref_idx=ri.cpu().numpy(), err_total=tot.cpu().numpy())
+    s.close()
+    return out
+
+
+def adapt_tdg_per_trajectory(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=30, linear=False, device=0, quirks=True):
+    """matlab/MAIN.m:29-166 for every trajectory of a batch at once, each on ITS OWN mesh (`dgadj_tdg_adapt_loop_pt`):
+    one warp per trajectory builds its element blocks T0 + h T1, marches, solves the adjoint at order n+1, refines its own
+    argmax element.  Returns dict(times[B, Ks+iters+1], ref_idx[B, iters+1], err_total[B, iters+1], y_last[B, Ks+iters, n+1],
+    its_last[B, Ks+iters]) -- the first three as NumPy arrays."""
+    s = TimeDG(linear=linear, device=device, quirks=quirks)
+    torch = s.torch
+    y0 = y0.contiguous().view(-1)
+    B, Kmax, W, Np = y0.numel(), Ks + iters, Ks + iters + 2, n + 1
+    tp = _tdg_templates(s, n)
+    times0 = np.linspace(tspan[0], tspan[1], Ks + 1)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    args = _lib.TdgLoopArgs(B=B, iters=iters, Ks0=Ks, Np=Np, nq_march=tp["nq_m"], nq_adj=tp["nq_a"], linear=int(s.linear),
+                            maxit=s.maxit, y0_per_trajectory=1, tol=s.tol, y0_hard=1.0, times0_host=None,
+                            march_T0_host=p(tp["m0"]), march_T1_host=p(tp["m1"]), adj_T0_host=p(tp["a0"]), adj_T1_host=p(tp["a1"]))
+    kw = dict(dtype=torch.float64, device=y0.device)
+    tm = torch.zeros((B, W), **kw)
+    tm[:, :Ks + 1] = torch.as_tensor(times0, device=y0.device)
+    ri = torch.zeros((B, iters + 1), dtype=torch.int32, device=y0.device)
+    tot = torch.zeros((B, iters + 1), **kw)
+    yl = torch.zeros((B, Kmax, Np), **kw)
+    il = torch.zeros((B, Kmax), dtype=torch.int32, device=y0.device)
+    d = lambda t: C.c_void_p(t.data_ptr())
+    rc = s.lib.dgadj_tdg_adapt_loop_pt(s._h, C.byref(args), d(y0), d(tm), d(ri), d(tot), d(yl), d(il), s._stream())
+    if rc != _lib.OK:
+        raise _lib.DgadjError(rc, s.lib.dgadj_last_error(s._h).decode())
+    out = dict(times=tm[:, :Kmax + 1].cpu().numpy(), ref_idx=ri.cpu().numpy(), err_total=tot.cpu().numpy(), y_last=yl, its_last=il)
+    s.close()
+    return out
+
+
 def adapt_fd(u0, tspan=(0.0, 2.0), n_steps=2, iters=30, ode="sin", functional="int_u2", ref_factor=4,
              tol=None, device=0, B_global=None, device_loop=None):
     """python/Main_finite_difference.py:263-343 (batched): start from n_steps uniform steps,

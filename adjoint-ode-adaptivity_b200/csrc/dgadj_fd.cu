@@ -337,3 +337,158 @@ extern "C" int dgadj_fd_adapt_loop(dgadj_handle* h, int64_t B, int32_t iters, in
   }
   return DGADJ_OK;
 }
+
+// =======================================================================================================
+// Per-trajectory meshes: the reference's own single-trajectory loop (python/Main_finite_difference.py:263-343)
+// for every trajectory of a batch at once -- each thread runs the WHOLE loop on its own mesh: forwardSolve,
+// the interpolation of interpU (np.interp's interval search on its own cumulative times), adjSolve's
+// recurrence, errEst, the window sums, np.argmax and the midpoint insertion.  Same unfused arithmetic as
+// fd_awr_kernel; scratch arrays are [index][B] (coalesced across the warp).
+// =======================================================================================================
+namespace dgadj {
+
+__global__ void fd_adapt_pt_kernel(long long B, int iters, int n0, int rf, int ode, int func,
+                                   const double* __restrict__ times0, const double* __restrict__ u0,
+                                   double* __restrict__ times /*[nmax+1][B]*/, double* __restrict__ tc /*[nmax+1][B]*/,
+                                   double* __restrict__ tf /*[nfmax+1][B]*/, double* __restrict__ uc /*[nmax+1][B]*/,
+                                   int* __restrict__ ref_hist /*[B][iters+1]*/, double* __restrict__ tot_hist /*[B][iters+1]*/,
+                                   double* __restrict__ times_out /*[B][nmax+1]*/) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const size_t sB = (size_t)B;
+  double* t = times + b;
+  double* c = tc + b;
+  double* f = tf + b;
+  double* ub = uc + b;
+  for (int j = 0; j <= n0; ++j) t[(size_t)j * sB] = times0[j];
+  for (int it = 0; it <= iters; ++it) {
+    const int n = n0 + it, nf = n * rf;
+    // cumulative times of the coarse and the refined mesh (np.diff, refineAll, np.cumsum: sequential sums)
+    c[0] = 0.0;
+    f[0] = 0.0;
+    for (int j = 0; j < n; ++j) {
+      const double dt = __dadd_rn(t[(size_t)(j + 1) * sB], -t[(size_t)j * sB]);
+      c[(size_t)(j + 1) * sB] = __dadd_rn(c[(size_t)j * sB], dt);
+      const double dtf = __ddiv_rn(dt, (double)rf);
+      for (int q = 0; q < rf; ++q) f[(size_t)(j * rf + q + 1) * sB] = __dadd_rn(f[(size_t)(j * rf + q) * sB], dtf);
+    }
+    // forwardSolve
+    double u = u0[b];
+    ub[0] = u;
+    for (int m = 1; m <= n; ++m) {
+      const double dt = __dadd_rn(t[(size_t)m * sB], -t[(size_t)(m - 1) * sB]);
+      u = (ode == FD_ODE_LINEAR) ? __dmul_rn(__dadd_rn(1.0, dt), u) : __dadd_rn(u, __dmul_rn(sin(u), dt));
+      ub[(size_t)m * sB] = u;
+    }
+    const double tcn = c[(size_t)n * sB];
+    auto interp = [&](int i) -> double {   // np.interp(t_fine[i], t_coarse, u)
+      const double x = f[(size_t)i * sB];
+      int j;
+      if (x >= tcn) {
+        j = n;
+      } else {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) / 2;
+          if (c[(size_t)mid * sB] <= x) lo = mid; else hi = mid - 1;
+        }
+        j = lo;
+      }
+      const double tj = c[(size_t)j * sB];
+      const double uj = ub[(size_t)j * sB];
+      if (j >= n || tj == x) return uj;
+      const double den = __dadd_rn(c[(size_t)(j + 1) * sB], -tj);
+      const double slope = __ddiv_rn(__dadd_rn(ub[(size_t)(j + 1) * sB], -uj), den);
+      return __dadd_rn(__dmul_rn(slope, __dadd_rn(x, -tj)), uj);
+    };
+    // one backward sweep: adjoint recurrence, residual, window sums, argmax (as fd_awr_kernel)
+    double v_next = 0.0, uf_next = interp(nf), win[FD_MAX_REF], best = -1.0, tot = 0.0;
+    int best_idx = 0;
+    for (int i = nf - 1; i >= 0; --i) {
+      const double uf = interp(i);
+      const int jc = i / rf;
+      const double dtc = __dadd_rn(t[(size_t)(jc + 1) * sB], -t[(size_t)jc * sB]);
+      const double dt = __ddiv_rn(dtc, (double)rf);
+      double k, jf, upd;
+      if (ode == FD_ODE_LINEAR) {
+        jf = __dadd_rn(1.0, dt);
+        upd = __dmul_rn(__dadd_rn(1.0, dt), uf);
+      } else {
+        jf = __dadd_rn(1.0, __dmul_rn(cos(uf), dt));
+        upd = __dadd_rn(uf, __dmul_rn(sin(uf), dt));
+      }
+      if (func == FD_FUNC_INT_U2) k = __dmul_rn(__dmul_rn(2.0, uf), dt);
+      else if (func == FD_FUNC_INT_U) k = dt;
+      else k = (i == nf - 1) ? 1.0 : 0.0;
+      const double err = __dmul_rn(__dadd_rn(uf_next, -upd), v_next);
+      const int pos = i + 1 - 2;
+      if (pos >= 0) {
+        const int r = pos / rf, q = pos - r * rf;
+        if (q < rf - 1) {
+          win[q] = fabs(err);
+          if (q == 0) {
+            double s = win[0];
+            for (int qq = 1; qq < rf - 1; ++qq) s = __dadd_rn(s, win[qq]);
+            tot += s;
+            if (s >= best) {
+              best = s;
+              best_idx = r;
+            }
+          }
+        }
+      }
+      v_next = __dadd_rn(k, __dmul_rn(jf, v_next));
+      uf_next = uf;
+    }
+    ref_hist[(size_t)b * (iters + 1) + it] = best_idx;
+    if (tot_hist) tot_hist[(size_t)b * (iters + 1) + it] = tot;
+    if (it < iters) {   // midpoint insertion (:338-341)
+      const double mid = __ddiv_rn(__dadd_rn(t[(size_t)best_idx * sB], t[(size_t)(best_idx + 1) * sB]), 2.0);
+      for (int j = n; j > best_idx; --j) t[(size_t)(j + 1) * sB] = t[(size_t)j * sB];
+      t[(size_t)(best_idx + 1) * sB] = mid;
+    }
+  }
+  const int nlast = n0 + iters;
+  if (times_out)
+    for (int j = 0; j <= nlast; ++j) times_out[(size_t)b * (nlast + 1) + j] = t[(size_t)j * sB];
+}
+
+}  // namespace dgadj
+
+extern "C" int dgadj_fd_adapt_loop_pt(dgadj_handle* h, int64_t B, int32_t iters, int32_t n0, int32_t ref_factor, int32_t ode,
+                                      int32_t functional, const double* times0_host, const double* u0_dev,
+                                      double* times_out_dev, int32_t* ref_hist_dev, double* tot_hist_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (B <= 0 || iters < 0 || n0 < 1 || !times0_host || !u0_dev || !ref_hist_dev)
+    return fail(h, DGADJ_ERR_INVALID, "bad fd_adapt_loop_pt arguments");
+  if (ref_factor < 3 || ref_factor > FD_MAX_REF)
+    return fail(h, DGADJ_ERR_UNSUPPORTED, "ref_factor must be in [3, %d] (the reference requires > 2)", FD_MAX_REF);
+  if (ode != FD_ODE_SIN && ode != FD_ODE_LINEAR) return fail(h, DGADJ_ERR_INVALID, "unknown ode %d", ode);
+  if (functional < FD_FUNC_INT_U || functional > FD_FUNC_INT_U2) return fail(h, DGADJ_ERR_INVALID, "unknown functional %d", functional);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nmax = (size_t)n0 + iters, nfmax = nmax * ref_factor;
+  const size_t n_d = (size_t)(n0 + 1) + (size_t)B * (3 * (nmax + 1) + (nfmax + 1));
+  const size_t need = n_d * sizeof(double) + 64;
+  if (need > h->fd_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->fd_scratch);
+    h->fd_scratch = nullptr;
+    h->fd_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->fd_scratch, need));
+    h->fd_bytes = need;
+  }
+  double* d = (double*)h->fd_scratch;
+  double* t0 = d;
+  double* times = t0 + (n0 + 1);
+  double* tc = times + (size_t)B * (nmax + 1);
+  double* uc = tc + (size_t)B * (nmax + 1);
+  double* tf = uc + (size_t)B * (nmax + 1);
+  CUDA_TRY(h, cudaMemcpyAsync(t0, times0_host, (size_t)(n0 + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+  const int block = (B <= 16384) ? 32 : 128;
+  fd_adapt_pt_kernel<<<(unsigned)((B + block - 1) / block), block, 0, st>>>(B, iters, n0, ref_factor, ode, functional, t0, u0_dev,
+                                                                            times, tc, tf, uc, ref_hist_dev, tot_hist_dev, times_out_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return DGADJ_OK;
+}

@@ -720,3 +720,317 @@ extern "C" int dgadj_tdg_adapt_loop(dgadj_handle* h, const dgadj_tdg_loop_args* 
   }
   return rc;
 }
+
+// =======================================================================================================
+// Per-trajectory meshes (build plan step 8 "second"): every trajectory refines ITS OWN mesh --
+// the reference's single-trajectory loop (matlab/MAIN.m:29-166) run for a whole batch at once, no batch rule.
+// One warp per trajectory: the lanes build the element block T0 + h T1 of the trajectory's current element in
+// shared memory, share the quadrature points (as tdg_march_warp_kernel), and repeat the small solves.
+// Meshes times[B][W] (W = Ks0 + iters + 2) live on the device; one call enqueues all iterations.
+// =======================================================================================================
+namespace dgadj {
+
+template <int NP>
+__global__ void tdg_march_pt_kernel(long long B, int Ks, int W, int nq, int linear, double tol, int maxit,
+                                    const double* __restrict__ T0, const double* __restrict__ T1,
+                                    const double* __restrict__ times, const double* __restrict__ y0,
+                                    double* __restrict__ y, int ystride, int* __restrict__ its) {
+  extern __shared__ double tdg_sm[];
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  if (b >= B) return;
+  const int blk = NP * NP + 2 * nq * NP + nq + 2;
+  double* sb = tdg_sm + (size_t)wl * blk;
+  const double* tb = times + (size_t)b * W;
+  double uR = y0[b];
+  for (int k = 0; k < Ks; ++k) {
+    const double h = tb[k + 1] - tb[k];
+    __syncwarp();
+    for (int i = lane; i < blk; i += 32) sb[i] = fma(h, T1[i], T0[i]);
+    __syncwarp();
+    const double* A = sb;
+    const double* Iq = A + NP * NP;
+    const double* Phi = Iq + nq * NP;
+    const double* w = Phi + nq * NP;
+    const double hk2 = 0.5 * w[nq];
+    double U[NP];
+    int it = 0;
+    if (linear) {
+      double M[NP][NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        U[i] = (i == 0) ? uR : 0.0;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) M[i][j] = A[i * NP + j];
+      }
+      solve_dense<NP>(M, U);
+      it = 1;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) U[i] = uR;
+      double err = 1.0;
+      while (it <= maxit && err > tol) {
+        double Mt[NP], J[NP][NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          Mt[i] = 0.0;
+#pragma unroll
+          for (int j = 0; j < NP; ++j) J[i][j] = 0.0;
+        }
+        for (int q = lane; q < nq; q += 32) {
+          double ur = 0.0, ph[NP];
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            ur = fma(Iq[q * NP + i], U[i], ur);
+            ph[i] = Phi[q * NP + i];
+          }
+          double sn, cs;
+          sincos(ur, &sn, &cs);
+          const double ws = w[q] * sn, wc = w[q] * cs;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            Mt[i] = fma(ph[i], ws, Mt[i]);
+            const double pw = ph[i] * wc;
+#pragma unroll
+            for (int j = i; j < NP; ++j) J[i][j] = fma(pw, ph[j], J[i][j]);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            Mt[i] += __shfl_xor_sync(0xffffffffu, Mt[i], o);
+#pragma unroll
+            for (int j = i; j < NP; ++j) J[i][j] += __shfl_xor_sync(0xffffffffu, J[i][j], o);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+#pragma unroll
+          for (int j = 0; j < i; ++j) J[i][j] = J[j][i];
+        }
+        double R[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          double r = fma(hk2, Mt[i], (i == 0) ? uR : 0.0);
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            r = fma(A[i * NP + j], U[j], r);
+            J[i][j] = fma(hk2, J[i][j], A[i * NP + j]);
+          }
+          R[i] = r;
+        }
+        solve_dense<NP>(J, R);
+        double e2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          U[i] -= R[i];
+          e2 = fma(R[i], R[i], e2);
+        }
+        err = sqrt(e2);
+        ++it;
+      }
+    }
+    uR = U[NP - 1];
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) y[((size_t)b * ystride + k) * NP + i] = U[i];
+      if (its) its[(size_t)b * ystride + k] = it;
+    }
+  }
+}
+
+template <int NPP>
+__global__ void tdg_adjoint_pt_kernel(long long B, int Ks, int W, int nq, int linear, const double* __restrict__ y0,
+                                      const double* __restrict__ T0, const double* __restrict__ T1,
+                                      const double* __restrict__ times, const double* __restrict__ y, int ystride,
+                                      double* __restrict__ err) {
+  constexpr int NA = NPP + 1;
+  extern __shared__ double tdg_sm[];
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  if (b >= B) return;
+  const int blk = NA * NA + NA + NA * NA + NA * NPP + nq * NPP + nq * NA + nq + 3;
+  double* sb = tdg_sm + (size_t)wl * blk;
+  const double* tb = times + (size_t)b * W;
+  double vL = 0.0;
+  for (int k = Ks - 1; k >= 0; --k) {
+    const double h = tb[k + 1] - tb[k];
+    __syncwarp();
+    for (int i = lane; i < blk; i += 32) sb[i] = fma(h, T1[i], T0[i]);
+    __syncwarp();
+    const double* A0 = sb;
+    const double* f1 = A0 + NA * NA;
+    const double* A2 = f1 + NA;
+    const double* Ix = A2 + NA * NA;
+    const double* Iq = Ix + NA * NPP;
+    const double* Phi = Iq + nq * NPP;
+    const double* w = Phi + nq * NA;
+    const double hk2 = 0.5 * w[nq];
+    double Uk[NPP];
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) Uk[i] = y[((size_t)b * ystride + k) * NPP + i];
+    double Mt[NA], M[NA][NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      Mt[i] = 0.0;
+#pragma unroll
+      for (int j = 0; j < NA; ++j) M[i][j] = 0.0;
+    }
+    if (!linear) {
+      for (int q = lane; q < nq; q += 32) {
+        double ur = 0.0, ph[NA];
+#pragma unroll
+        for (int i = 0; i < NPP; ++i) ur = fma(Iq[q * NPP + i], Uk[i], ur);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) ph[i] = Phi[q * NA + i];
+        double sn, cs;
+        sincos(ur, &sn, &cs);
+        const double ws = w[q] * sn, wc = w[q] * cs;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          Mt[i] = fma(ph[i], ws, Mt[i]);
+          const double pw = ph[i] * wc;
+#pragma unroll
+          for (int j = i; j < NA; ++j) M[i][j] = fma(pw, ph[j], M[i][j]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          Mt[i] += __shfl_xor_sync(0xffffffffu, Mt[i], o);
+#pragma unroll
+          for (int j = i; j < NA; ++j) M[i][j] += __shfl_xor_sync(0xffffffffu, M[i][j], o);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+#pragma unroll
+        for (int j = 0; j < i; ++j) M[i][j] = M[j][i];
+      }
+    }
+    double F[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      F[i] = f1[i] - ((i == NA - 1) ? vL : 0.0);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) M[i][j] = fma(-hk2, M[i][j], A0[i * NA + j]);
+    }
+    solve_dense<NA>(M, F);
+    vL = F[0];
+    double uh[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NPP; ++j) s = fma(Ix[i * NPP + j], Uk[j], s);
+      uh[i] = s;
+    }
+    const double f0 = (k == 0) ? y0[b] : y[((size_t)b * ystride + (k - 1)) * NPP + (NPP - 1)];
+    double e = 0.0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double s = fma(-hk2, Mt[i], (i == 0) ? f0 : 0.0);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) s = fma(-A2[i * NA + j], uh[j], s);
+      e = fma(F[i], s, e);
+    }
+    if (lane == 0) err[(size_t)b * ystride + k] = e;
+  }
+}
+
+// each trajectory: argmax |err| (lowest index on ties, MAIN.m:137), midpoint insertion (MAIN.m:138-141)
+__global__ void tdg_refine_pt_kernel(long long B, int Ks, int W, int estride, const double* __restrict__ err,
+                                     double* __restrict__ times, int* __restrict__ ref_hist, int hstride, int it,
+                                     double* __restrict__ tot_hist, bool insert) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* e = err + (size_t)b * estride;
+  int best = 0;
+  double bv = fabs(e[0]), tot = 0.0;
+  for (int k = 0; k < Ks; ++k) {
+    const double v = fabs(e[k]);
+    tot += v;
+    if (v > bv) {
+      bv = v;
+      best = k;
+    }
+  }
+  ref_hist[(size_t)b * hstride + it] = best;
+  if (tot_hist) tot_hist[(size_t)b * hstride + it] = tot;
+  if (insert) {
+    double* t = times + (size_t)b * W;
+    const double mid = (t[best] + t[best + 1]) / 2.0;
+    for (int j = Ks; j > best; --j) t[j + 1] = t[j];
+    t[best + 1] = mid;
+  }
+}
+
+}  // namespace dgadj
+
+extern "C" int dgadj_tdg_adapt_loop_pt(dgadj_handle* h, const dgadj_tdg_loop_args* a, const double* y0_dev,
+                                       double* times_dev, int32_t* ref_hist_dev, double* tot_hist_dev,
+                                       double* y_last_dev, int32_t* its_last_dev, void* stream) {
+  if (!h) return DGADJ_ERR_INVALID;
+  if (!a || a->B <= 0 || a->iters < 0 || a->Ks0 < 1 || !a->march_T0_host || !a->march_T1_host || !a->adj_T0_host ||
+      !a->adj_T1_host || !y0_dev || !times_dev || !ref_hist_dev)
+    return fail(h, DGADJ_ERR_INVALID, "bad tdg_adapt_loop_pt arguments");
+  const int Np = a->Np, Na = Np + 1;
+  if (Np < 2 || Np > 6) return fail(h, DGADJ_ERR_UNSUPPORTED, "time-DG loop supports 1 <= N <= 5 (Np = %d)", Np);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nqm = a->nq_march, nqa = a->nq_adj;
+  const size_t blk_m = (size_t)Np * Np + 2 * (size_t)nqm * Np + nqm + 2;
+  const size_t blk_a = (size_t)Na * Na + Na + (size_t)Na * Na + (size_t)Na * Np + (size_t)nqa * Np + (size_t)nqa * Na + nqa + 3;
+  const int Kmax = a->Ks0 + a->iters, W = Kmax + 2;
+  const long long B = a->B;
+  const size_t n_d = 2 * blk_m + 2 * blk_a + (size_t)B * Kmax * Np + (size_t)B * Kmax + 8;
+  const size_t need = n_d * sizeof(double) + (size_t)B * Kmax * sizeof(int) + 64;
+  if (need > h->tdg_bytes) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(h->tdg_scratch);
+    h->tdg_scratch = nullptr;
+    h->tdg_bytes = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->tdg_scratch, need));
+    h->tdg_bytes = need;
+  }
+  double* d = h->tdg_scratch;
+  double *m0 = d, *m1 = m0 + blk_m, *a0 = m1 + blk_m, *a1 = a0 + blk_a;
+  double* y = a1 + blk_a;
+  double* err = y + (size_t)B * Kmax * Np;
+  int* its = (int*)(err + (size_t)B * Kmax + 8);
+  CUDA_TRY(h, cudaMemcpyAsync(m0, a->march_T0_host, blk_m * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(m1, a->march_T1_host, blk_m * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(a0, a->adj_T0_host, blk_a * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(a1, a->adj_T1_host, blk_a * sizeof(double), cudaMemcpyHostToDevice, st));
+  const int wpb = 4, block = 32 * wpb;
+  const unsigned grid = (unsigned)((B + wpb - 1) / wpb);
+  const size_t sm_m = wpb * blk_m * sizeof(double), sm_a = wpb * blk_a * sizeof(double);
+  if (sm_m > 200 * 1024 || sm_a > 200 * 1024) return fail(h, DGADJ_ERR_UNSUPPORTED, "element blocks too large for shared memory");
+  for (int it = 0; it <= a->iters; ++it) {
+    const int Ks = a->Ks0 + it;
+    const bool last = (it == a->iters);
+    double* yo = (last && y_last_dev) ? y_last_dev : y;
+    int* io = (last && its_last_dev) ? its_last_dev : its;
+#define DGADJ_PT_M(n)                                                                                                      \
+  case n:                                                                                                                 \
+    CUDA_TRY(h, cudaFuncSetAttribute(tdg_march_pt_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_m));     \
+    tdg_march_pt_kernel<n><<<grid, block, sm_m, st>>>(B, Ks, W, nqm, a->linear, a->tol, a->maxit, m0, m1, times_dev, y0_dev, yo, Kmax, io); \
+    break;
+    switch (Np) { DGADJ_PT_M(2) DGADJ_PT_M(3) DGADJ_PT_M(4) DGADJ_PT_M(5) DGADJ_PT_M(6) }
+#undef DGADJ_PT_M
+#define DGADJ_PT_A(n)                                                                                                      \
+  case n:                                                                                                                 \
+    CUDA_TRY(h, cudaFuncSetAttribute(tdg_adjoint_pt_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));   \
+    tdg_adjoint_pt_kernel<n><<<grid, block, sm_a, st>>>(B, Ks, W, nqa, a->linear, y0_dev, a0, a1, times_dev, yo, Kmax, err);   \
+    break;
+    switch (Np) { DGADJ_PT_A(2) DGADJ_PT_A(3) DGADJ_PT_A(4) DGADJ_PT_A(5) DGADJ_PT_A(6) }
+#undef DGADJ_PT_A
+    tdg_refine_pt_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(B, Ks, W, Kmax, err, times_dev, ref_hist_dev, a->iters + 1,
+                                                                      it, tot_hist_dev, !last);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 3;
+  }
+  return DGADJ_OK;
+}

@@ -315,6 +315,21 @@ int dgadj_fd_adapt_loop(dgadj_handle* h, int64_t B, int32_t iters, int32_t n0, i
                         int32_t functional, const double* times0_host, const double* u0_dev, double* times_hist_dev,
                         double* err_hist_dev, int32_t* ref_idx_dev, double* total_dev, void* stream);
 
+/* Per-trajectory meshes (build plan step 8): the reference's single-trajectory loops run for
+ * every trajectory of a batch at once, each on ITS OWN mesh (no batch rule) -- matlab/MAIN.m:29-166 and
+ * python/Main_finite_difference.py:263-343.  All iterations in one call, meshes on the device.
+ *   tdg: times_dev[B][Ks0+iters+2] in (every row the initial mesh) / out (every row that trajectory's final mesh);
+ *        ref_hist_dev[B][iters+1] the element each trajectory refined per iteration; tot_hist_dev[B][iters+1] (or
+ *        NULL) = sum_k |err_k|; y_last_dev[B][Ks0+iters][Np], its_last_dev[B][Ks0+iters] (or NULL): the last solve.
+ *        Uses args->{B, iters, Ks0, Np, nq_*, linear, maxit, tol, templates}; y0 is per trajectory.
+ *   fd:  times_out_dev[B][n0+iters+1] (or NULL) the final meshes; ref_hist_dev / tot_hist_dev as above.       */
+int dgadj_tdg_adapt_loop_pt(dgadj_handle* h, const dgadj_tdg_loop_args* args, const double* y0_dev, double* times_dev,
+                            int32_t* ref_hist_dev, double* tot_hist_dev, double* y_last_dev, int32_t* its_last_dev,
+                            void* stream);
+int dgadj_fd_adapt_loop_pt(dgadj_handle* h, int64_t B, int32_t iters, int32_t n0, int32_t ref_factor, int32_t ode,
+                           int32_t functional, const double* times0_host, const double* u0_dev, double* times_out_dev,
+                           int32_t* ref_hist_dev, double* tot_hist_dev, void* stream);
+
 /* Inviscid Burgers forward march (LSERK4) with SlopeLimitN (utils/SlopeLimitN.m:9-32,
  * SlopeLimitLin.m:10-18, minmod.m:6-12) applied to the initial state and after every stage,
  * on the handle's primal operators (dgadj_set_operators) and boundary type (periodic, or

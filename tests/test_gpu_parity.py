@@ -665,6 +665,47 @@ def test_adaptive_loop_tdg(pkg, torch):
         assert np.array_equal(hd[-1]["times"], hh[-1]["times"])
 
 
+def test_adaptive_loops_per_trajectory_meshes(pkg, torch):
+    """Every trajectory refining ITS OWN mesh (SURVEY build plan step 8, "per-trajectory meshes second"): the
+    reference's single-trajectory loops (python/Main_finite_difference.py:263-343; matlab/MAIN.m:29-166) for a whole
+    batch in one call, against the oracle loop run trajectory by trajectory -- refined elements and final meshes."""
+    from oracle import fd as ofd
+    from oracle import tdg as otdg
+    rng = np.random.default_rng(8)
+    u0 = np.concatenate(([1.0], rng.uniform(-3, 3, 23)))
+    iters = 14
+    out = pkg.adapt_fd_per_trajectory(torch.tensor(u0, device="cuda"), iters=iters)
+    for b in range(u0.size):
+        times = np.linspace(0.0, 2.0, 3)
+        for it in range(iters + 1):
+            idx = int(ofd.fd_awr(u0[b:b + 1], np.diff(times))["ref_idx"][0])
+            assert out["ref_idx"][b, it] == idx, (b, it)
+            if it < iters:
+                times = np.insert(times, idx + 1, 0.5 * (times[idx] + times[idx + 1]))
+        assert np.array_equal(out["times"][b], times), b
+    assert out["ref_idx"][0, :3].tolist() == [0, 0, 3]                      # SURVEY App. B.3 (u0 = 1)
+    assert len({tuple(r) for r in out["ref_idx"].tolist()}) > 3              # the trajectories do refine differently
+    # DG in time
+    y0 = np.concatenate(([1.0], rng.uniform(0.2, 2.5, 11)))
+    iters = 8
+    out = pkg.adapt_tdg_per_trajectory(torch.tensor(y0, device="cuda"), iters=iters)
+    for b in range(y0.size):
+        times, Ns, Ks = np.linspace(0.0, 2.0, 3), np.ones(2, dtype=int), 2
+        for it in range(iters + 1):
+            t1, y1, _ = otdg.dg_march(Ns, Ks, times, y0[b:b + 1])
+            _, _, err = otdg.adj_march(Ns + 1, Ks, times, y1, t1, y0_hard=y0[b:b + 1])
+            ref_i = int(np.argmax(np.abs(err[0])))
+            assert out["ref_idx"][b, it] == ref_i, (b, it)
+            assert out["err_total"][b, it] == pytest.approx(np.abs(err[0]).sum(), rel=1e-8)
+            if it < iters:
+                times, Ns, _ = otdg.refine(times, Ns, np.abs(err[0]), 1)
+                Ks += 1
+            else:
+                assert rel(out["y_last"][b, :Ks].cpu().numpy(), np.stack([yk[0] for yk in y1])) < 1e-10
+        assert np.array_equal(out["times"][b], times), b
+    assert len({tuple(r) for r in out["ref_idx"].tolist()}) > 1
+
+
 def test_tdg_warp_march_equals_thread_march(pkg, torch):
     """The warp-per-trajectory Newton march (small batches) against the thread-per-trajectory one: the same
     Newton iteration counts, states equal to rounding (the quadrature sums are associated differently)."""
