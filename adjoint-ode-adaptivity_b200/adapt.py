@@ -37,6 +37,9 @@ def _batch_reduce(obj, eta, B_global=None):
     return (sums[:K] / float(Bg)).cpu().numpy()
 
 
+LAST_LOOP_DEVICE_MS = {}    # CUDA-event time of the last device-resident loop (enqueue of the first kernel .. last kernel done)
+
+
 def _distributed():
     try:
         import torch.distributed as dist
@@ -56,12 +59,17 @@ def _fd_device_loop(s, u0, times, iters):
     eh = torch.zeros((iters + 1, nmax), dtype=torch.float64, device=u0.device)
     ri = torch.zeros(iters + 1, dtype=torch.int32, device=u0.device)
     tot = torch.zeros(iters + 1, dtype=torch.float64, device=u0.device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     rc = s.lib.dgadj_fd_adapt_loop(s._h, B, iters, n0, s.ref_factor, _lib.FD_ODE[s.ode], _lib.FD_FUNCTIONAL[s.functional],
                                    C.c_void_p(times.ctypes.data), C.c_void_p(u0.data_ptr()), C.c_void_p(th.data_ptr()),
                                    C.c_void_p(eh.data_ptr()), C.c_void_p(ri.data_ptr()), C.c_void_p(tot.data_ptr()),
                                    C.c_void_p(torch.cuda.current_stream(s.device).cuda_stream))
+    e1.record()
     if rc != _lib.OK:
         raise _lib.DgadjError(rc, s.lib.dgadj_last_error(s._h).decode())
+    e1.synchronize()
+    LAST_LOOP_DEVICE_MS["fd"] = e0.elapsed_time(e1)
     th, eh, ri, tot = th.cpu().numpy(), eh.cpu().numpy(), ri.cpu().numpy(), tot.cpu().numpy()   # the one read-back
     return [dict(it=it, times=th[it, :n0 + it + 1].copy(), err_steps=eh[it, :n0 + it].copy(), ref_idx=int(ri[it]),
                  err_total=float(tot[it])) for it in range(iters + 1)]
@@ -152,7 +160,17 @@ def adapt_fd(u0, tspan=(0.0, 2.0), n_steps=2, iters=30, ode="sin", functional="i
     return hist
 
 
+_TEMPLATES = {}     # (order, linear, quirks) -> template blocks: host work done once per process
+
+
 def _tdg_templates(s, n):
+    key = (int(n), s.linear, s.quirks)
+    if key not in _TEMPLATES:
+        _TEMPLATES[key] = _build_tdg_templates(s, n)
+    return _TEMPLATES[key]
+
+
+def _build_tdg_templates(s, n):
     """Element blocks of the time-DG march / adjoint as affine functions of the element width,
     block(h) = T0 + h T1: the host builds the blocks of the second element of the meshes [0, 1, 2] and
     [0, 2, 4] (fem_setup operators, the polyfit/polyval matrices, the mirrored quadrature interval: everything
@@ -193,9 +211,14 @@ def _tdg_device_loop(s, y0, times, n, iters):
     ri = torch.zeros(iters + 1, dtype=torch.int32, device=y0.device)
     st, ist = torch.zeros((iters + 1, 2), **kw), torch.zeros((iters + 1, 3), dtype=torch.int32, device=y0.device)
     d = lambda t: C.c_void_p(t.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     rc = s.lib.dgadj_tdg_adapt_loop(s._h, C.byref(args), d(y0), d(th), d(eh), d(ri), d(st), d(ist), C.c_void_p(0), s._stream())
+    e1.record()
     if rc != _lib.OK:
         raise _lib.DgadjError(rc, s.lib.dgadj_last_error(s._h).decode())
+    e1.synchronize()
+    LAST_LOOP_DEVICE_MS["tdg"] = e0.elapsed_time(e1)
     th, eh, ri, st, ist = (t.cpu().numpy() for t in (th, eh, ri, st, ist))        # the one read-back
     return [dict(it=it, times=th[it, :Ks0 + it + 1].copy(), err=eh[it, :Ks0 + it].copy(), ref_idx=int(ri[it]),
                  err_total=float(st[it, 1]), max_newton_its=int(ist[it, 0]), yT_mean=float(st[it, 0]),

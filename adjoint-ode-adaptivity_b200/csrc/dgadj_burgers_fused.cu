@@ -283,15 +283,25 @@ __device__ __forceinline__ void bg_stage(const BgFusedArgs& p, const BgLevel& L,
   constexpr int NW = BD / 32;
   const BgStageOps& Ls = L.ops(s);
   // ---- exchange 1: traces and the mesh-wide max|u| (value first; where it sits is voted afterwards)
+  // (independent chains, one per element and node parity: a single running maximum would be a dependent chain
+  //  of EPT*NPX compare-select pairs at the head of every stage)
   double m = -1.0;
   if (cx.in) {
+    double mc[EPT][2];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
+      mc[e][0] = fabs(u[e][0]);
+      mc[e][1] = (NPX > 1) ? fabs(u[e][1]) : 0.0;
 #pragma unroll
-      for (int i = 0; i < NPX; ++i) {
+      for (int i = 2; i < NPX; ++i) {
         const double t = fabs(u[e][i]);
-        m = (t > m) ? t : m;
+        mc[e][i & 1] = (t > mc[e][i & 1]) ? t : mc[e][i & 1];
       }
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const double t = (mc[e][1] > mc[e][0]) ? mc[e][1] : mc[e][0];
+      m = (t > m) ? t : m;
     }
   }
   const double mw = warp_max_nn(m);

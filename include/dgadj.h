@@ -14,6 +14,13 @@
  *   - `*_dev` pointers are CUDA device pointers on the handle's device, caller-owned and
  *     borrowed for the call; work is enqueued on `stream` (a cudaStream_t cast to void*,
  *     NULL = the legacy default stream) and is asynchronous -- the caller synchronises.
+ *     Exceptions, which block the host until their constants are on the device (they take per-call
+ *     HOST arrays of mesh constants): dgadj_burgers_forward / dgadj_burgers_adjoint, dgadj_tdg_march /
+ *     _adjoint / _adjoint_rec / _err_contribution, dgadj_fd_awr, and dgadj_fwd_adj_windowed (scratch is
+ *     released on return).  The fused / loop entry points (dgadj_fwd_adj, dgadj_burgers_fwd_adj,
+ *     dgadj_*_adapt_loop*) stage their constants with stream-ordered copies and do not block.
+ *   - scratch buffers belong to the handle: use a handle from ONE stream at a time (a second call on
+ *     another stream may overwrite constants a running kernel still reads).
  *   - `*_host` entry points take host pointers (pinned or pageable), copy H2D in chunks,
  *     run the same kernels overlapped with the copies, copy D2H and synchronise before
  *     returning.

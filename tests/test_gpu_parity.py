@@ -897,6 +897,34 @@ def test_burgers_fused_fwd_adj_indicator(pkg, torch, N, K, bc, ept):
     assert rel(z["lam0"].cpu().numpy(), np.broadcast_to(jwf, z["lam0"].shape)) < 1e-15
 
 
+def test_burgers_fused_modes_and_edges(pkg, torch):
+    """The fused kernel in the limiter's other modes (SlopeLimit1, TVB minmod, no limiter), with a time step per
+    trajectory and a ragged batch, against the two-call path (whose forward march is checked against the oracle in
+    test_limiter_variants_slopelimit1_and_tvb); the status word on a non-finite trajectory."""
+    N, K, B = 3, 64, 37
+    s = pkg.BurgersDG1D(N, K, domain=(-1.0, 1.0), bc="periodic")
+    rng = np.random.default_rng(12)
+    x = s.g.x
+    u0 = torch.tensor(rng.uniform(-0.3, 0.3, (B, 1, 1)) + rng.uniform(0.6, 1.2, (B, 1, 1)) * np.sin(np.pi * x[None] + rng.uniform(0, 6.28, (B, 1, 1))),
+                      device="cuda")
+    dt = torch.tensor(s.stable_dt(1.6) * rng.uniform(0.6, 1.0, B), device="cuda")
+    S = 90
+    for limit, tvb in ((True, 0.0), ("1", 0.0), (True, 20.0), (False, 0.0)):
+        two_f = s.forward(u0, dt, S, limit=limit, tvb_M=tvb, checkpoints=True)
+        two = s.adjoint(two_f)
+        one = s.fwd_adj(u0, dt, S, limit=limit, tvb_M=tvb, indicator=False)
+        assert rel(one["uT"].cpu().numpy(), two_f["uT"].cpu().numpy()) < 1e-11, (limit, tvb)
+        assert rel(one["lam0"].cpu().numpy(), two["lam0"].cpu().numpy()) < 1e-9, (limit, tvb)
+        nl = ((two_f["lim"].int() & 31).view(B, -1).cpu().numpy()[..., None] >> np.arange(5) & 1).sum((1, 2))
+        assert np.array_equal(one["nlim"][:, 0].cpu().numpy(), nl), (limit, tvb)
+        ind = s.fwd_adj(u0, dt, S, limit=limit, tvb_M=tvb, indicator=True)
+        assert torch.equal(ind["uT"], one["uT"]) and bool(torch.isfinite(ind["eta"]).all())
+    bad = u0.clone()
+    bad[5, 1, 7] = float("inf")
+    st = s.fwd_adj(bad, dt, 10, indicator=False)["status"]
+    assert int(st[5]) == 1 and int(st.sum()) == 1
+
+
 def test_cfg3_full_size_post_shock(pkg, torch):
     """BASELINE config 3 as SURVEY section 8(d) states it: Burgers + SlopeLimitN, N=4, K=256, B=16384, T past
     shock formation (t ~ 1/(pi A), here T = 0.4, ~2400 LSERK4 steps) -- through the fused kernel, whose forward

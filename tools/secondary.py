@@ -351,17 +351,23 @@ def cfg5(pkg, torch, dev, pool=None, B=4096, iters=30):
     h_dg, t_dg = timed(lambda: pkg.adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=iters, device=dev.index, device_loop=True))
     h_fd, t_fd = timed(lambda: pkg.adapt_fd(y0, tspan=(0.0, 2.0), n_steps=2, iters=iters, functional="int_u2", device=dev.index,
                                             device_loop=True))
+    from adjoint_ode_adaptivity_b200 import adapt as _adapt
+    dev_ms = dict(_adapt.LAST_LOOP_DEVICE_MS)
     solves = sum(2 * (h["times"].size - 1) for h in h_dg) * B
     fine = sum((h["times"].size - 1) * 9 for h in h_fd) * B
     res = dict(
         workload="config 5: adjoint-driven refinement loops, B=%d ICs u0 ~ U(-3,3), u' = sin u on [0,2], shared mesh, batch-mean "
                  "indicator, %d argmax refinements from 2 elements / steps (matlab/MAIN.m:29-166; Main_finite_difference.py:263-343), "
                  "device-resident loops: one C-ABI call each, one read-back at the end" % (B, iters),
+        timing_note="ms_per_iteration: wall clock of the whole call (handle creation, the one C-ABI call, synchronisation, the final "
+                    "read-back of the histories); device_ms_per_iteration: CUDA events around the C-ABI call",
         tdg=dict(metric="element-solves/s (Newton march or adjoint solve + indicator), whole loop incl. mesh updates", value=solves / t_dg,
-                 unit="element-solves/s", ms_per_iteration=1e3 * t_dg / (iters + 1), final_elements=int(h_dg[-1]["times"].size - 1),
+                 unit="element-solves/s", ms_per_iteration=1e3 * t_dg / (iters + 1),
+                 device_ms_per_iteration=dev_ms.get("tdg", float("nan")) / (iters + 1), final_elements=int(h_dg[-1]["times"].size - 1),
                  refined_first=[int(h["ref_idx"]) for h in h_dg[:3]], max_newton_its=int(max(h["max_newton_its"] for h in h_dg))),
         fd=dict(metric="fine-step updates/s (forward, adjoint recurrence, residual), whole loop incl. mesh updates", value=fine / t_fd,
-                unit="fine-step updates/s", ms_per_iteration=1e3 * t_fd / (iters + 1), final_steps=int(h_fd[-1]["times"].size - 1),
+                unit="fine-step updates/s", ms_per_iteration=1e3 * t_fd / (iters + 1),
+                device_ms_per_iteration=dev_ms.get("fd", float("nan")) / (iters + 1), final_steps=int(h_fd[-1]["times"].size - 1),
                 refined_first=[int(h["ref_idx"]) for h in h_fd[:3]]))
     if pool is not None:
         t0 = time.perf_counter()
