@@ -67,6 +67,7 @@ PROTOTYPES = {
     "dgadj_set_enriched": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P]),
     "dgadj_set_functional_weights": (C.c_int, [_P, _P, _P]),
     "dgadj_set_inflow_table": (C.c_int, [_P, C.c_int, _P]),
+    "dgadj_set_element_orders": (C.c_int, [_P, _P]),
     "dgadj_set_tuning": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "dgadj_forward": (C.c_int, [_P, C.POINTER(MarchArgs), _P, _P, _P, _P, _P]),
     "dgadj_ckpt_bytes": (C.c_int64, [_P, C.c_int64, C.c_int32]),

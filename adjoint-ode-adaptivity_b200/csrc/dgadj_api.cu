@@ -542,6 +542,7 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->d_jwm_c);
   cudaFree(h->d_jwm_f);
   cudaFree(h->d_uin);
+  cudaFree(h->d_npk);
   cudaFree(h->ring);
   cudaFree(h->red_scratch);
   cudaFree(h->fd_scratch);
@@ -674,8 +675,13 @@ extern "C" int dgadj_set_operators(dgadj_handle* h, int Np, int K, const double*
   // one handle and sets the operators of each refined mesh (matlab/MAIN.m:138-141 applied to space)
   if (Np != h->Np || K < 1 || K > h->cfg.K)
     return fail(h, DGADJ_ERR_INVALID, "Np/K (%d,%d) do not fit the handle's (%d, capacity %d)", Np, K, h->Np, h->cfg.K);
-  if (K != h->K) {   // a new mesh size: the enriched operators and the functional weights of the old mesh are void
+  if (K != h->K) {   // a new mesh size: the enriched operators, the functional weights and the element orders of the old mesh are void
     h->K = K;
+    if (h->d_npk) {
+      cudaDeviceSynchronize();
+      cudaFree(h->d_npk);
+      h->d_npk = nullptr;
+    }
     h->enr_set = false;
     h->jw_set = false;
   }
@@ -756,6 +762,25 @@ extern "C" int dgadj_set_inflow_table(dgadj_handle* h, int n, const double* uin)
   int rc = upload(h, &h->d_uin, uin, (size_t)n);
   if (rc) return rc;
   h->uin_n = n;
+  return DGADJ_OK;
+}
+
+extern "C" int dgadj_set_element_orders(dgadj_handle* h, const int32_t* nodes_per_element_host) {
+  if (!h) return DGADJ_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!nodes_per_element_host) {   // back to the uniform order of the handle
+    if (h->d_npk) {
+      CUDA_TRY(h, cudaDeviceSynchronize());
+      cudaFree(h->d_npk);
+      h->d_npk = nullptr;
+    }
+    return DGADJ_OK;
+  }
+  for (int k = 0; k < h->K; ++k)
+    if (nodes_per_element_host[k] < 2 || nodes_per_element_host[k] > h->Np)
+      return fail(h, DGADJ_ERR_INVALID, "element %d: %d nodes, must be in [2, %d]", k, nodes_per_element_host[k], h->Np);
+  if (!h->d_npk) CUDA_TRY(h, cudaMalloc((void**)&h->d_npk, (size_t)h->cfg.K * sizeof(int)));
+  CUDA_TRY(h, cudaMemcpy(h->d_npk, nodes_per_element_host, (size_t)h->K * sizeof(int), cudaMemcpyHostToDevice));
   return DGADJ_OK;
 }
 
@@ -891,6 +916,7 @@ static void fill_params(dgadj_handle* h, const dgadj_march_args* a, const Launch
   p.jw_f = h->d_jwm_f;
   p.uin_table = h->d_uin;
   p.tma_store = pl.tma_store;
+  p.npk = h->d_npk;
 }
 
 // 128-bit state I/O when every [B][Np][K] pointer of the call is 16-byte aligned (K is a multiple of the
@@ -904,6 +930,8 @@ static void set_vec_io(KArgs* ka, const LaunchPlan& pl) {
 static int launch(dgadj_handle* h, int variant, const LaunchPlan& pl, cudaStream_t st, KArgs* ka) {
   march_launch_fn fn = launch_table[h->Np];
   if (!fn) return fail(h, DGADJ_ERR_UNSUPPORTED, "no kernel for Np=%d", h->Np);
+  if (ka->p.npk && variant != VAR_FWD && variant != VAR_FUSED)
+    return fail(h, DGADJ_ERR_UNSUPPORTED, "per-element orders: only dgadj_forward (without checkpoints) and dgadj_fwd_adj are built for them");
   set_vec_io(ka, pl);
   cudaError_t e = fn(variant, pl.ept, pl.grid, pl.block, pl.smem, st, ka);
   if (e != cudaSuccess) return fail(h, DGADJ_ERR_CUDA, "march kernel launch failed: %s", cudaGetErrorString(e));
@@ -1041,6 +1069,7 @@ extern "C" int dgadj_fwd_adj_windowed(dgadj_handle* h, const dgadj_march_args* a
   if (rc) return rc;
   if (!u0_dev) return fail(h, DGADJ_ERR_INVALID, "u0_dev is null");
   if (window < 1 || batch_chunk < 0) return fail(h, DGADJ_ERR_INVALID, "window must be >= 1 and batch_chunk >= 0");
+  if (h->d_npk) return fail(h, DGADJ_ERR_UNSUPPORTED, "per-element orders: the windowed march is not built for them");
   const int S = args->S, W = window;
   const int nwin = (S + W - 1) / W;
   if (nwin <= 1) return dgadj_fwd_adj(h, args, u0_dev, uT_dev, J_dev, lam0_dev, eta_dev, stream);

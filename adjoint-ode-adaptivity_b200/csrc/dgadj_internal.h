@@ -36,6 +36,7 @@ struct dgadj_handle {
   double* d_jwm_f;
   double* d_uin;
   int uin_n;
+  int* d_npk;             // hp: [K] modes per element of the primal space, or null (uniform order)
   double* ring;
   size_t ring_bytes;
   double* red_scratch;

@@ -125,6 +125,9 @@ struct MarchParams {
   int eta_acc;
   int n0;
   int in_modal, out_modal;   // the input state / uT are modal coefficients (window hand-over: no V^-1 V round trip)
+  const int* npk;            // hp (HP kernels only): [K] modes of each element's primal space, <= NP; the enriched
+                             // space has one more.  Modes beyond an element's count are held at zero (padded hp:
+                             // in the orthonormal modal basis a lower order IS the truncated space)
   int tma_store;             // forward checkpoints leave through bulk-TMA from a double-buffered park (host: fits, not warp_local)
   int vec_io;                // every [B][Np][K] pointer is 16-byte aligned and EPT is even: 128-bit state I/O
 };
@@ -314,10 +317,13 @@ __device__ __forceinline__ void traces(const double (&pv)[MAXNP], const MVec<NPX
 //                                            read the buffer -- every thread that passes this barrier may
 //                                            overwrite it (it does at the top of step n+1).
 // No barrier is added: the store rides on the exchanges the stages need anyway.
-template <int NPX, int LV, int EPT, bool STORE_HOOK = false, int TILE_ELEMS = 0>
+// HP: nm[e] = number of modes of element e in this space; the surface term (the only one that feeds a mode from
+// below) skips the modes beyond it, so they stay exactly zero.
+template <int NPX, int LV, int EPT, bool STORE_HOOK = false, int TILE_ELEMS = 0, bool HP = false>
 __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __restrict__ tr,
                                          const double* __restrict__ coef, MVec<NPX> (&z)[EPT],
-                                         MVec<NPX> (&r)[EPT], long long b, double time, int n) {
+                                         MVec<NPX> (&r)[EPT], long long b, double time, int n,
+                                         const int (&nm)[EPT]) {
   const ConstOps& c = ka.c;
   const int nst = ka.p.nstages;
 #pragma unroll 1   // (fully unrolling the stages was measured 7 % slower: 5x the code, more spills)
@@ -367,6 +373,7 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
       const double bm = rkb * coef[(size_t)e * cx.BD];
 #pragma unroll
       for (int i = 0; i < NPX; ++i) {
+        if (HP && i >= nm[e]) continue;
         r[e].v[i] = fma(c.p[LV][i], (i & 1) ? sd : se, r[e].v[i]);
         z[e].v[i] = fma(bm, r[e].v[i], z[e].v[i]);
       }
@@ -381,10 +388,10 @@ __device__ __forceinline__ void fwd_step(const KArgs& ka, Ctx& cx, double* __res
 //   w~ += (bsga_s m) mu ; Gse = sum_even p_i w_i, Gso = sum_odd p_i w_i ;
 //   gam0 = q0 (Gse - Gso), gam1 = q1 (Gse + Gso) ; a0 = gam0 - gam1[left], aN = gam1 - gam0[right] ;
 //   mu_j += sum_{i < j, i+j odd} D^_ij w_i + p_j {aN + a0 | aN - a0}.
-template <int NPX, int LV, int EPT>
+template <int NPX, int LV, int EPT, bool HP = false>
 __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __restrict__ tr,
                                          const double* __restrict__ coef, MVec<NPX> (&mu)[EPT],
-                                         MVec<NPX> (&w)[EPT]) {
+                                         MVec<NPX> (&w)[EPT], const int (&nm)[EPT]) {
   const ConstOps& c = ka.c;
 #pragma unroll 1
   for (int s = ka.p.nstages - 1; s >= 0; --s) {
@@ -413,7 +420,10 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
       for (int i = 0; i + d < NPX; ++i) {
         const double cij = so.D[nz_index(NPX, i, i + d)];
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) mu[e].v[i + d] = fma(cij, w[e].v[i], mu[e].v[i + d]);
+        for (int e = 0; e < EPT; ++e) {
+          if (HP && i + d >= nm[e]) continue;   // (the transposed derivative feeds HIGHER modes: held at zero beyond the element's space)
+          mu[e].v[i + d] = fma(cij, w[e].v[i], mu[e].v[i + d]);
+        }
       }
     }
     trace_wait(cx, ka.p.warp_local);
@@ -430,7 +440,10 @@ __device__ __forceinline__ void adj_step(const KArgs& ka, Ctx& cx, double* __res
       const double aN = gam1[e] - ((e == EPT - 1) ? gam0R : gam0[e + 1]);
       const double ae = aN + a0, ao = aN - a0;
 #pragma unroll
-      for (int i = 0; i < NPX; ++i) mu[e].v[i] = fma(c.p[LV][i], (i & 1) ? ao : ae, mu[e].v[i]);
+      for (int i = 0; i < NPX; ++i) {
+        if (HP && i >= nm[e]) continue;
+        mu[e].v[i] = fma(c.p[LV][i], (i & 1) ? ao : ae, mu[e].v[i]);
+      }
     }
   }
 }
@@ -514,7 +527,7 @@ __device__ __forceinline__ void apply_matrix(const double* M, const double (&x)[
 // BDT > 0: blockDim.x is the compile-time constant BDT (all shared-memory strides fold into
 // immediate offsets); BDT = 0: any block size.
 // ---------------------------------------------------------------------------------------
-template <int NP, int EPT, int BDT, bool DO_FWD, bool RESID, bool DO_ADJ>
+template <int NP, int EPT, int BDT, bool DO_FWD, bool RESID, bool DO_ADJ, bool HP = false>
 __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_kernel(const __grid_constant__ KArgs ka) {
   constexpr int NPF = NP + 1;
   const MarchParams& p = ka.p;
@@ -602,6 +615,12 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
     }
     const size_t gofs = (size_t)bs * NP * K + k0;  // this thread's column in [B][NP][K]
 
+    int nmc[EPT], nmf[EPT];   // hp: modes of the thread's elements in the primal / the enriched space
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      nmc[e] = (HP && in_tile) ? p.npk[k0 + e] : NP;
+      nmf[e] = nmc[e] + 1;
+    }
     MVec<NP> z[EPT];  // primal modal state (at the end of the forward phase: u^(T))
     // ------------------------------------------------------------------ forward phase
     {
@@ -616,6 +635,10 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
           for (int i = 0; i < NP; ++i) z[e].v[i] = un[e][i];
         } else {
           apply_matrix<NP, false>(c.iV, un[e], z[e].v);
+        }
+        if (HP) {   // the element's own space: the L2 projection of the input onto it
+#pragma unroll
+          for (int i = 0; i < NP; ++i) z[e].v[i] = (i < nmc[e]) ? z[e].v[i] : 0.0;
         }
       }
     }
@@ -646,7 +669,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
             rf[e].zero();
             z[e].store(park + (size_t)e * BD, cstride);
           }
-          fwd_step<NPF, 1, EPT, true, NPF * EPT>(ka, cx, sm_tr, sm_coef + (size_t)3 * EPT * BD, f, rf, bs, time, n);
+          fwd_step<NPF, 1, EPT, true, NPF * EPT, HP>(ka, cx, sm_tr, sm_coef + (size_t)3 * EPT * BD, f, rf, bs, time, n, nmf);
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
             z[e].load(park + (size_t)e * BD, cstride);
@@ -659,7 +682,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
           MVec<NP> r[EPT];
 #pragma unroll
           for (int e = 0; e < EPT; ++e) r[e].zero();
-          fwd_step<NP, 0, EPT, RESID, NPF * EPT>(ka, cx, sm_tr, sm_coef, z, r, bs, time, n);
+          fwd_step<NP, 0, EPT, RESID, NPF * EPT, HP>(ka, cx, sm_tr, sm_coef, z, r, bs, time, n, nmc);
         }
         time += p.dt_arr ? p.dt_arr[bs] : p.dt;  // `time = time+dt` accumulation of the mlx
         if (RESID) {
@@ -760,6 +783,13 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
           jpart = fma(jacC, n2, jpart);
         }
       }
+      if (HP) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+          for (int i = 0; i < NPF; ++i) mu[e].v[i] = (i < nmf[e]) ? mu[e].v[i] : 0.0;
+        }
+      }
       const double Jtot = traj_sum(sm_tr, tid, KT, (cx.flags & CX_FIRST) != 0, jpart);
       if (p.J && active && (cx.flags & CX_FIRST)) p.J[b] = Jtot;
       if (p.mu_in && active) {   // a window of a longer march: continue the later window's adjoint
@@ -790,7 +820,7 @@ __global__ void __launch_bounds__(MAXBD / EPT, march_min_ctas(NP, EPT)) march_ke
         }
 #pragma unroll
         for (int e = 0; e < EPT; ++e) w[e].zero();  // w~ restarts every step (rka[0] = 0)
-        adj_step<NPF, 1, EPT>(ka, cx, sm_tr, sm_coef + (size_t)3 * EPT * BD, mu, w);
+        adj_step<NPF, 1, EPT, HP>(ka, cx, sm_tr, sm_coef + (size_t)3 * EPT * BD, mu, w, nmf);
       }
       if (active) {
 #pragma unroll

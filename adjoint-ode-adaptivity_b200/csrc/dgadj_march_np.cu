@@ -10,14 +10,14 @@
 
 namespace dgadj {
 
-template <int NP, int EPT, int BDT, bool F, bool R, bool A>
+template <int NP, int EPT, int BDT, bool F, bool R, bool A, bool HP = false>
 static cudaError_t launch_bd(int variant, int grid, int block, size_t smem, cudaStream_t stream, const KArgs* ka) {
   // the opt-in shared-memory size is a per-device function attribute: remembered per (instantiation,
   // device), so that a process with handles on several GPUs sets it on each of them
   static bool attr_set[64] = {};
   if (block > MAXBD / EPT) return cudaErrorInvalidConfiguration;
   if (smem < march_smem_bytes(NP, EPT, block, variant)) return cudaErrorInvalidConfiguration;
-  auto kern = march_kernel<NP, EPT, BDT, F, R, A>;
+  auto kern = march_kernel<NP, EPT, BDT, F, R, A, HP>;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -43,6 +43,18 @@ static cudaError_t launch_one(int variant, int grid, int block, size_t smem, cud
   return launch_bd<NP, EPT, 0, F, R, A>(variant, grid, block, smem, stream, ka);
 }
 
+// hp (per-element orders, p.npk set): the forward march and the fused march, any block size (BDT = 0)
+template <int EPT>
+static cudaError_t launch_ept_hp(int variant, int grid, int block, size_t smem, cudaStream_t stream, const KArgs* ka) {
+  switch (variant) {
+    case VAR_FWD: return launch_bd<DGADJ_NP, EPT, 0, true, false, false, true>(variant, grid, block, smem, stream, ka);
+#if DGADJ_NP + 1 <= 10
+    case VAR_FUSED: return launch_bd<DGADJ_NP, EPT, 0, true, true, true, true>(variant, grid, block, smem, stream, ka);
+#endif
+    default: return cudaErrorNotSupported;
+  }
+}
+
 template <int EPT>
 static cudaError_t launch_ept(int variant, int grid, int block, size_t smem, cudaStream_t stream, const KArgs* ka) {
   switch (variant) {
@@ -58,6 +70,12 @@ static cudaError_t launch_ept(int variant, int grid, int block, size_t smem, cud
 
 cudaError_t DGADJ_CAT(march_launch_np, DGADJ_NP)(int variant, int ept, int grid, int block, size_t smem,
                                                  cudaStream_t stream, const KArgs* ka) {
+  if (ka->p.npk) {
+    if (ept == 1) return launch_ept_hp<1>(variant, grid, block, smem, stream, ka);
+    if (ept == 2) return launch_ept_hp<2>(variant, grid, block, smem, stream, ka);
+    if (ept == 4) return launch_ept_hp<4>(variant, grid, block, smem, stream, ka);
+    return cudaErrorInvalidValue;
+  }
   if (ept == 1) return launch_ept<1>(variant, grid, block, smem, stream, ka);
   if (ept == 2) return launch_ept<2>(variant, grid, block, smem, stream, ka);
   if (ept == 4) return launch_ept<4>(variant, grid, block, smem, stream, ka);

@@ -388,6 +388,23 @@ class AdvecDG1D:
             out = st if out is None else (out | st)
         return out
 
+    def set_element_orders(self, orders=None):
+        """hp (Ns(k), matlab/MAIN.m:21,141, applied to the DG-in-space march; `dgadj_set_element_orders`): the
+        polynomial order of every element, each in [1, N]; None returns to the uniform order N.  Fields keep the
+        (B, N+1, K) layout on the order-N LGL nodes -- an element of lower order holds its polynomial's values there
+        (it is L2-projected onto its own space on input).  The enriched space has one order more per element.
+        Built for `forward` (without history) and `fwd_adj`."""
+        if orders is None:
+            self._check(self.lib.dgadj_set_element_orders(self._h, C.c_void_p(0)))
+            self.orders = None
+            return
+        o = np.ascontiguousarray(orders, dtype=np.int32).ravel()
+        if o.size != self.K:
+            raise ValueError(f"one order per element: expected {self.K}, got {o.size}")
+        nodes = np.ascontiguousarray(o + 1, dtype=np.int32)
+        self._check(self.lib.dgadj_set_element_orders(self._h, _np_ptr(nodes)))
+        self.orders = o.copy()
+
     def refine_shared(self, ind, v_x_dev, topk=1):
         """Split the `topk` elements with the largest |ind[k]| (lowest index on ties) of the mesh v_x_dev[:K+1]
         (a float64 CUDA tensor with room for K+topk+1 vertices) at their midpoints, on the device

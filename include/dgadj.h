@@ -108,6 +108,15 @@ int dgadj_set_enriched(dgadj_handle* h, int NpF, const double* DrF, const double
  * (jw_c[Np*K], jw_f[NpF*K]); used when cfg.functional == DGADJ_FUNC_LINEAR.              */
 int dgadj_set_functional_weights(dgadj_handle* h, const double* jw_c, const double* jw_f);
 
+/* hp (per-element orders Ns(k), matlab/MAIN.m:21,141, applied to the DG-in-space march):
+ * nodes_per_element_host[K], each in [2, Np]; NULL returns to the uniform order.  Fields keep the handle's
+ * [B][Np][K] layout on its LGL nodes (an element of lower order holds its polynomial's values there; on input it
+ * is L2-projected onto its own space); the kernels hold the modes beyond an element's space at zero -- in the
+ * orthonormal modal basis a lower order IS the truncated space, so this is the hp scheme, not an approximation
+ * of it.  The enriched space of the adjoint / indicator has one order more per element.  Built for
+ * dgadj_forward (without checkpoints) and dgadj_fwd_adj(_host); DGADJ_ERR_UNSUPPORTED elsewhere.        */
+int dgadj_set_element_orders(dgadj_handle* h, const int32_t* nodes_per_element_host);
+
 /* Caller-supplied inflow values uin[S*nstages] (cfg.inflow == DGADJ_INFLOW_TABLE).       */
 int dgadj_set_inflow_table(dgadj_handle* h, int n, const double* uin);
 

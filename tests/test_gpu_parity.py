@@ -223,6 +223,48 @@ def test_rx_cancellation_noise_of_the_reference(pkg, torch):
     assert rel(out["uT"].cpu().numpy(), ref_node["uT"]) < TOL
 
 
+@pytest.mark.parametrize("bc,alpha", [("periodic", 0.0), ("inflow", 0.3)])
+def test_hp_per_element_orders(pkg, torch, bc, alpha):
+    """hp for the DG-in-space march (Ns(k) of matlab/MAIN.m:21,141): per-element orders through
+    `dgadj_set_element_orders` (padded layout, modes beyond an element's space held at zero) against the ragged,
+    dense-matrix oracle oracle/advec_hp.py, which carries every element at its own order with its own StartUp1D
+    operators and agrees with oracle/advec.py for uniform orders (tests/test_oracle_golden.py)."""
+    from oracle import advec_hp as ohp
+    Nmax, orders = 4, [2, 4, 3, 4, 1, 2, 4, 1]
+    vx = np.array([0.0, 0.5, 1.1, 1.6, 2.4, 3.0, 3.9, 4.6, 2 * math.pi])           # non-uniform h as well
+    K, B = len(orders), 5
+    s = pkg.AdvecDG1D(Nmax, v_x=vx, alpha=alpha, bc=bc, inflow="zero")
+    s.set_element_orders(orders)
+    c = ohp.HpSpace(orders, vx)
+    rng = np.random.default_rng(17)
+    u0r = [np.concatenate([np.sin(x + rng.uniform(0, 6)) + 0.4 * rng.standard_normal(x.size) for x in c.x]) for _ in range(B)]
+    u0p = np.stack([ohp.pad(c, u, Nmax) for u in u0r])
+    a, dt, S = 1.3, 2e-3, 60
+    out = s.fwd_adj(torch.tensor(u0p, device="cuda"), a, dt, S, want_lam0=True)
+    uT_f = s.forward(torch.tensor(u0p, device="cuda"), a, dt, S)
+    assert torch.equal(uT_f, out["uT"])
+    for b in range(B):
+        ref = ohp.fwd_adj_indicator(u0r[b], orders, vx, a, dt, S, alpha, bc == "periodic")
+        f = ref["spaces"][1]
+        uT = out["uT"][b].cpu().numpy()
+        assert rel(ohp.unpad(c, uT, Nmax), ref["uT"]) < TOL
+        assert rel(ohp.pad(c, ohp.unpad(c, uT, Nmax), Nmax), uT) < 1e-13              # the output lies in the elements' own spaces
+        assert abs(float(out["J"][b]) - ref["J"]) < TOL * max(1.0, abs(ref["J"]))
+        assert rel(ohp.unpad_covector(f, out["lam0"][b].cpu().numpy(), Nmax + 1), ref["lam0"]) < TOL
+        assert np.max(np.abs(out["eta"][b].cpu().numpy() - ref["eta"]) / ref["eta_scale"]) < TOL
+    # uniform orders through the hp kernels = the uniform kernels
+    s.set_element_orders([Nmax] * K)
+    o1 = s.fwd_adj(torch.tensor(u0p, device="cuda"), a, dt, S, want_lam0=True)
+    s.set_element_orders(None)
+    o2 = s.fwd_adj(torch.tensor(u0p, device="cuda"), a, dt, S, want_lam0=True)
+    assert all(torch.equal(o1[k], o2[k]) for k in ("uT", "J", "eta", "lam0"))
+    with pytest.raises(pkg.DgadjError):
+        s.set_element_orders([Nmax + 1] * K)
+    s.set_element_orders(orders)
+    with pytest.raises(pkg.DgadjError):
+        s.fwd_adj(torch.tensor(u0p, device="cuda"), a, dt, S, window=8)             # not built for hp
+
+
 def test_fused_functional_int_u2_and_weighted(pkg, torch):
     dom = (0.0, 2.0)
     a, dt, S = 1.7, 2e-3, 40

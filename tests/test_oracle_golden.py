@@ -357,3 +357,37 @@ def test_burgers_indicator_effectivity_and_adjoint_identities():
     assert np.max(np.abs(out["lam0"] - wq(gf))) < 1e-13
     rec = burgers.burgers_record(u0, gc, dt, S)
     assert np.array_equal(rec["uT"], uT)
+
+
+def test_hp_oracle_reduces_to_the_uniform_oracle():
+    """oracle/advec_hp.py (ragged per-element orders, dense global matrix) against oracle/advec.py for uniform
+    orders -- march, adjoint, indicator -- and its effectivity identity for mixed orders."""
+    from oracle import advec_hp as hp
+    N, K = 3, 6
+    vx = np.array([0.0, 0.7, 1.9, 3.0, 4.2, 5.1, 2 * math.pi])
+    g, gf = ops.startup_mesh(N, vx), ops.startup_mesh(N + 1, vx)
+    for gg in (g, gf):
+        gg.rx = np.broadcast_to(gg.rx.mean(0, keepdims=True), gg.rx.shape).copy()
+    rng = np.random.default_rng(0)
+    u0 = np.sin(g.x) + 0.3 * rng.standard_normal(g.x.shape)
+    a, dt, S = 2 * math.pi, 1e-3, 25
+    for alpha, bc, per in ((0.0, advec.BC_PERIODIC, True), (0.3, advec.BC_INFLOW, False)):
+        ref = advec.fwd_adj_indicator(u0, g, gf, a, dt, S, alpha, bc, advec.INFLOW_ZERO)
+        out = hp.fwd_adj_indicator(u0.T.ravel(), [N] * K, vx, a, dt, S, alpha, per)
+        assert np.max(np.abs(out["uT"].reshape(K, N + 1).T - ref["uT"])) < 1e-13
+        assert np.max(np.abs(out["lam0"].reshape(K, N + 2).T - ref["lam0"])) < 1e-13
+        assert abs(out["J"] - ref["J"]) < 1e-13
+        assert np.max(np.abs(out["eta"] - ref["eta"]) / ref["eta_scale"]) < 1e-14
+    orders = [2, 3, 1, 3, 2, 1]
+    c = hp.HpSpace(orders, vx)
+    u0h = np.concatenate([np.sin(x) + 0.3 * rng.standard_normal(x.size) for x in c.x])
+    psi = lambda x: np.exp(-(x - 3.0) ** 2)      # the mean is conserved: weight the output so that dJ != 0
+    out = hp.fwd_adj_indicator(u0h, orders, vx, a, dt, S, 0.0, True, psi)
+    cf = out["spaces"][1]
+    P, Lf = hp.prolongation(c, cf), cf.rhs_matrix(a, 0.0, True)
+    uf = P @ u0h
+    for _ in range(S):
+        uf = hp.step(uf, Lf, dt)
+    dJ = cf.weights(psi) @ (P @ out["uT"]) - cf.weights(psi) @ uf
+    assert abs(dJ) > 1e-6 and out["eta"].sum() == pytest.approx(dJ, rel=1e-9)
+    assert np.max(np.abs(hp.unpad(c, hp.pad(c, u0h, 3), 3) - u0h)) < 1e-14

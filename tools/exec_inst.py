@@ -107,7 +107,7 @@ def main():
     ap.add_argument("--sass-out", default=None, help="also write the kernel's SASS listing here")
     a = ap.parse_args()
     obj = os.path.join(CSRC, "build", f"dgadj_march_np{a.np}.o")
-    fun = f"_ZN5dgadj12march_kernelILi{a.np}ELi{a.ept}ELi{a.bd}ELb1ELb1ELb1EEEvNS_5KArgsE"
+    fun = f"_ZN5dgadj12march_kernelILi{a.np}ELi{a.ept}ELi{a.bd}ELb1ELb1ELb1ELb0EEEvNS_5KArgsE"
     text = subprocess.run(["cuobjdump", "-sass", "-fun", fun, obj], stdout=subprocess.PIPE, text=True, check=True).stdout
     if a.sass_out:
         open(a.sass_out, "w").write(text)
