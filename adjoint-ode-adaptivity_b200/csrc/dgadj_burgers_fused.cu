@@ -59,10 +59,16 @@ namespace dgadj {
 //   split exchanges (BG_SPLIT 1) vs a plain hardware barrier at the arrive point (0): 4.399 / 4.415e10 -- no
 //   difference; nor does the suspend-time hint of the mbarrier wait matter (BG_SUSPEND_NS 0 vs 2000).
 //   Four elements per thread (64-thread CTAs): 2.25e10 (half the warps: latency bound); one per thread: 2.4e10.
-// ncu of the final form (profiles/r2_burgers_fused_ncu.json): fp64 pipe 47.3 %, issue slots 51 % busy, 46 % of
-// the issued instructions on the fp64 pipe; per issued instruction 1.49 cycles of fixed-latency waits, 0.91 on the
-// exchange mbarrier, 0.35 on the hardware barrier -- 12 warps per SM (3 CTAs: the five stage states of a
-// trajectory take 61 KB of shared memory) leave the schedulers without an eligible warp half of the time.
+//   + no division sequences in the limited cells' path (div_rn: the quotient's bits from the host-rounded
+//     reciprocal; 2/h tabulated): the warps that hold limited cells are the last to reach the next exchange,
+//     so their divergent path is the CTA's critical path -- 36 % of the warp-stages enter it      5.03e10 / 5.96e10
+//   one divergent region for all of a thread's cells (detection first, reconstructions side by side)
+//     instead of one per cell: 4.79e10 / 5.67e10 -- slower, not kept.
+// ncu of the final form (profiles/r2_burgers_fused_ncu.json): fp64 pipe 51.0 % (47.3 % before the last step), issue
+// slots 55 % busy, 44 % of the issued instructions on the fp64 pipe (183.7 of 418.5 per update); per issued
+// instruction 1.33 cycles of fixed-latency waits, 0.57 on the exchange mbarrier, 0.30 on the hardware barrier --
+// 12 warps per SM (3 CTAs: the five stage states of a trajectory take 61 KB of shared memory) leave the
+// schedulers without an eligible warp 45 % of the time.
 #ifndef BG_SPLIT
 #define BG_SPLIT 1
 #endif
@@ -91,7 +97,7 @@ struct BgFusedArgs {
   int K, S, periodic, limit;
   double tvbM, eps0, dt;
   const double* dt_arr;
-  const double* hk;            // [K] x(Np,k) - x(1,k)
+  const double* hk;            // [3][K]: h = x(Np,k) - x(1,k);  1/h and 2/h as the host's IEEE divisions round them
   BgLevel lv[2];
   double P[MAXNP * MAXNP];     // nodal prolongation [NPF][NP]
   const double* jw[2];         // [NPX][K] weights of J = sum jw o u(T) in both spaces
@@ -135,6 +141,15 @@ __device__ __forceinline__ double mm3b(double a, double b, double c, int* br) {
   if (fc < m) { m = fc; w = 3; }
   *br = w;
   return pos ? m : -m;
+}
+// x / h from the correctly rounded reciprocal r = RN(1/h): q = RN(x r) is within an ulp of the quotient, the
+// residual x - h q is exact in an fma, and RN(q + residual r) is the correctly rounded quotient (Markstein's
+// theorem) -- the bits of a division without the 30-instruction division sequence in the limited cells' path.
+// (4e8 random pairs against the division on the host: no difference.)  Not for non-finite x: the march's
+// status word reports those.
+__device__ __forceinline__ double div_rn(double x, double h, double r) {
+  const double q = x * r;
+  return fma(fma(-h, q, x), r, q);
 }
 __device__ __forceinline__ double warp_max_nn(double m) {   // values >= 0 or exactly -1.0
   const int hi = __double2hiint(m);
@@ -260,14 +275,15 @@ __device__ __forceinline__ void bg_limiter(const BgFusedArgs& p, const BgLevel& 
     const double ve1 = v[e] - mm3(v[e] - ue1, q);
     const double ve2 = v[e] + mm3(ue2 - v[e], q);
     if (!(fabs(ve1 - ue1) > p.eps0 || fabs(ve2 - ue2) > p.eps0)) continue;
-    const double h = __ldg(p.hk + k0 + e);
+    const double h = __ldg(p.hk + k0 + e), rh = __ldg(p.hk + p.K + k0 + e), th = __ldg(p.hk + 2 * p.K + k0 + e);
     double d = 0.0;
 #pragma unroll
     for (int i = 0; i < NPX; ++i) d = fma(L.sl[i], u[e][i], d);
-    const double ux = (2.0 / h) * d;
+    const double ux = th * d;   // (2/h) d
     int br = 1;
     double slope = ux;   // minmodB: a slope below M h^2 passes (recorded as argument 1 winning)
-    if (!(p.tvbM > 0.0 && fabs(ux) <= p.tvbM * (h * h))) slope = mm3b(ux, (vp - v[e]) / h, (v[e] - vm) / h, &br);
+    if (!(p.tvbM > 0.0 && fabs(ux) <= p.tvbM * (h * h)))
+      slope = mm3b(ux, div_rn(vp - v[e], h, rh), div_rn(v[e] - vm, h, rh), &br);
     const double sh = slope * (0.5 * h);
 #pragma unroll
     for (int i = 0; i < NPX; ++i) u[e][i] = fma(L.xcn[i], sh, v[e]);
@@ -454,7 +470,7 @@ __device__ __forceinline__ void bg_limiter_T(const BgFusedArgs& p, const BgLevel
         c[e] = fma(L.xcn[i], lu[e][i], c[e]);
       }
       c[e] *= 0.5 * h;
-      if (br >= 2) ch[e] = c[e] / h;
+      if (br >= 2) ch[e] = div_rn(c[e], h, __ldg(p.hk + p.K + k0 + e));
     }
     tr[e] = (br == 2) ? ch[e] : 0.0;    // goes to cell k+1
     tl[e] = (br == 3) ? -ch[e] : 0.0;   // goes to cell k-1
@@ -476,7 +492,7 @@ __device__ __forceinline__ void bg_limiter_T(const BgFusedArgs& p, const BgLevel
     const double lv = (flag ? a[e] : 0.0) + ((br == 2) ? -ch[e] : ((br == 3) ? ch[e] : 0.0)) + fromL + fromR;
     if (code[e] || lv != 0.0) {
       double cs = 0.0;
-      if (br == 1) cs = (2.0 / __ldg(p.hk + k0 + e)) * c[e];
+      if (br == 1) cs = __ldg(p.hk + 2 * p.K + k0 + e) * c[e];
 #pragma unroll
       for (int i = 0; i < NPX; ++i) lu[e][i] = (flag ? 0.0 : lu[e][i]) + Ls.aw[i] * lv + L.sl[i] * cs;
     }
@@ -1044,20 +1060,25 @@ extern "C" int dgadj_burgers_fwd_adj(dgadj_handle* h, const dgadj_burgers_args* 
     for (int i = 0; i < NpF * Np; ++i) k.P[i] = h->P_host[i];
   // per-call constants: element widths and functional weights (pageable host memory: the copies are staged
   // before cudaMemcpyAsync returns, and ordered on the stream)
-  const size_t nconst = (size_t)K + (size_t)Np * K + (size_t)NpF * K;
+  const size_t nconst = (size_t)3 * K + (size_t)Np * K + (size_t)NpF * K;
   rc = bgf_ensure(h, &h->bgf_consts, &h->bgf_consts_bytes, nconst * sizeof(double));
   if (rc) return rc;
   {
-    std::vector<double> hk(K);
-    for (int e = 0; e < K; ++e) hk[e] = a->x_host[(size_t)(Np - 1) * K + e] - a->x_host[e];
-    CUDA_TRY(h, cudaMemcpyAsync(h->bgf_consts, hk.data(), K * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(h, cudaMemcpyAsync(h->bgf_consts + K, a->jw_host, (size_t)Np * K * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<double> hk((size_t)3 * K);
+    for (int e = 0; e < K; ++e) {
+      const double w = a->x_host[(size_t)(Np - 1) * K + e] - a->x_host[e];
+      hk[e] = w;
+      hk[K + e] = 1.0 / w;
+      hk[2 * K + e] = 2.0 / w;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->bgf_consts, hk.data(), (size_t)3 * K * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->bgf_consts + 3 * K, a->jw_host, (size_t)Np * K * sizeof(double), cudaMemcpyHostToDevice, st));
     if (ind)
-      CUDA_TRY(h, cudaMemcpyAsync(h->bgf_consts + K + (size_t)Np * K, a->jwF_host, (size_t)NpF * K * sizeof(double), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(h, cudaMemcpyAsync(h->bgf_consts + 3 * K + (size_t)Np * K, a->jwF_host, (size_t)NpF * K * sizeof(double), cudaMemcpyHostToDevice, st));
   }
   k.hk = h->bgf_consts;
-  k.jw[0] = h->bgf_consts + K;
-  k.jw[1] = h->bgf_consts + K + (size_t)Np * K;
+  k.jw[0] = h->bgf_consts + 3 * K;
+  k.jw[1] = h->bgf_consts + 3 * K + (size_t)Np * K;
   // the per-CTA state ring
   const size_t need = (size_t)ring_step * (size_t)std::max(a->S, 1);
   if (need > h->ring_bytes) {
