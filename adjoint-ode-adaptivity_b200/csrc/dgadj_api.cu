@@ -547,6 +547,10 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->red_scratch);
   cudaFree(h->fd_scratch);
   cudaFree(h->tdg_scratch);
+  for (auto& sl : h->tdg_cache) {
+    cudaFree(sl.dev);
+    free(sl.host);
+  }
   cudaFree(h->bg_scratch);
   cudaFree(h->bgs_scratch);
   cudaFree(h->bgf_consts);

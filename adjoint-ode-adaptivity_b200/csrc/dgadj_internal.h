@@ -43,8 +43,18 @@ struct dgadj_handle {
   size_t red_bytes;
   void* fd_scratch;     // dgadj_fd_awr: interpolation tables + coarse states
   size_t fd_bytes;
-  double* tdg_scratch;  // dgadj_tdg_*: per-element constant blocks
+  double* tdg_scratch;  // dgadj_tdg_*adapt_loop*: templates, element blocks, mesh history
   size_t tdg_bytes;
+  // dgadj_tdg_march / _adjoint / _adjoint_rec / _err_contribution: the per-element constant blocks of the last few
+  // meshes stay on the device (host copy kept for the comparison), so a repeated call is a kernel launch and nothing
+  // else -- no upload, no stream synchronisation
+  struct TdgConstSlot {
+    double* dev;
+    double* host;
+    size_t cap, n;
+    unsigned long long stamp;
+  } tdg_cache[4];
+  unsigned long long tdg_clock;
   double* bg_scratch;   // dgadj_burgers_forward: limiter geometry
   size_t bg_bytes;
   double* bgs_scratch;  // dgadj_burgers_adjoint: per-CTA stage states

@@ -20,6 +20,8 @@
 // (||dU||_2 <= tol, at most maxit+1 iterations: dg_march.m:36,44), the dense solves
 // (Gaussian elimination with partial pivoting, MATLAB's `\`), the indicator dot product.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "dgadj_internal.h"
 
@@ -417,18 +419,39 @@ __global__ void tdg_errcon_kernel(long long B, int Ks, int Np, const double* __r
   err[t] = e;
 }
 
-static int tdg_consts(dgadj_handle* h, const double* host, size_t n, cudaStream_t st) {
+// The constant blocks of a call on the device: found among the handle's last few (same length, same bytes), or
+// uploaded into the least recently used slot.  A hit costs a memcmp of a few KB; a miss the pageable upload (staged by
+// the driver before cudaMemcpyAsync returns, so the caller may release its buffer; stream-ordered after the kernels
+// that may still read the slot).
+static int tdg_consts(dgadj_handle* h, const double* host, size_t n, cudaStream_t st, const double** dev_out) {
   const size_t need = n * sizeof(double);
-  if (need > h->tdg_bytes) {
-    CUDA_TRY(h, cudaDeviceSynchronize());
-    cudaFree(h->tdg_scratch);
-    h->tdg_scratch = nullptr;
-    h->tdg_bytes = 0;
-    CUDA_TRY(h, cudaMalloc((void**)&h->tdg_scratch, need));
-    h->tdg_bytes = need;
+  dgadj_handle::TdgConstSlot* lru = &h->tdg_cache[0];
+  for (auto& sl : h->tdg_cache) {
+    if (sl.dev && sl.n == n && memcmp(sl.host, host, need) == 0) {
+      sl.stamp = ++h->tdg_clock;
+      *dev_out = sl.dev;
+      return DGADJ_OK;
+    }
+    if (sl.stamp < lru->stamp) lru = &sl;
   }
-  CUDA_TRY(h, cudaMemcpyAsync(h->tdg_scratch, host, need, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(h, cudaStreamSynchronize(st));  // pageable source may be released by the caller
+  if (n > lru->cap) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(lru->dev);
+    free(lru->host);
+    lru->dev = nullptr;
+    lru->host = nullptr;
+    lru->cap = lru->n = 0;
+    lru->host = (double*)malloc(need);
+    if (!lru->host) return fail(h, DGADJ_ERR_NOMEM, "host copy of the time-DG constant blocks (%zu B)", need);
+    CUDA_TRY(h, cudaMalloc((void**)&lru->dev, need));
+    lru->cap = n;
+  }
+  lru->n = 0;   // (not a valid entry until the upload is queued)
+  memcpy(lru->host, host, need);
+  CUDA_TRY(h, cudaMemcpyAsync(lru->dev, host, need, cudaMemcpyHostToDevice, st));
+  lru->n = n;
+  lru->stamp = ++h->tdg_clock;
+  *dev_out = lru->dev;
   return DGADJ_OK;
 }
 
@@ -479,9 +502,10 @@ extern "C" int dgadj_tdg_march(dgadj_handle* h, int64_t B, int32_t Ks, int32_t N
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t blk = (size_t)Np * Np + 2 * (size_t)nq * Np + nq + 2;
-  int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
+  const double* ec = nullptr;
+  int rc = tdg_consts(h, elem_consts_host, blk * Ks, st, &ec);
   if (rc) return rc;
-  rc = tdg_launch_march(h, B, Ks, Np, nq, linear, tol, maxit, h->tdg_scratch, y0_dev, y_dev, its_dev, st);
+  rc = tdg_launch_march(h, B, Ks, Np, nq, linear, tol, maxit, ec, y0_dev, y_dev, its_dev, st);
   if (rc) return rc;
   h->launches++;
   return DGADJ_OK;
@@ -498,9 +522,10 @@ extern "C" int dgadj_tdg_adjoint(dgadj_handle* h, int64_t B, int32_t Ks, int32_t
   cudaStream_t st = (cudaStream_t)stream;
   const size_t Na = Np_primal + 1;
   const size_t blk = Na * Na + Na + Na * Na + Na * Np_primal + (size_t)nq * Np_primal + (size_t)nq * Na + nq + 3;
-  int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
+  const double* ec = nullptr;
+  int rc = tdg_consts(h, elem_consts_host, blk * Ks, st, &ec);
   if (rc) return rc;
-  rc = tdg_launch_adjoint(h, B, Ks, Np_primal, nq, linear, y0_hard, y0_dev, h->tdg_scratch, y_dev, v_dev, err_dev, st);
+  rc = tdg_launch_adjoint(h, B, Ks, Np_primal, nq, linear, y0_hard, y0_dev, ec, y_dev, v_dev, err_dev, st);
   if (rc) return rc;
   h->launches++;
   return DGADJ_OK;
@@ -517,11 +542,12 @@ extern "C" int dgadj_tdg_adjoint_rec(dgadj_handle* h, int64_t B, int32_t Ks, int
   cudaStream_t st = (cudaStream_t)stream;
   const size_t Np = Np_primal, Na = Np + 1;
   const size_t blk = Np * Np + Np + Np * Np + Na * Na + Na * Na + Na * Np + 2;
-  int rc = tdg_consts(h, elem_consts_host, blk * Ks, st);
+  const double* ec = nullptr;
+  int rc = tdg_consts(h, elem_consts_host, blk * Ks, st, &ec);
   if (rc) return rc;
   const int block = 128;
   const unsigned grid = (unsigned)((B + block - 1) / block);
-#define DGADJ_TDG_R(n) case n: tdg_adjrec_kernel<n><<<grid, block, 0, st>>>(B, Ks, y0_hard, y0_dev, h->tdg_scratch, y_dev, v_dev, err_dev); break;
+#define DGADJ_TDG_R(n) case n: tdg_adjrec_kernel<n><<<grid, block, 0, st>>>(B, Ks, y0_hard, y0_dev, ec, y_dev, v_dev, err_dev); break;
   switch (Np_primal) { DGADJ_TDG_R(2) DGADJ_TDG_R(3) DGADJ_TDG_R(4) DGADJ_TDG_R(5) }
 #undef DGADJ_TDG_R
   CUDA_TRY(h, cudaGetLastError());
@@ -536,11 +562,12 @@ extern "C" int dgadj_tdg_err_contribution(dgadj_handle* h, int64_t B, int32_t Ks
   if (B <= 0 || Ks <= 0 || Np < 2 || !cvec_host || !y_dev || !err_dev) return fail(h, DGADJ_ERR_INVALID, "bad tdg_err_contribution arguments");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = tdg_consts(h, cvec_host, (size_t)Ks * Np, st);
+  const double* ec = nullptr;
+  int rc = tdg_consts(h, cvec_host, (size_t)Ks * Np, st, &ec);
   if (rc) return rc;
   const int block = 128;
   const long long n = (long long)B * Ks;
-  tdg_errcon_kernel<<<(unsigned)((n + block - 1) / block), block, 0, st>>>(B, Ks, Np, h->tdg_scratch, y_dev, err_dev);
+  tdg_errcon_kernel<<<(unsigned)((n + block - 1) / block), block, 0, st>>>(B, Ks, Np, ec, y_dev, err_dev);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return DGADJ_OK;
