@@ -109,6 +109,123 @@ __global__ void fd_awr_kernel(long long B, int n, int rf, int ode, int func, FdT
   if (idx_out) idx_out[b] = best_idx;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Small batches: ONE WARP per trajectory.  A thread-per-trajectory launch of a few thousand trajectories
+// leaves one warp per SM to run n + 2 nf dependent sin / cos evaluations (118 us at B = 4096, n = 31).
+// Only two recurrences are sequential -- the forward Euler steps and v_i = k_i + jf_i v_{i+1} -- and of
+// those only the first costs transcendentals; interpolation, jf / fwdUpdate (the 2 nf sin / cos), the
+// residuals, the window sums and the argmax are independent per fine node and go lane-strided through
+// the warp's shared arrays.  Every value is produced by the arithmetic of fd_awr_kernel in the same
+// order (the recurrences run redundantly in all lanes), so the results are bit-identical.
+//   shared per warp: uc[n+1] | uf[nf+1] | jf[nf] | rs[nf+1] (residual, then |err|) | v[nf+1]
+// ------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t fd_warp_doubles(int n, int rf) { return (size_t)(n + 1) + 4 * ((size_t)n * rf + 1); }
+
+__global__ void fd_awr_warp_kernel(long long B, int n, int rf, int ode, int func, FdTables t,
+                                   const double* __restrict__ u0, double* __restrict__ u_out, double* __restrict__ v_out,
+                                   double* __restrict__ err_out, double* __restrict__ steps_out, int* __restrict__ idx_out) {
+  extern __shared__ double fdsm[];
+  const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const long long b = (long long)blockIdx.x * wpc + (threadIdx.x >> 5);
+  if (b >= B) return;   // (whole warps; no CTA-wide barrier below)
+  const int nf = n * rf;
+  double* uc = fdsm + (size_t)(threadIdx.x >> 5) * fd_warp_doubles(n, rf);
+  double* uf = uc + (n + 1);
+  double* jfa = uf + (nf + 1);
+  double* rs = jfa + (nf + 1);
+  double* va = rs + (nf + 1);
+  // ---- forwardSolve (sequential; all lanes carry the same value)
+  double u = u0[b];
+  if (lane == 0) uc[0] = u;
+  for (int m = 1; m <= n; ++m) {
+    const double dt = t.dtn[m - 1];
+    u = (ode == FD_ODE_LINEAR) ? __dmul_rn(__dadd_rn(1.0, dt), u) : __dadd_rn(u, __dmul_rn(sin(u), dt));
+    if (lane == 0) uc[m] = u;
+  }
+  __syncwarp();
+  if (u_out)
+    for (int m = lane; m <= n; m += 32) u_out[(size_t)b * (n + 1) + m] = uc[m];
+  // ---- fine nodes: interpolated state, Jacobian factor, residual  res[i+1] = u_f[i+1] - fwdUpdate(u_f[i])
+  for (int i = lane; i <= nf; i += 32) uf[i] = fd_interp(uc, 1, t, i, n);
+  __syncwarp();
+  for (int i = lane; i < nf; i += 32) {
+    const double ufi = uf[i], dt = t.dtf[i];
+    double jf, upd;
+    if (ode == FD_ODE_LINEAR) {
+      jf = __dadd_rn(1.0, dt);
+      upd = __dmul_rn(__dadd_rn(1.0, dt), ufi);
+    } else {
+      jf = __dadd_rn(1.0, __dmul_rn(cos(ufi), dt));
+      upd = __dadd_rn(ufi, __dmul_rn(sin(ufi), dt));
+    }
+    jfa[i] = jf;
+    rs[i + 1] = __dadd_rn(uf[i + 1], -upd);
+  }
+  // ---- adjoint recurrence (sequential, two flops per step; all lanes)
+  double v = 0.0;
+  if (lane == 0) va[nf] = 0.0;
+  __syncwarp();
+  for (int i = nf - 1; i >= 0; --i) {
+    const double dt = t.dtf[i];
+    double k;
+    if (func == FD_FUNC_INT_U2) k = __dmul_rn(__dmul_rn(2.0, uf[i]), dt);
+    else if (func == FD_FUNC_INT_U) k = dt;
+    else k = (i == nf - 1) ? 1.0 : 0.0;
+    v = __dadd_rn(k, __dmul_rn(jfa[i], v));
+    if (lane == 0) va[i] = v;
+  }
+  __syncwarp();
+  // ---- err[i] = res[i] * v[i]; |err| stays in rs for the windows
+  for (int i = lane; i <= nf; i += 32) {
+    const double e = (i == 0) ? __dmul_rn(0.0, va[0]) : __dmul_rn(rs[i], va[i]);
+    if (err_out) err_out[(size_t)b * (nf + 1) + i] = e;
+    if (v_out) v_out[(size_t)b * (nf + 1) + i] = va[i];
+    rs[i] = fabs(e);
+  }
+  __syncwarp();
+  // ---- windows (entries 2 + r rf + q, q = 0..rf-2, summed in ascending order), argmax with the lowest index
+  double best = -1.0;
+  int best_idx = 0x7fffffff;
+  for (int r = lane; r < n; r += 32) {
+    double sum = rs[2 + r * rf];
+    for (int q = 1; q < rf - 1; ++q) sum = __dadd_rn(sum, rs[2 + r * rf + q]);
+    if (steps_out) steps_out[(size_t)b * n + r] = sum;
+    if (sum > best) {   // ascending r: strict keeps the lowest index
+      best = sum;
+      best_idx = r;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    if (ob > best || (ob == best && oi < best_idx)) {
+      best = ob;
+      best_idx = oi;
+    }
+  }
+  if (idx_out && lane == 0) idx_out[b] = (best_idx == 0x7fffffff) ? 0 : best_idx;
+}
+
+// launches the warp form when the batch is small and a warp's arrays fit; else one thread per trajectory
+static cudaError_t fd_launch_awr(dgadj_handle* h, long long B, int n, int rf, int ode, int func, const FdTables& t,
+                                 const double* u0, double* uc, double* u_out, double* v_out, double* err_out,
+                                 double* steps_out, int* idx_out, cudaStream_t st) {
+  const size_t per_warp = fd_warp_doubles(n, rf) * sizeof(double);
+  const bool warp = h->tune_block == 32 || (h->tune_block != 1 && B <= 16384);
+  if (warp && per_warp <= 48 * 1024) {
+    int wpc = (int)((48 * 1024) / per_warp);
+    wpc = wpc > 4 ? 4 : wpc;
+    fd_awr_warp_kernel<<<(unsigned)((B + wpc - 1) / wpc), wpc * 32, wpc * per_warp, st>>>(B, n, rf, ode, func, t, u0, u_out, v_out,
+                                                                                        err_out, steps_out, idx_out);
+  } else {
+    const int block = 128;
+    fd_awr_kernel<<<(unsigned)((B + block - 1) / block), block, 0, st>>>(B, n, rf, ode, func, t, u0, uc, u_out, v_out, err_out,
+                                                                        steps_out, idx_out);
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace dgadj
 
 extern "C" int dgadj_fd_awr(dgadj_handle* h, int64_t B, int32_t n, int32_t ref_factor, int32_t ode,
@@ -182,10 +299,8 @@ extern "C" int dgadj_fd_awr(dgadj_handle* h, int64_t B, int32_t n, int32_t ref_f
   t.exact = (const unsigned char*)put(exact.data(), nf + 1, 1);
   CUDA_TRY(h, cudaStreamSynchronize(st));   // the host vectors go out of scope (pageable source)
   double* uc = (double*)(base + ((tbl_bytes + 255) / 256) * 256);
-  const int block = 128;
-  fd_awr_kernel<<<(unsigned)((B + block - 1) / block), block, 0, st>>>(
-      B, n, ref_factor, ode, functional, t, u0_dev, uc, u_dev, v_dev, err_fine_dev, err_steps_dev, ref_idx_dev);
-  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, fd_launch_awr(h, B, n, ref_factor, ode, functional, t, u0_dev, uc, u_dev, v_dev, err_fine_dev, err_steps_dev,
+                            ref_idx_dev, st));
   h->launches++;
   return DGADJ_OK;
 }
@@ -321,13 +436,11 @@ extern "C" int dgadj_fd_adapt_loop(dgadj_handle* h, int64_t B, int32_t iters, in
   double* uc = (double*)(base + o_uc);
   double* steps = (double*)(base + o_steps);
   CUDA_TRY(h, cudaMemcpyAsync(times_hist_dev, times0_host, (size_t)(n0 + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
-  const int block = (B <= 16384) ? 32 : 128;   // small batches: spread the trajectories over more SMs
   for (int it = 0; it <= iters; ++it) {
     const int n = n0 + it;
     const double* times = times_hist_dev + (size_t)it * W;
     fd_tables_kernel<<<1, 128, 0, st>>>(n, ref_factor, times, tw, tc, tf);
-    fd_awr_kernel<<<(unsigned)((B + block - 1) / block), block, 0, st>>>(B, n, ref_factor, ode, functional, t, u0_dev, uc,
-                                                                        nullptr, nullptr, nullptr, steps, nullptr);
+    CUDA_TRY(h, fd_launch_awr(h, B, n, ref_factor, ode, functional, t, u0_dev, uc, nullptr, nullptr, nullptr, steps, nullptr, st));
     double* mrow = err_hist_dev + (size_t)it * nmax;
     fd_loop_mean_kernel<<<n, 256, 0, st>>>(B, n, steps, mrow);
     fd_refine_kernel<<<1, 32, 0, st>>>(n, mrow, times, it == iters ? nullptr : times_hist_dev + (size_t)(it + 1) * W,

@@ -123,7 +123,9 @@ int dgadj_set_element_orders(dgadj_handle* h, const int32_t* nodes_per_element_h
 int dgadj_set_inflow_table(dgadj_handle* h, int n, const double* uin);
 
 /* Launch-shape overrides for tuning sweeps (0 = automatic): elements per thread (1, 2 or 4),
- * target threads per CTA, CTAs in the persistent grid.                                   */
+ * target threads per CTA, CTAs in the persistent grid.  For the time-DG march and the FD path
+ * block_threads = 1 / 32 forces the thread-per-trajectory / warp-per-trajectory kernel (automatic:
+ * a warp per trajectory up to 16 384 trajectories).                                        */
 int dgadj_set_tuning(dgadj_handle* h, int32_t elems_per_thread, int32_t block_threads,
                      int32_t grid_ctas);
 

@@ -766,6 +766,26 @@ def test_tdg_warp_march_equals_thread_march(pkg, torch):
         assert float((res["thread"][1] - res["warp"][1]).abs().max()) < 1e-13
 
 
+def test_fd_warp_kernel_equals_thread_kernel(pkg, torch):
+    """The warp-per-trajectory FD kernel (small batches: the lanes share the 2 nf sin / cos evaluations, the window
+    sums and the argmax; the two recurrences run in every lane) against the thread-per-trajectory kernel: every
+    output bit for bit, for both ODEs, the three functionals and ref_factor 3 / 4 / 7, ragged batch sizes."""
+    rng = np.random.default_rng(23)
+    for ode, func, rf, B, n in (("sin", "int_u2", 4, 777, 31), ("sin", "int_u", 3, 33, 7), ("sin", "u_N", 7, 1, 50),
+                                ("linear", "int_u2", 4, 100, 2), ("sin", "int_u2", 4, 64, 61)):
+        u0 = torch.tensor(rng.uniform(-3, 3, B), device="cuda")
+        dt = rng.uniform(0.01, 0.2, n)
+        res = {}
+        for form, blk in (("thread", 1), ("warp", 32)):
+            f = pkg.FDAdjoint(ode=ode, functional=func, ref_factor=rf)
+            assert f.lib.dgadj_set_tuning(f._h, 0, blk, 0) == 0
+            res[form] = f.solve(u0, dt)
+            torch.cuda.synchronize()
+            f.close()
+        for k in ("u", "v", "err_fine", "err_steps", "ref_idx"):
+            assert torch.equal(res["thread"][k], res["warp"][k]), (ode, func, rf, k)
+
+
 def test_tdg_quirk_c3_switch(pkg, torch):
     """TimeDG(quirks=False) switches off SURVEY quirk C-3 only (adjoint linearised inside the element
     instead of the mirrored interval of adj_march.m:72,78): parity with the oracle's switch, and what
