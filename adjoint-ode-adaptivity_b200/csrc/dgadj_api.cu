@@ -546,6 +546,8 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->ring);
   cudaFree(h->red_scratch);
   cudaFree(h->fd_scratch);
+  cudaFree(h->fd_tbl);
+  free(h->fd_tbl_dt);
   cudaFree(h->tdg_scratch);
   for (auto& sl : h->tdg_cache) {
     cudaFree(sl.dev);

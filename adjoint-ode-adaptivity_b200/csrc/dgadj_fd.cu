@@ -11,6 +11,8 @@
 // interpU, :24-31) are built once on the host and shared by the batch.  All arithmetic is
 // written unfused (__dmul_rn / __dadd_rn) to mirror NumPy's separate multiply and add.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -208,12 +210,15 @@ __global__ void fd_awr_warp_kernel(long long B, int n, int rf, int ode, int func
 }
 
 // launches the warp form when the batch is small and a warp's arrays fit; else one thread per trajectory
+static bool fd_uses_warp(const dgadj_handle* h, long long B, int n, int rf) {
+  const bool warp = h->tune_block == 32 || (h->tune_block != 1 && B <= 16384);
+  return warp && fd_warp_doubles(n, rf) * sizeof(double) <= 48 * 1024;
+}
 static cudaError_t fd_launch_awr(dgadj_handle* h, long long B, int n, int rf, int ode, int func, const FdTables& t,
                                  const double* u0, double* uc, double* u_out, double* v_out, double* err_out,
                                  double* steps_out, int* idx_out, cudaStream_t st) {
   const size_t per_warp = fd_warp_doubles(n, rf) * sizeof(double);
-  const bool warp = h->tune_block == 32 || (h->tune_block != 1 && B <= 16384);
-  if (warp && per_warp <= 48 * 1024) {
+  if (fd_uses_warp(h, B, n, rf)) {
     int wpc = (int)((48 * 1024) / per_warp);
     wpc = wpc > 4 ? 4 : wpc;
     fd_awr_warp_kernel<<<(unsigned)((B + wpc - 1) / wpc), wpc * 32, wpc * per_warp, st>>>(B, n, rf, ode, func, t, u0, u_out, v_out,
@@ -241,64 +246,94 @@ extern "C" int dgadj_fd_awr(dgadj_handle* h, int64_t B, int32_t n, int32_t ref_f
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const int nf = n * ref_factor;
-  // ---- host tables: refineAll (:16-21), cumulative times, np.interp's interval search (:24-31)
-  std::vector<double> dtf(nf), tc(n + 1), tf(nf + 1), dx(nf + 1), den(n);
-  std::vector<int> jc(nf + 1);
-  std::vector<unsigned char> exact(nf + 1);
-  for (int j = 0; j < n; ++j)
-    for (int f = 0; f < ref_factor; ++f) dtf[j * ref_factor + f] = dt_host[j] / ref_factor;
-  tc[0] = 0.0;
-  for (int j = 0; j < n; ++j) tc[j + 1] = tc[j] + dt_host[j];   // np.cumsum: sequential
-  tf[0] = 0.0;
-  for (int i = 0; i < nf; ++i) tf[i + 1] = tf[i] + dtf[i];
-  for (int j = 0; j < n; ++j) den[j] = tc[j + 1] - tc[j];
-  for (int i = 0; i <= nf; ++i) {
-    const double x = tf[i];
-    int j;
-    if (x >= tc[n]) {
-      j = n;  // x beyond / at the last node: np.interp returns fp[-1] (right fill = fp[-1])
-    } else {
-      j = 0;  // largest j with tc[j] <= x
-      int lo = 0, hi = n;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) / 2;
-        if (tc[mid] <= x) lo = mid; else hi = mid - 1;
+  // ---- the tables of this mesh: kept on the device (their own buffer) for as long as the same steps come back -- a
+  // repeated call is a kernel launch, no table build, no upload, no synchronisation
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_dx = 0, o_den = o_dx + al(sizeof(double) * (nf + 1)), o_dtf = o_den + al(sizeof(double) * n),
+               o_dtn = o_dtf + al(sizeof(double) * nf), o_jc = o_dtn + al(sizeof(double) * n),
+               o_ex = o_jc + al(sizeof(int) * (nf + 1)), tbl_bytes = o_ex + al(nf + 1);
+  const bool hit = h->fd_tbl && h->fd_tbl_n == n && h->fd_tbl_rf == ref_factor &&
+                   memcmp(h->fd_tbl_dt, dt_host, sizeof(double) * n) == 0;
+  if (!hit) {
+    // host tables: refineAll (:16-21), cumulative times, np.interp's interval search (:24-31)
+    std::vector<double> dtf(nf), tc(n + 1), tf(nf + 1), dx(nf + 1), den(n);
+    std::vector<int> jc(nf + 1);
+    std::vector<unsigned char> exact(nf + 1);
+    for (int j = 0; j < n; ++j)
+      for (int f = 0; f < ref_factor; ++f) dtf[j * ref_factor + f] = dt_host[j] / ref_factor;
+    tc[0] = 0.0;
+    for (int j = 0; j < n; ++j) tc[j + 1] = tc[j] + dt_host[j];   // np.cumsum: sequential
+    tf[0] = 0.0;
+    for (int i = 0; i < nf; ++i) tf[i + 1] = tf[i] + dtf[i];
+    for (int j = 0; j < n; ++j) den[j] = tc[j + 1] - tc[j];
+    for (int i = 0; i <= nf; ++i) {
+      const double x = tf[i];
+      int j;
+      if (x >= tc[n]) {
+        j = n;  // x beyond / at the last node: np.interp returns fp[-1] (right fill = fp[-1])
+      } else {
+        j = 0;  // largest j with tc[j] <= x
+        int lo = 0, hi = n;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) / 2;
+          if (tc[mid] <= x) lo = mid; else hi = mid - 1;
+        }
+        j = lo;
       }
-      j = lo;
+      jc[i] = j;
+      dx[i] = x - tc[j];
+      exact[i] = (j >= n || tc[j] == x) ? 1 : 0;
     }
-    jc[i] = j;
-    dx[i] = x - tc[j];
-    exact[i] = (j >= n || tc[j] == x) ? 1 : 0;
+    h->fd_tbl_n = 0;   // (no valid entry until everything below is queued)
+    if (tbl_bytes > h->fd_tbl_bytes || (size_t)n > h->fd_tbl_dt_cap) {
+      CUDA_TRY(h, cudaDeviceSynchronize());
+      cudaFree(h->fd_tbl);
+      free(h->fd_tbl_dt);
+      h->fd_tbl = nullptr;
+      h->fd_tbl_dt = nullptr;
+      h->fd_tbl_bytes = h->fd_tbl_dt_cap = 0;
+      h->fd_tbl_dt = (double*)malloc(sizeof(double) * n);
+      if (!h->fd_tbl_dt) return fail(h, DGADJ_ERR_NOMEM, "host copy of the FD steps");
+      h->fd_tbl_dt_cap = n;
+      CUDA_TRY(h, cudaMalloc(&h->fd_tbl, tbl_bytes));
+      h->fd_tbl_bytes = tbl_bytes;
+    }
+    unsigned char* tb = (unsigned char*)h->fd_tbl;
+    // (stream-ordered after the kernels that may still read the old tables; the pageable sources are staged by the
+    //  driver before cudaMemcpyAsync returns)
+    CUDA_TRY(h, cudaMemcpyAsync(tb + o_dx, dx.data(), sizeof(double) * (nf + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(tb + o_den, den.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(tb + o_dtf, dtf.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(tb + o_dtn, dt_host, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(tb + o_jc, jc.data(), sizeof(int) * (nf + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(tb + o_ex, exact.data(), nf + 1, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));   // the host vectors go out of scope
+    memcpy(h->fd_tbl_dt, dt_host, sizeof(double) * n);
+    h->fd_tbl_n = n;
+    h->fd_tbl_rf = ref_factor;
   }
-  // ---- device scratch: tables + coarse states [n+1][B]
-  const size_t tbl_bytes = sizeof(int) * (nf + 1) + sizeof(double) * ((nf + 1) + n + nf + n) + (nf + 1) + 64;
-  const size_t need = ((tbl_bytes + 255) / 256) * 256 + sizeof(double) * (size_t)(n + 1) * (size_t)B;
-  if (need > h->fd_bytes) {
-    CUDA_TRY(h, cudaDeviceSynchronize());
-    cudaFree(h->fd_scratch);
-    h->fd_scratch = nullptr;
-    h->fd_bytes = 0;
-    CUDA_TRY(h, cudaMalloc(&h->fd_scratch, need));
-    h->fd_bytes = need;
-  }
-  unsigned char* base = (unsigned char*)h->fd_scratch;
-  size_t off = 0;
-  auto put = [&](const void* src, size_t bytes, size_t align) -> void* {
-    off = (off + align - 1) / align * align;
-    void* d = base + off;
-    cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
-    off += bytes;
-    return d;
-  };
+  const unsigned char* tb = (const unsigned char*)h->fd_tbl;
   FdTables t;
-  t.dx = (const double*)put(dx.data(), sizeof(double) * (nf + 1), 8);
-  t.den = (const double*)put(den.data(), sizeof(double) * n, 8);
-  t.dtf = (const double*)put(dtf.data(), sizeof(double) * nf, 8);
-  t.dtn = (const double*)put(dt_host, sizeof(double) * n, 8);
-  t.jc = (const int*)put(jc.data(), sizeof(int) * (nf + 1), 4);
-  t.exact = (const unsigned char*)put(exact.data(), nf + 1, 1);
-  CUDA_TRY(h, cudaStreamSynchronize(st));   // the host vectors go out of scope (pageable source)
-  double* uc = (double*)(base + ((tbl_bytes + 255) / 256) * 256);
+  t.dx = (const double*)(tb + o_dx);
+  t.den = (const double*)(tb + o_den);
+  t.dtf = (const double*)(tb + o_dtf);
+  t.dtn = (const double*)(tb + o_dtn);
+  t.jc = (const int*)(tb + o_jc);
+  t.exact = tb + o_ex;
+  // ---- coarse states [n+1][B] of the thread-per-trajectory form
+  double* uc = nullptr;
+  if (!fd_uses_warp(h, B, n, ref_factor)) {
+    const size_t need = sizeof(double) * (size_t)(n + 1) * (size_t)B;
+    if (need > h->fd_bytes) {
+      CUDA_TRY(h, cudaDeviceSynchronize());
+      cudaFree(h->fd_scratch);
+      h->fd_scratch = nullptr;
+      h->fd_bytes = 0;
+      CUDA_TRY(h, cudaMalloc(&h->fd_scratch, need));
+      h->fd_bytes = need;
+    }
+    uc = (double*)h->fd_scratch;
+  }
   CUDA_TRY(h, fd_launch_awr(h, B, n, ref_factor, ode, functional, t, u0_dev, uc, u_dev, v_dev, err_fine_dev, err_steps_dev,
                             ref_idx_dev, st));
   h->launches++;

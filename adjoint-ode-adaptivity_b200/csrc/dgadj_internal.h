@@ -41,8 +41,12 @@ struct dgadj_handle {
   size_t ring_bytes;
   double* red_scratch;
   size_t red_bytes;
-  void* fd_scratch;     // dgadj_fd_awr: interpolation tables + coarse states
+  void* fd_scratch;     // dgadj_fd_awr: coarse states of the thread form; the FD loops' tables / states
   size_t fd_bytes;
+  void* fd_tbl;         // dgadj_fd_awr: interpolation tables of the last mesh (kept while the same steps come back)
+  size_t fd_tbl_bytes, fd_tbl_dt_cap;
+  double* fd_tbl_dt;    //   host copy of the steps the tables were built from
+  int fd_tbl_n, fd_tbl_rf;
   double* tdg_scratch;  // dgadj_tdg_*adapt_loop*: templates, element blocks, mesh history
   size_t tdg_bytes;
   // dgadj_tdg_march / _adjoint / _adjoint_rec / _err_contribution: the per-element constant blocks of the last few

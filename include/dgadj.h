@@ -15,11 +15,11 @@
  *     borrowed for the call; work is enqueued on `stream` (a cudaStream_t cast to void*,
  *     NULL = the legacy default stream) and is asynchronous -- the caller synchronises.
  *     Exceptions, which block the host until their constants are on the device (they take per-call
- *     HOST arrays of mesh constants): dgadj_burgers_forward / dgadj_burgers_adjoint, dgadj_fd_awr, and
+ *     HOST arrays of mesh constants): dgadj_burgers_forward / dgadj_burgers_adjoint, and
  *     dgadj_fwd_adj_windowed (scratch is released on return).  dgadj_tdg_march / _adjoint / _adjoint_rec /
- *     _err_contribution keep the constant blocks of the last four meshes on the device: a call whose blocks
- *     are among them is a kernel launch only; a new mesh costs one pageable upload (the host array may be
- *     released on return).  The fused / loop entry points (dgadj_fwd_adj, dgadj_burgers_fwd_adj,
+ *     _err_contribution keep the constant blocks of the last four meshes on the device, dgadj_fd_awr the
+ *     tables of the last one: a call on a mesh that is still there is a kernel launch only; a new mesh
+ *     costs the table build and one pageable upload (the host array may be released on return).  The fused / loop entry points (dgadj_fwd_adj, dgadj_burgers_fwd_adj,
  *     dgadj_*_adapt_loop*) stage their constants with stream-ordered copies and do not block.
  *   - scratch buffers belong to the handle: use a handle from ONE stream at a time (a second call on
  *     another stream may overwrite constants a running kernel still reads).

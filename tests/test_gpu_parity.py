@@ -786,6 +786,37 @@ def test_fd_warp_kernel_equals_thread_kernel(pkg, torch):
             assert torch.equal(res["thread"][k], res["warp"][k]), (ode, func, rf, k)
 
 
+def test_constant_caches_follow_the_mesh(pkg, torch):
+    """The time-DG entry points keep the constant blocks of the last four meshes on the device and the FD entry point
+    the tables of the last one (a repeated call is a launch only): six meshes in turn through ONE handle, the first
+    ones again after they have been evicted, same-length meshes with different nodes -- every result equal to a fresh
+    handle's, bit for bit."""
+    rng = np.random.default_rng(31)
+    y0 = torch.tensor(rng.uniform(-3, 3, 50), device="cuda")
+    meshes = [np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.05, 1.95, 6)))) for _ in range(6)]
+    seq = [0, 1, 0, 2, 3, 4, 5, 0, 1, 5, 5, 2]
+    s = pkg.TimeDG()
+    f = pkg.FDAdjoint()
+    for m in seq:
+        times = meshes[m]
+        Ks = times.size - 1
+        Ns = np.ones(Ks, dtype=int)
+        t1, y1, its = s.dg_march(Ns, Ks, times, y0)
+        _, v, err = s.adj_march(Ns + 1, Ks, times, y1, t1)
+        out = f.solve(y0, np.diff(times))
+        s2, f2 = pkg.TimeDG(), pkg.FDAdjoint()
+        t1r, y1r, itsr = s2.dg_march(Ns, Ks, times, y0)
+        _, vr, errr = s2.adj_march(Ns + 1, Ks, times, y1r, t1r)
+        outr = f2.solve(y0, np.diff(times))
+        torch.cuda.synchronize()
+        assert torch.equal(y1, y1r) and torch.equal(its, itsr) and torch.equal(v, vr) and torch.equal(err, errr), m
+        assert all(torch.equal(out[k], outr[k]) for k in out), m
+        s2.close()
+        f2.close()
+    s.close()
+    f.close()
+
+
 def test_tdg_quirk_c3_switch(pkg, torch):
     """TimeDG(quirks=False) switches off SURVEY quirk C-3 only (adjoint linearised inside the element
     instead of the mirrored interval of adj_march.m:72,78): parity with the oracle's switch, and what

@@ -340,26 +340,33 @@ def cfg5(pkg, torch, dev, pool=None, B=4096, iters=30):
     rng = np.random.default_rng(0)
     y0 = torch.tensor(rng.uniform(-3, 3, B), device=dev)
 
-    def timed(fn):
-        fn()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        h = fn()
-        torch.cuda.synchronize()
-        return h, time.perf_counter() - t0
-    # device_loop=True: one C-ABI call per loop, no collective (this runs on rank 0 alone)
-    h_dg, t_dg = timed(lambda: pkg.adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=iters, device=dev.index, device_loop=True))
-    h_fd, t_fd = timed(lambda: pkg.adapt_fd(y0, tspan=(0.0, 2.0), n_steps=2, iters=iters, functional="int_u2", device=dev.index,
-                                            device_loop=True))
     from adjoint_ode_adaptivity_b200 import adapt as _adapt
-    dev_ms = dict(_adapt.LAST_LOOP_DEVICE_MS)
+    dev_ms = {}
+
+    def timed(fn, key):
+        fn()                                      # warm-up (scratch allocation, module load)
+        torch.cuda.synchronize()
+        best, h = float("inf"), None
+        for _ in range(3):                        # best of 3 whole loops (a loop is ~10 ms)
+            t0 = time.perf_counter()
+            h = fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if dt < best:
+                best = dt
+                dev_ms[key] = _adapt.LAST_LOOP_DEVICE_MS.get(key, float("nan"))
+        return h, best
+    # device_loop=True: one C-ABI call per loop, no collective (this runs on rank 0 alone)
+    h_dg, t_dg = timed(lambda: pkg.adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=iters, device=dev.index, device_loop=True), "tdg")
+    h_fd, t_fd = timed(lambda: pkg.adapt_fd(y0, tspan=(0.0, 2.0), n_steps=2, iters=iters, functional="int_u2", device=dev.index,
+                                            device_loop=True), "fd")
     solves = sum(2 * (h["times"].size - 1) for h in h_dg) * B
     fine = sum((h["times"].size - 1) * 9 for h in h_fd) * B
     res = dict(
         workload="config 5: adjoint-driven refinement loops, B=%d ICs u0 ~ U(-3,3), u' = sin u on [0,2], shared mesh, batch-mean "
                  "indicator, %d argmax refinements from 2 elements / steps (matlab/MAIN.m:29-166; Main_finite_difference.py:263-343), "
                  "device-resident loops: one C-ABI call each, one read-back at the end" % (B, iters),
-        timing_note="ms_per_iteration: wall clock of the whole call (handle creation, the one C-ABI call, synchronisation, the final "
+        timing_note="best of 3 loops after one warm-up loop; ms_per_iteration: wall clock of the whole call (handle creation, the one C-ABI call, synchronisation, the final "
                     "read-back of the histories); device_ms_per_iteration: CUDA events around the C-ABI call",
         tdg=dict(metric="element-solves/s (Newton march or adjoint solve + indicator), whole loop incl. mesh updates", value=solves / t_dg,
                  unit="element-solves/s", ms_per_iteration=1e3 * t_dg / (iters + 1),
