@@ -331,6 +331,174 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
   }
 }
 
+// solve_dense in two parts: everything that does not touch the right-hand side (pivot search, row swaps of
+// the matrix, the multipliers, the reciprocals of the pivots) and the part that does.  lu_apply performs on b
+// exactly the operations solve_dense performs on it, in the same order -- the final divisions through div_rn_q
+// (the quotient's bits from the correctly rounded reciprocal: Markstein) -- so solve_dense(A, b) and
+// lu_factor(A, ..) + lu_apply(A, .., b) give the same bits.
+__device__ __forceinline__ double div_rn_q(double x, double h, double r) {
+  const double q = x * r;
+  return fma(fma(-h, q, x), r, q);
+}
+template <int N>
+__device__ __forceinline__ void lu_factor(double (&A)[N][N], unsigned& swmask, double (&rcp)[N]) {
+  swmask = 0u;
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+#pragma unroll
+    for (int r = c + 1; r < N; ++r) {
+      const bool sw = fabs(A[r][c]) > fabs(A[c][c]);
+      // (the multipliers already stored in columns < c travel with their rows: solve_dense has applied them to b
+      //  before this swap, so lu_apply replays swaps and eliminations in the original order, column by column)
+#pragma unroll
+      for (int j = c; j < N; ++j) {
+        const double t = A[c][j];
+        A[c][j] = sw ? A[r][j] : t;
+        A[r][j] = sw ? t : A[r][j];
+      }
+      swmask |= sw ? (1u << (c * N + r)) : 0u;
+    }
+    const double inv = 1.0 / A[c][c];
+#pragma unroll
+    for (int r = c + 1; r < N; ++r) {
+      const double f = A[r][c] * inv;
+#pragma unroll
+      for (int j = c + 1; j < N; ++j) A[r][j] = fma(-f, A[c][j], A[r][j]);
+      A[r][c] = f;   // kept in the eliminated position
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < N; ++r) rcp[r] = 1.0 / A[r][r];
+}
+template <int N>
+__device__ __forceinline__ void lu_apply(const double (&A)[N][N], unsigned swmask, const double (&rcp)[N], double (&b)[N]) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+#pragma unroll
+    for (int r = c + 1; r < N; ++r) {
+      const bool sw = (swmask >> (c * N + r)) & 1u;
+      const double tb = b[c];
+      b[c] = sw ? b[r] : tb;
+      b[r] = sw ? tb : b[r];
+    }
+#pragma unroll
+    for (int r = c + 1; r < N; ++r) b[r] = fma(-A[r][c], b[c], b[r]);
+  }
+#pragma unroll
+  for (int r = N - 1; r >= 0; --r) {
+    double s = b[r];
+#pragma unroll
+    for (int j = r + 1; j < N; ++j) s = fma(-A[r][j], b[j], s);
+    b[r] = div_rn_q(s, A[r][r], rcp[r]);
+  }
+}
+
+// Small batches: one WARP per trajectory, one LANE per element.  Everything expensive in an element of the adjoint
+// march depends on the PRIMAL only -- the nq sin / cos evaluations, the mass-type matrices, the factorisation of the
+// element matrix, the weights of the indicator -- and is done for 32 elements at once; what is sequential is the
+// right-hand side (the inflow value vL of the element behind) and the substitution, done by the lane that owns the
+// element while the others wait, vL handed on by a shuffle.  Same arithmetic per element as tdg_adjoint_kernel, in
+// the same order: bit-identical outputs.
+template <int NPP>
+__global__ void tdg_adjoint_warp_kernel(long long B, int Ks, int nq, int linear, double y0_hard,
+                                        const double* __restrict__ y0_arr, const double* __restrict__ ec,
+                                        const double* __restrict__ y, double* __restrict__ v, double* __restrict__ err) {
+  constexpr int NA = NPP + 1;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;   // whole warps leave together
+  const int blk = NA * NA + NA + NA * NA + NA * NPP + nq * NPP + nq * NA + nq + 3;
+  double vL = 0.0;
+  for (int base = ((Ks - 1) >> 5) << 5; base >= 0; base -= 32) {
+    const int k = base + lane;
+    const bool act = k < Ks;
+    const int kk = act ? k : Ks - 1;   // idle lanes repeat the last element (results unused)
+    const double* A0 = ec + (size_t)kk * blk;
+    const double* f1 = A0 + NA * NA;
+    const double* A2 = f1 + NA;
+    const double* Ix = A2 + NA * NA;
+    const double* Iq = Ix + NA * NPP;
+    const double* Phi = Iq + nq * NPP;
+    const double* w = Phi + nq * NA;
+    const double hk2 = 0.5 * w[nq];
+    const int nak = (int)w[nq + 1], lastprev = (int)w[nq + 2];
+    double Uk[NPP];
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) Uk[i] = y[((size_t)b * Ks + kk) * NPP + i];
+    double Mt[NA], M[NA][NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      Mt[i] = 0.0;
+#pragma unroll
+      for (int j = 0; j < NA; ++j) M[i][j] = 0.0;
+    }
+    if (!linear) {
+      for (int q = 0; q < nq; ++q) {
+        double ur = 0.0, ph[NA];
+#pragma unroll
+        for (int i = 0; i < NPP; ++i) ur = fma(Iq[q * NPP + i], Uk[i], ur);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) ph[i] = Phi[q * NA + i];
+        double sn, cs;
+        sincos(ur, &sn, &cs);
+        const double ws = w[q] * sn, wc = w[q] * cs;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          Mt[i] = fma(ph[i], ws, Mt[i]);
+          const double pw = ph[i] * wc;
+#pragma unroll
+          for (int j = 0; j < NA; ++j) M[i][j] = fma(pw, ph[j], M[i][j]);
+        }
+      }
+    }
+    double F0[NA], Sw[NA], rcp[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      F0[i] = f1[i];
+#pragma unroll
+      for (int j = 0; j < NA; ++j) M[i][j] = fma(-hk2, M[i][j], A0[i * NA + j]);
+    }
+    unsigned swmask;
+    lu_factor<NA>(M, swmask, rcp);
+    double uh[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NPP; ++j) s = fma(Ix[i * NPP + j], Uk[j], s);
+      uh[i] = s;
+    }
+    const double f0 = (kk == 0) ? (y0_arr ? y0_arr[b] : y0_hard) : y[((size_t)b * Ks + (kk - 1)) * NPP + lastprev];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double s = fma(-hk2, Mt[i], (i == 0) ? f0 : 0.0);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) s = fma(-A2[i * NA + j], uh[j], s);
+      Sw[i] = s;
+    }
+    // ---- the sequential part: elements base+31 .. base, each by its lane
+    const int top = (Ks - 1 - base) < 31 ? (Ks - 1 - base) : 31;
+    for (int src = top; src >= 0; --src) {
+      double v0 = 0.0;
+      if (lane == src) {
+        double F[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) F[i] = F0[i] - ((i == nak - 1) ? vL : 0.0);
+        lu_apply<NA>(M, swmask, rcp, F);
+        v0 = F[0];
+        double e = 0.0;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          e = fma(F[i], Sw[i], e);
+          if (v) v[((size_t)b * Ks + k) * NA + i] = F[i];
+        }
+        if (err) err[(size_t)b * Ks + k] = e;
+      }
+      vL = __shfl_sync(0xffffffffu, v0, src);
+    }
+  }
+}
+
 // Radau-reconstructed adjoint, matlab/adj_rec.m:18-71 (linear branch; the reference's nonlinear
 // branch is unfinished and returns zeros, handled by the host): adjoint solved at the PRIMAL
 // order, interpolated to the element's Radau points, extended by the inflow value and
@@ -481,12 +649,21 @@ static int tdg_launch_march(dgadj_handle* h, long long B, int Ks, int Np, int nq
 static int tdg_launch_adjoint(dgadj_handle* h, long long B, int Ks, int Npp, int nq, int linear, double y0_hard,
                               const double* y0_dev, const double* ec_dev, const double* y_dev, double* v_dev,
                               double* err_dev, cudaStream_t st) {
-  // small batches: 32 threads per CTA spread the trajectories over four times as many SMs
-  const int block = (B <= TDG_WARP_BATCH) ? 32 : 128;
-  const unsigned grid = (unsigned)((B + block - 1) / block);
+  const bool warp = h->tune_block == 32 || (h->tune_block != 1 && B <= TDG_WARP_BATCH);
+  if (warp) {   // one warp per trajectory, one lane per element
+    const int block = 128;
+    const unsigned grid = (unsigned)((B * 32 + block - 1) / block);
+#define DGADJ_TDG_AW(n) case n: tdg_adjoint_warp_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, y0_hard, y0_dev, ec_dev, y_dev, v_dev, err_dev); break;
+    switch (Npp) { DGADJ_TDG_AW(2) DGADJ_TDG_AW(3) DGADJ_TDG_AW(4) DGADJ_TDG_AW(5) DGADJ_TDG_AW(6) }
+#undef DGADJ_TDG_AW
+  } else {
+    // (forced thread form on a small batch: 32 threads per CTA spread the trajectories over four times as many SMs)
+    const int block = (B <= TDG_WARP_BATCH) ? 32 : 128;
+    const unsigned grid = (unsigned)((B + block - 1) / block);
 #define DGADJ_TDG_A(n) case n: tdg_adjoint_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, linear, y0_hard, y0_dev, ec_dev, y_dev, v_dev, err_dev); break;
-  switch (Npp) { DGADJ_TDG_A(2) DGADJ_TDG_A(3) DGADJ_TDG_A(4) DGADJ_TDG_A(5) DGADJ_TDG_A(6) }
+    switch (Npp) { DGADJ_TDG_A(2) DGADJ_TDG_A(3) DGADJ_TDG_A(4) DGADJ_TDG_A(5) DGADJ_TDG_A(6) }
 #undef DGADJ_TDG_A
+  }
   CUDA_TRY(h, cudaGetLastError());
   return DGADJ_OK;
 }

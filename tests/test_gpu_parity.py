@@ -766,6 +766,30 @@ def test_tdg_warp_march_equals_thread_march(pkg, torch):
         assert float((res["thread"][1] - res["warp"][1]).abs().max()) < 1e-13
 
 
+def test_tdg_warp_adjoint_equals_thread_adjoint(pkg, torch):
+    """The warp-per-trajectory adjoint (one lane per element: the quadrature, the element matrices and their
+    factorisation for 32 elements at once, the substitution element by element) against the thread-per-trajectory
+    kernel: v and err bit for bit -- nonlinear and linear branch, mixed orders, more than 32 elements, a batch of
+    initial values, both settings of quirk C-3."""
+    rng = np.random.default_rng(12)
+    for Ks, nmax, B, linear, quirks in ((10, 1, 77, False, True), (45, 2, 33, False, True), (70, 1, 5, False, False),
+                                        (9, 3, 40, True, True), (33, 4, 3, False, True)):
+        y0 = torch.tensor(rng.uniform(-3, 3, B), device="cuda")
+        times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.05, 1.95, Ks - 1))))
+        Ns = rng.integers(1, nmax + 1, Ks)
+        res = {}
+        for form, blk in (("thread", 1), ("warp", 32)):
+            s = pkg.TimeDG(linear=linear, quirks=quirks)
+            s._check(s.lib.dgadj_set_tuning(s._h, 0, 1, 0))                      # the same primal for both
+            t1, y1, _ = s.dg_march(Ns, Ks, times, y0)
+            s._check(s.lib.dgadj_set_tuning(s._h, 0, blk, 0))
+            res[form] = s.adj_march(Ns + 1, Ks, times, y1, t1, y0=y0)
+            torch.cuda.synchronize()
+            s.close()
+        assert torch.equal(res["thread"][1], res["warp"][1]), (Ks, nmax, linear)
+        assert torch.equal(res["thread"][2], res["warp"][2]), (Ks, nmax, linear)
+
+
 def test_fd_warp_kernel_equals_thread_kernel(pkg, torch):
     """The warp-per-trajectory FD kernel (small batches: the lanes share the 2 nf sin / cos evaluations, the window
     sums and the argmax; the two recurrences run in every lane) against the thread-per-trajectory kernel: every

@@ -2,7 +2,7 @@
 TAG=${1:-r2u}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-echo "== fd / adaptive tests"; timeout 900 python -m pytest tests -q -m gpu -k "fd or tdg or adaptive or reference_argument or cfg5 or caches" > $OUT/pytest_fd.log 2>&1; echo "rc=$?"; grep -E "passed|failed|Error|^E  " $OUT/pytest_fd.log | cut -c1-250 | head -20
+echo "== fd / adaptive tests"; timeout 900 python -m pytest tests -q -m gpu -k "fd or tdg or adaptive or reference_argument or cfg5 or caches or matlab or time_dg" > $OUT/pytest_fd.log 2>&1; echo "rc=$?"; grep -E "passed|failed|Error|^E  " $OUT/pytest_fd.log | cut -c1-250 | head -20
 echo "== tdg / fd small batch"; timeout 600 python tools/bench_secondary.py tdg_fd > $OUT/tdg_fd.jsonl 2> $OUT/tdg_fd.err; echo "rc=$?"; cut -c1-300 $OUT/tdg_fd.jsonl; tail -3 $OUT/tdg_fd.err
 timeout 600 python - > $OUT/cfg5.json 2> $OUT/cfg5.err <<PY
 import sys, json, os
