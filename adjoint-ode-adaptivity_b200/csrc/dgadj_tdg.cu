@@ -27,8 +27,20 @@
 
 namespace dgadj {
 
+// x / h from the correctly rounded reciprocal r = RN(1/h): q = RN(x r) is within an ulp of the quotient, the
+// residual x - h q is exact in an fma, and RN(q + residual r) is the correctly rounded quotient (Markstein's
+// theorem): the bits of the division without a second division sequence.
+__device__ __forceinline__ double div_rn_q(double x, double h, double r) {
+  const double q = x * r;
+  return fma(fma(-h, q, x), r, q);
+}
+
+// Gaussian elimination with partial pivoting.  The pivots' reciprocals of the elimination serve the back
+// substitution as well (b[r] = s / A[r][r] through div_rn_q: same bits, half the division sequences -- they are a
+// fifth of a Newton iteration of the 2 x 2 systems of N = 1).
 template <int N>
 __device__ __forceinline__ void solve_dense(double (&A)[N][N], double (&b)[N]) {
+  double inv[N];
 #pragma unroll
   for (int c = 0; c < N; ++c) {
     // partial pivoting: bring the largest |A[r][c]|, r >= c, to row c (branch-free row swaps)
@@ -45,10 +57,10 @@ __device__ __forceinline__ void solve_dense(double (&A)[N][N], double (&b)[N]) {
       b[c] = sw ? b[r] : tb;
       b[r] = sw ? tb : b[r];
     }
-    const double inv = 1.0 / A[c][c];
+    inv[c] = 1.0 / A[c][c];
 #pragma unroll
     for (int r = c + 1; r < N; ++r) {
-      const double f = A[r][c] * inv;
+      const double f = A[r][c] * inv[c];
 #pragma unroll
       for (int j = c + 1; j < N; ++j) A[r][j] = fma(-f, A[c][j], A[r][j]);
       b[r] = fma(-f, b[c], b[r]);
@@ -59,7 +71,7 @@ __device__ __forceinline__ void solve_dense(double (&A)[N][N], double (&b)[N]) {
     double s = b[r];
 #pragma unroll
     for (int j = r + 1; j < N; ++j) s = fma(-A[r][j], b[j], s);
-    b[r] = s / A[r][r];
+    b[r] = div_rn_q(s, A[r][r], inv[r]);
   }
 }
 
@@ -151,20 +163,28 @@ __global__ void tdg_march_kernel(long long B, int Ks, int nq, int linear, double
     if (its) its[(size_t)b * Ks + k] = it;
   }
 }
-
-// The same march with one WARP per trajectory (small batches: config 5 has 4096 initial values, a handful
-// of warps for the whole device in the thread-per-trajectory form).  The lanes share the quadrature points
-// of an element (30 N + 1 of them, dg_march.m:29: the sin / cos evaluations are what a Newton iteration
-// costs), the partial sums meet in a butterfly of shuffles -- every lane ends with the same bits -- and each
-// lane then repeats the small dense solve.  Same stopping rule; the quadrature sums are associated
-// differently from the sequential kernel (rounding-level differences in U).
-template <int NP>
-__global__ void tdg_march_warp_kernel(long long B, int Ks, int nq, double tol, int maxit,
-                                      const double* __restrict__ ec, const double* __restrict__ y0,
-                                      double* __restrict__ y, int* __restrict__ its) {
-  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (b >= B) return;   // whole warps leave together
+// Small batches (nonlinear branch): a GROUP of G lanes per trajectory (G = 16: two trajectories per warp).  A
+// thread-per-trajectory launch of a few thousand trajectories leaves one warp per SM.  A group's lanes take the
+// 30 N + 1 quadrature points of an element (dg_march.m:29) in turns, the partial sums meet in a butterfly of
+// shuffles -- every lane of the group ends with the same bits -- and each lane repeats the small dense solve.  Same
+// stopping rule per trajectory (a group that has converged idles through the iterations its warp-mate still
+// needs); the quadrature sums are associated differently from the sequential kernel (rounding-level differences in
+// U, same Newton iteration counts).
+// MEASURED (B = 4096, Ks = 31, N = 1; ncu launch list): G = 4: 249 us, 8: 164 us, 16: 134 us (129 us with the
+// stopping rule decided without the square root), 32: 169 us (thread
+// form: ~1 ms).  With 32 lanes everything but the sin / cos is replicated 32 times and the fp64 pipe (16 lanes per
+// cycle, whatever they compute) is the bound; below 16 the march is bound by the latency of one Newton iteration
+// (~3000 cycles: two reciprocal sequences and the substitution of the solve, the sin / cos pair, the butterfly, the
+// square root of the stopping rule), 85 of which follow one another along a trajectory.
+template <int NP, int G>
+__global__ void tdg_march_group_kernel(long long B, int Ks, int nq, double tol, int maxit,
+                                       const double* __restrict__ ec, const double* __restrict__ y0,
+                                       double* __restrict__ y, int* __restrict__ its) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long bb = gt / G;
+  const int l = (int)(gt % G);
+  const bool act = bb < B;              // (idle groups of the last warp compute on the last trajectory, write nothing)
+  const long long b = act ? bb : B - 1;
   const int blk = NP * NP + 2 * nq * NP + nq + 2;
   double uR = y0[b];
   for (int k = 0; k < Ks; ++k) {
@@ -178,8 +198,14 @@ __global__ void tdg_march_warp_kernel(long long B, int Ks, int nq, double tol, i
 #pragma unroll
     for (int i = 0; i < NP; ++i) U[i] = (i < npk) ? uR : 0.0;
     int it = 0;
-    double err = 1.0;
-    while (it <= maxit && err > tol) {   // uniform over the warp: every lane holds the same err
+    // the stopping rule `err > tol`, err = sqrt(sum R^2) (dg_march.m:66-68), decided without the square root
+    // wherever the sum is clear of tol^2 (sqrt is monotone and correctly rounded: a sum beyond tol^2 (1 +- 1e-12)
+    // cannot round across tol); the square root only inside that band -- the same decisions (measured: 3 % of the
+    // kernel time)
+    const double tol2 = tol * tol, t2hi = tol2 * (1.0 + 1e-12), t2lo = tol2 * (1.0 - 1e-12);
+    bool above = 1.0 > tol;
+    while (__any_sync(0xffffffffu, it <= maxit && above)) {   // (warp-uniform trip count: the shuffles below)
+      const bool go = it <= maxit && above;                  // this trajectory's own stopping rule
       double Mt[NP], J[NP][NP];
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
@@ -187,26 +213,31 @@ __global__ void tdg_march_warp_kernel(long long B, int Ks, int nq, double tol, i
 #pragma unroll
         for (int j = 0; j < NP; ++j) J[i][j] = 0.0;
       }
-      for (int q = lane; q < nq; q += 32) {
-        double ur = 0.0, ph[NP];
+#pragma unroll 4   // (the sin / cos evaluations of a lane's points side by side: one after the other they are the
+                   //  longest dependent chain of an iteration)
+      for (int q0 = 0; q0 < nq; q0 += G) {
+        const int q = q0 + l;
+        if (q < nq) {
+          double ur = 0.0, ph[NP];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          ur = fma(Iq[q * NP + i], U[i], ur);
-          ph[i] = Phi[q * NP + i];
-        }
-        double sn, cs;
-        sincos(ur, &sn, &cs);
-        const double ws = w[q] * sn, wc = w[q] * cs;
+          for (int i = 0; i < NP; ++i) {
+            ur = fma(Iq[q * NP + i], U[i], ur);
+            ph[i] = Phi[q * NP + i];
+          }
+          double sn, cs;
+          sincos(ur, &sn, &cs);
+          const double ws = w[q] * sn, wc = w[q] * cs;
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          Mt[i] = fma(ph[i], ws, Mt[i]);
-          const double pw = ph[i] * wc;
+          for (int i = 0; i < NP; ++i) {
+            Mt[i] = fma(ph[i], ws, Mt[i]);
+            const double pw = ph[i] * wc;
 #pragma unroll
-          for (int j = i; j < NP; ++j) J[i][j] = fma(pw, ph[j], J[i][j]);   // symmetric: upper triangle
+            for (int j = i; j < NP; ++j) J[i][j] = fma(pw, ph[j], J[i][j]);   // symmetric: upper triangle
+          }
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = G / 2; o > 0; o >>= 1) {
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
           Mt[i] += __shfl_xor_sync(0xffffffffu, Mt[i], o);
@@ -234,18 +265,20 @@ __global__ void tdg_march_warp_kernel(long long B, int Ks, int nq, double tol, i
       double e2 = 0.0;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        U[i] -= R[i];
+        U[i] = go ? U[i] - R[i] : U[i];
         e2 = fma(R[i], R[i], e2);
       }
-      err = sqrt(e2);
-      ++it;
+      bool ab = e2 > t2hi;
+      if (!ab && !(e2 < t2lo)) ab = sqrt(e2) > tol;   // (NaN lands here: sqrt(NaN) > tol is false, as in the plain rule)
+      above = go ? ab : above;
+      it += go ? 1 : 0;
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       if (i == npk - 1) uR = U[i];
-      if (lane == 0) y[((size_t)b * Ks + k) * NP + i] = U[i];
+      if (act && l == 0) y[((size_t)b * Ks + k) * NP + i] = U[i];
     }
-    if (its && lane == 0) its[(size_t)b * Ks + k] = it;
+    if (its && act && l == 0) its[(size_t)b * Ks + k] = it;
   }
 }
 
@@ -333,13 +366,8 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
 
 // solve_dense in two parts: everything that does not touch the right-hand side (pivot search, row swaps of
 // the matrix, the multipliers, the reciprocals of the pivots) and the part that does.  lu_apply performs on b
-// exactly the operations solve_dense performs on it, in the same order -- the final divisions through div_rn_q
-// (the quotient's bits from the correctly rounded reciprocal: Markstein) -- so solve_dense(A, b) and
+// exactly the operations solve_dense performs on it, in the same order, so solve_dense(A, b) and
 // lu_factor(A, ..) + lu_apply(A, .., b) give the same bits.
-__device__ __forceinline__ double div_rn_q(double x, double h, double r) {
-  const double q = x * r;
-  return fma(fma(-h, q, x), r, q);
-}
 template <int N>
 __device__ __forceinline__ void lu_factor(double (&A)[N][N], unsigned& swmask, double (&rcp)[N]) {
   swmask = 0u;
@@ -358,17 +386,15 @@ __device__ __forceinline__ void lu_factor(double (&A)[N][N], unsigned& swmask, d
       }
       swmask |= sw ? (1u << (c * N + r)) : 0u;
     }
-    const double inv = 1.0 / A[c][c];
+    rcp[c] = 1.0 / A[c][c];
 #pragma unroll
     for (int r = c + 1; r < N; ++r) {
-      const double f = A[r][c] * inv;
+      const double f = A[r][c] * rcp[c];
 #pragma unroll
       for (int j = c + 1; j < N; ++j) A[r][j] = fma(-f, A[c][j], A[r][j]);
       A[r][c] = f;   // kept in the eliminated position
     }
   }
-#pragma unroll
-  for (int r = 0; r < N; ++r) rcp[r] = 1.0 / A[r][r];
 }
 template <int N>
 __device__ __forceinline__ void lu_apply(const double (&A)[N][N], unsigned swmask, const double (&rcp)[N], double (&b)[N]) {
@@ -623,7 +649,7 @@ static int tdg_consts(dgadj_handle* h, const double* host, size_t n, cudaStream_
   return DGADJ_OK;
 }
 
-// One warp per trajectory below this batch size (nonlinear branch): the thread-per-trajectory kernel needs
+// Lane groups / warps per trajectory below this batch size: the thread-per-trajectory kernels need
 // ~150k trajectories to fill the device.  dgadj_set_tuning(block_threads = 1 / 32) forces either form.
 constexpr long long TDG_WARP_BATCH = 16384;
 static int tdg_launch_march(dgadj_handle* h, long long B, int Ks, int Np, int nq, int linear, double tol, int maxit,
@@ -631,8 +657,8 @@ static int tdg_launch_march(dgadj_handle* h, long long B, int Ks, int Np, int nq
   const bool warp = !linear && (h->tune_block == 32 || (h->tune_block != 1 && B <= TDG_WARP_BATCH));
   if (warp) {
     const int block = 128;
-    const unsigned grid = (unsigned)((B * 32 + block - 1) / block);
-#define DGADJ_TDG_W(n) case n: tdg_march_warp_kernel<n><<<grid, block, 0, st>>>(B, Ks, nq, tol, maxit, ec_dev, y0_dev, y_dev, its_dev); break;
+    constexpr int G = 16;   // lanes per trajectory
+#define DGADJ_TDG_W(n) case n: tdg_march_group_kernel<n, G><<<(unsigned)((B * G + block - 1) / block), block, 0, st>>>(B, Ks, nq, tol, maxit, ec_dev, y0_dev, y_dev, its_dev); break;
     switch (Np) { DGADJ_TDG_W(2) DGADJ_TDG_W(3) DGADJ_TDG_W(4) DGADJ_TDG_W(5) DGADJ_TDG_W(6) }
 #undef DGADJ_TDG_W
   } else {
@@ -929,7 +955,7 @@ extern "C" int dgadj_tdg_adapt_loop(dgadj_handle* h, const dgadj_tdg_loop_args* 
 // Per-trajectory meshes (build plan step 8 "second"): every trajectory refines ITS OWN mesh --
 // the reference's single-trajectory loop (matlab/MAIN.m:29-166) run for a whole batch at once, no batch rule.
 // One warp per trajectory: the lanes build the element block T0 + h T1 of the trajectory's current element in
-// shared memory, share the quadrature points (as tdg_march_warp_kernel), and repeat the small solves.
+// shared memory, share the quadrature points (as tdg_march_group_kernel), and repeat the small solves.
 // Meshes times[B][W] (W = Ks0 + iters + 2) live on the device; one call enqueues all iterations.
 // =======================================================================================================
 namespace dgadj {

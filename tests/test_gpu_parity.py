@@ -749,7 +749,7 @@ def test_adaptive_loops_per_trajectory_meshes(pkg, torch):
 
 
 def test_tdg_warp_march_equals_thread_march(pkg, torch):
-    """The warp-per-trajectory Newton march (small batches) against the thread-per-trajectory one: the same
+    """The lane-group Newton march (small batches: 16 lanes per trajectory) against the thread-per-trajectory one: the same
     Newton iteration counts, states equal to rounding (the quadrature sums are associated differently)."""
     rng = np.random.default_rng(11)
     y0 = torch.tensor(rng.uniform(-3, 3, 777), device="cuda")
