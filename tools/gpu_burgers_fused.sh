@@ -1,5 +1,5 @@
 #!/bin/bash
-TAG=${1:-r2q}
+TAG=${1:-bgf}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 echo "== burgers fused tests"; timeout 1200 python -m pytest tests -q -m gpu -k "burgers_fused or cfg3_full" > $OUT/pytest_bgf.log 2>&1; echo "rc=$?"; grep -E "passed|failed|AssertionError|^E  " $OUT/pytest_bgf.log | cut -c1-250 | head -30

@@ -1,5 +1,5 @@
 #!/bin/bash
-TAG=${1:-r2u}
+TAG=${1:-small_batch}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 echo "== fd / adaptive tests"; timeout 900 python -m pytest tests -q -m gpu -k "fd or tdg or adaptive or reference_argument or cfg5 or caches or matlab or time_dg" > $OUT/pytest_fd.log 2>&1; echo "rc=$?"; grep -E "passed|failed|Error|^E  " $OUT/pytest_fd.log | cut -c1-250 | head -20
