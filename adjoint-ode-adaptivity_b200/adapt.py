@@ -258,7 +258,7 @@ def adapt_tdg(y0, tspan=(0.0, 2.0), Ks=2, n=1, iters=30, linear=False, device=0,
 
 
 def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic", inflow="zero", cfl=0.25, psi=None,
-                device=0, B_global=None, ic_term=True, keep_indicators=True):
+                device=0, B_global=None, ic_term=True, keep_indicators=True, orders=None):
     """Adjoint-driven h-refinement of the DG-in-space advection march (BASELINE config 5 for the
     PDE path: non-uniform h): per iteration the batch is marched forward and backward on the
     current mesh, the per-element indicators are reduced over the batch in a fixed order, and the
@@ -271,8 +271,10 @@ def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic",
     ic_term the interpolation defect of the initial data enters too, weighted by the adjoint at
     t = 0:  eta_k += lam0_k . (P u0(x_c) - u0(x_f))_k  -- so that sum_k eta_k is the whole difference
     between the functional of the coarse solution and that of the order-N+1 solution of the true
-    initial data.  Returns the history (mesh, mean indicator, refined elements, J mean, the signed
-    batch-mean estimate) per iteration."""
+    initial data.  orders: per-element orders N_k <= N of the initial mesh (hp; `Ns(k)`, matlab/MAIN.m:21) --
+    the two halves of a split element keep its order (MAIN.m:141 gives the new element the order of the run).
+    Returns the history (mesh, mean indicator, refined elements, J mean, the signed batch-mean estimate, the
+    element orders) per iteration."""
     import torch
     v_x = np.asarray(v_x, dtype=np.float64)
     hist = []
@@ -284,9 +286,14 @@ def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic",
     dev = torch.device("cuda", device)
     d_vx = torch.zeros(s.capacity + topk + 1, dtype=torch.float64, device=dev)
     d_vx[:v_x.size] = torch.as_tensor(v_x, device=dev)
+    orders = None if orders is None else np.asarray(orders, dtype=np.int64).copy()
+    if orders is not None and orders.size != v_x.size - 1:
+        raise ValueError("orders: one entry per element of the initial mesh")
     for it in range(iters + 1):
         if it:
             s.set_mesh(v_x)
+        if orders is not None:
+            s.set_element_orders(orders)
         xmin = np.min(np.abs(s.g.x[0, :] - s.g.x[1, :]))
         S = int(np.ceil(T / (cfl * xmin / abs(a))))
         dt = T / S
@@ -304,9 +311,11 @@ def adapt_advec(u0_fn, N, v_x, a, T, iters=10, topk=1, alpha=0.0, bc="periodic",
         hist.append(dict(it=it, v_x=v_x.copy(), K=K, S=S, mean_eta=mean_eta, refined=order,
                          eta_total=float(sums[K]) / float(Bg) if keep_indicators else None,
                          J_mean=float(sums[K + 3]) / float(Bg) if keep_indicators else None,
-                         J=out["J"], estimate=eta.sum(1)))
+                         J=out["J"], estimate=eta.sum(1), orders=None if orders is None else orders.copy()))
         mids = 0.5 * (v_x[order] + v_x[order + 1])                     # host mirror of the device mesh (same arithmetic)
         v_x = np.sort(np.concatenate([v_x, mids]))
+        if orders is not None:
+            orders = np.insert(orders, order + 1, orders[order])       # both halves keep the parent's order
     if not np.array_equal(d_vx[:v_x.size].cpu().numpy(), v_x):       # the device mesh and its host mirror
         raise RuntimeError("adapt_advec: the host mirror of the mesh has left the device mesh")
     s.close()

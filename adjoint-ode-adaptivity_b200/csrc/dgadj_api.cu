@@ -407,13 +407,18 @@ __global__ void __launch_bounds__(1024, 1) dfma_peak_cst_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------
 // initial-data term of the indicator: eta[b][k] += sum_i lam0[b][i][k] ((P u0)[i][k] - u0f[b][i][k]).
 // One thread per (trajectory, element); memory-bound, once per march.
+// npk != null (per-element orders): P holds one matrix per node count n, P_n = P V diag(1_n, 0) V^-1 -- the
+// prolongation of the L2 projection of the coarse data onto the element's own space (what the march starts from);
+// lam0 of such a march is a covector of the element's enriched space, so it projects u0f by itself.
 __global__ void ic_indicator_kernel(long long B, int K, int Np, int NpF, const double* __restrict__ P,
+                                    const int* __restrict__ npk,
                                     const double* __restrict__ u0, const double* __restrict__ u0f,
                                     const double* __restrict__ lam0, double* __restrict__ eta) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * K) return;
   const long long b = t / K;
   const int k = (int)(t - b * K);
+  if (npk) P += (size_t)npk[k] * NpF * Np;
   double uc[MAXNP];
   for (int j = 0; j < Np; ++j) uc[j] = u0[((size_t)b * Np + j) * K + k];
   double e = 0.0;
@@ -543,6 +548,7 @@ extern "C" void dgadj_destroy(dgadj_handle* h) {
   cudaFree(h->d_jwm_f);
   cudaFree(h->d_uin);
   cudaFree(h->d_npk);
+  cudaFree(h->d_Php);
   cudaFree(h->ring);
   cudaFree(h->red_scratch);
   cudaFree(h->fd_scratch);
@@ -937,7 +943,7 @@ static int launch(dgadj_handle* h, int variant, const LaunchPlan& pl, cudaStream
   march_launch_fn fn = launch_table[h->Np];
   if (!fn) return fail(h, DGADJ_ERR_UNSUPPORTED, "no kernel for Np=%d", h->Np);
   if (ka->p.npk && variant != VAR_FWD && variant != VAR_FUSED)
-    return fail(h, DGADJ_ERR_UNSUPPORTED, "per-element orders: only dgadj_forward (without checkpoints) and dgadj_fwd_adj are built for them");
+    return fail(h, DGADJ_ERR_UNSUPPORTED, "per-element orders: only dgadj_forward (without checkpoints), dgadj_fwd_adj and dgadj_fwd_adj_windowed are built for them");
   set_vec_io(ka, pl);
   cudaError_t e = fn(variant, pl.ept, pl.grid, pl.block, pl.smem, st, ka);
   if (e != cudaSuccess) return fail(h, DGADJ_ERR_CUDA, "march kernel launch failed: %s", cudaGetErrorString(e));
@@ -950,6 +956,7 @@ extern "C" int dgadj_forward(dgadj_handle* h, const dgadj_march_args* args, cons
   int rc = check_args(h, args, ckpt_dev != nullptr);
   if (rc) return rc;
   if (!u0_dev) return fail(h, DGADJ_ERR_INVALID, "u0_dev is null");
+  if (h->d_npk && hist_dev) return fail(h, DGADJ_ERR_UNSUPPORTED, "per-element orders: the state history is not built for them");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const int variant = ckpt_dev ? VAR_FWD_RESID : VAR_FWD;
   LaunchPlan pl;
@@ -1075,7 +1082,6 @@ extern "C" int dgadj_fwd_adj_windowed(dgadj_handle* h, const dgadj_march_args* a
   if (rc) return rc;
   if (!u0_dev) return fail(h, DGADJ_ERR_INVALID, "u0_dev is null");
   if (window < 1 || batch_chunk < 0) return fail(h, DGADJ_ERR_INVALID, "window must be >= 1 and batch_chunk >= 0");
-  if (h->d_npk) return fail(h, DGADJ_ERR_UNSUPPORTED, "per-element orders: the windowed march is not built for them");
   const int S = args->S, W = window;
   const int nwin = (S + W - 1) / W;
   if (nwin <= 1) return dgadj_fwd_adj(h, args, u0_dev, uT_dev, J_dev, lam0_dev, eta_dev, stream);
@@ -1408,10 +1414,34 @@ extern "C" int dgadj_ic_indicator(dgadj_handle* h, int64_t B, const double* u0_d
   if (!h->enr_set) return fail(h, DGADJ_ERR_STATE, "dgadj_set_enriched has not been called");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
+  const double* Pd = h->d_P;
+  if (h->d_npk) {
+    // per-element orders: P_n = P V diag(1_n, 0) V^-1 for every node count n <= Np (a few hundred doubles, per call)
+    const int Np = h->Np, NpF = h->NpF;
+    std::vector<double> Pn((size_t)(Np + 1) * NpF * Np, 0.0), T((size_t)Np * Np);
+    for (int n = 0; n <= Np; ++n) {
+      for (int i = 0; i < Np; ++i)
+        for (int j = 0; j < Np; ++j) {
+          double acc = 0.0;
+          for (int m = 0; m < n; ++m) acc += h->Vhost[0][i * Np + m] * h->cops.iV[m * Np + j];
+          T[(size_t)i * Np + j] = acc;
+        }
+      for (int i = 0; i < NpF; ++i)
+        for (int j = 0; j < Np; ++j) {
+          double acc = 0.0;
+          for (int m = 0; m < Np; ++m) acc += h->P_host[i * Np + m] * T[(size_t)m * Np + j];
+          Pn[((size_t)n * NpF + i) * Np + j] = acc;
+        }
+    }
+    if (!h->d_Php) CUDA_TRY(h, cudaMalloc((void**)&h->d_Php, (size_t)(MAXNP + 1) * MAXNP * MAXNP * sizeof(double)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_Php, Pn.data(), Pn.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));   // the host vector goes out of scope
+    Pd = h->d_Php;
+  }
   const long long n = (long long)B * h->K;
   const int block = 256;
-  ic_indicator_kernel<<<(unsigned)((n + block - 1) / block), block, 0, st>>>(B, h->K, h->Np, h->NpF, h->d_P, u0_dev, u0f_dev,
-                                                                             lam0_dev, eta_dev);
+  ic_indicator_kernel<<<(unsigned)((n + block - 1) / block), block, 0, st>>>(B, h->K, h->Np, h->NpF, Pd, h->d_npk, u0_dev,
+                                                                             u0f_dev, lam0_dev, eta_dev);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return DGADJ_OK;
@@ -1426,6 +1456,7 @@ extern "C" int dgadj_rhs(dgadj_handle* h, int64_t B, int32_t level, const double
   // time t does not have: refuse instead of silently using the first entry
   if (h->cfg.bc == DGADJ_BC_INFLOW && h->cfg.inflow == DGADJ_INFLOW_TABLE)
     return fail(h, DGADJ_ERR_UNSUPPORTED, "dgadj_rhs cannot evaluate a tabulated inflow at a time t (the table is indexed by step and stage)");
+  if (h->d_npk) return fail(h, DGADJ_ERR_UNSUPPORTED, "per-element orders: dgadj_rhs is the uniform-order nodal right-hand side");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const int Np = level ? h->NpF : h->Np;
   const long long n = (long long)B * h->K;

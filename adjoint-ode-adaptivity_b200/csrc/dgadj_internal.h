@@ -37,6 +37,7 @@ struct dgadj_handle {
   double* d_uin;
   int uin_n;
   int* d_npk;             // hp: [K] modes per element of the primal space, or null (uniform order)
+  double* d_Php;          // hp: projected prolongations P_n, n = 0..Np (dgadj_ic_indicator)
   double* ring;
   size_t ring_bytes;
   double* red_scratch;

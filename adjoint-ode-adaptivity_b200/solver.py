@@ -393,7 +393,8 @@ class AdvecDG1D:
         polynomial order of every element, each in [1, N]; None returns to the uniform order N.  Fields keep the
         (B, N+1, K) layout on the order-N LGL nodes -- an element of lower order holds its polynomial's values there
         (it is L2-projected onto its own space on input).  The enriched space has one order more per element.
-        Built for `forward` (without history) and `fwd_adj`."""
+        Built for `forward` (without history), `fwd_adj` (also with `window=`) and `ic_indicator`; `adapt_advec(...,
+        orders=)` runs the refinement loop with them."""
         if orders is None:
             self._check(self.lib.dgadj_set_element_orders(self._h, C.c_void_p(0)))
             self.orders = None

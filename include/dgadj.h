@@ -116,7 +116,9 @@ int dgadj_set_functional_weights(dgadj_handle* h, const double* jw_c, const doub
  * is L2-projected onto its own space); the kernels hold the modes beyond an element's space at zero -- in the
  * orthonormal modal basis a lower order IS the truncated space, so this is the hp scheme, not an approximation
  * of it.  The enriched space of the adjoint / indicator has one order more per element.  Built for
- * dgadj_forward (without checkpoints) and dgadj_fwd_adj(_host); DGADJ_ERR_UNSUPPORTED elsewhere.        */
+ * dgadj_forward (without checkpoints / history), dgadj_fwd_adj(_host), dgadj_fwd_adj_windowed and
+ * dgadj_ic_indicator (the coarse data enter through the L2 projection onto each element's space);
+ * DGADJ_ERR_UNSUPPORTED elsewhere (two-call adjoint, dgadj_rhs).                                       */
 int dgadj_set_element_orders(dgadj_handle* h, const int32_t* nodes_per_element_host);
 
 /* Caller-supplied inflow values uin[S*nstages] (cfg.inflow == DGADJ_INFLOW_TABLE).       */

@@ -260,9 +260,12 @@ def test_hp_per_element_orders(pkg, torch, bc, alpha):
     assert all(torch.equal(o1[k], o2[k]) for k in ("uT", "J", "eta", "lam0"))
     with pytest.raises(pkg.DgadjError):
         s.set_element_orders([Nmax + 1] * K)
+    # the windowed march (two-level checkpointing) with per-element orders: the one-pass results bit for bit
     s.set_element_orders(orders)
+    o3 = s.fwd_adj(torch.tensor(u0p, device="cuda"), a, dt, S, want_lam0=True, window=8)
+    assert all(torch.equal(out[k], o3[k]) for k in ("uT", "J", "eta", "lam0"))      # (periodic / zero inflow data)
     with pytest.raises(pkg.DgadjError):
-        s.fwd_adj(torch.tensor(u0p, device="cuda"), a, dt, S, window=8)             # not built for hp
+        s.rhs(torch.tensor(u0p, device="cuda"), 0.0, a)                             # uniform-order entry point
 
 
 def test_fused_functional_int_u2_and_weighted(pkg, torch):
@@ -1282,6 +1285,55 @@ def test_adaptive_loop_advection_nonuniform_h(pkg, torch):
     jw_f = torch.tensor(s.jw_f, device="cuda")
     diff = (jw_f * (torch.einsum("ij,bjk->bik", torch.tensor(s.P, device="cuda"), uc) - uf)).sum((1, 2))
     assert float((h2["estimate"] - diff).abs().max()) < 1e-11 * float((jw_f.abs() * uf.abs()).sum((1, 2)).max())
+
+
+def test_adaptive_loop_advection_hp_orders(pkg, torch):
+    """The PDE refinement loop with per-element orders (hp): the halves of a split element keep its order, the
+    indicators agree with the ragged hp oracle on the same meshes, and with the initial-data term (projected
+    prolongations P_n) the signed estimate is the whole difference J_f(P u_c^S) - J_f(u_f^S) between the hp march and
+    the march of the space one order higher per element."""
+    from oracle import advec_hp as ohp
+    B, N = 6, 3
+    rng = np.random.default_rng(5)
+    centres = rng.uniform(0.8, 1.2, B)
+
+    def u0_np(x):
+        return np.exp(-((x[None] - centres[:, None, None]) / 0.2) ** 2)
+
+    u0_fn = lambda x: torch.tensor(u0_np(x), device="cuda")
+    v_x0 = np.linspace(0.0, 3.0, 11)
+    orders0 = np.array([3, 2, 3, 3, 1, 2, 3, 2, 1, 3])
+    a, T = 1.0, 0.5
+    hist = pkg.adapt_advec(u0_fn, N, v_x0, a, T, iters=3, topk=2, bc="inflow", inflow="zero", alpha=0.0, ic_term=False,
+                           orders=orders0)
+    assert [h["K"] for h in hist] == [10, 12, 14, 16]
+    for h0, h1 in zip(hist[:-1], hist[1:]):               # children inherit the parent's order
+        exp = np.insert(h0["orders"], h0["refined"] + 1, h0["orders"][h0["refined"]])
+        assert np.array_equal(h1["orders"], exp)
+    for h in hist[:3]:                                    # the ragged oracle on the same meshes / orders
+        c = ohp.HpSpace(h["orders"], h["v_x"])
+        x_pad = ops.startup_mesh(N, h["v_x"]).x
+        eta = np.zeros((B, h["K"]))
+        for b in range(B):
+            u0r = ohp.unpad(c, u0_np(x_pad)[b], N)
+            eta[b] = ohp.fwd_adj_indicator(u0r, h["orders"], h["v_x"], a, T / h["S"], h["S"], 0.0, False)["eta"]
+        mean_ref = np.abs(eta).mean(axis=0)
+        np.testing.assert_allclose(h["mean_eta"], mean_ref, rtol=1e-6, atol=1e-9 * mean_ref.max())
+        assert np.array_equal(h["refined"], np.sort(np.argsort(-mean_ref, kind="stable")[:2]))
+    # the initial-data term
+    h2 = pkg.adapt_advec(u0_fn, N, v_x0, a, T, iters=1, topk=2, bc="inflow", inflow="zero", alpha=0.0, orders=orders0)[1]
+    c, f = ohp.HpSpace(h2["orders"], h2["v_x"]), ohp.HpSpace(h2["orders"] + 1, h2["v_x"])
+    Lc, Lf = c.rhs_matrix(a, 0.0, False), f.rhs_matrix(a, 0.0, False)
+    P = ohp.prolongation(c, f)
+    xc, xf = ops.startup_mesh(N, h2["v_x"]).x, ops.startup_mesh(N + 1, h2["v_x"]).x
+    dt = T / h2["S"]
+    for b in range(B):
+        uc, uf = ohp.unpad(c, u0_np(xc)[b], N), ohp.unpad(f, u0_np(xf)[b], N + 1)
+        for _ in range(h2["S"]):
+            uc, uf = ohp.step(uc, Lc, dt), ohp.step(uf, Lf, dt)
+        diff = f.weights() @ (P @ uc) - f.weights() @ uf
+        scale = np.abs(f.weights()) @ np.abs(uf)
+        assert abs(float(h2["estimate"][b]) - diff) < 1e-10 * scale, (b, float(h2["estimate"][b]), diff)
 
 
 def test_matlab_named_entry_points(pkg, torch):
