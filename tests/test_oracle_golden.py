@@ -391,3 +391,16 @@ def test_hp_oracle_reduces_to_the_uniform_oracle():
     dJ = cf.weights(psi) @ (P @ out["uT"]) - cf.weights(psi) @ uf
     assert abs(dJ) > 1e-6 and out["eta"].sum() == pytest.approx(dJ, rel=1e-9)
     assert np.max(np.abs(hp.unpad(c, hp.pad(c, u0h, 3), 3) - u0h)) < 1e-14
+    # with the initial-data term the indicators sum to the whole difference between the hp march from projected data
+    # and the march of the enriched spaces from THEIR projection of the same data (what adapt_advec(orders=) reports)
+    true = lambda x: np.sin(x) + 0.2 * np.cos(3 * x)
+    xc, xf = ops.startup_mesh(3, vx).x, ops.startup_mesh(4, vx).x
+    u0c, u0f = hp.unpad(c, true(xc), 3), hp.unpad(cf, true(xf), 4)
+    out = hp.fwd_adj_indicator(u0c, orders, vx, a, dt, S, 0.0, True, psi)
+    uc, uf = u0c.copy(), u0f.copy()
+    Lc = c.rhs_matrix(a, 0.0, True)
+    for _ in range(S):
+        uc, uf = hp.step(uc, Lc, dt), hp.step(uf, Lf, dt)
+    whole = cf.weights(psi) @ (P @ uc) - cf.weights(psi) @ uf
+    est = out["eta"].sum() + out["lam0"] @ (P @ u0c - u0f)
+    assert abs(whole) > 1e-8 and est == pytest.approx(whole, rel=1e-9)
