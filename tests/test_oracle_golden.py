@@ -404,3 +404,36 @@ def test_hp_oracle_reduces_to_the_uniform_oracle():
     whole = cf.weights(psi) @ (P @ uc) - cf.weights(psi) @ uf
     est = out["eta"].sum() + out["lam0"] @ (P @ u0c - u0f)
     assert abs(whole) > 1e-8 and est == pytest.approx(whole, rel=1e-9)
+
+
+def test_time_dg_jacobian_complex_step():
+    """The check of matlab/test_jacobian.m:12-57 with an assertion: the Jacobian the Newton iteration of dg_march
+    uses, dR/dU = A + hk/2 Phi' diag(w cos(u_r)) Phi (dg_march.m:52,54,62), against the complex-step derivative of
+    the residual R(U) = A U + M~(U) + F (:61) -- 30 random draws per order, steps 1e-1 .. 1e-13 as the script plots
+    them: the error falls like h^2 and sits at rounding below 1e-6 (the complex step has no cancellation)."""
+    rng = np.random.default_rng(0)
+    for N in (1, 2, 3):
+        el = tdg.primal_element(N, (0.0, 1.0))
+        A, Iq, Phi, w, hk, Np = el["A"], el["Iq"], el["Phi"], el["w"], el["hk"], el["Np"]
+
+        def residual(U):
+            ur = Iq @ U
+            F = np.zeros(Np, dtype=U.dtype); F[0] = 1.0
+            return A @ U + hk / 2 * Phi.T @ (w * np.sin(ur)) + F
+
+        def jacobian(U):
+            return A + hk / 2 * Phi.T @ np.diag(w * np.cos(Iq @ U)) @ Phi
+
+        errs = np.zeros((30, 13))
+        hs = 10.0 ** -np.arange(1, 14)
+        for k in range(30):
+            U = rng.random(Np)
+            d = rng.random(Np); d /= np.linalg.norm(d)
+            Jd = jacobian(U) @ d
+            for j, h in enumerate(hs):
+                errs[k, j] = np.linalg.norm(np.imag(residual(U + 1j * h * d)) / h - Jd) / np.linalg.norm(Jd)
+        mean = errs.mean(axis=0)
+        assert mean[0] < 1e-2 and mean[1] < 1e-4 and mean[2] < 1e-6          # h = 1e-1, 1e-2, 1e-3: second order
+        assert 50 < mean[0] / mean[1] < 200 and 50 < mean[1] / mean[2] < 200
+        assert errs[:, 7:].max() < 1e-14                                     # h <= 1e-8: rounding
+
