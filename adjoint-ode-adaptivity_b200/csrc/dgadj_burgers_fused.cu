@@ -64,6 +64,9 @@ namespace dgadj {
 //     so their divergent path is the CTA's critical path -- 36 % of the warp-stages enter it      5.03e10 / 5.96e10
 //   one divergent region for all of a thread's cells (detection first, reconstructions side by side)
 //     instead of one per cell: 4.79e10 / 5.67e10 -- slower, not kept.
+//   the exchange of the limiter's transpose split (arrive, the stage-state loads, wait) instead of one hardware
+//     barrier: 4.98e10 / 6.06e10 (the state's longer live range at the 168-register cap costs the indicator mode
+//     what the plain mode gains); split in plain mode only: 5.03e10 / 5.85e10 -- not kept.
 // ncu of the final form (profiles/r2_burgers_fused_ncu.json): fp64 pipe 51.0 % (47.3 % before the last step), issue
 // slots 55 % busy, 44 % of the issued instructions on the fp64 pipe (183.7 of 418.5 per update); per issued
 // instruction 1.33 cycles of fixed-latency waits, 0.57 on the exchange mbarrier, 0.30 on the hardware barrier --
