@@ -148,7 +148,7 @@ __device__ __forceinline__ double mm3b(double a, double b, double c, int* br) {
 // x / h from the correctly rounded reciprocal r = RN(1/h): q = RN(x r) is within an ulp of the quotient, the
 // residual x - h q is exact in an fma, and RN(q + residual r) is the correctly rounded quotient (Markstein's
 // theorem) -- the bits of a division without the 30-instruction division sequence in the limited cells' path.
-// (4e8 random pairs against the division on the host: no difference.)  Not for non-finite x: the march's
+// (tests/div_rn_check.c: random pairs against the division on the host, bit for bit.)  Not for non-finite x: the march's
 // status word reports those.
 __device__ __forceinline__ double div_rn(double x, double h, double r) {
   const double q = x * r;

@@ -306,6 +306,17 @@ def test_c_client_compiles_and_refuses_cpu(tmp_path):
         assert "create rc -2" in r.stdout
 
 
+def test_division_free_quotient_has_the_bits_of_the_division(tmp_path):
+    """tests/div_rn_check.c: the quotient the kernels form from the correctly rounded reciprocal (the limited cells'
+    path of the fused Burgers kernel, the substitutions of the time-DG solves) equals the IEEE division bit for bit."""
+    exe = str(tmp_path / "div_rn_check")
+    r = subprocess.run(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-Wall", "-Werror",
+                        os.path.join(ROOT, "tests", "div_rn_check.c"), "-o", exe, "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "2000000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "0 differences" in r.stdout, r.stdout
+
+
 def test_missing_library_fails_loudly(tmp_path):
     """No CPU fallback: with libdgadj.so absent the package import raises ImportError."""
     code = ("import sys; sys.path.insert(0, %r); import dgadj_loader\n"
