@@ -64,12 +64,14 @@ namespace dgadj {
 //     so their divergent path is the CTA's critical path -- 36 % of the warp-stages enter it      5.03e10 / 5.96e10
 //   one divergent region for all of a thread's cells (detection first, reconstructions side by side)
 //     instead of one per cell: 4.79e10 / 5.67e10 -- slower, not kept.
+//   + the transposed volume term through the even / odd blocks of the forward one (half the multiply-adds and
+//     constant loads of the dense transpose; the exact transpose of the forward term as computed)  5.10e10 / 6.22e10
 //   the exchange of the limiter's transpose split (arrive, the stage-state loads, wait) instead of one hardware
 //     barrier: 4.98e10 / 6.06e10 (the state's longer live range at the 168-register cap costs the indicator mode
 //     what the plain mode gains); split in plain mode only: 5.03e10 / 5.85e10 -- not kept.
-// ncu of the final form (profiles/r2_burgers_fused_ncu.json): fp64 pipe 51.0 % (47.3 % before the last step), issue
-// slots 55 % busy, 44 % of the issued instructions on the fp64 pipe (183.7 of 418.5 per update); per issued
-// instruction 1.33 cycles of fixed-latency waits, 0.57 on the exchange mbarrier, 0.30 on the hardware barrier --
+// ncu of the final form (profiles/r2_burgers_fused_ncu.json): fp64 pipe 50.7 % (47.3 % before the last two steps),
+// issue slots 54 % busy, 44 % of the issued instructions on the fp64 pipe (179.7 of 405.0 per update); per issued
+// instruction 1.41 cycles of fixed-latency waits, 0.58 on the exchange mbarrier, 0.32 on the hardware barrier --
 // 12 warps per SM (3 CTAs: the five stage states of a trajectory take 61 KB of shared memory) leave the
 // schedulers without an eligible warp 45 % of the time.
 #ifndef BG_SPLIT
@@ -80,6 +82,9 @@ namespace dgadj {
 #endif
 #ifndef BG_STAGE_CONSTS
 #define BG_STAGE_CONSTS 1
+#endif
+#ifndef BG_TRANSPOSED_EO
+#define BG_TRANSPOSED_EO 1   // the transposed volume term through the even / odd blocks of the forward one
 #endif
 struct BgStageOps {
   StageOps so;                 // even/odd blocks of the nodal Dr / LIFT (forward volume and lift terms)
@@ -818,6 +823,43 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
         // then the residual's own scaling lk *= rka (everything that reads lk of this stage is done)
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
+#if BG_TRANSPOSED_EO
+          // the transpose of the forward volume term AS COMPUTED there (even/odd blocks): with w = (-rx dt / 2) lk,
+          //   we_i = w_i + w_{N-i} (2 w_mid), wo_i = w_i - w_{N-i};  A_j = sum_i DE_ij we_i,  B_j = sum_i DO_ij wo_i;
+          //   lu_j += us_j (A_j + B_j),  lu_{N-j} += us_{N-j} (B_j - A_j),  lu_mid += us_mid B_mid
+          // -- half the multiply-adds and constant loads of the dense transpose
+          constexpr int HE = (NPX + 1) / 2, HO = NPX / 2;
+          const double mh = cx.in ? -0.5 * __ldg(LXv.rxk + k0 + e) * dt : 0.0;
+          double we[HE], wo[HO > 0 ? HO : 1];
+#pragma unroll
+          for (int i = 0; i < HO; ++i) {
+            const double a = mh * lk[e][i], b = mh * lk[e][NPX - 1 - i];
+            we[i] = a + b;
+            wo[i] = a - b;
+          }
+          if (NPX & 1) we[HO] = (mh + mh) * lk[e][HO];
+#pragma unroll
+          for (int j = 0; j < HE; ++j) {
+            double Bj = 0.0;
+#pragma unroll
+            for (int i = 0; i < HO; ++i) {
+              const double2 c2 = LXs.so.DO2[i * HP + j / 2];
+              Bj = fma((j & 1) ? c2.y : c2.x, wo[i], Bj);
+            }
+            if (j < HO) {
+              double Aj = 0.0;
+#pragma unroll
+              for (int i = 0; i < HE; ++i) {
+                const double2 c2 = LXs.so.DE2[i * HP + j / 2];
+                Aj = fma((j & 1) ? c2.y : c2.x, we[i], Aj);
+              }
+              lu[e][j] = fma(us[e][j], Aj + Bj, lu[e][j]);
+              lu[e][NPX - 1 - j] = fma(us[e][NPX - 1 - j], Bj - Aj, lu[e][NPX - 1 - j]);
+            } else {
+              lu[e][j] = fma(us[e][j], Bj, lu[e][j]);   // the middle node of an odd node count
+            }
+          }
+#else
           const double mrx = cx.in ? -__ldg(LXv.rxk + k0 + e) * dt : 0.0;
           double w[NPX];
 #pragma unroll
@@ -829,6 +871,7 @@ __global__ void __launch_bounds__(BD, BG_MINB(BD, IND)) burgers_fused_kernel(con
             for (int i = 0; i < NPX; ++i) acc = fma(LXs.Dr[i * NPX + j], w[i], acc);
             lu[e][j] = fma(us[e][j], acc, lu[e][j]);
           }
+#endif
 #pragma unroll
           for (int i = 0; i < NPX; ++i) lk[e][i] *= rka;
         }
