@@ -58,8 +58,10 @@ def stage_scalings(rka):
     return sig, sga
 
 
-def fwd_step(L, z, rk, uin_fn):
-    """z: (Np, K) modal coefficients of one trajectory (kernel: fwd_step)."""
+def fwd_step(L, z, rk, uin_fn, mask=None):
+    """z: (Np, K) modal coefficients of one trajectory (kernel: fwd_step).  mask (Np, K) bool: hp -- the modes of
+    each element's own space; the surface term and the update skip the others (kernel: `HP && i >= nm[e]`)."""
+    mk = 1.0 if mask is None else mask.astype(float)
     rka, rkb, _ = rk
     o, p = L.o, L.o["p"]
     ev = (np.arange(len(p)) % 2 == 0)
@@ -75,12 +77,13 @@ def fwd_step(L, z, rk, uin_fn):
             uR[-1] = uB[-1]
         g0, g1 = (uF - uL) * L.q0, (uB - uR) * L.q1
         se, sd = (g1 + g0) / sig[s], (g1 - g0) / sig[s]
-        r = r + (o["D"] / sig[s]) @ z + p[:, None] * np.where(ev[:, None], se, sd)
-        z = z + (rkb[s] * sig[s] * L.m) * r
+        r = r + (o["D"] / sig[s]) @ z + mk * (p[:, None] * np.where(ev[:, None], se, sd))
+        z = z + mk * ((rkb[s] * sig[s] * L.m) * r)
     return z
 
 
-def adj_step(L, mu, rk):
+def adj_step(L, mu, rk, mask=None):
+    mk = 1.0 if mask is None else mask.astype(float)
     rka, rkb, _ = rk
     o, p = L.o, L.o["p"]
     ev = (np.arange(len(p)) % 2 == 0)
@@ -96,29 +99,39 @@ def adj_step(L, mu, rk):
             gam1L[0] = 0.0
             gam0R[-1] = 0.0
         a0, aN = gam0 - gam1L, gam1 - gam0R
-        mu = mu + (o["D"] * sga[s]).T @ w + p[:, None] * np.where(ev[:, None], aN + a0, aN - a0)
+        mu = mu + mk * ((o["D"] * sga[s]).T @ w) + mk * (p[:, None] * np.where(ev[:, None], aN + a0, aN - a0))
     return mu
 
 
-def fused(lib, gc, gf, u0, a, dt, S, alpha, periodic, rk, jw_c, jw_f, inflow_fn=None, t0=0.0):
-    """One trajectory through the fused kernel's algorithm.  Returns dict(uT, J, eta, lam0)."""
+def fused(lib, gc, gf, u0, a, dt, S, alpha, periodic, rk, jw_c, jw_f, inflow_fn=None, t0=0.0, nodes_per_element=None):
+    """One trajectory through the fused kernel's algorithm.  Returns dict(uT, J, eta, lam0).
+    nodes_per_element (K ints <= Np): hp, the HP kernels' mode masks (the enriched space has one mode more)."""
     Lc, Lf = Level(lib, gc, a, dt, alpha, periodic), Level(lib, gf, a, dt, alpha, periodic)
     K = u0.shape[1]
+    mc = mf = None
+    if nodes_per_element is not None:
+        nm = np.asarray(nodes_per_element)
+        mc = np.arange(gc.n_p)[:, None] < nm[None, :]
+        mf = np.arange(gf.n_p)[:, None] < (nm[None, :] + 1)
     zc = Lc.o["iV"] @ u0
+    if mc is not None:
+        zc = zc * mc                     # the L2 projection of the input onto each element's own space
     ckpt = []
     time = t0
     for n in range(S):
         uin = (lambda s: inflow_fn(time + rk[2][s] * dt)) if inflow_fn else (lambda s: 0.0)
-        sig = fwd_step(Lf, np.vstack([zc, np.zeros((1, K))]), rk, uin)     # sigma = Phi_f(P u^n), P = injection
-        zc = fwd_step(Lc, zc, rk, uin)
+        sig = fwd_step(Lf, np.vstack([zc, np.zeros((1, K))]), rk, uin, mf)     # sigma = Phi_f(P u^n), P = injection
+        zc = fwd_step(Lc, zc, rk, uin, mc)
         time = time + dt
         ckpt.append(np.vstack([zc, np.zeros((1, K))]) - sig)
     uT = Lc.o["V"] @ zc
     J = np.sum((Lc.o["V"].T @ jw_c) * zc)
     mu = Lf.o["V"].T @ jw_f
+    if mf is not None:
+        mu = mu * mf                     # the functional's covector restricted to the elements' enriched spaces
     eta = np.zeros(K)
     for n in range(S - 1, -1, -1):
         eta += np.sum(mu * ckpt[n], axis=0)
-        mu = adj_step(Lf, mu, rk)
+        mu = adj_step(Lf, mu, rk, mf)
     lam0 = Lf.o["iV"].T @ mu
     return dict(uT=uT, J=J, eta=eta, lam0=lam0, viol=max(Lc.o["viol"], Lf.o["viol"]))

@@ -97,6 +97,37 @@ def test_modal_algebra_matches_oracle(pkg, lib, N, K, bc, alpha):
     assert np.all(np.abs(out["eta"] - ref["eta"]) <= 1e-12 * ref["eta_scale"])
 
 
+@pytest.mark.parametrize("bc", ["periodic", "inflow"])
+def test_hp_mode_masks_are_the_hp_scheme(pkg, lib, bc):
+    """The claim behind `dgadj_set_element_orders` checked without a GPU: the padded modal march with the HP kernels'
+    mode masks (tests/modal_emulator.py, on the operators of the C library's host code) IS the hp scheme -- every
+    element with the StartUp1D operators of its own order, ragged arrays, a dense global matrix (oracle/advec_hp.py):
+    terminal state, functional, the adjoint as a covector of each element's own enriched space, the indicators."""
+    from oracle import advec_hp as ohp
+    N, orders = 4, [2, 4, 3, 4, 1, 2, 4, 1]
+    vx = np.array([0.0, 0.5, 1.1, 1.6, 2.4, 3.0, 3.9, 4.6, 2 * math.pi])
+    K = len(orders)
+    gc, gf = pkg.BaseGalerkin1D(n=N, v_x=vx), pkg.BaseGalerkin1D(n=N + 1, v_x=vx)
+    c = ohp.HpSpace(orders, vx)
+    rng = np.random.default_rng(17)
+    u0r = np.concatenate([np.sin(x + 0.7) + 0.4 * rng.standard_normal(x.size) for x in c.x])
+    u0p = ohp.pad(c, u0r, N)
+    a, dt, S = 1.3, 2e-3, 40
+    per = bc == "periodic"
+    alpha = 0.0 if per else 0.3
+    ref = ohp.fwd_adj_indicator(u0r, orders, vx, a, dt, S, alpha, per)
+    rk = (ops.rk4a, ops.rk4b, ops.rk4c)
+    out = em.fused(lib, gc, gf, u0p, a, dt, S, alpha, per, rk, gc.quad_weights(), gf.quad_weights(),
+                   nodes_per_element=np.asarray(orders) + 1)
+    f = ref["spaces"][1]
+    scale = np.max(np.abs(ref["uT"]))
+    assert np.max(np.abs(ohp.unpad(c, out["uT"], N) - ref["uT"])) < 1e-12 * scale
+    assert np.max(np.abs(ohp.pad(c, ohp.unpad(c, out["uT"], N), N) - out["uT"])) < 1e-13 * scale   # stays in the spaces
+    assert abs(out["J"] - ref["J"]) < 1e-12 * max(1.0, abs(ref["J"]))
+    assert np.max(np.abs(ohp.unpad_covector(f, out["lam0"], N + 1) - ref["lam0"])) < 1e-12 * np.max(np.abs(ref["lam0"]))
+    assert np.max(np.abs(out["eta"] - ref["eta"]) / ref["eta_scale"]) < 1e-12
+
+
 def test_modal_operator_structure(pkg, lib):
     """V^-1 Dr V is strictly upper triangular and parity sparse (floor(Np^2/4) non-zeros), the
     lift is V^T E, the prolongation is the injection; a wrong V is reported."""
