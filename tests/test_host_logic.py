@@ -168,6 +168,45 @@ def test_even_odd_blocks_reproduce_the_nodal_derivative(pkg, lib):
         np.testing.assert_allclose(eo.from_eo(E, O, 0.5), g.d_r @ u + g.lift @ g2, atol=1e-11)
 
 
+def test_transposed_volume_term_through_the_even_odd_blocks(pkg, lib):
+    """The fused Burgers kernel transposes its volume term through the SAME even / odd blocks the forward term uses
+    (csrc/dgadj_burgers_fused.cu, BG_TRANSPOSED_EO): the forward form as the kernel computes it equals 2 Dr F, and the
+    transposed form is its exact transpose (dot-product identity at rounding) -- for even and odd node counts."""
+    for N in range(1, 9):
+        g = pkg.BaseGalerkin1D(n=N, k=2)
+        b = eo.eo_blocks(lib, g)
+        DE, DO, HE, HO, Np = b["DE"], b["DO"], b["HE"], b["HO"], N + 1
+        rng = np.random.default_rng(N)
+
+        def forward(F):                          # bg_stage: fe / fo, E = DE fo, O = DO fe, rhs_i = E + O, rhs_{N-i} = E - O
+            fe = np.array([F[i] + F[Np - 1 - i] for i in range(HO)] + ([F[HO]] if Np & 1 else []))
+            fo = np.array([F[i] - F[Np - 1 - i] for i in range(HO)])
+            E, O = DE @ fo, DO @ fe
+            rhs = np.zeros(Np)
+            for i in range(HO):
+                rhs[i], rhs[Np - 1 - i] = E[i] + O[i], E[i] - O[i]
+            if Np & 1:
+                rhs[HO] = E[HO] + E[HO]
+            return rhs
+
+        def transposed(w):                       # the reverse stage: we / wo, A = DE^T we, B = DO^T wo
+            we = np.array([w[i] + w[Np - 1 - i] for i in range(HO)] + ([2.0 * w[HO]] if Np & 1 else []))
+            wo = np.array([w[i] - w[Np - 1 - i] for i in range(HO)])
+            A, B = DE.T @ we, DO.T @ wo
+            acc = np.zeros(Np)
+            for j in range(HO):
+                acc[j], acc[Np - 1 - j] = A[j] + B[j], B[j] - A[j]
+            if Np & 1:
+                acc[HO] = B[HO]
+            return acc
+
+        for _ in range(5):
+            F, w = rng.standard_normal(Np), rng.standard_normal(Np)
+            np.testing.assert_allclose(forward(F), 2.0 * g.d_r @ F, atol=1e-11)
+            assert abs(transposed(w) @ F - w @ forward(F)) < 1e-12 * (np.abs(w) @ np.abs(forward(F)) + 1.0)
+            np.testing.assert_allclose(transposed(w), 2.0 * g.d_r.T @ w, atol=1e-11)
+
+
 def test_eo_rejects_asymmetric_operator(lib):
     Np = 4
     Dr = np.arange(16, dtype=float).reshape(4, 4)
