@@ -367,10 +367,11 @@ __global__ void tdg_adjoint_kernel(long long B, int Ks, int nq, int linear, doub
 // solve_dense in two parts: everything that does not touch the right-hand side (pivot search, row swaps of
 // the matrix, the multipliers, the reciprocals of the pivots) and the part that does.  lu_apply performs on b
 // exactly the operations solve_dense performs on it, in the same order, so solve_dense(A, b) and
-// lu_factor(A, ..) + lu_apply(A, .., b) give the same bits.
+// lu_factor(A, ..) + lu_apply(A, .., b) give the same bits (tests/lu_split_check.c restates both on the host and
+// compares them on random systems with row swaps).
 template <int N>
-__device__ __forceinline__ void lu_factor(double (&A)[N][N], unsigned& swmask, double (&rcp)[N]) {
-  swmask = 0u;
+__device__ __forceinline__ void lu_factor(double (&A)[N][N], unsigned long long& swmask, double (&rcp)[N]) {
+  swmask = 0ull;   // (bit c N + r: up to 41 at N = 7)
 #pragma unroll
   for (int c = 0; c < N; ++c) {
 #pragma unroll
@@ -384,7 +385,7 @@ __device__ __forceinline__ void lu_factor(double (&A)[N][N], unsigned& swmask, d
         A[c][j] = sw ? A[r][j] : t;
         A[r][j] = sw ? t : A[r][j];
       }
-      swmask |= sw ? (1u << (c * N + r)) : 0u;
+      swmask |= sw ? (1ull << (c * N + r)) : 0ull;
     }
     rcp[c] = 1.0 / A[c][c];
 #pragma unroll
@@ -397,12 +398,12 @@ __device__ __forceinline__ void lu_factor(double (&A)[N][N], unsigned& swmask, d
   }
 }
 template <int N>
-__device__ __forceinline__ void lu_apply(const double (&A)[N][N], unsigned swmask, const double (&rcp)[N], double (&b)[N]) {
+__device__ __forceinline__ void lu_apply(const double (&A)[N][N], unsigned long long swmask, const double (&rcp)[N], double (&b)[N]) {
 #pragma unroll
   for (int c = 0; c < N; ++c) {
 #pragma unroll
     for (int r = c + 1; r < N; ++r) {
-      const bool sw = (swmask >> (c * N + r)) & 1u;
+      const bool sw = (swmask >> (c * N + r)) & 1ull;
       const double tb = b[c];
       b[c] = sw ? b[r] : tb;
       b[r] = sw ? tb : b[r];
@@ -484,7 +485,7 @@ __global__ void tdg_adjoint_warp_kernel(long long B, int Ks, int nq, int linear,
 #pragma unroll
       for (int j = 0; j < NA; ++j) M[i][j] = fma(-hk2, M[i][j], A0[i * NA + j]);
     }
-    unsigned swmask;
+    unsigned long long swmask;
     lu_factor<NA>(M, swmask, rcp);
     double uh[NA];
 #pragma unroll

@@ -776,7 +776,7 @@ def test_tdg_warp_adjoint_equals_thread_adjoint(pkg, torch):
     initial values, both settings of quirk C-3."""
     rng = np.random.default_rng(12)
     for Ks, nmax, B, linear, quirks in ((10, 1, 77, False, True), (45, 2, 33, False, True), (70, 1, 5, False, False),
-                                        (9, 3, 40, True, True), (33, 4, 3, False, True)):
+                                        (9, 3, 40, True, True), (33, 4, 3, False, True), (12, 5, 9, False, True)):
         y0 = torch.tensor(rng.uniform(-3, 3, B), device="cuda")
         times = np.sort(np.concatenate(([0.0, 2.0], rng.uniform(0.05, 1.95, Ks - 1))))
         Ns = rng.integers(1, nmax + 1, Ks)

@@ -387,6 +387,18 @@ def test_division_free_quotient_has_the_bits_of_the_division(tmp_path):
     assert r.returncode == 0 and "0 differences" in r.stdout, r.stdout
 
 
+def test_split_dense_solve_equals_the_one_piece_solve(tmp_path):
+    """tests/lu_split_check.c: the time-DG kernels' dense solve restated on the host -- the reused pivot reciprocals
+    give the bits of the IEEE divisions, and lu_factor + lu_apply (the lane-per-element adjoint kernel) the bits of the
+    one-piece solve, on random systems of size 2..7 of which a good share needs row swaps."""
+    exe = str(tmp_path / "lu_split_check")
+    r = subprocess.run(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-Wall", "-Werror",
+                        os.path.join(ROOT, "tests", "lu_split_check.c"), "-o", exe, "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and " 0 differences to the IEEE divisions, 0 between" in r.stdout, r.stdout
+
+
 def test_missing_library_fails_loudly(tmp_path):
     """No CPU fallback: with libdgadj.so absent the package import raises ImportError."""
     code = ("import sys; sys.path.insert(0, %r); import dgadj_loader\n"
