@@ -35,5 +35,24 @@ int main(int argc, char** argv) {
     }
   }
   printf("%ld pairs, %ld differences\n", n, bad);
-  return bad ? 1 : 0;
+  /* the stopping rule of the lane-group Newton march (csrc/dgadj_tdg.cu): `sqrt(e2) > tol` decided without the square
+   * root outside a band around tol^2 -- the same decision everywhere, densely sampled around the band's edges */
+  long badrule = 0;
+  const double tols[4] = {1e-7, 1e-10, 3.3e-5, 0.25};
+  for (int t = 0; t < 4; ++t) {
+    const double tol = tols[t], tol2 = tol * tol, t2hi = tol2 * (1.0 + 1e-12), t2lo = tol2 * (1.0 - 1e-12);
+    for (long i = 0; i < n / 4; ++i) {
+      double e2;
+      switch (rnd() % 3) {
+        case 0: e2 = tol2 * (1.0 + (ur() - 0.5) * 4e-12); break;             /* inside and just outside the band */
+        case 1: e2 = tol2 * (1.0 + (ur() - 0.5) * 1e-15 * (double)(rnd() % 64)); break;   /* the last ulps around tol^2 */
+        default: e2 = tol2 * ldexp(1.0 + ur(), (int)(rnd() % 40) - 20); break;
+      }
+      int ab = e2 > t2hi;
+      if (!ab && !(e2 < t2lo)) ab = sqrt(e2) > tol;
+      if (ab != (sqrt(e2) > tol)) ++badrule;
+    }
+  }
+  printf("stopping rule: %ld differences\n", badrule);
+  return (bad || badrule) ? 1 : 0;
 }

@@ -378,13 +378,14 @@ def test_c_client_compiles_and_refuses_cpu(tmp_path):
 
 def test_division_free_quotient_has_the_bits_of_the_division(tmp_path):
     """tests/div_rn_check.c: the quotient the kernels form from the correctly rounded reciprocal (the limited cells'
-    path of the fused Burgers kernel, the substitutions of the time-DG solves) equals the IEEE division bit for bit."""
+    path of the fused Burgers kernel, the substitutions of the time-DG solves) equals the IEEE division bit for bit;
+    the Newton march's stopping rule decided without the square root equals `sqrt(e2) > tol` everywhere."""
     exe = str(tmp_path / "div_rn_check")
     r = subprocess.run(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-Wall", "-Werror",
                         os.path.join(ROOT, "tests", "div_rn_check.c"), "-o", exe, "-lm"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe, "2000000"], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "0 differences" in r.stdout, r.stdout
+    assert r.returncode == 0 and "pairs, 0 differences" in r.stdout and "stopping rule: 0 differences" in r.stdout, r.stdout
 
 
 def test_split_dense_solve_equals_the_one_piece_solve(tmp_path):
