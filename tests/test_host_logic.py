@@ -388,6 +388,17 @@ def test_division_free_quotient_has_the_bits_of_the_division(tmp_path):
     assert r.returncode == 0 and "pairs, 0 differences" in r.stdout and "stopping rule: 0 differences" in r.stdout, r.stdout
 
 
+def test_division_free_minmod_equals_the_reference_formulation(tmp_path):
+    """tests/minmod_check.c: the kernels' minmod (compares and selects only) against utils/minmod.m:6-12
+    (sign sum, min of the absolute values), bit for bit on triples rich in zeros, ties and mixed signs."""
+    exe = str(tmp_path / "minmod_check")
+    r = subprocess.run(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-Wall", "-Werror",
+                        os.path.join(ROOT, "tests", "minmod_check.c"), "-o", exe, "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and ": 0 differences" in r.stdout, r.stdout
+
+
 def test_split_dense_solve_equals_the_one_piece_solve(tmp_path):
     """tests/lu_split_check.c: the time-DG kernels' dense solve restated on the host -- the reused pivot reciprocals
     give the bits of the IEEE divisions, and lu_factor + lu_apply (the lane-per-element adjoint kernel) the bits of the
