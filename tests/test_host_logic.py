@@ -390,13 +390,14 @@ def test_division_free_quotient_has_the_bits_of_the_division(tmp_path):
 
 def test_division_free_minmod_equals_the_reference_formulation(tmp_path):
     """tests/minmod_check.c: the kernels' minmod (compares and selects only) against utils/minmod.m:6-12
-    (sign sum, min of the absolute values), bit for bit on triples rich in zeros, ties and mixed signs."""
+    (sign sum, min of the absolute values), bit for bit on triples rich in zeros, ties and mixed signs; and the warp
+    maximum of |u| as two 32-bit reductions on the bit pattern (idle lanes at -1) against the plain maximum."""
     exe = str(tmp_path / "minmod_check")
     r = subprocess.run(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-Wall", "-Werror",
                         os.path.join(ROOT, "tests", "minmod_check.c"), "-o", exe, "-lm"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and ": 0 differences" in r.stdout, r.stdout
+    assert r.returncode == 0 and "result): 0 differences" in r.stdout and "bit pattern: 0 differences" in r.stdout, r.stdout
 
 
 def test_split_dense_solve_equals_the_one_piece_solve(tmp_path):
